@@ -1,0 +1,207 @@
+"""TEST INFRASTRUCTURE — ctypes access to the CPU oracle.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package.  The product (``eventcalib_b200``) never does.
+
+Libraries (built by ``oracle/Makefile``; see the headers of the .cpp files for what each restates):
+  * ``_build/libecb_oracle.so``  — the CPU restatement (always buildable)
+  * ``_ref/libref_dbscan.so``    — the UNMODIFIED reference ``dbscan.h`` + ``kdtree.cpp`` compiled in place
+  * ``_ref/libref_frontend.so``  — restated glue + verbatim reference DBSCAN (the "reference" CPU baseline)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT = os.path.join(_HERE, "_build", "libecb_oracle.so")
+_REF_DB = os.path.join(_HERE, "_ref", "libref_dbscan.so")
+_REF_FE = os.path.join(_HERE, "_ref", "libref_frontend.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_up = C.POINTER(C.c_uint)
+_bp = C.POINTER(C.c_uint8)
+_lp = C.POINTER(C.c_int64)
+
+
+def build(force=False):
+    """Compile the restatement and, when /root/reference is present, oracle/_ref."""
+    if force or not os.path.exists(_PORT) or (os.path.isdir("/root/reference") and not os.path.exists(_REF_DB)):
+        subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
+    return _PORT
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+_libs = {}
+
+
+def _load(path):
+    if path not in _libs:
+        if not os.path.exists(path):
+            build()
+        _libs[path] = C.CDLL(path)
+    return _libs[path]
+
+
+def port():
+    lib = _load(_PORT)
+    lib.orc_hash_double.restype = C.c_uint64
+    lib.orc_hash_double.argtypes = [C.c_double]
+    lib.orc_hash_p2.restype = C.c_uint64
+    lib.orc_hash_p2.argtypes = [C.c_double, C.c_double]
+    lib.orc_radius_threshold.restype = C.c_double
+    lib.orc_radius_threshold.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    lib.orc_frontend_windows.restype = C.c_int64
+    return lib
+
+
+def have_ref():
+    return os.path.exists(_REF_DB)
+
+
+def ref_dbscan_lib():
+    return _load(_REF_DB)
+
+
+def ref_frontend_lib():
+    lib = _load(_REF_FE)
+    lib.orc_frontend_windows.restype = C.c_int64
+    return lib
+
+
+def _dbscan(fn, xy, eps, minpts):
+    xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    n = xy.shape[0]
+    labels = np.full(max(n, 1), -1, np.int32)
+    members = np.zeros(max(n, 1), np.uint32)
+    off = np.zeros(n + 2, np.uint32)
+    noise = np.zeros(max(n, 1), np.uint32)
+    nc = C.c_int(0)
+    nn = C.c_int(0)
+    rc = fn(_p(xy, _dp), C.c_int(n), C.c_double(eps), C.c_uint(minpts), _p(labels, _ip), C.byref(nc),
+            _p(members, _up), _p(off, _up), _p(noise, _up), C.byref(nn))
+    clusters = [members[off[c]:off[c + 1]].copy() for c in range(nc.value)]
+    return dict(rc=rc, labels=labels[:n].copy(), clusters=clusters, noise=noise[:nn.value].copy())
+
+
+def dbscan(xy, eps, minpts):
+    """Restated ordered DBSCAN (oracle/ecb_oracle_frontend.cpp)."""
+    return _dbscan(port().orc_dbscan_run, xy, eps, minpts)
+
+
+def ref_dbscan(xy, eps, minpts):
+    """The unmodified reference DBSCAN<Vector2d,double>::Run (oracle/_ref)."""
+    return _dbscan(ref_dbscan_lib().ref_dbscan_run, xy, eps, minpts)
+
+
+def kd_range(xy, q, eps, ref=False):
+    xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    out = np.zeros(xy.shape[0], np.uint32)
+    fn = ref_dbscan_lib().ref_kd_range if ref else port().orc_kd_range
+    k = fn(_p(xy, _dp), C.c_int(xy.shape[0]), C.c_int(q), C.c_double(eps), _p(out, _up))
+    return out[:k].copy()
+
+
+def kd_flags(xy):
+    xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    fl = np.zeros(max(xy.shape[0], 1), np.uint8)
+    port().orc_kd_flags(_p(xy, _dp), C.c_int(xy.shape[0]), _p(fl, _bp))
+    return fl[:xy.shape[0]]
+
+
+def event_frame(t, x, y, pol, t0, t1):
+    """EventFrame ctor: window [t0,t1] closed, per-pixel dedupe, +/- cancel, libstdc++ hash-set order."""
+    t = np.ascontiguousarray(t, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    pol = np.ascontiguousarray(pol, np.uint8)
+    n = t.shape[0]
+    lo = C.c_int64(0)
+    hi = C.c_int64(0)
+    lib = port()
+    npos = C.c_int(0)
+    nneg = C.c_int(0)
+    # first call sizes
+    cap = n
+    pos = np.zeros((max(cap, 1), 2))
+    neg = np.zeros((max(cap, 1), 2))
+    lib.orc_event_frame(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_int64(n), C.c_double(t0), C.c_double(t1),
+                        _p(pos, _dp), C.byref(npos), _p(neg, _dp), C.byref(nneg), C.byref(lo), C.byref(hi))
+    return pos[:npos.value].copy(), neg[:nneg.value].copy(), lo.value, hi.value
+
+
+def uset_order(xy):
+    xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    out = np.zeros_like(xy)
+    k = port().orc_uset_order(_p(xy, _dp), C.c_int(xy.shape[0]), _p(out, _dp))
+    return out[:k].copy()
+
+
+def radius_threshold(W, H, rows, cols, asym, square, radius):
+    return port().orc_radius_threshold(W, H, rows, cols, asym, square, radius)
+
+
+def fit_circle(pxy, nxy):
+    pxy = np.ascontiguousarray(pxy, np.float64).reshape(-1, 2)
+    nxy = np.ascontiguousarray(nxy, np.float64).reshape(-1, 2)
+    out = np.zeros(3)
+    port().orc_fit_circle(_p(pxy, _dp), C.c_int(len(pxy)), _p(nxy, _dp), C.c_int(len(nxy)), _p(out, _dp))
+    return out
+
+
+def extract(pxy, nxy, eps=4.0, minS=2, clusterMin=5, knn_num=3, fitCircle=0, Rthr=15.51, rows_cols=36,
+            canonical_median=False, lib=None):
+    """extractFeatures up to findCirclesGrid on explicit point sets (V order given)."""
+    pxy = np.ascontiguousarray(pxy, np.float64).reshape(-1, 2)
+    nxy = np.ascontiguousarray(nxy, np.float64).reshape(-1, 2)
+    np_, nn = len(pxy), len(nxy)
+    pl = np.full(max(np_, 1), -1, np.int32)
+    nl = np.full(max(nn, 1), -1, np.int32)
+    pm = np.zeros(max(np_, 1), np.uint32)
+    nm = np.zeros(max(nn, 1), np.uint32)
+    po = np.zeros(np_ + 2, np.uint32)
+    no = np.zeros(nn + 2, np.uint32)
+    kp = np.zeros(max(np_, 1), np.int32)
+    kn = np.zeros(max(nn, 1), np.int32)
+    mp = np.zeros(max(np_, 1), np.int32)
+    mn = np.zeros(max(nn, 1), np.int32)
+    cap = max(np_, 1)
+    cand = np.zeros((cap, 5))
+    info = np.zeros(8, np.int32)
+    lib = lib or port()
+    lib.orc_extract(_p(pxy, _dp), C.c_int(np_), _p(nxy, _dp), C.c_int(nn), C.c_double(eps), C.c_uint(minS),
+                    C.c_uint(clusterMin), C.c_int(knn_num), C.c_int(fitCircle), C.c_double(Rthr), C.c_uint(rows_cols),
+                    C.c_int(int(canonical_median)), _p(pl, _ip), _p(nl, _ip), _p(pm, _up), _p(po, _up), _p(nm, _up),
+                    _p(no, _up), _p(kp, _ip), _p(kn, _ip), _p(mp, _ip), _p(mn, _ip), _p(cand, _dp), C.c_int(cap),
+                    _p(info, _ip))
+    return dict(p_labels=pl[:np_].copy(), n_labels=nl[:nn].copy(),
+                p_clusters=[pm[po[c]:po[c + 1]].copy() for c in range(info[0])],
+                n_clusters=[nm[no[c]:no[c + 1]].copy() for c in range(info[1])],
+                kept_p=kp[:info[2]].copy(), kept_n=kn[:info[3]].copy(), enough=int(info[4]),
+                med_p=mp[:info[2]].copy() if info[4] else np.zeros(0, np.int32),
+                med_n=mn[:info[3]].copy() if info[4] else np.zeros(0, np.int32),
+                cand=cand[:info[5]].copy())
+
+
+def frontend_windows(t, x, y, pol, windows, eps=4.0, minS=2, clusterMin=5, knn_num=3, fitCircle=0, Rthr=15.51,
+                     rows_cols=36, threads=1, ref=True):
+    """CPU baseline: reference-shaped front end over a list of windows with `threads` std::threads.
+    ref=True uses oracle/_ref (verbatim reference DBSCAN) when available. Returns (candidates, events, per-window)."""
+    lib = ref_frontend_lib() if (ref and os.path.exists(_REF_FE)) else port()
+    t = np.ascontiguousarray(t, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    pol = np.ascontiguousarray(pol, np.uint8)
+    win = np.ascontiguousarray(windows, np.float64).reshape(-1, 2)
+    nev = C.c_int64(0)
+    per = np.zeros(max(len(win), 1), np.int32)
+    tot = lib.orc_frontend_windows(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_int64(len(t)), _p(win, _dp),
+                                   C.c_int(len(win)), C.c_double(eps), C.c_uint(minS), C.c_uint(clusterMin),
+                                   C.c_int(knn_num), C.c_int(fitCircle), C.c_double(Rthr), C.c_uint(rows_cols),
+                                   C.c_int(threads), C.byref(nev), _p(per, _ip))
+    return int(tot), int(nev.value), per[:len(win)].copy()
