@@ -1,0 +1,221 @@
+"""eventcalib_b200 — Python mirror of the C ABI in ``include/eventcalib_b200.h``.
+
+The product is the CUDA library ``libecb.so`` (built in-tree by ``eventcalib_b200.build``); this module only
+binds it with ctypes for the tests, ``bench.py`` and ``__graft_entry__``.  There is no CPU fallback: if the
+library is missing or no CUDA device is present, every compute call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libecb.so")
+
+OK, FAILED, ERR_CUDA, ERR_ARG, ERR_UNSUPPORTED, ERR_STATE = 0, 1, -1, -2, -3, -4
+PB_DUPLICATE, PB_CLUSTER_CAP, PB_RANGE = 2, 4, 8
+
+
+class EcbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ecb error %d: %s" % (code, msg))
+        self.code = code
+
+
+class FrontendParams(C.Structure):
+    _fields_ = [("dbscan_eps", C.c_double), ("dbscan_min_pts", C.c_uint32), ("cluster_min", C.c_uint32),
+                ("knn_num", C.c_int32), ("fit_circle", C.c_int32), ("radius_threshold", C.c_double),
+                ("rows_cols", C.c_uint32), ("order_mode", C.c_int32), ("max_clusters", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class WindowSummary(C.Structure):
+    _fields_ = [("ev_lo", C.c_int64), ("ev_hi", C.c_int64), ("n_points", C.c_int32 * 2), ("n_clusters", C.c_int32 * 2),
+                ("n_kept", C.c_int32 * 2), ("n_candidates", C.c_int32), ("status", C.c_uint32),
+                ("point_offset", C.c_int64 * 2)]
+
+
+SUMMARY_DTYPE = np.dtype([("ev_lo", "<i8"), ("ev_hi", "<i8"), ("n_points", "<i4", 2), ("n_clusters", "<i4", 2),
+                          ("n_kept", "<i4", 2), ("n_candidates", "<i4"), ("status", "<u4"), ("point_offset", "<i8", 2)])
+assert SUMMARY_DTYPE.itemsize == C.sizeof(WindowSummary)
+
+# every symbol include/eventcalib_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_count", "ecb_synchronize", "ecb_version",
+           "ecb_set_sensor", "ecb_load_events_host", "ecb_load_events_device", "ecb_num_events", "ecb_frontend_run",
+           "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
+           "ecb_frontend_clusters", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
+           "ecb_fit_circles"]
+
+_lib = None
+
+
+def load_library():
+    """Loads libecb.so; raises if the CUDA extension was not built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EcbError(ERR_CUDA, "libecb.so not built (run `python -m eventcalib_b200.build`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_double
+    lib.ecb_ctx_create.argtypes = [i32, vp, C.POINTER(vp)]
+    lib.ecb_ctx_destroy.argtypes = [vp]
+    lib.ecb_ctx_destroy.restype = None
+    lib.ecb_last_error.argtypes = [vp]
+    lib.ecb_last_error.restype = C.c_char_p
+    lib.ecb_launch_count.argtypes = [vp]
+    lib.ecb_launch_count.restype = C.c_uint64
+    lib.ecb_synchronize.argtypes = [vp]
+    lib.ecb_version.restype = C.c_char_p
+    lib.ecb_set_sensor.argtypes = [vp, i32, i32]
+    lib.ecb_load_events_host.argtypes = [vp, vp, i64]
+    lib.ecb_load_events_device.argtypes = [vp, vp, i64]
+    lib.ecb_num_events.argtypes = [vp]
+    lib.ecb_num_events.restype = i64
+    lib.ecb_frontend_run.argtypes = [vp, vp, i32, C.POINTER(FrontendParams)]
+    lib.ecb_frontend_summary.argtypes = [vp, vp, i32]
+    lib.ecb_frontend_total_points.argtypes = [vp, i32]
+    lib.ecb_frontend_total_points.restype = i64
+    lib.ecb_frontend_points.argtypes = [vp, i32, vp, vp]
+    lib.ecb_frontend_candidates.argtypes = [vp, vp, i32]
+    lib.ecb_frontend_clusters.argtypes = [vp, i32, i32, vp, vp, vp, i32]
+    lib.ecb_frontend_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
+    lib.ecb_dbscan_run.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32)]
+    lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
+    lib.ecb_fit_circles.argtypes = [vp, vp, vp, i32, vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_params(eps=4.0, min_pts=2, cluster_min=5, knn_num=3, fit_circle=0, radius_threshold=15.511363636363637,
+                   rows_cols=36, order_mode=0, max_clusters=128):
+    """CirclesEventFrame::Params defaults + parameter/event_calibration/example.yaml."""
+    return FrontendParams(eps, min_pts, cluster_min, knn_num, fit_circle, radius_threshold, rows_cols, order_mode,
+                          max_clusters, 0)
+
+
+def radius_threshold(width, height, rows, cols, asymmetric, square, radius):
+    """circleRadiusThreshold_ of the CirclesEventFrame ctor (CirclesEventFrame.cpp:16-33)."""
+    c2 = 2.0 * cols if asymmetric else float(cols)
+    W, H = float(width), float(height)
+    return min(max(W, H) / max(float(rows), c2), min(W, H) / min(float(rows), c2)) / square * radius * 1.5
+
+
+class Context:
+    """One CUDA device + stream + buffers (``ecb_ctx``)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.ecb_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != OK:
+            raise EcbError(rc, "ecb_ctx_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
+        self.h = h
+        self.n_win = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ecb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0 or rc == FAILED:
+            raise EcbError(rc, self.lib.ecb_last_error(self.h).decode())
+        return rc
+
+    @property
+    def launches(self):
+        return int(self.lib.ecb_launch_count(self.h))
+
+    def synchronize(self):
+        self._chk(self.lib.ecb_synchronize(self.h))
+
+    # ---- ingest ----
+    def set_sensor(self, width, height):
+        self._chk(self.lib.ecb_set_sensor(self.h, width, height))
+
+    def load_events(self, records):
+        """records: numpy structured array / bytes of packed 25-byte reference records (host)."""
+        buf = np.ascontiguousarray(records)
+        n = buf.nbytes // 25
+        self._keep = buf
+        self._chk(self.lib.ecb_load_events_host(self.h, _ptr(buf), n))
+        return n
+
+    def load_events_device(self, dptr, n):
+        self._chk(self.lib.ecb_load_events_device(self.h, C.c_void_p(dptr), n))
+
+    # ---- front end ----
+    def frontend_run(self, windows, params=None):
+        win = np.ascontiguousarray(windows, np.float64).reshape(-1, 2)
+        params = params or default_params()
+        self._chk(self.lib.ecb_frontend_run(self.h, _ptr(win), len(win), C.byref(params)))
+        self.n_win = len(win)
+
+    def summary(self):
+        out = np.zeros(self.n_win, SUMMARY_DTYPE)
+        if self.n_win:
+            self._chk(self.lib.ecb_frontend_summary(self.h, _ptr(out), self.n_win))
+        return out
+
+    def points(self, polarity):
+        n = int(self.lib.ecb_frontend_total_points(self.h, polarity))
+        xy = np.zeros((max(n, 1), 2))
+        lab = np.zeros(max(n, 1), np.int32)
+        self._chk(self.lib.ecb_frontend_points(self.h, polarity, _ptr(xy), _ptr(lab)))
+        return xy[:n], lab[:n]
+
+    def candidates(self, max_cand=64):
+        out = np.zeros((self.n_win, max_cand, 5))
+        if self.n_win:
+            self._chk(self.lib.ecb_frontend_candidates(self.h, _ptr(out), max_cand))
+        return out
+
+    def clusters(self, window, polarity, cap=512):
+        raw = np.zeros(cap, np.int32)
+        size = np.zeros(cap, np.int32)
+        med = np.zeros(cap, np.int32)
+        n = self._chk(self.lib.ecb_frontend_clusters(self.h, window, polarity, _ptr(raw), _ptr(size), _ptr(med), cap))
+        return raw[:n], size[:n], med[:n]
+
+    # ---- DBSCAN::Run boundary ----
+    def dbscan(self, xy, eps, min_pts):
+        """Returns (status, labels, n_clusters) like DBSCAN::Run: status 0 SUCCESS / 1 FAILED."""
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        n = len(xy)
+        labels = np.full(max(n, 1), -1, np.int32)
+        nc = C.c_int32(0)
+        rc = self.lib.ecb_dbscan_run(self.h, _ptr(xy), n, float(eps), int(min_pts), _ptr(labels), C.byref(nc))
+        if rc == FAILED:
+            return FAILED, labels[:0], 0
+        self._chk(rc)
+        return OK, labels[:n], nc.value
+
+    def dbscan_batch(self, xy, offsets, eps, min_pts):
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, np.int64)
+        k = len(off) - 1
+        labels = np.full(max(len(xy), 1), -1, np.int32)
+        nc = np.zeros(max(k, 1), np.int32)
+        st = np.zeros(max(k, 1), np.uint32)
+        self._chk(self.lib.ecb_dbscan_run_batch(self.h, _ptr(xy), _ptr(off), k, float(eps), int(min_pts), _ptr(labels),
+                                                _ptr(nc), _ptr(st)))
+        return labels[:len(xy)], nc[:k], st[:k]
+
+    def fit_circles(self, xy, offsets):
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, np.int64)
+        k = len(off) - 1
+        out = np.zeros((max(k, 1), 3))
+        self._chk(self.lib.ecb_fit_circles(self.h, _ptr(xy), _ptr(off), k, _ptr(out)))
+        return out[:k]

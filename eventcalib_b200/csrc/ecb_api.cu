@@ -1,0 +1,480 @@
+// C ABI of libecb: context, ingest, batched front end, DBSCAN::Run boundary, batched circle fit.
+// See include/eventcalib_b200.h for the reference interface each entry point replaces.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "ecb_window.cuh"
+
+int ecb_fail(ecb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int ecb_check(ecb_ctx *ctx, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return ECB_OK;
+    return ecb_fail(ctx, ECB_ERR_CUDA, "CUDA error %s: %s", what, cudaGetErrorString(e));
+}
+
+int ecb_reserve(ecb_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return ECB_OK;
+    if (b.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    ECB_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return ECB_OK;
+}
+
+static int reserve_pinned(ecb_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return ECB_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+    ECB_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_cap = bytes;
+    return ECB_OK;
+}
+
+extern "C" {
+
+const char *ecb_version(void) { return "eventcalib_b200 0.1 (sm_100a)"; }
+
+int ecb_ctx_create(int device, void *stream, ecb_ctx **out) {
+    if (!out) return ECB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return ECB_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ECB_ERR_CUDA;
+    ecb_ctx *c = new ecb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete c;
+        return ECB_ERR_CUDA;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = (int) prop.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = (cudaStream_t) stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return ECB_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return ECB_OK;
+}
+
+void ecb_cost_free(ecb_ctx *ctx);
+
+void ecb_ctx_destroy(ecb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    ecb_cost_free(c);
+    DevBuf *bufs[] = {&c->ev_raw, &c->ev_t, &c->ev_xyp, &c->ev_flag, &c->win_t, &c->win_lohi, &c->win_ptoff, &c->summary,
+                      &c->arrive, &c->pts[0], &c->pts[1], &c->labels[0], &c->labels[1], &c->scratch, &c->ktab, &c->kmem,
+                      &c->cand, &c->status, &c->db_pix, &c->db_off, &c->db_labels, &c->db_hdr, &c->db_scratch, &c->db_dims,
+                      &c->fit_in, &c->fit_off, &c->fit_out, &c->db_hdr_b, &c->db_ktab, &c->db_counter};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *ecb_last_error(const ecb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t ecb_launch_count(const ecb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ecb_synchronize(ecb_ctx *ctx) {
+    if (!ctx) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "stream synchronize");
+}
+
+int ecb_set_sensor(ecb_ctx *ctx, int width, int height) {
+    if (!ctx) return ECB_ERR_ARG;
+    if (width < 1 || height < 1 || width > 32767 || height > 32767 || (int64_t) width * height > (1 << 20))
+        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "sensor %dx%d outside the supported range (<= 2^20 pixels)", width, height);
+    ctx->width = width;
+    ctx->height = height;
+    return ECB_OK;
+}
+
+int64_t ecb_num_events(const ecb_ctx *ctx) { return ctx ? ctx->n_events : 0; }
+
+static int unpack_events(ecb_ctx *ctx, const void *d_raw, int64_t n) {
+    int rc;
+    if ((rc = ecb_reserve(ctx, ctx->ev_t, (size_t) n * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->ev_xyp, (size_t) n * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->ev_flag, 16))) return rc;
+    ECB_CUDA(ctx, cudaMemsetAsync(ctx->ev_flag.p, 0, 16, ctx->stream));
+    if ((rc = ecb_launch_ingest(ctx, d_raw, n))) return rc;
+    uint32_t flag = 0;
+    ECB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->ev_flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_events = n;
+    if (flag & 2u) {
+        ctx->n_events = 0;
+        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "event stream is not sorted by time stamp");
+    }
+    if (flag & 1u) {
+        ctx->n_events = 0;
+        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "event stream holds non-integer or out-of-sensor pixel coordinates");
+    }
+    return ECB_OK;
+}
+
+int ecb_load_events_device(ecb_ctx *ctx, const void *d_records, int64_t n) {
+    if (!ctx || (!d_records && n > 0) || n < 0) return ECB_ERR_ARG;
+    if (ctx->width <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "ecb_set_sensor must be called before loading events");
+    if (((uintptr_t) d_records & 15u) != 0) return ecb_fail(ctx, ECB_ERR_ARG, "device record buffer must be 16-byte aligned");
+    cudaSetDevice(ctx->device);
+    return unpack_events(ctx, d_records, n);
+}
+
+int ecb_load_events_host(ecb_ctx *ctx, const void *records, int64_t n) {
+    if (!ctx || (!records && n > 0) || n < 0) return ECB_ERR_ARG;
+    if (ctx->width <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "ecb_set_sensor must be called before loading events");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ecb_reserve(ctx, ctx->ev_raw, (size_t) n * 25 + 16))) return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->ev_raw.p, records, (size_t) n * 25, cudaMemcpyHostToDevice, ctx->stream));
+    return unpack_events(ctx, ctx->ev_raw.p, n);
+}
+
+// --------------------------------------------------------------------------------------- front end ----
+static int fill_stencil(ecb_ctx *ctx, ClusterArgs &a, double eps) {
+    if (!(eps >= 1.0) || eps > ECB_MAX_EPS)
+        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "dbscan eps %.3f outside the supported range [1, %d]", eps, ECB_MAX_EPS);
+    a.E = (int) floor(eps);
+    a.eps_int = (eps == floor(eps)) ? (int) eps : -1;
+    for (int dy = 0; dy <= ECB_MAX_EPS; ++dy) {
+        int w = -1;
+        if (dy <= a.E) {
+            // largest integer w with w*w + dy*dy <= eps*eps, evaluated like the reference: d2 <= SQ(range) in f64
+            w = 0;
+            while ((double) (w + 1) * (w + 1) + (double) dy * dy <= eps * eps) ++w;
+        }
+        a.halfw[dy] = (int8_t) w;
+    }
+    return ECB_OK;
+}
+
+int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_frontend_params *params) {
+    if (!ctx || !params || (n_win > 0 && !windows) || n_win < 0) return ECB_ERR_ARG;
+    if (ctx->n_events <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no events loaded");
+    if (params->dbscan_min_pts < 1) return ecb_fail(ctx, ECB_FAILED, "min_pts < 1 (DBSCAN::Run returns FAILED)");
+    if (params->order_mode != 0) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "order_mode %d not available", params->order_mode);
+    cudaSetDevice(ctx->device);
+    int rc;
+    ctx->fp = *params;
+    ctx->n_win = 0;
+    int max_k = params->max_clusters ? (int) params->max_clusters : 128;
+    if (max_k > ECB_MAXK_LIMIT) max_k = ECB_MAXK_LIMIT;
+    ClusterArgs ca;
+    memset(&ca, 0, sizeof ca);
+    if ((rc = fill_stencil(ctx, ca, params->dbscan_eps))) return rc;
+    if (n_win == 0) return ECB_OK;
+
+    // window bounds
+    if ((rc = ecb_reserve(ctx, ctx->win_t, (size_t) n_win * 16))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->win_lohi, (size_t) n_win * 16))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->win_ptoff, (size_t) n_win * 8))) return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->win_t.p, windows, (size_t) n_win * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ecb_launch_bounds(ctx, (const double *) ctx->win_t.p, n_win, (int64_t *) ctx->win_lohi.p))) return rc;
+    ctx->h_lohi.resize((size_t) 2 * n_win);
+    ctx->h_ptoff.resize((size_t) n_win);
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->h_lohi.data(), ctx->win_lohi.p, (size_t) n_win * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t total = 0, max_cnt = 0;
+    for (int w = 0; w < n_win; ++w) {
+        int64_t cnt = std::max<int64_t>(0, ctx->h_lohi[2 * w + 1] - ctx->h_lohi[2 * w]);
+        ctx->h_ptoff[w] = total;
+        total += cnt;
+        max_cnt = std::max(max_cnt, cnt);
+    }
+    if (max_cnt > 0x3FFFFFFF) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "window with %lld events", (long long) max_cnt);
+    ctx->total_points = total;
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->win_ptoff.p, ctx->h_ptoff.data(), (size_t) n_win * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+    const size_t slots = (size_t) std::max<int64_t>(total, 1);
+    if ((rc = ecb_reserve(ctx, ctx->arrive, 2 * slots * 4))) return rc;
+    for (int p = 0; p < 2; ++p) {
+        if ((rc = ecb_reserve(ctx, ctx->pts[p], slots * 4))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->labels[p], slots * 4))) return rc;
+    }
+    if ((rc = ecb_reserve(ctx, ctx->kmem, 2 * slots * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_dims, (size_t) 2 * n_win * sizeof(ProbDesc)))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_hdr, (size_t) 2 * n_win * sizeof(ProbHdr)))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->ktab, (size_t) 2 * n_win * max_k * sizeof(KeptCluster)))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->summary, (size_t) n_win * sizeof(ecb_window_summary)))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->status, 64))) return rc;
+    ctx->cand_stride = max_k;
+    if ((rc = ecb_reserve(ctx, ctx->cand, (size_t) n_win * ctx->cand_stride * 5 * 8))) return rc;
+
+    WindowArgs wa;
+    wa.xyp = (const uint32_t *) ctx->ev_xyp.p;
+    wa.lohi = (const int64_t *) ctx->win_lohi.p;
+    wa.ptoff = (const int64_t *) ctx->win_ptoff.p;
+    wa.arrive[0] = (uint32_t *) ctx->arrive.p;
+    wa.arrive[1] = (uint32_t *) ctx->arrive.p + slots;
+    wa.pts[0] = (uint32_t *) ctx->pts[0].p;
+    wa.pts[1] = (uint32_t *) ctx->pts[1].p;
+    wa.prob = (ProbDesc *) ctx->db_dims.p;
+    wa.n_win = n_win;
+    wa.W = ctx->width;
+    wa.H = ctx->height;
+    wa.max_n = (uint32_t *) ctx->status.p + 4;
+    ECB_CUDA(ctx, cudaMemsetAsync(ctx->status.p, 0, 64, ctx->stream));
+    if ((rc = ecb_launch_window(ctx, wa))) return rc;
+    uint32_t max_n = 0;
+    ECB_CUDA(ctx, cudaMemcpyAsync(&max_n, wa.max_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    ca.prob = (const ProbDesc *) ctx->db_dims.p;
+    ca.n_prob = 2 * n_win;
+    ca.work_counter = (unsigned *) ctx->status.p;
+    for (int p = 0; p < 2; ++p) {
+        ca.pix[p] = (const uint32_t *) ctx->pts[p].p;
+        ca.labels[p] = (int32_t *) ctx->labels[p].p;
+        ca.kmem[p] = (uint32_t *) ctx->kmem.p + p * slots;
+    }
+    ca.hdr = (ProbHdr *) ctx->db_hdr.p;
+    ca.ktab = (KeptCluster *) ctx->ktab.p;
+    ca.max_k = max_k;
+    ca.W = ctx->width;
+    ca.H = ctx->height;
+    ca.PW = ((ca.W + 2 * ca.E + 31) >> 5) + 1;
+    ca.PH = ca.H + 2 * ca.E;
+    ca.min_pts = params->dbscan_min_pts;
+    ca.cluster_min = params->cluster_min;
+    if ((rc = ecb_launch_cluster(ctx, ca, (int) max_n))) return rc;
+
+    PairArgs pa;
+    pa.prob = ca.prob;
+    pa.hdr = ca.hdr;
+    pa.ktab = ca.ktab;
+    for (int p = 0; p < 2; ++p) {
+        pa.pts[p] = ca.pix[p];
+        pa.kmem[p] = ca.kmem[p];
+    }
+    pa.lohi = wa.lohi;
+    pa.summary = (ecb_window_summary *) ctx->summary.p;
+    pa.cand = (double *) ctx->cand.p;
+    pa.n_win = n_win;
+    pa.max_k = max_k;
+    pa.cand_stride = ctx->cand_stride;
+    pa.fit_circle = params->fit_circle;
+    pa.knn_num = params->knn_num < 1 ? 1 : params->knn_num;
+    pa.rows_cols = params->rows_cols;
+    pa.rthr = params->radius_threshold;
+    if ((rc = ecb_launch_pair(ctx, pa))) return rc;
+    ctx->n_win = n_win;
+    return ECB_OK;
+}
+
+int ecb_frontend_summary(ecb_ctx *ctx, ecb_window_summary *out, int n_win) {
+    if (!ctx || !out) return ECB_ERR_ARG;
+    if (n_win > ctx->n_win) n_win = ctx->n_win;
+    cudaSetDevice(ctx->device);
+    ECB_CUDA(ctx, cudaMemcpyAsync(out, ctx->summary.p, (size_t) n_win * sizeof(ecb_window_summary), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "summary copy");
+}
+
+int64_t ecb_frontend_total_points(ecb_ctx *ctx, int polarity) {
+    (void) polarity;
+    return ctx ? ctx->total_points : 0;
+}
+
+int ecb_frontend_points(ecb_ctx *ctx, int polarity, double *xy, int32_t *labels) {
+    if (!ctx || polarity < 0 || polarity > 1) return ECB_ERR_ARG;
+    if (ctx->n_win <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no front-end results");
+    cudaSetDevice(ctx->device);
+    const size_t slots = (size_t) ctx->total_points;
+    if (labels)
+        ECB_CUDA(ctx, cudaMemcpyAsync(labels, ctx->labels[polarity].p, slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xy) {
+        std::vector<uint32_t> pix(slots);
+        ECB_CUDA(ctx, cudaMemcpyAsync(pix.data(), ctx->pts[polarity].p, slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < slots; ++i) {
+            xy[2 * i] = (double) ECB_PIX_X(pix[i]);
+            xy[2 * i + 1] = (double) ECB_PIX_Y(pix[i]);
+        }
+    }
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "points copy");
+}
+
+int ecb_frontend_candidates(ecb_ctx *ctx, double *out, int max_cand) {
+    if (!ctx || !out || max_cand < 1) return ECB_ERR_ARG;
+    if (ctx->n_win <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no front-end results");
+    cudaSetDevice(ctx->device);
+    const int k = std::min(max_cand, ctx->cand_stride);
+    ECB_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t) max_cand * 40, ctx->cand.p, (size_t) ctx->cand_stride * 40, (size_t) k * 40,
+                                    (size_t) ctx->n_win, cudaMemcpyDeviceToHost, ctx->stream));
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "candidate copy");
+}
+
+int ecb_frontend_clusters(ecb_ctx *ctx, int window, int polarity, int32_t *raw_id, int32_t *size, int32_t *median_pid,
+                          int cap) {
+    if (!ctx || window < 0 || window >= ctx->n_win || polarity < 0 || polarity > 1) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const int max_k = ctx->cand_stride;
+    std::vector<KeptCluster> k((size_t) max_k);
+    ProbHdr h;
+    const size_t pb = (size_t) 2 * window + polarity;
+    ECB_CUDA(ctx, cudaMemcpyAsync(&h, (ProbHdr *) ctx->db_hdr.p + pb, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(k.data(), (KeptCluster *) ctx->ktab.p + pb * max_k, sizeof(KeptCluster) * max_k,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int n = std::min(h.n_kept, cap);
+    for (int i = 0; i < n; ++i) {
+        if (raw_id) raw_id[i] = k[i].raw_id;
+        if (size) size[i] = k[i].size;
+        if (median_pid) median_pid[i] = k[i].med_pid;
+    }
+    return n;
+}
+
+int ecb_frontend_device_ptrs(ecb_ctx *ctx, void **d_summary, void **d_candidates, int *cand_stride) {
+    if (!ctx) return ECB_ERR_ARG;
+    if (d_summary) *d_summary = ctx->summary.p;
+    if (d_candidates) *d_candidates = ctx->cand.p;
+    if (cand_stride) *cand_stride = ctx->cand_stride;
+    return ECB_OK;
+}
+
+// ------------------------------------------------------------------------- DBSCAN::Run boundary ----
+int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
+                         uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status) {
+    if (!ctx || !offsets || n_problems < 0 || (!xy && n_problems > 0)) return ECB_ERR_ARG;
+    if (min_pts < 1) return ecb_fail(ctx, ECB_FAILED, "min < 1 (dbscan.h:123)");
+    cudaSetDevice(ctx->device);
+    int rc;
+    ClusterArgs ca;
+    memset(&ca, 0, sizeof ca);
+    if ((rc = fill_stencil(ctx, ca, eps))) return rc;
+    if (n_problems == 0) return ECB_OK;
+    const int64_t total = offsets[n_problems];
+    // host-side packing: integer check, bounding boxes (the window path does this on the device in k_ingest)
+    std::vector<uint32_t> pix((size_t) std::max<int64_t>(total, 1));
+    std::vector<ProbDesc> pd((size_t) n_problems);
+    int Wmax = 1, Hmax = 1, max_n = 0;
+    for (int k = 0; k < n_problems; ++k) {
+        const int64_t b = offsets[k], e = offsets[k + 1];
+        if (e - b < 1) return ecb_fail(ctx, ECB_FAILED, "problem %d: V->size() < 1 (dbscan.h:121)", k);
+        if (e - b > 0x3FFFFFFF) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "problem %d too large", k);
+        int xmin = 1 << 30, ymin = 1 << 30, xmax = -1, ymax = -1;
+        for (int64_t i = b; i < e; ++i) {
+            const double x = xy[2 * i], y = xy[2 * i + 1];
+            const int xi = (int) x, yi = (int) y;
+            if (!((double) xi == x && (double) yi == y && xi >= 0 && xi < 32768 && yi >= 0 && yi < 32768))
+                return ecb_fail(ctx, ECB_ERR_UNSUPPORTED,
+                                "problem %d point %lld = (%g, %g): only integer pixel coordinates in [0, 32767] are "
+                                "supported by the device DBSCAN",
+                                k, (long long) (i - b), x, y);
+            pix[(size_t) i] = (uint32_t) xi | ((uint32_t) yi << 15);
+            xmin = std::min(xmin, xi);
+            ymin = std::min(ymin, yi);
+            xmax = std::max(xmax, xi);
+            ymax = std::max(ymax, yi);
+        }
+        ProbDesc d;
+        memset(&d, 0, sizeof d);
+        d.off = b;
+        d.n = (int32_t) (e - b);
+        d.pol = 0;
+        d.x0 = xmin;
+        d.y0 = ymin;
+        pd[(size_t) k] = d;
+        Wmax = std::max(Wmax, xmax - xmin + 1);
+        Hmax = std::max(Hmax, ymax - ymin + 1);
+        max_n = std::max(max_n, d.n);
+    }
+    const size_t slots = (size_t) std::max<int64_t>(total, 1);
+    const int max_k = 128;
+    if ((rc = ecb_reserve(ctx, ctx->db_pix, slots * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_labels, slots * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_scratch, slots * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_off, (size_t) n_problems * sizeof(ProbDesc)))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_hdr_b, (size_t) n_problems * sizeof(ProbHdr)))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_ktab, (size_t) n_problems * max_k * sizeof(KeptCluster)))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->db_counter, 64))) return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->db_pix.p, pix.data(), slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->db_off.p, pd.data(), (size_t) n_problems * sizeof(ProbDesc), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    ca.prob = (const ProbDesc *) ctx->db_off.p;
+    ca.n_prob = n_problems;
+    ca.work_counter = (unsigned *) ctx->db_counter.p;
+    ca.pix[0] = ca.pix[1] = (const uint32_t *) ctx->db_pix.p;
+    ca.labels[0] = ca.labels[1] = (int32_t *) ctx->db_labels.p;
+    ca.kmem[0] = ca.kmem[1] = (uint32_t *) ctx->db_scratch.p;
+    ca.hdr = (ProbHdr *) ctx->db_hdr_b.p;
+    ca.ktab = (KeptCluster *) ctx->db_ktab.p;
+    ca.max_k = max_k;
+    ca.W = Wmax;
+    ca.H = Hmax;
+    ca.PW = ((ca.W + 2 * ca.E + 31) >> 5) + 1;
+    ca.PH = ca.H + 2 * ca.E;
+    ca.min_pts = min_pts;
+    ca.cluster_min = 0x7FFFFFFF;  // no kept-cluster tables on this path
+    if ((rc = ecb_launch_cluster(ctx, ca, max_n))) return rc;
+    std::vector<ProbHdr> hdr((size_t) n_problems);
+    if (labels) ECB_CUDA(ctx, cudaMemcpyAsync(labels, ctx->db_labels.p, (size_t) total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(hdr.data(), ctx->db_hdr_b.p, (size_t) n_problems * sizeof(ProbHdr), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n_problems; ++k) {
+        if (n_clusters) n_clusters[k] = hdr[(size_t) k].n_clusters;
+        if (status) status[k] = hdr[(size_t) k].status;
+        if ((hdr[(size_t) k].status & ECB_PB_DUPLICATE) && !status)
+            return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "problem %d holds duplicate points (the reference path never does)", k);
+    }
+    return ECB_OK;
+}
+
+int ecb_dbscan_run(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t min_pts, int32_t *labels,
+                   int32_t *n_clusters) {
+    if (!ctx) return ECB_ERR_ARG;
+    if (n < 1 || min_pts < 1) return ECB_FAILED;  // dbscan.h:121-123
+    const int64_t off[2] = {0, n};
+    return ecb_dbscan_run_batch(ctx, xy, off, 1, eps, min_pts, labels, n_clusters, nullptr);
+}
+
+// ----------------------------------------------------------------------------------- circle fit ----
+int ecb_fit_circles(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_sets, double *out) {
+    if (!ctx || !xy || !offsets || !out || n_sets < 0) return ECB_ERR_ARG;
+    if (n_sets == 0) return ECB_OK;
+    cudaSetDevice(ctx->device);
+    int rc;
+    const int64_t total = offsets[n_sets];
+    if ((rc = ecb_reserve(ctx, ctx->fit_in, (size_t) std::max<int64_t>(total, 1) * 16))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->fit_off, (size_t) (n_sets + 1) * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->fit_out, (size_t) n_sets * 24))) return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->fit_in.p, xy, (size_t) total * 16, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->fit_off.p, offsets, (size_t) (n_sets + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ecb_launch_fit(ctx, (const double *) ctx->fit_in.p, (const int64_t *) ctx->fit_off.p, n_sets,
+                             (double *) ctx->fit_out.p)))
+        return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(out, ctx->fit_out.p, (size_t) n_sets * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "fit copy");
+}
+
+}  // extern "C"

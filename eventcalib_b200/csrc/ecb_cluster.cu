@@ -1,0 +1,491 @@
+// k_cluster — the reference's DBSCAN (dbscan/include/dbscan.h:115-265 with the bundled kd-tree,
+// dbscan/src/kdtree.cpp:106-179) for one point set per CTA, re-derived as data-parallel set operations on a
+// shared-memory occupancy bitmap of the sensor plane (a perfect spatial hash with one pixel per cell):
+//
+//   1. occupancy bitmap U + word-prefix popcounts (pixel -> row-major rank)          [replaces the kd build]
+//   2. level-synchronous emulation of the kd INSERTION ORDER (kd_insert in pid order, kdtree.cpp:106-146):
+//      only two bits per point survive — "an ancestor splitting on axis d has the same d-coordinate" — which
+//      is exactly when find_nearest (kdtree.cpp:166-171, `fabs(dx) < range`) misses a neighbour at q+eps*e_d
+//   3. neighbour count = popcount of the eps-disc stencil on U, self excluded (dbscan.h:218), minus the
+//      missed neighbours; core <=> count >= minPts (dbscan.h:151,247)
+//   4. lock-free union-find over mutual core-core edges; the directed (one-way) edges left by the tie rule
+//      are resolved by min-label propagation: cluster(G) = min seed pid over all groups that reach G
+//      (equivalent to Run's ascending-pid seed loop + expandCluster BFS, dbscan.h:143-162,229-259)
+//   5. cluster id = rank of the seed pid (discovery order); non-core points are Noise (dbscan.h:164-168)
+//   6. cluster-size filter (CirclesEventFrame.cpp:89-117), member lists, exact integer moments for fitCircle
+//      (CirclesEventFrame.cpp:364-404) and the median-by-norm member (CirclesEventFrame.cpp:137-147)
+//
+// HBM traffic per point: 4 B pixel read + 4 B label write + 4 B member write; everything else is on-chip.
+#include "ecb_cluster.cuh"
+
+namespace {
+
+template <typename RankT>
+struct Smem {
+    uint32_t *U, *FX, *FY, *C;
+    RankT *wrank;
+    uint32_t *r_pix, *r_por, *r_lab, *r_kd, *r_st;
+};
+
+__device__ __forceinline__ uint32_t find_root(volatile uint32_t *parent, uint32_t a) {
+    uint32_t p = parent[a];
+    while (p != a) {
+        uint32_t g = parent[p];
+        if (g != p) parent[a] = g;  // path halving (benign race: only ever points to an ancestor)
+        a = p;
+        p = g;
+    }
+    return a;
+}
+
+__device__ __forceinline__ void unite(uint32_t *parent, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = find_root(parent, a);
+        b = find_root(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        if (atomicCAS(&parent[a], a, b) == a) return;  // link the larger root under the smaller
+    }
+}
+
+template <typename RankT>
+__global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a) {
+    extern __shared__ __align__(16) uint32_t smem_raw[];
+    __shared__ uint32_t ws[33];
+    __shared__ uint32_t s_pb, s_status, s_tmp[4];
+    __shared__ int32_t k_raw[ECB_MAXK_LIMIT], k_size[ECB_MAXK_LIMIT], k_off[ECB_MAXK_LIMIT + 1];
+
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
+    const int PW = a.PW, PH = a.PH, E = a.E, NW = PW * PH;
+    Smem<RankT> s;
+    s.U = smem_raw;
+    s.FX = s.U + NW;
+    s.FY = s.FX + NW;
+    s.C = s.FY + NW;
+    s.wrank = reinterpret_cast<RankT *>(s.C + NW);
+    uint32_t *arr = a.arrays_in_smem
+                        ? (s.C + NW + (NW * sizeof(RankT) + 3) / 4)
+                        : (a.gscratch + (size_t) blockIdx.x * a.gscratch_stride);
+    const int NC = a.n_cap;
+    s.r_pix = arr;
+    s.r_por = arr + NC;
+    s.r_lab = arr + 2 * NC;
+    s.r_kd = arr + 3 * NC;  // 2*NC words
+    s.r_st = arr + 5 * NC;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s_pb = atomicAdd(a.work_counter, 1u);
+            s_status = 0;
+        }
+        __syncthreads();
+        const uint32_t pb = s_pb;
+        if (pb >= (uint32_t) a.n_prob) break;
+        const ProbDesc d = a.prob[pb];
+        const int n = d.n;
+        const uint32_t *gpix = a.pix[d.pol] + d.off;
+        int32_t *glab = a.labels[d.pol] + d.off;
+
+        // ---- 0. clear planes -----------------------------------------------------------------
+        for (int i = tid; i < 4 * NW; i += nthr) s.U[i] = 0;
+        __syncthreads();
+        // ---- 1. occupancy bitmap ---------------------------------------------------------------
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t p = gpix[pid];
+            int x = (int) ECB_PIX_X(p) - d.x0, y = (int) ECB_PIX_Y(p) - d.y0;
+            uint32_t loc = ECB_NONE;
+            if (x >= 0 && x < a.W && y >= 0 && y < a.H && !(p & ECB_PIX_INVALID)) {
+                x += E;
+                y += E;
+                uint32_t bit = 1u << (x & 31);
+                uint32_t old = atomicOr(&s.U[y * PW + (x >> 5)], bit);
+                if (old & bit)
+                    atomicOr(&s_status, ECB_PB_DUPLICATE);
+                else
+                    loc = (uint32_t) x | ((uint32_t) y << 16);
+            } else {
+                atomicOr(&s_status, ECB_PB_RANGE);
+            }
+            s.r_pix[pid] = loc;
+        }
+        __syncthreads();
+        // ---- 2. word-prefix popcounts: rank(x,y) = wrank[word] + popc(bits below) ---------------
+        {
+            const int per = (NW + nthr - 1) / nthr;
+            const int b = tid * per, e = min(NW, b + per);
+            uint32_t c = 0;
+            for (int i = b; i < e; ++i) c += __popc(s.U[i]);
+            uint32_t tot;
+            uint32_t ex = block_excl_scan(c, ws, &tot);
+            for (int i = b; i < e; ++i) {
+                s.wrank[i] = (RankT) ex;
+                ex += __popc(s.U[i]);
+            }
+        }
+        __syncthreads();
+        auto rank_of = [&](int x, int y) -> uint32_t {
+            const int w = y * PW + (x >> 5);
+            return (uint32_t) s.wrank[w] + __popc(s.U[w] & ((1u << (x & 31)) - 1u));
+        };
+        // ---- 3. rank -> pid ----------------------------------------------------------------------
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t loc = s.r_pix[pid];
+            if (loc != ECB_NONE) s.r_por[rank_of(loc & 0xFFFF, loc >> 16)] = pid;
+        }
+        // ---- 4. kd insertion-order emulation -> tie flags ---------------------------------------
+        uint32_t *child = s.r_kd, *state = s.r_st;
+        const uint32_t DONE = 0x3FFFFFFFu;
+        for (int i = tid; i < 2 * n; i += nthr) child[i] = ECB_NONE;
+        for (int pid = tid; pid < n; pid += nthr) state[pid] = (pid == 0 || s.r_pix[pid] == ECB_NONE) ? DONE : 0u;
+        // NOTE: the root is pid 0 like kd_insert's first insertion; an out-of-range pid 0 is not supported
+        __syncthreads();
+        for (int round = 0;; ++round) {
+            const int dsh = (round & 1) ? 16 : 0;
+            bool any = false;
+            for (int pid = tid; pid < n; pid += nthr) {
+                uint32_t st = state[pid];
+                uint32_t cur = st & DONE;
+                if (cur == DONE) continue;
+                any = true;
+                uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
+                if (ci == ca) state[pid] = st | (0x40000000u << (round & 1));
+                atomicMin(&child[2 * cur + (ci < ca ? 0 : 1)], (uint32_t) pid);
+            }
+            if (!__syncthreads_or(any)) break;
+            for (int pid = tid; pid < n; pid += nthr) {
+                uint32_t st = state[pid];
+                uint32_t cur = st & DONE;
+                if (cur == DONE) continue;
+                uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
+                uint32_t c = child[2 * cur + (ci < ca ? 0 : 1)];
+                state[pid] = (st & 0xC0000000u) | (c == (uint32_t) pid ? DONE : c);
+            }
+            __syncthreads();
+        }
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t st = state[pid], loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            int x = loc & 0xFFFF, y = loc >> 16;
+            if (st & 0x40000000u) atomicOr(&s.FX[y * PW + (x >> 5)], 1u << (x & 31));
+            if (st & 0x80000000u) atomicOr(&s.FY[y * PW + (x >> 5)], 1u << (x & 31));
+        }
+        __syncthreads();
+        // ---- 5. neighbour count, core flag -----------------------------------------------------------
+        const int ei = a.eps_int;
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            const int x = loc & 0xFFFF, y = loc >> 16;
+            int cnt = -1;  // self
+            for (int dy = -E; dy <= E; ++dy) {
+                const int w = a.halfw[dy < 0 ? -dy : dy];
+                cnt += __popc(row_bits(s.U + (y + dy) * PW, x - w, 2 * w + 1));
+            }
+            if (ei > 0) {
+                cnt -= (int) (test_bit(s.U + y * PW, x + ei) & test_bit(s.FX + y * PW, x + ei));
+                cnt -= (int) (test_bit(s.U + (y + ei) * PW, x) & test_bit(s.FY + (y + ei) * PW, x));
+            }
+            if (cnt >= (int) a.min_pts) atomicOr(&s.C[y * PW + (x >> 5)], 1u << (x & 31));
+        }
+        uint32_t *parent = s.r_kd, *glabel = s.r_kd + NC;
+        for (int r = tid; r < n; r += nthr) {
+            parent[r] = r;
+            glabel[r] = ECB_NONE;
+        }
+        __syncthreads();
+        // ---- 6. union-find over mutual core edges (half-plane enumeration) ----------------------------
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            const int x = loc & 0xFFFF, y = loc >> 16;
+            if (!test_bit(s.C + y * PW, x)) continue;
+            const uint32_t rq = rank_of(x, y);
+            for (int dy = 0; dy <= E; ++dy) {
+                const int w = a.halfw[dy];
+                const int xs = dy == 0 ? x + 1 : x - w;
+                const int len = dy == 0 ? w : 2 * w + 1;
+                if (len <= 0) continue;
+                uint32_t bits = row_bits(s.C + (y + dy) * PW, xs, len);
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int nx = xs + b, ny = y + dy;
+                    if (ei > 0) {  // q -> p missed by the kd query: the pair is a one-way edge p -> q
+                        if (dy == 0 && nx - x == ei && test_bit(s.FX + ny * PW, nx)) continue;
+                        if (dy == ei && nx == x && test_bit(s.FY + ny * PW, nx)) continue;
+                    }
+                    unite(parent, rq, rank_of(nx, ny));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 7. flatten, group min pid, one-way edge propagation --------------------------------------
+        int n_core_local = 0;
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            const int x = loc & 0xFFFF, y = loc >> 16;
+            if (!test_bit(s.C + y * PW, x)) continue;
+            ++n_core_local;
+            const uint32_t r = rank_of(x, y);
+            const uint32_t root = find_root(parent, r);
+            atomicMin(&glabel[root], (uint32_t) pid);
+        }
+        __syncthreads();
+        for (int pid = tid; pid < n; pid += nthr) {  // full flatten (all unions are done)
+            uint32_t loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            const int x = loc & 0xFFFF, y = loc >> 16;
+            if (!test_bit(s.C + y * PW, x)) continue;
+            const uint32_t r = rank_of(x, y);
+            uint32_t root = r;
+            while (parent[root] != root) root = parent[root];
+            s.r_lab[pid] = root;  // stash; parent[] itself is rewritten after the barrier
+        }
+        __syncthreads();
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            const int x = loc & 0xFFFF, y = loc >> 16;
+            if (!test_bit(s.C + y * PW, x)) continue;
+            parent[rank_of(x, y)] = s.r_lab[pid];
+        }
+        __syncthreads();
+        if (ei > 0) {
+            for (;;) {
+                bool changed = false;
+                for (int pid = tid; pid < n; pid += nthr) {
+                    uint32_t loc = s.r_pix[pid];
+                    if (loc == ECB_NONE) continue;
+                    const int x = loc & 0xFFFF, y = loc >> 16;
+                    if (!test_bit(s.C + y * PW, x)) continue;
+                    const uint32_t gq = parent[rank_of(x, y)];
+                    // p = q + eps*e_x with FX(p): edge p -> q only
+                    if (test_bit(s.C + y * PW, x + ei) && test_bit(s.FX + y * PW, x + ei)) {
+                        uint32_t lp = ((volatile uint32_t *) glabel)[parent[rank_of(x + ei, y)]];
+                        if (lp < atomicMin(&glabel[gq], lp)) changed = true;
+                    }
+                    if (test_bit(s.C + (y + ei) * PW, x) && test_bit(s.FY + (y + ei) * PW, x)) {
+                        uint32_t lp = ((volatile uint32_t *) glabel)[parent[rank_of(x, y + ei)]];
+                        if (lp < atomicMin(&glabel[gq], lp)) changed = true;
+                    }
+                }
+                if (!__syncthreads_or(changed)) break;
+            }
+        }
+        // ---- 8. seeds -> cluster ids ---------------------------------------------------------------------
+        const int nw32 = (n + 31) >> 5;
+        uint32_t *seedmask = s.r_st, *seedpref = s.r_st + nw32;
+        for (int i = tid; i < nw32; i += nthr) seedmask[i] = 0;
+        __syncthreads();
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            const int x = loc & 0xFFFF, y = loc >> 16;
+            if (!test_bit(s.C + y * PW, x)) continue;
+            const uint32_t r = rank_of(x, y);
+            if (parent[r] != r) continue;  // roots only
+            const uint32_t lab = glabel[r];
+            // the group is a seed iff its final label is one of its own members (nothing smaller reached it)
+            const uint32_t ll = s.r_pix[lab];
+            if (parent[rank_of(ll & 0xFFFF, ll >> 16)] == r) atomicOr(&seedmask[lab >> 5], 1u << (lab & 31));
+        }
+        __syncthreads();
+        uint32_t n_clusters;
+        {
+            const int per = (nw32 + nthr - 1) / nthr;
+            const int b = tid * per, e = min(nw32, b + per);
+            uint32_t c = 0;
+            for (int i = b; i < e; ++i) c += __popc(seedmask[i]);
+            uint32_t ex = block_excl_scan(c, ws, &n_clusters);
+            for (int i = b; i < e; ++i) {
+                seedpref[i] = ex;
+                ex += __popc(seedmask[i]);
+            }
+        }
+        __syncthreads();
+        for (int pid = tid; pid < n; pid += nthr) {
+            uint32_t loc = s.r_pix[pid];
+            int32_t lab = -1;
+            if (loc != ECB_NONE) {
+                const int x = loc & 0xFFFF, y = loc >> 16;
+                if (test_bit(s.C + y * PW, x)) {
+                    const uint32_t seed = glabel[parent[rank_of(x, y)]];
+                    lab = (int32_t) (seedpref[seed >> 5] + __popc(seedmask[seed >> 5] & ((1u << (seed & 31)) - 1u)));
+                }
+            }
+            s.r_lab[pid] = (uint32_t) lab;
+            glab[pid] = lab;
+        }
+        __syncthreads();
+        // ---- 9. cluster sizes, size filter, member lists, moments, medians ----------------------------
+        uint32_t *csize = s.r_kd, *keptidx = s.r_kd + NC;
+        const int nc = (int) n_clusters;
+        for (int i = tid; i < nc; i += nthr) csize[i] = 0;
+        __syncthreads();
+        for (int pid = tid; pid < n; pid += nthr) {
+            int32_t lab = (int32_t) s.r_lab[pid];
+            if (lab >= 0) atomicAdd(&csize[lab], 1u);
+        }
+        __syncthreads();
+        uint32_t n_kept = 0;
+        {
+            const int per = (nc + nthr - 1) / nthr;
+            const int b = tid * per, e = min(nc, b + per);
+            uint32_t c = 0;
+            for (int i = b; i < e; ++i) c += csize[i] >= a.cluster_min;
+            uint32_t ex = block_excl_scan(c, ws, &n_kept);
+            for (int i = b; i < e; ++i) {
+                const bool k = csize[i] >= a.cluster_min;
+                keptidx[i] = k ? ex : ECB_NONE;
+                if (k && ex < (uint32_t) a.max_k) {
+                    k_raw[ex] = i;
+                    k_size[ex] = (int32_t) csize[i];
+                }
+                ex += k;
+            }
+        }
+        if (n_kept > (uint32_t) a.max_k) {
+            if (tid == 0) atomicOr(&s_status, ECB_PB_CLUSTER_CAP);
+            n_kept = a.max_k;
+        }
+        __syncthreads();
+        if (wid == 0) {  // member-list offsets: exclusive scan of k_size[0..n_kept)
+            uint32_t run = 0;
+            for (int base = 0; base < (int) n_kept; base += 32) {
+                uint32_t v = base + lane < (int) n_kept ? (uint32_t) k_size[base + lane] : 0;
+                uint32_t inc = warp_incl_scan(v);
+                if (base + lane < (int) n_kept) k_off[base + lane] = (int32_t) (run + inc - v);
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) k_off[n_kept] = (int32_t) run;
+        }
+        __syncthreads();
+        uint32_t *members = s.r_st;  // seedmask/seedpref are dead
+        uint32_t *gmem = a.kmem[d.pol] + d.off;
+        KeptCluster *kt = a.ktab + (size_t) pb * a.max_k;
+        for (int k = wid; k < (int) n_kept; k += nwarp) {
+            const int32_t cid = k_raw[k];
+            const int base = k_off[k], sz = k_size[k];
+            int pos = 0;
+            for (int st = 0; st < n; st += 32) {
+                const int pid = st + lane;
+                const bool m = pid < n && (int32_t) s.r_lab[pid] == cid;
+                const uint32_t ball = __ballot_sync(0xffffffffu, m);
+                if (m) members[base + pos + __popc(ball & ((1u << lane) - 1u))] = pid;
+                pos += __popc(ball);
+            }
+            __syncwarp();
+            long long S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            int med = -1;
+            for (int i = lane; i < sz; i += 32) {
+                const uint32_t pid = members[base + i];
+                gmem[base + i] = pid;
+                const uint32_t loc = s.r_pix[pid];
+                const long long x = (int) (loc & 0xFFFF) - E + d.x0, y = (int) (loc >> 16) - E + d.y0;
+                S[0] += x;
+                S[1] += y;
+                S[2] += x * x;
+                S[3] += y * y;
+                S[4] += x * y;
+                S[5] += x * x * x;
+                S[6] += y * y * y;
+                S[7] += x * y * y;
+                S[8] += x * x * y;
+                // rank of (norm^2, pid) among the members
+                const unsigned long long key = ((unsigned long long) (x * x + y * y) << 32) | pid;
+                int cnt = 0;
+                for (int j = 0; j < sz; ++j) {
+                    const uint32_t pj = members[base + j];
+                    const uint32_t lj = s.r_pix[pj];
+                    const long long xj = (int) (lj & 0xFFFF) - E + d.x0, yj = (int) (lj >> 16) - E + d.y0;
+                    const unsigned long long kj = ((unsigned long long) (xj * xj + yj * yj) << 32) | pj;
+                    cnt += kj < key;
+                }
+                if (cnt == sz / 2) med = (int) pid;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+                for (int o = 16; o > 0; o >>= 1) S[q] += __shfl_down_sync(0xffffffffu, S[q], o);
+            for (int o = 16; o > 0; o >>= 1) med = max(med, __shfl_down_sync(0xffffffffu, med, o));
+            if (lane == 0) {
+                KeptCluster kc;
+                kc.raw_id = cid;
+                kc.size = sz;
+                kc.med_pid = med;
+                const uint32_t lm = s.r_pix[med];
+                kc.med_x = (int) (lm & 0xFFFF) - E + d.x0;
+                kc.med_y = (int) (lm >> 16) - E + d.y0;
+                kc.mem_off = base;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) kc.m[q] = (double) S[q];
+                kt[k] = kc;
+            }
+        }
+        // ---- header -------------------------------------------------------------------------------------
+        {
+            uint32_t tot;
+            block_excl_scan((uint32_t) n_core_local, ws, &tot);
+            if (tid == 0) {
+                ProbHdr h;
+                h.n_clusters = nc;
+                h.n_kept = (int32_t) n_kept;
+                h.n_core = (int32_t) tot;
+                h.status = s_status;
+                a.hdr[pb] = h;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, bool arrays_in_smem, bool rank32) {
+    size_t NW = (size_t) PW * PH;
+    size_t b = 4 * NW * 4 + ((NW * (rank32 ? 4 : 2) + 3) / 4) * 4;
+    if (arrays_in_smem) b += (size_t) 6 * n_cap * 4;
+    return b;
+}
+
+int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
+    if (a.n_prob <= 0) return ECB_OK;
+    const bool rank32 = max_n >= 65535;
+    a.n_cap = max_n < 64 ? 64 : max_n;
+    const size_t limit = (size_t) ctx->smem_optin - 9 * 1024;  // static shared + reserve
+    size_t planes = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, false, rank32);
+    if (planes > limit)
+        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED,
+                        "bitmap of %dx%d px (+eps border) needs %zu B shared memory, limit %zu", a.W, a.H, planes, limit);
+    size_t with_arrays = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, true, rank32);
+    a.arrays_in_smem = with_arrays <= limit;  // else the per-point arrays live in per-CTA L2 scratch
+    size_t smem = a.arrays_in_smem ? with_arrays : planes;
+    int per_sm = 1;
+    if (rank32) {
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint32_t>, ECB_CL_THREADS, smem));
+    } else {
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint16_t>, ECB_CL_THREADS, smem));
+    }
+    if (per_sm < 1) per_sm = 1;
+    int grid = ctx->sm_count * per_sm;
+    if (grid > a.n_prob) grid = a.n_prob;
+    if (!a.arrays_in_smem) {
+        a.gscratch_stride = (size_t) 6 * a.n_cap;
+        int rc = ecb_reserve(ctx, ctx->scratch, (size_t) grid * a.gscratch_stride * 4);
+        if (rc) return rc;
+        a.gscratch = (uint32_t *) ctx->scratch.p;
+    }
+    ECB_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, 4, ctx->stream));
+    if (rank32)
+        k_cluster<uint32_t><<<grid, ECB_CL_THREADS, smem, ctx->stream>>>(a);
+    else
+        k_cluster<uint16_t><<<grid, ECB_CL_THREADS, smem, ctx->stream>>>(a);
+    ECB_LAUNCHED(ctx);
+    return ecb_check(ctx, cudaGetLastError(), "k_cluster launch");
+}

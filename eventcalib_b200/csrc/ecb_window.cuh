@@ -1,0 +1,35 @@
+// Launch interfaces of the ingest / window / pair kernels.
+#pragma once
+#include "ecb_cluster.cuh"
+
+struct WindowArgs {
+    const uint32_t *xyp;      // packed events
+    const int64_t *lohi;      // [n_win][2] event index range
+    const int64_t *ptoff;     // [n_win] offset of the window's point slots (capacity hi-lo per polarity)
+    uint32_t *arrive[2];      // distinct pixels per polarity in first-arrival order (before cancellation)
+    uint32_t *pts[2];         // surviving pixels in pid order
+    ProbDesc *prob;           // [2*n_win] clustering problems (index 2*w+pol)
+    uint32_t *max_n;          // device word: max points of any problem (sizes the cluster kernel's arrays)
+    int n_win, W, H, RW;
+};
+
+struct PairArgs {
+    const ProbDesc *prob;
+    const ProbHdr *hdr;
+    const KeptCluster *ktab;
+    const uint32_t *pts[2];
+    const uint32_t *kmem[2];
+    const int64_t *lohi;
+    ecb_window_summary *summary;
+    double *cand;             // [n_win][cand_stride][5]
+    int n_win, max_k, cand_stride;
+    int fit_circle, knn_num;
+    uint32_t rows_cols;
+    double rthr;
+};
+
+int ecb_launch_ingest(ecb_ctx *ctx, const void *d_raw, int64_t n);
+int ecb_launch_bounds(ecb_ctx *ctx, const double *d_win, int n_win, int64_t *d_lohi);
+int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a);
+int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a);
+int ecb_launch_fit(ecb_ctx *ctx, const double *d_xy, const int64_t *d_off, int n_sets, double *d_out);

@@ -1,0 +1,132 @@
+/* eventcalib_b200 — C ABI of the B200-native EventCalib hot path.
+ *
+ * Plain C, plain pointers and sizes, no exceptions, no torch / Eigen / OpenCV types.  Every entry point
+ * returns ECB_OK (0) or a negative ecb_status; ecb_last_error(ctx) gives the text.  A context owns one
+ * CUDA device + stream and all device buffers; distinct contexts may be used from distinct host threads
+ * (the reference calls DBSCAN::Run from hardware_concurrency()-2 threads, eventCameraCalib.cpp:181-187).
+ * There is NO CPU fallback: without a CUDA device every compute call fails with ECB_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/modules/camera_calibration/):
+ *   ecb_load_events_*      Event::operator>> (event/include/opengv2/event/Event.hpp:41-47) + the load loop
+ *                          (event_camera_calib/test/eventCameraCalib.cpp:154-163)
+ *   ecb_frontend_run       EventFrame::EventFrame (event/src/EventFrame.cpp:10-36) +
+ *                          CirclesEventFrame::extractFeatures up to findCirclesGrid
+ *                          (event_camera_calib/src/CirclesEventFrame.cpp:61-312) incl. fitCircle (:361-415)
+ *   ecb_dbscan_run[_batch] DBSCAN<Eigen::Vector2d,double>::Run (dbscan/include/dbscan.h:115-177)
+ *   ecb_fit_circles        CirclesEventFrame::fitCircle (CirclesEventFrame.cpp:361-415)
+ *   ecb_cost_*             EventCalibSpline::optimize association loop (src/EventCalibSpline.cpp:157-192),
+ *                          CalibReprojectionError::operator() (include/.../EventCalibSpline.hpp:168-229) as
+ *                          Ceres evaluates it (residual, Jacobian, Huber, quaternion local parameterisation)
+ *                          and the normal-equation build that feeds the LM step.
+ */
+#ifndef EVENTCALIB_B200_H
+#define EVENTCALIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ecb_ctx ecb_ctx;
+
+typedef enum {
+    ECB_OK = 0,
+    ECB_FAILED = 1,            /* mirrors DBSCAN::ERROR_TYPE::FAILED (dbscan.h:46-48,121-123) */
+    ECB_ERR_CUDA = -1,         /* no device / CUDA runtime error */
+    ECB_ERR_ARG = -2,          /* bad argument */
+    ECB_ERR_UNSUPPORTED = -3,  /* input outside what the device path handles (see ecb_last_error) */
+    ECB_ERR_STATE = -4         /* call order (e.g. no events loaded) */
+} ecb_status;
+
+/* per-problem status bits reported by the device kernels */
+#define ECB_PB_OK 0u
+#define ECB_PB_DUPLICATE 2u     /* duplicate points handed to ecb_dbscan_run (the reference path never does) */
+#define ECB_PB_CLUSTER_CAP 4u   /* more kept clusters than max_clusters: tables truncated, labels still exact */
+#define ECB_PB_RANGE 8u         /* pixel outside the sensor / bitmap */
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t (as void*) to run on, or NULL for a context-owned stream. */
+int ecb_ctx_create(int device, void *stream, ecb_ctx **out);
+void ecb_ctx_destroy(ecb_ctx *ctx);
+const char *ecb_last_error(const ecb_ctx *ctx);
+/* number of kernels of this library launched through ctx so far */
+uint64_t ecb_launch_count(const ecb_ctx *ctx);
+int ecb_synchronize(ecb_ctx *ctx);
+const char *ecb_version(void);
+
+/* ---- a1: event ingest ---------------------------------------------------------------------------- */
+/* Sensor size in pixels (Camera.width / Camera.height of the YAML). Must be set before loading events. */
+int ecb_set_sensor(ecb_ctx *ctx, int width, int height);
+/* records: n packed 25-byte reference records (f64 t, f64 x, f64 y, u8 polarity), time sorted.
+ * _host copies host->device inside the call; _device expects a device pointer (16-byte aligned).
+ * The records are unpacked to the SoA layout the kernels use (f64 t[n], u32 x|y<<15|pol<<31).
+ * Events with non-integer or out-of-sensor coordinates, or an unsorted stream, make the call fail
+ * with ECB_ERR_UNSUPPORTED (the reference would accept them; this path does not, loudly). */
+int ecb_load_events_host(ecb_ctx *ctx, const void *records, int64_t n);
+int ecb_load_events_device(ecb_ctx *ctx, const void *d_records, int64_t n);
+int64_t ecb_num_events(const ecb_ctx *ctx);
+
+/* ---- a2-a5: batched window front end --------------------------------------------------------------- */
+typedef struct {
+    double dbscan_eps;          /* CirclesEventFrame::Params (CirclesEventFrame.cpp:35-48) */
+    uint32_t dbscan_min_pts;    /* dbscan_startMinSample */
+    uint32_t cluster_min;       /* clusterMinSample */
+    int32_t knn_num;
+    int32_t fit_circle;         /* 0: mutual-nearest medians (example.yaml default), 1: fitted circles */
+    double radius_threshold;    /* circleRadiusThreshold_ (CirclesEventFrame.cpp:16-33) */
+    uint32_t rows_cols;         /* pattern rows*cols (need that many kept clusters per polarity, :127-129) */
+    int32_t order_mode;         /* 0: pid = first-arrival order; 1: libstdc++ unordered_set iteration order
+                                   (the reference's order, EventFrame.cpp:12-35) */
+    uint32_t max_clusters;      /* kept-cluster table capacity per (window,polarity); 0 -> 128 */
+    uint32_t reserved;
+} ecb_frontend_params;
+
+typedef struct {
+    int64_t ev_lo, ev_hi;       /* event index range of the CLOSED window [t0,t1] */
+    int32_t n_points[2];        /* [0]=negative, [1]=positive unique surviving pixels (pid count) */
+    int32_t n_clusters[2];      /* raw DBSCAN clusters */
+    int32_t n_kept[2];          /* after the clusterMinSample filter */
+    int32_t n_candidates;       /* candidate circles (pairs) */
+    uint32_t status;            /* ECB_PB_* bits */
+    int64_t point_offset[2];    /* offset of this window's points in the flat per-polarity arrays */
+} ecb_window_summary;
+
+/* windows: n_win closed intervals [t0,t1] (host doubles, interleaved).  Runs window selection, per-pixel
+ * dedupe, +/- cancellation, DBSCAN on both polarities, the cluster-size filter, medians, pairing and
+ * circle fit for every window in one batch. Results stay on the device until fetched. */
+int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_frontend_params *params);
+int ecb_frontend_summary(ecb_ctx *ctx, ecb_window_summary *out, int n_win);
+/* total number of point slots per polarity (size of the flat arrays below) */
+int64_t ecb_frontend_total_points(ecb_ctx *ctx, int polarity);
+/* flat per-polarity arrays: xy (2 doubles per point, pid order per window) and labels (cluster id in
+ * discovery order, -1 = Noise) */
+int ecb_frontend_points(ecb_ctx *ctx, int polarity, double *xy, int32_t *labels);
+/* per window up to max_cand candidates: pi, ni (kept-cluster indices), cx, cy, r  -> out[n_win][max_cand][5] */
+int ecb_frontend_candidates(ecb_ctx *ctx, double *out, int max_cand);
+/* kept-cluster table of one window/polarity: raw cluster id, size, median pid  (each up to cap entries) */
+int ecb_frontend_clusters(ecb_ctx *ctx, int window, int polarity, int32_t *raw_id, int32_t *size,
+                          int32_t *median_pid, int cap);
+/* device pointers of the results of the last run (for callers that keep working on the GPU) */
+int ecb_frontend_device_ptrs(ecb_ctx *ctx, void **d_summary, void **d_candidates, int *cand_stride);
+
+/* ---- a3: the DBSCAN::Run boundary ---------------------------------------------------------------- */
+/* xy: n x 2 doubles in pid order (integer-valued pixel coordinates, all distinct, bounding box within the
+ * shared-memory bitmap budget).  labels[n]: cluster id in the reference's discovery order, -1 = Noise.
+ * Returns ECB_FAILED for n<1 or min_pts<1 exactly like the reference. */
+int ecb_dbscan_run(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t min_pts, int32_t *labels,
+                   int32_t *n_clusters);
+/* batch: problem k is xy[offsets[k] .. offsets[k+1]); labels is flat; n_clusters[n_problems]; status
+ * (optional) receives ECB_PB_* bits per problem */
+int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
+                         uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status);
+
+/* ---- a5: batched circle fit ---------------------------------------------------------------------- */
+/* set k = points xy[offsets[k]..offsets[k+1]) (union of a + and a - index set); out[k] = cx, cy, r */
+int ecb_fit_circles(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_sets, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVENTCALIB_B200_H */

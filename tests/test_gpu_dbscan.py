@@ -1,0 +1,84 @@
+"""Parity of the CUDA DBSCAN (ecb_dbscan_run, through the C ABI) with the oracle on seeded inputs.
+
+Bar: labels bit-exact, including the discovery-order cluster ids and the reference's tie / border rules
+(dbscan.h:115-265, kdtree.cpp:148-179).  The oracle itself is pinned against the unmodified reference in
+tests/test_oracle_dbscan.py.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_points(rng, n, W, H):
+    pts = np.unique(np.stack([rng.integers(0, W, n), rng.integers(0, H, n)], axis=1), axis=0)
+    rng.shuffle(pts)
+    return pts.astype(np.float64)
+
+
+def test_toy_known_answer(ctx):
+    # end points have a single neighbour -> noise, not border members
+    xy = np.array([[4 * i, 0] for i in range(10)] + [[100, 100]], float)
+    rc, lab, nc = ctx.dbscan(xy, 4, 2)
+    assert rc == 0 and nc == 1
+    assert lab.tolist() == [-1, 0, 0, 0, 0, 0, 0, 0, 0, -1, -1]
+
+
+def test_failed_status(ctx):
+    import eventcalib_b200 as ecb
+    assert ctx.dbscan(np.zeros((0, 2)), 4, 2)[0] == ecb.FAILED
+    assert ctx.dbscan(np.zeros((3, 2)), 4, 0)[0] == ecb.FAILED
+
+
+@pytest.mark.parametrize("eps,minpts", [(4, 2), (2, 2), (3, 3), (6, 5), (8, 8), (4, 1), (2.5, 2), (4.5, 3)])
+def test_random_dense(ctx, oracle_mod, eps, minpts):
+    rng = np.random.default_rng(int(eps * 100) + minpts)
+    for it in range(12):
+        n = int(rng.integers(1, 3000))
+        W = int(rng.integers(12, 140))
+        pts = _rand_points(rng, n, W, W)
+        ref = oracle_mod.dbscan(pts, eps, minpts)
+        rc, lab, nc = ctx.dbscan(pts, eps, minpts)
+        assert rc == 0
+        assert nc == len(ref["clusters"])
+        assert np.array_equal(lab, ref["labels"]), "labels differ (n=%d W=%d)" % (len(pts), W)
+
+
+def test_single_point_and_offsets(ctx, oracle_mod):
+    rc, lab, nc = ctx.dbscan(np.array([[5.0, 7.0]]), 4, 2)
+    assert rc == 0 and nc == 0 and lab.tolist() == [-1]
+    rng = np.random.default_rng(5)
+    pts = _rand_points(rng, 800, 60, 40) + np.array([1000.0, 2000.0])  # bounding-box origin handling
+    ref = oracle_mod.dbscan(pts, 4, 2)
+    rc, lab, nc = ctx.dbscan(pts, 4, 2)
+    assert np.array_equal(lab, ref["labels"])
+
+
+def test_batch(ctx, oracle_mod):
+    rng = np.random.default_rng(11)
+    sets = [_rand_points(rng, int(rng.integers(1, 1500)), 90, 70) for _ in range(40)]
+    off = np.concatenate([[0], np.cumsum([len(s) for s in sets])])
+    lab, nc, st = ctx.dbscan_batch(np.concatenate(sets), off, 4, 2)
+    assert not st.any()
+    for k, s in enumerate(sets):
+        ref = oracle_mod.dbscan(s, 4, 2)
+        assert nc[k] == len(ref["clusters"])
+        assert np.array_equal(lab[off[k]:off[k + 1]], ref["labels"])
+
+
+def test_large_problem_global_scratch(ctx, oracle_mod):
+    # > shared-memory array budget: per-point arrays go to L2 scratch, 640x480 bitmap
+    rng = np.random.default_rng(3)
+    pts = _rand_points(rng, 60000, 640, 480)
+    ref = oracle_mod.dbscan(pts, 4, 2)
+    rc, lab, nc = ctx.dbscan(pts, 4, 2)
+    assert nc == len(ref["clusters"])
+    assert np.array_equal(lab, ref["labels"])
+
+
+def test_unsupported_inputs_fail_loudly(ctx):
+    import eventcalib_b200 as ecb
+    with pytest.raises(ecb.EcbError):
+        ctx.dbscan(np.array([[0.5, 1.0], [2.0, 3.0]]), 4, 2)
+    with pytest.raises(ecb.EcbError):
+        ctx.dbscan(np.array([[1.0, 1.0], [1.0, 1.0]]), 4, 2)  # duplicates

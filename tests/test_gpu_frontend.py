@@ -1,0 +1,138 @@
+"""Parity of the batched CUDA front end (ecb_load_events + ecb_frontend_run) with the oracle.
+
+Per window: event range, per-polarity pixel sets after dedupe and +/- cancellation (EventFrame.cpp:10-36),
+pid order (order_mode 0 = first arrival), DBSCAN labels bit-exact, kept clusters, medians, candidate pairs
+exact and circle centres / radii within 1e-9 relative (CirclesEventFrame.cpp:61-312,361-415).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _first_arrival(ev, lo, hi, pol):
+    x = ev["x"][lo:hi].astype(np.int64)
+    y = ev["y"][lo:hi].astype(np.int64)
+    p = ev["p"][lo:hi]
+    key = y * 100000 + x
+    own = key[p == pol]
+    other = set(key[p != pol].tolist())
+    seen = set()
+    out = []
+    for k in own.tolist():
+        if k not in seen:
+            seen.add(k)
+            if k not in other:
+                out.append((k % 100000, k // 100000))
+    return np.array(out, np.float64).reshape(-1, 2)
+
+
+def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4.0, min_pts=2):
+    import eventcalib_b200 as ecb
+    from eventcalib_b200 import synth
+    ctx.set_sensor(width, height)
+    n = ctx.load_events(synth.to_records(ev))
+    assert n == len(ev["t"])
+    rthr = ecb.radius_threshold(width, height, 9, 4, True, 5.5, 1.75)
+    prm = ecb.default_params(eps=eps, min_pts=min_pts, fit_circle=fit_circle, radius_threshold=rthr)
+    ctx.frontend_run(windows, prm)
+    summ = ctx.summary()
+    pts = [ctx.points(0), ctx.points(1)]
+    cand = ctx.candidates(64)
+    n_cand_total = 0
+    for w, (t0, t1) in enumerate(windows):
+        P, N, lo, hi = oracle_mod.event_frame(ev["t"], ev["x"], ev["y"], ev["p"], t0, t1)
+        s = summ[w]
+        assert (s["ev_lo"], s["ev_hi"]) == (lo, hi)
+        assert s["status"] == 0
+        V = []
+        for pol, ref_set in ((0, N), (1, P)):
+            o, k = int(s["point_offset"][pol]), int(s["n_points"][pol])
+            xy = pts[pol][0][o:o + k]
+            assert k == len(ref_set)
+            assert set(map(tuple, xy.tolist())) == set(map(tuple, ref_set.tolist()))
+            assert np.array_equal(xy, _first_arrival(ev, lo, hi, pol))
+            V.append(xy)
+        r = oracle_mod.extract(V[1], V[0], eps=eps, minS=min_pts, fitCircle=fit_circle, Rthr=rthr, canonical_median=True)
+        for pol, key in ((0, "n"), (1, "p")):
+            o, k = int(s["point_offset"][pol]), int(s["n_points"][pol])
+            assert np.array_equal(pts[pol][1][o:o + k], r[key + "_labels"]), "labels differ window %d pol %d" % (w, pol)
+            assert s["n_clusters"][pol] == len(r[key + "_clusters"])
+            raw, size, med = ctx.clusters(w, pol)
+            assert np.array_equal(raw, r["kept_" + key])
+            assert np.array_equal(size, [len(r[key + "_clusters"][c]) for c in raw])
+            if r["enough"]:
+                assert np.array_equal(med, r["med_" + key])
+        assert s["n_candidates"] == len(r["cand"])
+        n_cand_total += len(r["cand"])
+        if len(r["cand"]):
+            g = cand[w, :len(r["cand"])]
+            assert np.array_equal(g[:, :2], r["cand"][:, :2])
+            np.testing.assert_allclose(g[:, 2:], r["cand"][:, 2:], rtol=RTOL, atol=0)
+    return n_cand_total
+
+
+@pytest.mark.parametrize("fit_circle", [0, 1])
+def test_davis346_windows(ctx, oracle_mod, fit_circle):
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(120000, 346, 260, t0=5.0, duration=0.06, seed=1001)
+    win = synth.tiling_windows(5.0, 5.06, 1.5e-3)
+    total = _check_stream(ctx, oracle_mod, ev, win, 346, 260, fit_circle)
+    assert total > 30 * len(win)  # the synthetic board is found in (almost) every window
+
+
+def test_overlapping_and_empty_windows(ctx, oracle_mod):
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(40000, 346, 260, t0=5.0, duration=0.02, seed=7)
+    win = np.array([[5.0, 5.0015], [5.0005, 5.003], [4.0, 4.5], [5.019, 9.0], [5.002, 5.002], [5.0, 5.02]])
+    _check_stream(ctx, oracle_mod, ev, win, 346, 260, 0)
+
+
+def test_vga_large_windows(ctx, oracle_mod):
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(300000, 640, 480, t0=0.0, duration=0.03, seed=1003)
+    win = synth.tiling_windows(0.0, 0.03, 10e-3)
+    _check_stream(ctx, oracle_mod, ev, win, 640, 480, 1)
+
+
+def test_eps_minpts_sweep(ctx, oracle_mod):
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(30000, 346, 260, t0=5.0, duration=0.015, seed=1005, noise_frac=0.2, flip_frac=0.05)
+    win = synth.tiling_windows(5.0, 5.015, 1.5e-3)
+    for eps in (2, 3, 4, 6, 8):
+        for mp in (2, 3, 5, 8):
+            _check_stream(ctx, oracle_mod, ev, win, 346, 260, 0, eps=float(eps), min_pts=mp)
+
+
+def test_rejects_bad_streams(ctx):
+    import eventcalib_b200 as ecb
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(1000, 346, 260, duration=0.001, seed=3)
+    ctx.set_sensor(346, 260)
+    bad = dict(ev)
+    bad["x"] = ev["x"].copy()
+    bad["x"][10] = 12.5
+    with pytest.raises(ecb.EcbError):
+        ctx.load_events(synth.to_records(bad))
+    bad = dict(ev)
+    bad["t"] = ev["t"].copy()
+    bad["t"][500] = 0.0
+    with pytest.raises(ecb.EcbError):
+        ctx.load_events(synth.to_records(bad))
+
+
+def test_fit_circles_api(ctx, oracle_mod):
+    rng = np.random.default_rng(0)
+    sets, ref = [], []
+    for k in range(50):
+        c = rng.uniform(50, 200, 2)
+        r = rng.uniform(5, 15)
+        th = rng.uniform(0, 2 * np.pi, int(rng.integers(8, 200)))
+        p = np.rint(np.stack([c[0] + r * np.cos(th), c[1] + r * np.sin(th)], 1))
+        sets.append(p)
+        ref.append(oracle_mod.fit_circle(p[: len(p) // 2], p[len(p) // 2:]))
+    off = np.concatenate([[0], np.cumsum([len(s) for s in sets])])
+    out = ctx.fit_circles(np.concatenate(sets), off)
+    np.testing.assert_allclose(out, np.array(ref), rtol=RTOL)
