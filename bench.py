@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — events/s of the EventCalib hot path (detection: ingest -> windows -> DBSCAN -> circle fit).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--events E]
+
+Workload at every N: BASELINE.json configs[1] ("C2") per GPU — a synthetic 20 M-event DAVIS346 (346x260)
+circle-grid stream, 2 Mev/s, fixed tiling windows of 1.5 ms (= 3 x MotionTimeStep), both polarities, DBSCAN
+eps 4 / minPts 2, cluster filter and circle fit (fitCircle: 1).  One "step" = one pass of the whole front end
+over that stream.  N > 1: windows are independent, so rank r holds the r-th 10 s slice of a longer stream
+(weak scaling, no data-path collective); value = all events of all ranks / max-over-ranks device time.
+
+  value   device-resident: the packed 25-byte records are already in HBM when the timed region starts
+  e2e     through the C ABI with HOST buffers: pinned-host records -> H2D -> front end -> D2H of the per-window
+          summaries and candidate circles, every step
+  roofline / cpu_baseline / clocks: see DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "events/sec (detection: window+dedupe+DBSCAN+circle fit)"
+UNIT = "events/s"
+WIDTH, HEIGHT = 346, 260
+WINDOW = 1.5e-3
+RATE = 2.0e6  # events / s of stream time
+ALGO_BYTES_PER_EVENT = 29.0  # 25 B record read + 4 B label write
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(n_events, rank):
+    from eventcalib_b200 import synth
+    dur = n_events / RATE
+    t0 = 5.0 + rank * dur
+    workers = max(1, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    ev = synth.make_stream(n_events, WIDTH, HEIGHT, t0=t0, duration=dur, seed=1002 + rank, workers=workers)
+    win = synth.tiling_windows(t0, t0 + dur, WINDOW)
+    return ev, win
+
+
+def frontend_params():
+    import eventcalib_b200 as ecb
+    rthr = ecb.radius_threshold(WIDTH, HEIGHT, 9, 4, True, 5.5, 1.75)
+    return ecb.default_params(eps=4.0, min_pts=2, cluster_min=5, knn_num=3, fit_circle=1, radius_threshold=rthr,
+                              rows_cols=36), rthr
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_reference_rate(ev, win, rthr, budget_s=12.0, threads=None):
+    """Reference CPU path (verbatim reference DBSCAN from oracle/_ref + restated glue; oracle port if _ref is
+    absent) on a bounded sample of the workload's windows, threaded like the reference
+    (hardware_concurrency()-2 std::threads over windows, eventCameraCalib.cpp:172-190)."""
+    import oracle
+    oracle.build()
+    kind = "reference" if oracle.have_ref() else "port"
+    hw = os.cpu_count() or 4
+    threads = threads or max(1, hw - 2)
+    kw = dict(eps=4.0, minS=2, clusterMin=5, knn_num=3, fitCircle=1, Rthr=rthr, rows_cols=36, ref=True)
+    # calibrate on a few windows, then size the sample for ~budget_s of wall time
+    probe = win[: min(len(win), 4 * threads)]
+    t0 = time.perf_counter()
+    _, nev, _ = oracle.frontend_windows(ev["t"], ev["x"], ev["y"], ev["p"], probe, threads=threads, **kw)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    rate = nev / dt
+    n_s = int(min(len(win), max(len(probe), rate * budget_s / max(nev / len(probe), 1))))
+    sample = win[:n_s]
+    t0 = time.perf_counter()
+    cand, nev, _ = oracle.frontend_windows(ev["t"], ev["x"], ev["y"], ev["p"], sample, threads=threads, **kw)
+    dt = time.perf_counter() - t0
+    return dict(value=nev / dt, unit=UNIT, cores=threads, kind=kind, seconds=dt,
+                sample="first %d of %d windows (%d events), %d std::threads of %d host cores; %s" % (
+                    n_s, len(win), nev, threads, hw,
+                    "verbatim reference DBSCAN + restated glue (oracle/_ref)" if kind == "reference" else "oracle port")), cand
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path, same config / metric."""
+    if rank != 0:
+        return
+    n_events = args.events
+    ev, win = make_workload(min(n_events, 4_000_000), 0)  # a bounded slice is enough for the CPU arm
+    _, rthr = frontend_params()
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb, _ = cpu_reference_rate(ev, win, rthr, budget_s=max(2.0, 40.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(cb)
+    v = float(np.mean([c["value"] for c in vals]))
+    secs = float(np.mean([c["seconds"] for c in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = v
+    cb.pop("seconds", None)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32 pixels / f64 fit", "data": "synthetic",
+            "config": {"workload": "C2 per GPU: synthetic DAVIS346 circle-grid stream, 1.5 ms tiling windows, "
+                                   "DBSCAN eps 4 minPts 2 + circle fit; CPU arm runs a bounded sample of it"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--events", type=int, default=20_000_000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import eventcalib_b200 as ecb
+    from eventcalib_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ev, win = make_workload(args.events, rank)
+    n = len(ev["t"])
+    rec = synth.to_records(ev)
+    pinned = torch.empty(n * 25, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = rec.view(np.uint8).reshape(-1)
+    d_raw = torch.empty(n * 25 + 16, dtype=torch.uint8, device="cuda")
+    d_raw[: n * 25].copy_(pinned, non_blocking=False)
+
+    stream = torch.cuda.current_stream()
+    ctx = ecb.Context(local, stream.cuda_stream)
+    ctx.set_sensor(WIDTH, HEIGHT)
+    prm, rthr = frontend_params()
+
+    def step_device():
+        ctx.load_events_device(d_raw.data_ptr(), n)
+        ctx.frontend_run(win, prm)
+
+    def step_e2e():
+        ctx.load_events_ptr(pinned.data_ptr(), n)
+        ctx.frontend_run(win, prm)
+        s = ctx.summary()
+        c = ctx.candidates(48)
+        return s, c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    l0 = ctx.launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(step_device, args.steps)
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if sampler else None
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # per-kernel durations, measured live with CUDA events on the launching stream (separate pass)
+    ctx.set_profiling(True)
+    stage = {}
+    for _ in range(args.steps):
+        step_device()
+        for k, v in ctx.stage_ms().items():
+            stage.setdefault(k, []).append(v)
+    ctx.set_profiling(False)
+    stage = {k: float(np.mean(v)) for k, v in stage.items() if np.mean(v) > 0}
+
+    # end to end through the C ABI with host buffers
+    s, c = step_e2e()
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
+    h2d = n * 25 + win.nbytes
+    d2h = s.nbytes + c.nbytes
+
+    if rank == 0:
+        hbm, which = peaks()
+        npts = int(s["n_points"].sum())
+        # algorithmic bytes per launch of each kernel
+        algo = {"ingest": n * 37.0, "window": n * 4.0 + npts * 8.0, "cluster": npts * 12.0, "pair": npts * 8.0}
+        dom = max((k for k in stage if k in algo), key=lambda k: stage[k])
+        kernels = {k: {"ms": stage[k], "share": stage[k] / sum(stage.values()),
+                       "algo_gbs": algo[k] / (stage[k] * 1e-3) / 1e9 if k in algo else None} for k in stage}
+        achieved = algo[dom] / (stage[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                    "frac": achieved / hbm, "traffic": None, "peak_source": which,
+                    "path_frac": (value / world) * ALGO_BYTES_PER_EVENT / 1e9 / hbm,
+                    "note": "achieved = algorithmic bytes of the dominant kernel / its CUDA-event duration; "
+                            "path_frac = whole-path 29 B/event x events/s / peak", "kernels": kernels}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32 pixels / f64 fit", "data": "synthetic",
+                "config": {"workload": "C2 per GPU: synthetic %d-event DAVIS346 (346x260) circle-grid stream, %d tiling "
+                                       "windows of 1.5 ms, DBSCAN eps 4 minPts 2 + cluster filter + circle fit (fitCircle 1)"
+                                       % (n, len(win)),
+                           "events_per_gpu": n, "windows_per_gpu": int(len(win)), "parallelism": "windows sharded x%d" % world,
+                           "l2": "inputs larger than L2 (%.0f MB of records per step)" % (n * 25 / 1e6),
+                           "found_circles_per_window": float(s["n_candidates"].mean())},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)}}
+        if not args.no_cpu and world == 1:
+            cb, _ = cpu_reference_rate(ev, win, rthr)
+            cb.pop("seconds", None)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

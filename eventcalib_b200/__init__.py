@@ -44,7 +44,7 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_set_sensor", "ecb_load_events_host", "ecb_load_events_device", "ecb_num_events", "ecb_frontend_run",
            "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
            "ecb_frontend_clusters", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
-           "ecb_fit_circles"]
+           "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms"]
 
 _lib = None
 
@@ -83,6 +83,8 @@ def load_library():
     lib.ecb_dbscan_run.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32)]
     lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
     lib.ecb_fit_circles.argtypes = [vp, vp, vp, i32, vp]
+    lib.ecb_set_profiling.argtypes = [vp, i32]
+    lib.ecb_stage_ms.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -140,6 +142,16 @@ class Context:
     def synchronize(self):
         self._chk(self.lib.ecb_synchronize(self.h))
 
+    STAGES = ["ingest", "bounds", "window", "cluster", "pair", "assoc", "normal_eq", "cost"]
+
+    def set_profiling(self, on=True):
+        self._chk(self.lib.ecb_set_profiling(self.h, int(on)))
+
+    def stage_ms(self):
+        out = np.zeros(8, np.float32)
+        self._chk(self.lib.ecb_stage_ms(self.h, _ptr(out)))
+        return dict(zip(self.STAGES, out.tolist()))
+
     # ---- ingest ----
     def set_sensor(self, width, height):
         self._chk(self.lib.ecb_set_sensor(self.h, width, height))
@@ -150,6 +162,11 @@ class Context:
         n = buf.nbytes // 25
         self._keep = buf
         self._chk(self.lib.ecb_load_events_host(self.h, _ptr(buf), n))
+        return n
+
+    def load_events_ptr(self, host_ptr, n):
+        """host_ptr: address of n packed records in (ideally pinned) host memory."""
+        self._chk(self.lib.ecb_load_events_host(self.h, C.c_void_p(host_ptr), n))
         return n
 
     def load_events_device(self, dptr, n):

@@ -93,6 +93,9 @@ void ecb_ctx_destroy(ecb_ctx *c) {
                       &c->fit_in, &c->fit_off, &c->fit_out, &c->db_hdr_b, &c->db_ktab, &c->db_counter};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (int i = 0; i < ECB_N_STAGES; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (c->pev[i][j]) cudaEventDestroy(c->pev[i][j]);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -105,6 +108,28 @@ int ecb_synchronize(ecb_ctx *ctx) {
     if (!ctx) return ECB_ERR_ARG;
     cudaSetDevice(ctx->device);
     return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "stream synchronize");
+}
+
+int ecb_set_profiling(ecb_ctx *ctx, int on) {
+    if (!ctx) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (on && !ctx->pev[0][0])
+        for (int i = 0; i < ECB_N_STAGES; ++i)
+            for (int j = 0; j < 2; ++j) ECB_CUDA(ctx, cudaEventCreate(&ctx->pev[i][j]));
+    ctx->prof = on != 0;
+    for (int i = 0; i < ECB_N_STAGES; ++i) ctx->pev_used[i] = false;
+    return ECB_OK;
+}
+
+int ecb_stage_ms(ecb_ctx *ctx, float *out) {
+    if (!ctx || !out) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ECB_N_STAGES; ++i) {
+        out[i] = 0.f;
+        if (ctx->pev_used[i]) ECB_CUDA(ctx, cudaEventElapsedTime(&out[i], ctx->pev[i][0], ctx->pev[i][1]));
+    }
+    return ECB_OK;
 }
 
 int ecb_set_sensor(ecb_ctx *ctx, int width, int height) {

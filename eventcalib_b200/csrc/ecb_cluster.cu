@@ -482,10 +482,12 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
         a.gscratch = (uint32_t *) ctx->scratch.p;
     }
     ECB_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, 4, ctx->stream));
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_CLUSTER);
     if (rank32)
         k_cluster<uint32_t><<<grid, ECB_CL_THREADS, smem, ctx->stream>>>(a);
     else
         k_cluster<uint16_t><<<grid, ECB_CL_THREADS, smem, ctx->stream>>>(a);
+    ECB_PROF_END(ctx, ECB_STAGE_CLUSTER);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_cluster launch");
 }

@@ -32,6 +32,9 @@ struct ecb_ctx {
     int sm_count = 148;
     int smem_optin = 0;
     int width = 0, height = 0;
+    bool prof = false;
+    cudaEvent_t pev[ECB_N_STAGES][2] = {};
+    bool pev_used[ECB_N_STAGES] = {};
 
     // events (SoA)
     int64_t n_events = 0;
@@ -63,6 +66,9 @@ int ecb_check(ecb_ctx *ctx, cudaError_t e, const char *what);
         if (_rc) return _rc;                                  \
     } while (0)
 #define ECB_LAUNCHED(ctx) ((ctx)->launches++)
+// stage timing: ECB_PROF_BEGIN/END bracket a kernel launch with events when profiling is on
+#define ECB_PROF_BEGIN(ctx, st) do { if ((ctx)->prof) cudaEventRecord((ctx)->pev[st][0], (ctx)->stream); } while (0)
+#define ECB_PROF_END(ctx, st) do { if ((ctx)->prof) { cudaEventRecord((ctx)->pev[st][1], (ctx)->stream); (ctx)->pev_used[st] = true; } } while (0)
 
 // ---------------------------------------------------------------------------------------------------
 // device helpers

@@ -282,7 +282,9 @@ __global__ void k_fit(const double *__restrict__ xy, const int64_t *__restrict__
 int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     if (a.n_win <= 0) return ECB_OK;
     int grid = a.n_win < ctx->sm_count * 8 ? a.n_win : ctx->sm_count * 8;
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_PAIR);
     k_pair<<<grid, PAIR_THREADS, 0, ctx->stream>>>(a);
+    ECB_PROF_END(ctx, ECB_STAGE_PAIR);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_pair launch");
 }

@@ -214,9 +214,11 @@ int ecb_launch_ingest(ecb_ctx *ctx, const void *d_raw, int64_t n) {
     if (n <= 0) return ECB_OK;
     int64_t tiles = (n + ING_REC - 1) / ING_REC;
     int grid = (int) (tiles < (int64_t) ctx->sm_count * 16 ? tiles : (int64_t) ctx->sm_count * 16);
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_INGEST);
     k_ingest<<<grid, ING_THREADS, 0, ctx->stream>>>((const uint8_t *) d_raw, n, ctx->width, ctx->height,
                                                      (double *) ctx->ev_t.p, (uint32_t *) ctx->ev_xyp.p,
                                                      (uint32_t *) ctx->ev_flag.p);
+    ECB_PROF_END(ctx, ECB_STAGE_INGEST);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_ingest launch");
 }
@@ -224,8 +226,10 @@ int ecb_launch_ingest(ecb_ctx *ctx, const void *d_raw, int64_t n) {
 int ecb_launch_bounds(ecb_ctx *ctx, const double *d_win, int n_win, int64_t *d_lohi) {
     if (n_win <= 0) return ECB_OK;
     const int thr = 128;
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_BOUNDS);
     k_bounds<<<(2 * n_win + thr - 1) / thr, thr, 0, ctx->stream>>>((const double *) ctx->ev_t.p, ctx->n_events, d_win,
                                                                     n_win, d_lohi);
+    ECB_PROF_END(ctx, ECB_STAGE_BOUNDS);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_bounds launch");
 }
@@ -243,7 +247,9 @@ int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a) {
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_win) grid = a.n_win;
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_WINDOW);
     k_window<<<grid, WIN_THREADS, smem, ctx->stream>>>(a);
+    ECB_PROF_END(ctx, ECB_STAGE_WINDOW);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_window launch");
 }

@@ -73,7 +73,7 @@ class Camera:
         b = self.inv_poly
         return 1 + r2 * (b[0] + r2 * (b[1] + r2 * (b[2] + r2 * (b[3] + r2 * b[4]))))
 
-    def distort(self, xu, yu, iters=30):
+    def distort(self, xu, yu, iters=14):
         """invert the undistortion polynomial: find xd with xd * s(|xd|^2) = xu (fixed point)."""
         xd, yd = xu.copy(), yu.copy()
         for _ in range(iters):
@@ -148,55 +148,63 @@ def project(cam: Camera, R, tw, Xw):
     return cam.f * xd + cam.cx, cam.f * yd + cam.cy
 
 
-def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001, noise_frac=0.05, flip_frac=0.0,
-                jitter=0.7, board: Board = None, dist=None, chunk=1 << 21, return_truth=False):
-    """Returns dict(t, x, y, p) float64/uint8 arrays (time sorted, integer-valued pixel coordinates)."""
-    board = board or Board()
+def _gen_chunk(args):
+    (s, e, n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter, board, dist, k) = args
     cam = Camera(width, height)
-    if dist is None:
-        dist = 78.0
     traj = Trajectory(seed, board, dist)
     centres = board.centres()
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng([seed, k])
     dt = duration / n_events
-    T = np.empty(n_events)
-    X = np.empty(n_events)
-    Y = np.empty(n_events)
-    P = np.empty(n_events, np.uint8)
-    for s in range(0, n_events, chunk):
-        e = min(n_events, s + chunk)
-        m = e - s
-        t = t0 + (np.arange(s, e) + rng.uniform(0.05, 0.95, m)) * dt
-        k = rng.integers(0, len(centres), m)
-        th = rng.uniform(0, 2 * np.pi, m)
-        R, tw = traj.pose(t)
-        C = centres[k]
-        rim = C + board.radius * np.stack([np.cos(th), np.sin(th), np.zeros(m)], axis=1)
-        u, v = project(cam, R, tw, rim)
-        cu, cv = project(cam, R, tw, C)
-        R2, tw2 = traj.pose(t + 1e-4)
-        cu2, cv2 = project(cam, R2, tw2, C)
-        nx, ny = u - cu, v - cv
-        nn = np.sqrt(nx * nx + ny * ny) + 1e-12
-        pol = ((nx * (cu2 - cu) + ny * (cv2 - cv)) > 0)
-        j = rng.normal(0, jitter, m)
-        u = u + nx / nn * j
-        v = v + ny / nn * j
-        noise = rng.uniform(0, 1, m) < noise_frac
-        nz = int(noise.sum())
-        u[noise] = rng.uniform(0, width - 1, nz)
-        v[noise] = rng.uniform(0, height - 1, nz)
-        pol[noise] = rng.uniform(0, 1, nz) < 0.5
-        if flip_frac > 0:
-            fl = rng.uniform(0, 1, m) < flip_frac
-            pol[fl] = ~pol[fl]
-        T[s:e] = t
-        X[s:e] = np.clip(np.rint(u), 0, width - 1)
-        Y[s:e] = np.clip(np.rint(v), 0, height - 1)
-        P[s:e] = pol.astype(np.uint8)
+    m = e - s
+    t = t0 + (np.arange(s, e) + rng.uniform(0.05, 0.95, m)) * dt
+    k = rng.integers(0, len(centres), m)
+    th = rng.uniform(0, 2 * np.pi, m)
+    R, tw = traj.pose(t)
+    C = centres[k]
+    rim = C + board.radius * np.stack([np.cos(th), np.sin(th), np.zeros(m)], axis=1)
+    u, v = project(cam, R, tw, rim)
+    cu, cv = project(cam, R, tw, C)
+    R2, tw2 = traj.pose(t + 1e-4)
+    cu2, cv2 = project(cam, R2, tw2, C)
+    nx, ny = u - cu, v - cv
+    nn = np.sqrt(nx * nx + ny * ny) + 1e-12
+    pol = ((nx * (cu2 - cu) + ny * (cv2 - cv)) > 0)
+    j = rng.normal(0, jitter, m)
+    u = u + nx / nn * j
+    v = v + ny / nn * j
+    noise = rng.uniform(0, 1, m) < noise_frac
+    nz = int(noise.sum())
+    u[noise] = rng.uniform(0, width - 1, nz)
+    v[noise] = rng.uniform(0, height - 1, nz)
+    pol[noise] = rng.uniform(0, 1, nz) < 0.5
+    if flip_frac > 0:
+        fl = rng.uniform(0, 1, m) < flip_frac
+        pol[fl] = ~pol[fl]
+    return (t, np.clip(np.rint(u), 0, width - 1), np.clip(np.rint(v), 0, height - 1), pol.astype(np.uint8))
+
+
+def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001, noise_frac=0.05, flip_frac=0.0,
+                jitter=0.7, board: Board = None, dist=None, chunk=1 << 19, return_truth=False, workers=1):
+    """Returns dict(t, x, y, p) float64/uint8 arrays (time sorted, integer-valued pixel coordinates).
+    Deterministic in (seed, n_events, chunk) — independent of `workers` (processes used to generate chunks)."""
+    board = board or Board()
+    if dist is None:
+        dist = 78.0
+    jobs = [(s, min(n_events, s + chunk), n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter,
+             board, dist, k) for k, s in enumerate(range(0, n_events, chunk))]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            parts = pool.map(_gen_chunk, jobs)
+    else:
+        parts = [_gen_chunk(j) for j in jobs]
+    T = np.concatenate([p[0] for p in parts])
+    X = np.concatenate([p[1] for p in parts])
+    Y = np.concatenate([p[2] for p in parts])
+    P = np.concatenate([p[3] for p in parts])
     out = dict(t=T, x=X, y=Y, p=P, width=width, height=height)
     if return_truth:
-        out.update(camera=cam, trajectory=traj, board=board)
+        out.update(camera=Camera(width, height), trajectory=Trajectory(seed, board, dist), board=board)
     return out
 
 

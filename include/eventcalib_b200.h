@@ -54,6 +54,19 @@ const char *ecb_last_error(const ecb_ctx *ctx);
 /* number of kernels of this library launched through ctx so far */
 uint64_t ecb_launch_count(const ecb_ctx *ctx);
 int ecb_synchronize(ecb_ctx *ctx);
+/* Per-kernel device timing (CUDA events on the context stream around every launch; no extra syncs).
+ * ecb_stage_ms: durations of the most recent launch of each stage, out[ECB_N_STAGES]; synchronizes. */
+#define ECB_STAGE_INGEST 0
+#define ECB_STAGE_BOUNDS 1
+#define ECB_STAGE_WINDOW 2
+#define ECB_STAGE_CLUSTER 3
+#define ECB_STAGE_PAIR 4
+#define ECB_STAGE_ASSOC 5
+#define ECB_STAGE_NORMAL_EQ 6
+#define ECB_STAGE_COST 7
+#define ECB_N_STAGES 8
+int ecb_set_profiling(ecb_ctx *ctx, int on);
+int ecb_stage_ms(ecb_ctx *ctx, float *out);
 const char *ecb_version(void);
 
 /* ---- a1: event ingest ---------------------------------------------------------------------------- */
