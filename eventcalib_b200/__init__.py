@@ -44,7 +44,8 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_set_sensor", "ecb_load_events_host", "ecb_load_events_device", "ecb_num_events", "ecb_frontend_run",
            "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
            "ecb_frontend_clusters", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
-           "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms"]
+           "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_layout",
+           "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq"]
 
 _lib = None
 
@@ -85,6 +86,13 @@ def load_library():
     lib.ecb_fit_circles.argtypes = [vp, vp, vp, i32, vp]
     lib.ecb_set_profiling.argtypes = [vp, i32]
     lib.ecb_stage_ms.argtypes = [vp, vp]
+    lib.ecb_cost_setup.argtypes = [vp, i32, vp, vp, dbl, dbl]
+    lib.ecb_cost_layout.argtypes = [vp, vp, vp, vp, vp]
+    lib.ecb_cost_associate.argtypes = [vp, vp, vp, i32, i32, vp, dbl, vp]
+    lib.ecb_cost_get_association.argtypes = [vp, vp, vp, i64]
+    lib.ecb_cost_set_residuals.argtypes = [vp, vp, vp, vp, vp, i64]
+    lib.ecb_cost_eval.argtypes = [vp, vp, vp, vp, vp]
+    lib.ecb_cost_normal_eq.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -236,3 +244,65 @@ class Context:
         out = np.zeros((max(k, 1), 3))
         self._chk(self.lib.ecb_fit_circles(self.h, _ptr(xy), _ptr(off), k, _ptr(out)))
         return out[:k]
+
+    # ---- cost evaluation ----
+    def cost_setup(self, n_cp, knots, radius=1.75, huber=0.35):
+        n_cp = np.ascontiguousarray(np.atleast_1d(n_cp), np.int32)
+        kn = np.ascontiguousarray(np.concatenate([np.asarray(k, np.float64).ravel() for k in knots])
+                                  if isinstance(knots, (list, tuple)) else knots, np.float64)
+        assert len(kn) == int(n_cp.sum()) + 4 * len(n_cp)
+        self._chk(self.lib.ecb_cost_setup(self.h, len(n_cp), _ptr(n_cp), _ptr(kn), float(radius), float(huber)))
+
+    def cost_layout(self):
+        cp, sp = C.c_int32(), C.c_int32()
+        nr, nd = C.c_int64(), C.c_int64()
+        self._chk(self.lib.ecb_cost_layout(self.h, C.byref(cp), C.byref(sp), C.byref(nr), C.byref(nd)))
+        return dict(total_cp=cp.value, total_spans=sp.value, n_residuals=nr.value, out_doubles=nd.value)
+
+    def cost_associate(self, kf_t, circles, landmarks, step):
+        kf_t = np.ascontiguousarray(kf_t, np.float64)
+        circles = np.ascontiguousarray(circles, np.float64)
+        lm = np.ascontiguousarray(landmarks, np.float64)
+        n = C.c_int64(0)
+        self._chk(self.lib.ecb_cost_associate(self.h, _ptr(kf_t), _ptr(circles), len(kf_t), circles.shape[1], _ptr(lm),
+                                              float(step), C.byref(n)))
+        return n.value
+
+    def cost_association(self):
+        n = self.cost_layout()["n_residuals"]
+        ev = np.zeros(max(n, 1), np.int64)
+        ci = np.zeros(max(n, 1), np.int32)
+        self._chk(self.lib.ecb_cost_get_association(self.h, _ptr(ev), _ptr(ci), n))
+        return ev[:n], ci[:n]
+
+    def cost_set_residuals(self, obs, lm, t, spline):
+        obs = np.ascontiguousarray(obs, np.float64)
+        lm = np.ascontiguousarray(lm, np.float64)
+        t = np.ascontiguousarray(t, np.float64)
+        sp = np.ascontiguousarray(spline, np.int32)
+        self._chk(self.lib.ecb_cost_set_residuals(self.h, _ptr(obs), _ptr(lm), _ptr(t), _ptr(sp), len(t)))
+
+    def cost_eval(self, intr, rot, trans):
+        intr = np.ascontiguousarray(intr, np.float64)
+        rot = np.ascontiguousarray(rot, np.float64)
+        trans = np.ascontiguousarray(trans, np.float64)
+        c = C.c_double(0)
+        self._chk(self.lib.ecb_cost_eval(self.h, _ptr(intr), _ptr(rot), _ptr(trans), C.byref(c)))
+        return c.value
+
+    def cost_normal_eq(self, intr, rot, trans, d_out=None, host=True):
+        """Returns (cost, H[n_spans,33,33], g[n_spans,33]) when host=True, else leaves the packed result in d_out."""
+        intr = np.ascontiguousarray(intr, np.float64)
+        rot = np.ascontiguousarray(rot, np.float64)
+        trans = np.ascontiguousarray(trans, np.float64)
+        lay = self.cost_layout()
+        c = C.c_double(0)
+        if not host:
+            self._chk(self.lib.ecb_cost_normal_eq(self.h, _ptr(intr), _ptr(rot), _ptr(trans), C.c_void_p(d_out), None, None))
+            return None
+        out = np.zeros(lay["out_doubles"])
+        self._chk(self.lib.ecb_cost_normal_eq(self.h, _ptr(intr), _ptr(rot), _ptr(trans),
+                                              C.c_void_p(d_out) if d_out else None, _ptr(out), C.byref(c)))
+        ns = lay["total_spans"]
+        blk = out[:ns * 1122].reshape(ns, 1122)
+        return c.value, blk[:, :1089].reshape(ns, 33, 33).copy(), blk[:, 1089:].copy()

@@ -1,3 +1,678 @@
-// cost evaluation kernels (placeholder until the residual/Jacobian path lands)
+// Cost evaluation of the dynamic-calibration objective on the GPU.
+//
+//   k_associate_*   EventCalibSpline::optimize association loop (src/EventCalibSpline.cpp:157-192) + findCenter
+//                   (include/.../CirclesEventFrame.hpp:50-65): raw event -> nearest keyframe in time -> nearest circle
+//                   -> | ||p-c|| - r | < 5 px -> residual record (ordered compaction, two passes)
+//   k_prepare       findSpan + dersBasisFuns per residual (core/spline/.../BsplineReal.hpp:208-231,107-145); the basis
+//                   is constant over the LM iterations, so it is computed once here
+//   k_normal_eq     residual + closed-form Jacobian (ecb_residual.h) per lane, then the per-span Gram matrix
+//                   [J | r]^T [J | r] (34 x 34, padded to 40) on the FP64 tensor pipe: mma.sync m8n8k4 f64 (DMMA),
+//                   15 upper 8x8 tiles per warp kept in registers, J staged through shared memory transposed
+//                   (conflict-free for both the lane-per-residual stores and the fragment loads).
+//                   B200 measured: DMMA 37.0 TFLOP/s == DFMA 36.4 TFLOP/s (profiles/r1_fp64_peak.txt), so the
+//                   tensor path costs nothing in peak and removes the shared-memory/issue bottleneck of a
+//                   CUDA-core register-tiled SYRK.  tcgen05 has no f64 kind.
+//   k_reduce_*      fixed-order reduction of the per-work-item partials -> run-to-run identical J^T J / J^T r / cost
+//   k_cost          cost-only evaluation (LM step acceptance)
+#include <algorithm>
+#include <vector>
+
 #include "ecb_common.cuh"
-extern "C" void ecb_cost_free(ecb_ctx *ctx) { (void) ctx; }
+#include "ecb_residual.h"
+
+namespace {
+
+constexpr int NE_THREADS = 256;            // 8 warps
+constexpr int NE_WARPS = NE_THREADS / 32;
+constexpr int TILE_ROWS = 40, TILE_LD = 36;  // [param][residual], LD % 16 == 4 -> conflict-free fragment loads
+constexpr int N_TILES = 15;                 // upper 8x8 tiles of the 40x40 Gram matrix
+constexpr int PART_STRIDE = N_TILES * 64 + 8;  // per work item: 15 tiles + cost (+pad)
+constexpr int CHUNK = 2048;                 // residuals per work item
+constexpr int OUT_STRIDE = 33 * 33 + 33;    // per span: H (full symmetric) | g
+
+struct CostState {
+    int n_splines = 0, total_cp = 0, total_spans = 0;
+    std::vector<int> n_cp, cp_off, span_off, knot_off;
+    std::vector<double> knots;
+    double radius = 1.75, huber = 0.35;
+    int64_t n_res = 0;
+    int n_items = 0;
+    DevBuf d_knots, d_knot_off, d_ncp, d_cp_off, d_span_off;
+    DevBuf obs, lm, tt, spl, basis, cp0, span;        // residual records (SoA)
+    DevBuf span_start, items, part, out, params, cost_part, flags;
+    DevBuf ev_flag, ev_cnt, kf_t, kf_circ, lm_tab, sel_event, sel_circle;
+    std::vector<int64_t> h_span_start;
+};
+
+CostState *state(ecb_ctx *ctx) {
+    if (!ctx->cost) ctx->cost = new CostState();
+    return (CostState *) ctx->cost;
+}
+
+// ------------------------------------------------------------------------------------ prepare ----
+__device__ __forceinline__ int find_span_dev(const double *knots, int nk, double u) {  // BsplineReal.hpp:208-231
+    const int degree = 3;
+    const int n = nk - 2 - degree;
+    if (u == knots[n + 1]) return n;
+    int low = degree, high = n + 1, mid = (low + high) / 2;
+    while (u < knots[mid] || u >= knots[mid + 1]) {
+        if (u < knots[mid]) high = mid; else low = mid;
+        mid = (low + high) / 2;
+    }
+    return mid;
+}
+
+__device__ __forceinline__ void basis_dev(const double *knots, int span, double u, double *N) {  // BsplineReal.hpp:107-145
+    double ndu[4][4], left[4], right[4];
+    ndu[0][0] = 1;
+#pragma unroll
+    for (int j = 1; j <= 3; j++) {
+        left[j] = u - knots[span + 1 - j];
+        right[j] = knots[span + j] - u;
+        double saved = 0.0;
+#pragma unroll
+        for (int r = 0; r < j; ++r) {
+            ndu[j][r] = right[r + 1] + left[j - r];
+            double temp = __ddiv_rn(ndu[r][j - 1], ndu[j][r]);
+            ndu[r][j] = __dadd_rn(saved, __dmul_rn(right[r + 1], temp));
+            saved = __dmul_rn(left[j - r], temp);
+        }
+        ndu[j][j] = saved;
+    }
+#pragma unroll
+    for (int j = 0; j <= 3; j++) N[j] = ndu[j][3];
+}
+
+__global__ void k_prepare(const double *__restrict__ t, const int *__restrict__ spl, int64_t n, const double *__restrict__ knots,
+                          const int *__restrict__ knot_off, const int *__restrict__ ncp, const int *__restrict__ cp_off,
+                          const int *__restrict__ span_off, double *__restrict__ basis, int *__restrict__ cp0,
+                          int *__restrict__ span, uint32_t *__restrict__ flags) {
+    const int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int s = spl[k];
+    const double *kn = knots + knot_off[s];
+    const int nk = ncp[s] + 4;
+    const double u = t[k];
+    if (!(u >= kn[0] && u <= kn[nk - 1])) {  // outside the spline: the reference never creates such a block
+        atomicOr(flags, 1u);
+        span[k] = 0;
+        cp0[k] = 0;
+        return;
+    }
+    const int sp = find_span_dev(kn, nk, u);
+    double N[4];
+    basis_dev(kn, sp, u, N);
+    reinterpret_cast<double4 *>(basis)[k] = make_double4(N[0], N[1], N[2], N[3]);
+    cp0[k] = cp_off[s] + sp - 3;
+    const int gs = span_off[s] + sp - 3;
+    span[k] = gs;
+    if (k > 0) {  // records must be ordered by (spline, time) so that spans are contiguous
+        const int sprev = spl[k - 1];
+        if (sprev > s || (sprev == s && t[k - 1] > u)) atomicOr(flags, 2u);
+    }
+}
+
+__global__ void k_span_start(const int *__restrict__ span, int64_t n, int n_spans, int64_t *__restrict__ start) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_spans) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t m = (lo + hi) >> 1;
+        if (span[m] < s) lo = m + 1; else hi = m;
+    }
+    start[s] = lo;
+}
+
+// ---------------------------------------------------------------------------------- normal eq ----
+struct Item {
+    int64_t begin, end;
+    int span, pad;
+};
+
+struct NeArgs {
+    const double *obs, *lm, *basis;
+    const int *cp0;
+    const Item *items;
+    int n_items;
+    const double *params;  // intr[9] | rot[4*C] | trans[3*C]
+    int total_cp;
+    double radius, huber;
+    double *part;
+};
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(NE_THREADS, 2) k_normal_eq(const NeArgs a) {
+    extern __shared__ __align__(16) double sm_tiles[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *tile = sm_tiles + (size_t) wid * TILE_ROWS * TILE_LD;
+    const int g = lane >> 2, t = lane & 3;
+    for (int r = 34; r < TILE_ROWS; ++r) tile[r * TILE_LD + lane] = 0.0;  // padding rows stay zero
+    const double *intr = a.params, *rot = a.params + 9, *trans = a.params + 9 + 4 * (size_t) a.total_cp;
+    const int gw = blockIdx.x * NE_WARPS + wid, nw = gridDim.x * NE_WARPS;
+    for (int it = gw; it < a.n_items; it += nw) {
+        const Item item = a.items[it];
+        double acc[N_TILES][2];
+#pragma unroll
+        for (int i = 0; i < N_TILES; ++i) acc[i][0] = acc[i][1] = 0.0;
+        double cost = 0.0;
+        for (int64_t base = item.begin; base < item.end; base += 32) {
+            const int64_t k = base + lane;
+            double res = 0.0;
+            __syncwarp();  // the previous group's fragment loads are done
+            if (k < item.end) {
+                const int c0 = a.cp0[k];
+                const double4 b4 = reinterpret_cast<const double4 *>(a.basis)[k];
+                const double b[4] = {b4.x, b4.y, b4.z, b4.w};
+                const double2 o = reinterpret_cast<const double2 *>(a.obs)[k];
+                // the Jacobian is scattered straight into column `lane` of the shared tile (no register array)
+                const EcbResidualOut r = ecb_residual<true, TILE_LD>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x,
+                                                                     o.y, a.lm[3 * k], a.lm[3 * k + 1], a.lm[3 * k + 2],
+                                                                     a.radius, a.huber, tile + lane);
+                res = r.res;
+                cost += r.cost;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 33; ++c) tile[c * TILE_LD + lane] = 0.0;
+            }
+            tile[33 * TILE_LD + lane] = res;
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                double f[5];
+#pragma unroll
+                for (int G = 0; G < 5; ++G) f[G] = tile[(8 * G + g) * TILE_LD + 4 * ks + t];
+                int ti = 0;
+#pragma unroll
+                for (int I = 0; I < 5; ++I)
+#pragma unroll
+                    for (int Jt = I; Jt < 5; ++Jt) {
+                        dmma(acc[ti][0], acc[ti][1], f[I], f[Jt]);
+                        ++ti;
+                    }
+            }
+        }
+        // partial of this work item
+        double *p = a.part + (size_t) it * PART_STRIDE;
+#pragma unroll
+        for (int ti = 0; ti < N_TILES; ++ti) reinterpret_cast<double2 *>(p + ti * 64)[lane] = make_double2(acc[ti][0], acc[ti][1]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+        if (lane == 0) p[N_TILES * 64] = cost;
+    }
+}
+
+// out[s] = sum over the span's work items, fixed order; tiles -> full symmetric 33x33 + gradient
+__global__ void k_reduce_spans(const double *__restrict__ part, const int *__restrict__ item_start, int n_spans,
+                               double *__restrict__ out) {
+    const int s = blockIdx.x;
+    if (s >= n_spans) return;
+    const int i0 = item_start[s], i1 = item_start[s + 1];
+    double *o = out + (size_t) s * OUT_STRIDE;
+    for (int e = threadIdx.x; e < N_TILES * 64; e += blockDim.x) {
+        double v = 0.0;
+        for (int it = i0; it < i1; ++it) v += part[(size_t) it * PART_STRIDE + e];
+        const int ti = e >> 6, r = (e >> 3) & 7, c = e & 7;
+        int I = 0, rem = ti;  // tile index -> (I, Jt), I <= Jt over 5 groups
+        while (rem >= 5 - I) {
+            rem -= 5 - I;
+            ++I;
+        }
+        const int Jt = I + rem;
+        const int i = 8 * I + r, j = 8 * Jt + c;
+        if (i < 33 && j < 33) {
+            if (I != Jt || i <= j) {
+                o[i * 33 + j] = v;
+                o[j * 33 + i] = v;
+            }
+        } else if (i < 33 && j == 33) {
+            o[1089 + i] = v;
+        }
+    }
+}
+
+__global__ void k_reduce_cost(const double *__restrict__ part, int n, int stride, int offset, double *__restrict__ out) {
+    // single block, fixed order: thread-strided partial sums, then a shared-memory tree
+    __shared__ double sh[256];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) v += part[(size_t) i * stride + offset];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+__global__ void __launch_bounds__(256) k_cost(const double *__restrict__ obs, const double *__restrict__ lm,
+                                             const double *__restrict__ basis, const int *__restrict__ cp0, int64_t n,
+                                             const double *__restrict__ params, int total_cp, double radius, double huber,
+                                             double *__restrict__ block_part) {
+    __shared__ double sh[256];
+    const double *intr = params, *rot = params + 9, *trans = params + 9 + 4 * (size_t) total_cp;
+    double c = 0.0;
+    for (int64_t k = (int64_t) blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t) gridDim.x * 256) {
+        const int c0 = cp0[k];
+        const double4 b4 = reinterpret_cast<const double4 *>(basis)[k];
+        const double b[4] = {b4.x, b4.y, b4.z, b4.w};
+        const double2 o = reinterpret_cast<const double2 *>(obs)[k];
+        c += ecb_residual<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, lm[3 * k], lm[3 * k + 1],
+                                 lm[3 * k + 2], radius, huber, nullptr).cost;
+    }
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_part[blockIdx.x] = sh[0];
+}
+
+// -------------------------------------------------------------------------------- association ----
+struct AssocArgs {
+    const double *ev_t;
+    const uint32_t *ev_xyp;
+    int64_t n_ev;
+    const double *knots;
+    const int *knot_off, *ncp;
+    int n_splines;
+    const double *kf_t, *kf_circ, *lm_tab;
+    int K, n_circ;
+    double gate2;  // (5 step)^2
+};
+
+// returns the spline index and the circle id (or -1) of one raw event
+__device__ __forceinline__ int assoc_one(const AssocArgs &a, int64_t i, int *spline_out) {
+    const double u = a.ev_t[i];
+    int s = -1;
+    for (int q = 0; q < a.n_splines; ++q) {
+        const double *kn = a.knots + a.knot_off[q];
+        if (u >= kn[0] && u <= kn[a.ncp[q] + 3]) {
+            s = q;
+            break;
+        }
+    }
+    if (s < 0) return -1;
+    *spline_out = s;
+    int lo = 0, hi = a.K;  // lower_bound over keyframe times
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (a.kf_t[m] < u) lo = m + 1; else hi = m;
+    }
+    int best = lo < a.K ? lo : a.K - 1;
+    if (lo > 0 && (lo >= a.K || (u - a.kf_t[lo - 1]) <= (a.kf_t[lo] - u))) best = lo - 1;
+    const double dt = u - a.kf_t[best];
+    if (!(__dmul_rn(dt, dt) < a.gate2)) return -1;
+    const uint32_t e = a.ev_xyp[i];
+    if (e & ECB_PIX_INVALID) return -1;
+    const double x = (double) ECB_PIX_X(e), y = (double) ECB_PIX_Y(e);
+    const double *c = a.kf_circ + (size_t) best * a.n_circ * 3;
+    int bi = -1;
+    double bd = 0.0;
+    for (int q = 0; q < a.n_circ; ++q) {
+        if (c[3 * q + 2] < 0) continue;
+        const double dx = x - c[3 * q], dy = y - c[3 * q + 1];
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (bi < 0 || d2 < bd) {
+            bi = q;
+            bd = d2;
+        }
+    }
+    if (bi < 0) return -1;
+    if (!(fabs(sqrt(bd) - c[3 * bi + 2]) < 5.0)) return -1;
+    return bi;
+}
+
+constexpr int AS_THREADS = 256;
+
+__global__ void __launch_bounds__(AS_THREADS) k_assoc_count(const AssocArgs a, uint32_t *__restrict__ block_cnt) {
+    __shared__ uint32_t ws[33];
+    const int64_t i = (int64_t) blockIdx.x * AS_THREADS + threadIdx.x;
+    int s;
+    const bool ok = i < a.n_ev && assoc_one(a, i, &s) >= 0;
+    uint32_t tot;
+    block_excl_scan(ok ? 1u : 0u, ws, &tot);
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = tot;
+}
+
+__global__ void k_scan_blocks(uint32_t *cnt, int n, int64_t *off, int64_t *total) {  // single block, serial over chunks
+    __shared__ uint32_t ws[33];
+    __shared__ int64_t run;
+    if (threadIdx.x == 0) run = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += blockDim.x) {
+        const int i = c0 + threadIdx.x;
+        const uint32_t v = i < n ? cnt[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(v, ws, &tot);
+        if (i < n) off[i] = run + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) run += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = run;
+}
+
+__global__ void __launch_bounds__(AS_THREADS) k_assoc_write(const AssocArgs a, const int64_t *__restrict__ block_off,
+                                                           double *__restrict__ obs, double *__restrict__ lm,
+                                                           double *__restrict__ tt, int *__restrict__ spl,
+                                                           int64_t *__restrict__ sel_event, int *__restrict__ sel_circle) {
+    __shared__ uint32_t ws[33];
+    const int64_t i = (int64_t) blockIdx.x * AS_THREADS + threadIdx.x;
+    int s = 0;
+    const int bi = i < a.n_ev ? assoc_one(a, i, &s) : -1;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(bi >= 0 ? 1u : 0u, ws, &tot);
+    if (bi >= 0) {
+        const int64_t k = block_off[blockIdx.x] + ex;
+        const uint32_t e = a.ev_xyp[i];
+        obs[2 * k] = (double) ECB_PIX_X(e);
+        obs[2 * k + 1] = (double) ECB_PIX_Y(e);
+        lm[3 * k] = a.lm_tab[3 * bi];
+        lm[3 * k + 1] = a.lm_tab[3 * bi + 1];
+        lm[3 * k + 2] = a.lm_tab[3 * bi + 2];
+        tt[k] = a.ev_t[i];
+        spl[k] = s;
+        sel_event[k] = i;
+        sel_circle[k] = bi;
+    }
+}
+
+int prepare_records(ecb_ctx *ctx, CostState *st) {
+    int rc;
+    const int64_t n = st->n_res;
+    const size_t nn = (size_t) std::max<int64_t>(n, 1);
+    if ((rc = ecb_reserve(ctx, st->basis, nn * 32))) return rc;
+    if ((rc = ecb_reserve(ctx, st->cp0, nn * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, st->span, nn * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, st->flags, 16))) return rc;
+    if ((rc = ecb_reserve(ctx, st->span_start, (size_t) (st->total_spans + 2) * 8))) return rc;
+    ECB_CUDA(ctx, cudaMemsetAsync(st->flags.p, 0, 16, ctx->stream));
+    st->h_span_start.assign((size_t) st->total_spans + 1, 0);
+    st->n_items = 0;
+    if (n == 0) return ECB_OK;
+    k_prepare<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(
+        (const double *) st->tt.p, (const int *) st->spl.p, n, (const double *) st->d_knots.p, (const int *) st->d_knot_off.p,
+        (const int *) st->d_ncp.p, (const int *) st->d_cp_off.p, (const int *) st->d_span_off.p, (double *) st->basis.p,
+        (int *) st->cp0.p, (int *) st->span.p, (uint32_t *) st->flags.p);
+    ECB_LAUNCHED(ctx);
+    k_span_start<<<(st->total_spans + 1 + 127) / 128, 128, 0, ctx->stream>>>((const int *) st->span.p, n, st->total_spans,
+                                                                           (int64_t *) st->span_start.p);
+    ECB_LAUNCHED(ctx);
+    uint32_t flag = 0;
+    ECB_CUDA(ctx, cudaMemcpyAsync(&flag, st->flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->h_span_start.data(), st->span_start.p, (size_t) (st->total_spans + 1) * 8,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag & 1u) return ecb_fail(ctx, ECB_ERR_ARG, "a residual's time stamp lies outside its spline's knot range");
+    if (flag & 2u) return ecb_fail(ctx, ECB_ERR_ARG, "residual records must be ordered by (spline, time)");
+    // work items: chunks of <= CHUNK residuals inside one span (fixed => deterministic reduction order)
+    std::vector<Item> items;
+    std::vector<int> item_start((size_t) st->total_spans + 1, 0);
+    for (int s = 0; s < st->total_spans; ++s) {
+        item_start[(size_t) s] = (int) items.size();
+        for (int64_t b = st->h_span_start[(size_t) s]; b < st->h_span_start[(size_t) s + 1]; b += CHUNK)
+            items.push_back(Item{b, std::min<int64_t>(b + CHUNK, st->h_span_start[(size_t) s + 1]), s, 0});
+    }
+    item_start[(size_t) st->total_spans] = (int) items.size();
+    st->n_items = (int) items.size();
+    const size_t ni = std::max<size_t>(items.size(), 1);
+    if ((rc = ecb_reserve(ctx, st->items, ni * sizeof(Item) + item_start.size() * 4 + 64))) return rc;
+    if ((rc = ecb_reserve(ctx, st->part, ni * PART_STRIDE * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, st->out, ((size_t) st->total_spans * OUT_STRIDE + 8) * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
+    if (!items.empty())
+        ECB_CUDA(ctx, cudaMemcpyAsync(st->items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync((char *) st->items.p + ni * sizeof(Item), item_start.data(), item_start.size() * 4,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ECB_OK;
+}
+
+int upload_params(ecb_ctx *ctx, CostState *st, const double *intr, const double *rot, const double *trans) {
+    int rc;
+    const size_t C = (size_t) st->total_cp;
+    if ((rc = ecb_reserve(ctx, st->params, (9 + 7 * C) * 8))) return rc;
+    double *p = (double *) st->params.p;
+    ECB_CUDA(ctx, cudaMemcpyAsync(p, intr, 72, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(p + 9, rot, 32 * C, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(p + 9 + 4 * C, trans, 24 * C, cudaMemcpyHostToDevice, ctx->stream));
+    return ECB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ecb_cost_free(ecb_ctx *ctx) {
+    if (!ctx || !ctx->cost) return;
+    CostState *st = (CostState *) ctx->cost;
+    DevBuf *bufs[] = {&st->d_knots, &st->d_knot_off, &st->d_ncp, &st->d_cp_off, &st->d_span_off, &st->obs, &st->lm, &st->tt,
+                      &st->spl, &st->basis, &st->cp0, &st->span, &st->span_start, &st->items, &st->part, &st->out, &st->params,
+                      &st->cost_part, &st->flags, &st->ev_flag, &st->ev_cnt, &st->kf_t, &st->kf_circ, &st->lm_tab,
+                      &st->sel_event, &st->sel_circle};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    delete st;
+    ctx->cost = nullptr;
+}
+
+int ecb_cost_setup(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const double *knots, double circle_radius,
+                   double huber_delta) {
+    if (!ctx || n_splines < 1 || !n_cp || !knots) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CostState *st = state(ctx);
+    st->n_splines = n_splines;
+    st->n_cp.assign(n_cp, n_cp + n_splines);
+    st->cp_off.clear();
+    st->span_off.clear();
+    st->knot_off.clear();
+    int co = 0, so = 0, ko = 0;
+    for (int s = 0; s < n_splines; ++s) {
+        if (n_cp[s] < 4) return ecb_fail(ctx, ECB_ERR_ARG, "spline %d has %d control points (< degree + 1)", s, n_cp[s]);
+        st->cp_off.push_back(co);
+        st->span_off.push_back(so);
+        st->knot_off.push_back(ko);
+        co += n_cp[s];
+        so += n_cp[s] - 3;
+        ko += n_cp[s] + 4;
+    }
+    st->total_cp = co;
+    st->total_spans = so;
+    st->knots.assign(knots, knots + ko);
+    st->radius = circle_radius;
+    st->huber = huber_delta;
+    st->n_res = 0;
+    st->n_items = 0;
+    int rc;
+    if ((rc = ecb_reserve(ctx, st->d_knots, (size_t) ko * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, st->d_knot_off, (size_t) n_splines * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, st->d_ncp, (size_t) n_splines * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, st->d_cp_off, (size_t) n_splines * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, st->d_span_off, (size_t) n_splines * 4))) return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->d_knots.p, knots, (size_t) ko * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->d_knot_off.p, st->knot_off.data(), (size_t) n_splines * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->d_ncp.p, st->n_cp.data(), (size_t) n_splines * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->d_cp_off.p, st->cp_off.data(), (size_t) n_splines * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->d_span_off.p, st->span_off.data(), (size_t) n_splines * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "cost setup");
+}
+
+int ecb_cost_layout(ecb_ctx *ctx, int32_t *total_cp, int32_t *total_spans, int64_t *n_residuals, int64_t *out_doubles) {
+    if (!ctx || !ctx->cost) return ECB_ERR_STATE;
+    CostState *st = (CostState *) ctx->cost;
+    if (total_cp) *total_cp = st->total_cp;
+    if (total_spans) *total_spans = st->total_spans;
+    if (n_residuals) *n_residuals = st->n_res;
+    if (out_doubles) *out_doubles = (int64_t) st->total_spans * OUT_STRIDE + 2;
+    return ECB_OK;
+}
+
+int ecb_cost_set_residuals(ecb_ctx *ctx, const double *obs_xy, const double *lm_xyz, const double *t, const int32_t *spline,
+                           int64_t n) {
+    if (!ctx || !ctx->cost) return ecb_fail(ctx, ECB_ERR_STATE, "ecb_cost_setup first");
+    if (n < 0 || (n > 0 && (!obs_xy || !lm_xyz || !t || !spline))) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CostState *st = (CostState *) ctx->cost;
+    int rc;
+    const size_t nn = (size_t) std::max<int64_t>(n, 1);
+    if ((rc = ecb_reserve(ctx, st->obs, nn * 16))) return rc;
+    if ((rc = ecb_reserve(ctx, st->lm, nn * 24))) return rc;
+    if ((rc = ecb_reserve(ctx, st->tt, nn * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, st->spl, nn * 4))) return rc;
+    if (n > 0) {
+        ECB_CUDA(ctx, cudaMemcpyAsync(st->obs.p, obs_xy, (size_t) n * 16, cudaMemcpyHostToDevice, ctx->stream));
+        ECB_CUDA(ctx, cudaMemcpyAsync(st->lm.p, lm_xyz, (size_t) n * 24, cudaMemcpyHostToDevice, ctx->stream));
+        ECB_CUDA(ctx, cudaMemcpyAsync(st->tt.p, t, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ECB_CUDA(ctx, cudaMemcpyAsync(st->spl.p, spline, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    st->n_res = n;
+    return prepare_records(ctx, st);
+}
+
+int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_circles, int n_keyframes, int n_circles,
+                       const double *landmarks_xyz, double motion_time_step, int64_t *n_residuals) {
+    if (!ctx || !ctx->cost) return ecb_fail(ctx, ECB_ERR_STATE, "ecb_cost_setup first");
+    if (!kf_time || !kf_circles || !landmarks_xyz || n_keyframes < 1 || n_circles < 1) return ECB_ERR_ARG;
+    if (ctx->n_events <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no events loaded");
+    cudaSetDevice(ctx->device);
+    CostState *st = (CostState *) ctx->cost;
+    int rc;
+    const int64_t n = ctx->n_events;
+    const int nb = (int) ((n + AS_THREADS - 1) / AS_THREADS);
+    if ((rc = ecb_reserve(ctx, st->kf_t, (size_t) n_keyframes * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, st->kf_circ, (size_t) n_keyframes * n_circles * 24))) return rc;
+    if ((rc = ecb_reserve(ctx, st->lm_tab, (size_t) n_circles * 24))) return rc;
+    if ((rc = ecb_reserve(ctx, st->ev_cnt, (size_t) nb * 4 + 16))) return rc;
+    if ((rc = ecb_reserve(ctx, st->ev_flag, (size_t) nb * 8 + 16))) return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->kf_t.p, kf_time, (size_t) n_keyframes * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->kf_circ.p, kf_circles, (size_t) n_keyframes * n_circles * 24, cudaMemcpyHostToDevice, ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync(st->lm_tab.p, landmarks_xyz, (size_t) n_circles * 24, cudaMemcpyHostToDevice, ctx->stream));
+    AssocArgs a;
+    a.ev_t = (const double *) ctx->ev_t.p;
+    a.ev_xyp = (const uint32_t *) ctx->ev_xyp.p;
+    a.n_ev = n;
+    a.knots = (const double *) st->d_knots.p;
+    a.knot_off = (const int *) st->d_knot_off.p;
+    a.ncp = (const int *) st->d_ncp.p;
+    a.n_splines = st->n_splines;
+    a.kf_t = (const double *) st->kf_t.p;
+    a.kf_circ = (const double *) st->kf_circ.p;
+    a.lm_tab = (const double *) st->lm_tab.p;
+    a.K = n_keyframes;
+    a.n_circ = n_circles;
+    a.gate2 = 5 * motion_time_step * 5 * motion_time_step;  // EventCalibSpline.cpp:168
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_ASSOC);
+    k_assoc_count<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (uint32_t *) st->ev_cnt.p);
+    ECB_LAUNCHED(ctx);
+    int64_t *d_total = (int64_t *) st->ev_flag.p + nb;
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>((uint32_t *) st->ev_cnt.p, nb, (int64_t *) st->ev_flag.p, d_total);
+    ECB_LAUNCHED(ctx);
+    int64_t total = 0;
+    ECB_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t nn = (size_t) std::max<int64_t>(total, 1);
+    if ((rc = ecb_reserve(ctx, st->obs, nn * 16))) return rc;
+    if ((rc = ecb_reserve(ctx, st->lm, nn * 24))) return rc;
+    if ((rc = ecb_reserve(ctx, st->tt, nn * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, st->spl, nn * 4))) return rc;
+    if ((rc = ecb_reserve(ctx, st->sel_event, nn * 8))) return rc;
+    if ((rc = ecb_reserve(ctx, st->sel_circle, nn * 4))) return rc;
+    k_assoc_write<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (const int64_t *) st->ev_flag.p, (double *) st->obs.p, (double *) st->lm.p,
+                                                      (double *) st->tt.p, (int *) st->spl.p, (int64_t *) st->sel_event.p,
+                                                      (int *) st->sel_circle.p);
+    ECB_LAUNCHED(ctx);
+    ECB_PROF_END(ctx, ECB_STAGE_ASSOC);
+    if ((rc = ecb_check(ctx, cudaGetLastError(), "association kernels"))) return rc;
+    st->n_res = total;
+    if (n_residuals) *n_residuals = total;
+    return prepare_records(ctx, st);
+}
+
+int ecb_cost_get_association(ecb_ctx *ctx, int64_t *event_index, int32_t *circle_id, int64_t cap) {
+    if (!ctx || !ctx->cost) return ECB_ERR_STATE;
+    CostState *st = (CostState *) ctx->cost;
+    cudaSetDevice(ctx->device);
+    const int64_t n = std::min<int64_t>(cap, st->n_res);
+    if (n > 0 && event_index)
+        ECB_CUDA(ctx, cudaMemcpyAsync(event_index, st->sel_event.p, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n > 0 && circle_id)
+        ECB_CUDA(ctx, cudaMemcpyAsync(circle_id, st->sel_circle.p, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "association copy");
+}
+
+int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, double *cost) {
+    if (!ctx || !ctx->cost || !intrinsics || !rot_cp || !trans_cp || !cost) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CostState *st = (CostState *) ctx->cost;
+    int rc;
+    if ((rc = upload_params(ctx, st, intrinsics, rot_cp, trans_cp))) return rc;
+    if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
+    *cost = 0.0;
+    if (st->n_res == 0) return ECB_OK;
+    int grid = (int) std::min<int64_t>((st->n_res + 255) / 256, (int64_t) ctx->sm_count * 8);
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_COST);
+    k_cost<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p, (const double *) st->basis.p,
+                                          (const int *) st->cp0.p, st->n_res, (const double *) st->params.p, st->total_cp,
+                                          st->radius, st->huber, (double *) st->cost_part.p);
+    ECB_LAUNCHED(ctx);
+    k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->cost_part.p, grid, 1, 0, (double *) st->cost_part.p + 4000);
+    ECB_LAUNCHED(ctx);
+    ECB_PROF_END(ctx, ECB_STAGE_COST);
+    ECB_CUDA(ctx, cudaMemcpyAsync(cost, (double *) st->cost_part.p + 4000, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "cost evaluation");
+}
+
+// Packed result (device or host): per span s  [H 33x33 full symmetric | g 33], then [cost, 0].
+// d_out (device pointer, may be NULL -> internal buffer); h_out (host, may be NULL).
+int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, void *d_out,
+                       double *h_out, double *cost) {
+    if (!ctx || !ctx->cost || !intrinsics || !rot_cp || !trans_cp) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CostState *st = (CostState *) ctx->cost;
+    int rc;
+    if ((rc = upload_params(ctx, st, intrinsics, rot_cp, trans_cp))) return rc;
+    const size_t n_out = (size_t) st->total_spans * OUT_STRIDE + 2;
+    if ((rc = ecb_reserve(ctx, st->out, (n_out + 8) * 8))) return rc;
+    double *out = d_out ? (double *) d_out : (double *) st->out.p;
+    ECB_CUDA(ctx, cudaMemsetAsync(out, 0, n_out * 8, ctx->stream));
+    if (st->n_items > 0) {
+        NeArgs a;
+        a.obs = (const double *) st->obs.p;
+        a.lm = (const double *) st->lm.p;
+        a.basis = (const double *) st->basis.p;
+        a.cp0 = (const int *) st->cp0.p;
+        a.items = (const Item *) st->items.p;
+        a.n_items = st->n_items;
+        a.params = (const double *) st->params.p;
+        a.total_cp = st->total_cp;
+        a.radius = st->radius;
+        a.huber = st->huber;
+        a.part = (double *) st->part.p;
+        const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * 2);
+        ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
+        k_normal_eq<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
+        ECB_LAUNCHED(ctx);
+        const int *item_start = (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
+        k_reduce_spans<<<st->total_spans, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start, st->total_spans, out);
+        ECB_LAUNCHED(ctx);
+        k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, N_TILES * 64,
+                                                  out + (size_t) st->total_spans * OUT_STRIDE);
+        ECB_LAUNCHED(ctx);
+        ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);
+        if ((rc = ecb_check(ctx, cudaGetLastError(), "normal equation kernels"))) return rc;
+    }
+    if (h_out) ECB_CUDA(ctx, cudaMemcpyAsync(h_out, out, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cost) ECB_CUDA(ctx, cudaMemcpyAsync(cost, out + (size_t) st->total_spans * OUT_STRIDE, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_out || cost) return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "normal equation copy");
+    return ECB_OK;
+}
+
+}  // extern "C"

@@ -139,6 +139,35 @@ int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets,
 /* set k = points xy[offsets[k]..offsets[k+1]) (union of a + and a - index set); out[k] = cx, cy, r */
 int ecb_fit_circles(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_sets, double *out);
 
+/* ---- a7-a12: cost evaluation of the dynamic-calibration objective ------------------------------------ */
+/* Spline structure (EventCalibSpline ctor, src/EventCalibSpline.cpp:63-91): n_splines segments, n_cp[s] control
+ * points each, knots = concatenation of the (n_cp[s] + 4) clamped cubic knot vectors.  Control points are passed to
+ * the evaluation calls as flat arrays over all segments: rot_cp 4 doubles each (x,y,z,w), trans_cp 3 doubles each.
+ * huber_delta = 0.2 * circle_radius in the reference (:197). */
+int ecb_cost_setup(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const double *knots, double circle_radius,
+                   double huber_delta);
+/* total control points, total span blocks (sum of n_cp-3), residual count, doubles in the packed result */
+int ecb_cost_layout(ecb_ctx *ctx, int32_t *total_cp, int32_t *total_spans, int64_t *n_residuals, int64_t *out_doubles);
+/* Residual blocks from the loaded events (association loop of optimize(), :157-192, with findCenter,
+ * CirclesEventFrame.hpp:50-65): kf_time[K] ascending key-frame stamps, kf_circles[K][n_circles][3] = (cx, cy, r) of
+ * each frame's features (r < 0 marks an absent feature), landmarks_xyz[n_circles][3] the board points. */
+int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_circles, int n_keyframes, int n_circles,
+                       const double *landmarks_xyz, double motion_time_step, int64_t *n_residuals);
+int ecb_cost_get_association(ecb_ctx *ctx, int64_t *event_index, int32_t *circle_id, int64_t cap);
+/* ... or explicit residual blocks (host arrays, ordered by (spline, time)) */
+int ecb_cost_set_residuals(ecb_ctx *ctx, const double *obs_xy, const double *lm_xyz, const double *t,
+                           const int32_t *spline, int64_t n);
+/* cost = sum 1/2 rho(r^2)  (Ceres Evaluate without Jacobians; LM step acceptance) */
+int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, double *cost);
+/* Normal equations in the tangent space, packed per knot span s (33 local parameters: intrinsics 9 | rotation
+ * tangent of control points s..s+3, 3 each | translation of the same control points, 3 each):
+ *   out[s*1122 .. +1089) = J^T J of the span's residual blocks (33x33, full symmetric, row major)
+ *   out[s*1122+1089 .. +33) = J^T r ;  out[n_spans*1122] = cost
+ * d_out: device buffer to fill (e.g. one a collective will all-reduce), or NULL for the context's own;
+ * h_out: optional host copy; cost: optional.  Deterministic (fixed-order reductions). */
+int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, void *d_out,
+                       double *h_out, double *cost);
+
 #ifdef __cplusplus
 }
 #endif

@@ -205,3 +205,115 @@ def frontend_windows(t, x, y, pol, windows, eps=4.0, minS=2, clusterMin=5, knn_n
                                    C.c_int(knn_num), C.c_int(fitCircle), C.c_double(Rthr), C.c_uint(rows_cols),
                                    C.c_int(threads), C.byref(nev), _p(per, _ip))
     return int(tot), int(nev.value), per[:len(win)].copy()
+
+
+# ------------------------------------------------------------------------------- cost evaluation ----
+def inverse_radial(k4):
+    k = np.ascontiguousarray(k4, np.float64)
+    b = np.zeros(5)
+    port().orc_inverse_radial(_p(k, _dp), _p(b, _dp))
+    return b
+
+
+def inverse_distortion_roundtrip():
+    f = port().orc_inverse_distortion_roundtrip
+    f.restype = C.c_double
+    return f()
+
+
+def basis(knots, u):
+    kn = np.ascontiguousarray(knots, np.float64)
+    N = np.zeros(4)
+    sp = C.c_int(0)
+    port().orc_basis(_p(kn, _dp), C.c_int(len(kn)), C.c_double(u), C.byref(sp), _p(N, _dp))
+    return sp.value, N
+
+
+def knots(us, n_cp):
+    us = np.ascontiguousarray(us, np.float64)
+    kn = np.zeros(n_cp + 4)
+    port().orc_knots(_p(us, _dp), C.c_int(len(us)), C.c_int(n_cp), _p(kn, _dp))
+    return kn
+
+
+def residual_jac(intr, rcp, tcp, obs, lm, radius, b):
+    a = [np.ascontiguousarray(v, np.float64) for v in (intr, rcp, tcp, obs, lm, b)]
+    jac = np.zeros(37)
+    f = port().orc_residual_jac
+    f.restype = C.c_double
+    r = f(_p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), _p(a[3], _dp), _p(a[4], _dp), C.c_double(radius), _p(a[5], _dp),
+          _p(jac, _dp))
+    return r, jac
+
+
+def quat_plus(x, d):
+    x = np.ascontiguousarray(x, np.float64)
+    d = np.ascontiguousarray(d, np.float64)
+    out = np.zeros(4)
+    port().orc_quat_plus(_p(x, _dp), _p(d, _dp), _p(out, _dp))
+    return out
+
+
+class CostProblem:
+    """Oracle of the cost path: association, cost, per-span normal equations (oracle/ecb_oracle_cost.cpp)."""
+
+    def __init__(self, n_cp, knots_list, radius=1.75, huber=0.35):
+        self.lib = port()
+        self.lib.orc_problem_create.restype = C.c_void_p
+        self.lib.orc_cost.restype = C.c_double
+        self.lib.orc_normal_eq.restype = C.c_double
+        self.lib.orc_associate.restype = C.c_int64
+        self.lib.orc_problem_num_residuals.restype = C.c_int64
+        ncp = np.ascontiguousarray(np.atleast_1d(n_cp), np.int32)
+        kn = np.ascontiguousarray(np.concatenate([np.asarray(k, np.float64).ravel() for k in knots_list]), np.float64)
+        self.h = C.c_void_p(self.lib.orc_problem_create(C.c_int(len(ncp)), _p(ncp, _ip), _p(kn, _dp), C.c_double(radius),
+                                                        C.c_double(huber)))
+        self.n_spans = int(self.lib.orc_problem_num_spans(self.h))
+
+    def __del__(self):
+        try:
+            self.lib.orc_problem_free(self.h)
+        except Exception:
+            pass
+
+    def set_residuals(self, obs, lm, t, spline):
+        obs = np.ascontiguousarray(obs, np.float64)
+        lm = np.ascontiguousarray(lm, np.float64)
+        t = np.ascontiguousarray(t, np.float64)
+        sp = np.ascontiguousarray(spline, np.int32)
+        self.lib.orc_problem_set_residuals(self.h, _p(obs, _dp), _p(lm, _dp), _p(t, _dp), _p(sp, _ip), C.c_int64(len(t)))
+
+    def associate(self, ev_t, ev_x, ev_y, kf_t, circles, landmarks, step):
+        ev_t = np.ascontiguousarray(ev_t, np.float64)
+        ev_x = np.ascontiguousarray(ev_x, np.float64)
+        ev_y = np.ascontiguousarray(ev_y, np.float64)
+        kf_t = np.ascontiguousarray(kf_t, np.float64)
+        circles = np.ascontiguousarray(circles, np.float64)
+        lm = np.ascontiguousarray(landmarks, np.float64)
+        oe = np.zeros(max(len(ev_t), 1), np.int64)
+        oc = np.zeros(max(len(ev_t), 1), np.int32)
+        n = self.lib.orc_associate(self.h, _p(ev_t, _dp), _p(ev_x, _dp), _p(ev_y, _dp), C.c_int64(len(ev_t)), _p(kf_t, _dp),
+                                   _p(circles, _dp), C.c_int(len(kf_t)), C.c_int(circles.shape[1]), _p(lm, _dp),
+                                   C.c_double(step), _p(oe, _lp), _p(oc, _ip))
+        return oe[:n].copy(), oc[:n].copy()
+
+    @property
+    def n_residuals(self):
+        return int(self.lib.orc_problem_num_residuals(self.h))
+
+    def cost(self, intr, rot, trans):
+        a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans)]
+        return self.lib.orc_cost(self.h, _p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp))
+
+    def normal_eq(self, intr, rot, trans, want_rows=False):
+        a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans)]
+        H = np.zeros((self.n_spans, 33, 33))
+        g = np.zeros((self.n_spans, 33))
+        n = self.n_residuals
+        r = np.zeros(max(n, 1)) if want_rows else None
+        J = np.zeros((max(n, 1), 33)) if want_rows else None
+        c = self.lib.orc_normal_eq(self.h, _p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), _p(H, _dp), _p(g, _dp),
+                                   _p(r, _dp) if want_rows else None, _p(J, _dp) if want_rows else None)
+        if want_rows:
+            return c, H, g, r[:n], J[:n]
+        return c, H, g

@@ -1,0 +1,101 @@
+"""Parity of the CUDA cost evaluation (association, residual/Jacobian, per-span normal equations, cost) with
+the dual-number oracle.  Tolerance: 1e-9 relative (north star); measured agreement is ~1e-12."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def problem(ctx, oracle_mod):
+    from eventcalib_b200 import synth, calib_problem
+    ev = synth.make_stream(300000, 346, 260, t0=5.0, duration=0.3, seed=1004, return_truth=True)
+    pb = calib_problem.build(ev, seed=3)
+    ctx.set_sensor(346, 260)
+    ctx.load_events(synth.to_records(ev))
+    ctx.cost_setup([pb["n_cp"]], [pb["knots"]], pb["radius"], pb["huber"])
+    n = ctx.cost_associate(pb["kf_t"], pb["circles"], pb["landmarks"], pb["step"])
+    P = oracle_mod.CostProblem([pb["n_cp"]], [pb["knots"]], pb["radius"], pb["huber"])
+    oe, oc = P.associate(ev["t"], ev["x"], ev["y"], pb["kf_t"], pb["circles"], pb["landmarks"], pb["step"])
+    return ev, pb, P, n, oe, oc
+
+
+def test_association_exact(ctx, problem):
+    ev, pb, P, n, oe, oc = problem
+    assert n == len(oe) and n > 0.8 * len(ev["t"])
+    ge, gc = ctx.cost_association()
+    assert np.array_equal(ge, oe)
+    assert np.array_equal(gc, oc)
+
+
+def test_cost_and_normal_equations(ctx, problem):
+    ev, pb, P, n, oe, oc = problem
+    x = (pb["intrinsics"], pb["rot_cp"], pb["trans_cp"])
+    c_ref, H_ref, g_ref = P.normal_eq(*x)
+    assert abs(ctx.cost_eval(*x) - c_ref) <= RTOL * c_ref
+    c, H, g = ctx.cost_normal_eq(*x)
+    assert abs(c - c_ref) <= RTOL * c_ref
+    assert H.shape == H_ref.shape
+    for s in range(H.shape[0]):
+        np.testing.assert_allclose(H[s], H_ref[s], rtol=0, atol=RTOL * np.abs(H_ref[s]).max())
+        np.testing.assert_allclose(g[s], g_ref[s], rtol=0, atol=RTOL * np.abs(g_ref[s]).max())
+        assert np.array_equal(H[s], H[s].T)
+    # measured agreement is far tighter than the bar
+    assert np.abs(H - H_ref).max() / np.abs(H_ref).max() < 1e-11
+
+
+def test_deterministic(ctx, problem):
+    ev, pb, P, n, oe, oc = problem
+    x = (pb["intrinsics"], pb["rot_cp"], pb["trans_cp"])
+    a = ctx.cost_normal_eq(*x)
+    b = ctx.cost_normal_eq(*x)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert ctx.cost_eval(*x) == ctx.cost_eval(*x)
+
+
+def test_explicit_residuals_multi_spline_and_huber(ctx, oracle_mod):
+    # two spline segments, non-integer observations, residuals far outside the Huber band
+    from eventcalib_b200 import synth, spline
+    rng = np.random.default_rng(9)
+    cam, board = synth.Camera(), synth.Board()
+    traj = synth.Trajectory(3, board, 78.0)
+    knots, ncp, rot, trans, obs, lm, tt, sp = [], [], [], [], [], [], [], []
+    for s, (a, b, n_cp) in enumerate([(1.0, 1.4, 7), (2.0, 2.25, 5)]):
+        us = np.linspace(a, b, 40)
+        kn = spline.knot_vector(us, n_cp)
+        q, tw = traj.quat_xyzw(us)
+        rot.append(spline.fit_control_points(kn, us, q, n_cp))
+        trans.append(spline.fit_control_points(kn, us, tw, n_cp))
+        knots.append(kn)
+        ncp.append(n_cp)
+        t = np.sort(rng.uniform(a, b, 5000))
+        t[0], t[-1] = a, b  # both clamped ends, incl. the u == last-knot special case
+        tt.append(t)
+        sp.append(np.full(len(t), s))
+        obs.append(np.stack([rng.uniform(10, 330, len(t)), rng.uniform(10, 250, len(t))], 1))
+        lm.append(board.centres()[rng.integers(0, 36, len(t))])
+    rot, trans = np.concatenate(rot), np.concatenate(trans)
+    obs, lm, tt, sp = map(np.concatenate, (obs, lm, tt, sp))
+    ctx.cost_setup(ncp, knots, 1.75, 0.35)
+    ctx.cost_set_residuals(obs, lm, tt, sp)
+    P = oracle_mod.CostProblem(ncp, knots, 1.75, 0.35)
+    P.set_residuals(obs, lm, tt, sp)
+    intr = cam.intrinsics()
+    c_ref, H_ref, g_ref = P.normal_eq(intr, rot, trans)
+    c, H, g = ctx.cost_normal_eq(intr, rot, trans)
+    assert abs(c - c_ref) <= RTOL * c_ref
+    assert np.abs(H - H_ref).max() <= RTOL * np.abs(H_ref).max()
+    assert np.abs(g - g_ref).max() <= RTOL * np.abs(g_ref).max()
+    assert abs(ctx.cost_eval(intr, rot, trans) - c_ref) <= RTOL * c_ref
+
+
+def test_rejects_unordered_residuals(ctx):
+    import eventcalib_b200 as ecb
+    from eventcalib_b200 import spline
+    kn = spline.knot_vector(np.linspace(0, 1, 20), 6)
+    ctx.cost_setup([6], [kn])
+    with pytest.raises(ecb.EcbError):
+        ctx.cost_set_residuals(np.zeros((2, 2)), np.zeros((2, 3)), np.array([0.5, 0.2]), np.zeros(2))
+    with pytest.raises(ecb.EcbError):
+        ctx.cost_set_residuals(np.zeros((1, 2)), np.zeros((1, 3)), np.array([1.5]), np.zeros(1))
