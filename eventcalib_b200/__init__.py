@@ -29,6 +29,20 @@ class FrontendParams(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class LmOptions(C.Structure):
+    _fields_ = [("max_iterations", C.c_int32), ("jacobi_scaling", C.c_int32), ("fixed_iterations", C.c_int32),
+                ("reserved", C.c_int32), ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double), ("max_radius", C.c_double),
+                ("min_radius", C.c_double), ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
+                ("max_lm_diagonal", C.c_double)]
+
+
+class LmSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("successful_steps", C.c_int32), ("termination", C.c_int32),
+                ("reserved", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("gradient_max_norm", C.c_double), ("radius", C.c_double)]
+
+
 class WindowSummary(C.Structure):
     _fields_ = [("ev_lo", C.c_int64), ("ev_hi", C.c_int64), ("n_points", C.c_int32 * 2), ("n_clusters", C.c_int32 * 2),
                 ("n_kept", C.c_int32 * 2), ("n_candidates", C.c_int32), ("status", C.c_uint32),
@@ -45,7 +59,9 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
            "ecb_frontend_clusters", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
            "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_layout",
-           "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq"]
+           "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq", "ecb_lm_default_options", "ecb_lm_create",
+           "ecb_lm_destroy", "ecb_lm_dimension", "ecb_lm_begin", "ecb_lm_propose", "ecb_lm_feedback", "ecb_lm_update",
+           "ecb_lm_state", "ecb_lm_trace", "ecb_calibrate"]
 
 _lib = None
 
@@ -93,6 +109,20 @@ def load_library():
     lib.ecb_cost_set_residuals.argtypes = [vp, vp, vp, vp, vp, i64]
     lib.ecb_cost_eval.argtypes = [vp, vp, vp, vp, vp]
     lib.ecb_cost_normal_eq.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.ecb_lm_default_options.argtypes = [C.POINTER(LmOptions)]
+    lib.ecb_lm_default_options.restype = None
+    lib.ecb_lm_create.argtypes = [i32, vp, C.POINTER(LmOptions)]
+    lib.ecb_lm_create.restype = vp
+    lib.ecb_lm_destroy.argtypes = [vp]
+    lib.ecb_lm_destroy.restype = None
+    lib.ecb_lm_dimension.argtypes = [vp]
+    lib.ecb_lm_begin.argtypes = [vp, vp, vp, vp, vp]
+    lib.ecb_lm_propose.argtypes = [vp, vp, vp, vp]
+    lib.ecb_lm_feedback.argtypes = [vp, dbl]
+    lib.ecb_lm_update.argtypes = [vp, vp]
+    lib.ecb_lm_state.argtypes = [vp, vp, vp, vp, C.POINTER(LmSummary)]
+    lib.ecb_lm_trace.argtypes = [vp, vp, i32]
+    lib.ecb_calibrate.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(LmOptions), C.POINTER(LmSummary), vp, i32]
     _lib = lib
     return lib
 
@@ -306,3 +336,68 @@ class Context:
         ns = lay["total_spans"]
         blk = out[:ns * 1122].reshape(ns, 1122)
         return c.value, blk[:, :1089].reshape(ns, 33, 33).copy(), blk[:, 1089:].copy()
+
+    def calibrate(self, n_cp, intr, rot, trans, options=None, trace_rows=256):
+        """EventCalibSpline::optimize on one GPU: returns (intr, rot, trans, summary dict, trace[rows,4])."""
+        n_cp = np.ascontiguousarray(np.atleast_1d(n_cp), np.int32)
+        intr = np.array(intr, np.float64, copy=True)
+        rot = np.array(rot, np.float64, copy=True)
+        trans = np.array(trans, np.float64, copy=True)
+        opt = options or lm_options()
+        summ = LmSummary()
+        tr = np.zeros((trace_rows, 4))
+        self._chk(self.lib.ecb_calibrate(self.h, len(n_cp), _ptr(n_cp), _ptr(intr), _ptr(rot), _ptr(trans), C.byref(opt),
+                                         C.byref(summ), _ptr(tr), trace_rows))
+        rows = int(np.count_nonzero(tr[:, 2]))
+        return intr, rot, trans, {f[0]: getattr(summ, f[0]) for f in LmSummary._fields_}, tr[:rows]
+
+
+def lm_options(**kw):
+    o = LmOptions()
+    load_library().ecb_lm_default_options(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class LmState:
+    """Host-only LM state machine (ecb_lm_*), for callers that all-reduce the normal equations between GPUs."""
+
+    def __init__(self, n_cp, options=None):
+        self.lib = load_library()
+        self.n_cp = np.ascontiguousarray(np.atleast_1d(n_cp), np.int32)
+        self.C = int(self.n_cp.sum())
+        self.h = C.c_void_p(self.lib.ecb_lm_create(len(self.n_cp), _ptr(self.n_cp), C.byref(options or lm_options())))
+
+    def __del__(self):
+        try:
+            self.lib.ecb_lm_destroy(self.h)
+        except Exception:
+            pass
+
+    def begin(self, intr, rot, trans, packed):
+        a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans, packed)]
+        return self.lib.ecb_lm_begin(self.h, *[_ptr(v) for v in a])
+
+    def propose(self):
+        ci, cr, ct = np.zeros(9), np.zeros((self.C, 4)), np.zeros((self.C, 3))
+        st = self.lib.ecb_lm_propose(self.h, _ptr(ci), _ptr(cr), _ptr(ct))
+        return st, ci, cr, ct
+
+    def feedback(self, cost):
+        return self.lib.ecb_lm_feedback(self.h, float(cost))
+
+    def update(self, packed):
+        p = np.ascontiguousarray(packed, np.float64)
+        return self.lib.ecb_lm_update(self.h, _ptr(p))
+
+    def state(self):
+        i, r, t = np.zeros(9), np.zeros((self.C, 4)), np.zeros((self.C, 3))
+        s = LmSummary()
+        self.lib.ecb_lm_state(self.h, _ptr(i), _ptr(r), _ptr(t), C.byref(s))
+        return i, r, t, {f[0]: getattr(s, f[0]) for f in LmSummary._fields_}
+
+    def trace(self, rows=512):
+        tr = np.zeros((rows, 4))
+        n = self.lib.ecb_lm_trace(self.h, _ptr(tr), rows)
+        return tr[:n]

@@ -85,7 +85,7 @@ class Camera:
 class Trajectory:
     """Smooth camera pose (R_wb, t_wb) in the board frame: sum of sinusoids, board always in view."""
 
-    def __init__(self, seed, board: Board, dist=75.0):
+    def __init__(self, seed, board: Board, dist=75.0, rot_amp=None):
         r = np.random.default_rng(seed)
         c = board.centres()
         self.mid = np.array([c[:, 0].mean(), c[:, 1].mean(), 0.0])
@@ -93,7 +93,7 @@ class Trajectory:
         self.w = r.uniform(1.5, 4.5, size=(6, 3))  # rad/s
         self.ph = r.uniform(0, 2 * np.pi, size=(6, 3))
         self.amp_t = np.array([3.0, 3.0, 6.0]) / 3.0  # cm per sinusoid
-        self.amp_r = np.array([0.10, 0.10, 0.15]) / 3.0  # rad per sinusoid
+        self.amp_r = np.array(rot_amp if rot_amp is not None else [0.10, 0.10, 0.15]) / 3.0  # rad per sinusoid
 
     def _sig(self, t, k):
         return np.sin(self.w[k][None, :] * t[:, None] + self.ph[k][None, :]).sum(axis=1)
@@ -149,9 +149,9 @@ def project(cam: Camera, R, tw, Xw):
 
 
 def _gen_chunk(args):
-    (s, e, n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter, board, dist, k) = args
+    (s, e, n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter, board, dist, k, rot_amp) = args
     cam = Camera(width, height)
-    traj = Trajectory(seed, board, dist)
+    traj = Trajectory(seed, board, dist, rot_amp)
     centres = board.centres()
     rng = np.random.default_rng([seed, k])
     dt = duration / n_events
@@ -184,14 +184,14 @@ def _gen_chunk(args):
 
 
 def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001, noise_frac=0.05, flip_frac=0.0,
-                jitter=0.7, board: Board = None, dist=None, chunk=1 << 19, return_truth=False, workers=1):
+                jitter=0.7, board: Board = None, dist=None, chunk=1 << 19, return_truth=False, workers=1, rot_amp=None):
     """Returns dict(t, x, y, p) float64/uint8 arrays (time sorted, integer-valued pixel coordinates).
     Deterministic in (seed, n_events, chunk) — independent of `workers` (processes used to generate chunks)."""
     board = board or Board()
     if dist is None:
         dist = 78.0
     jobs = [(s, min(n_events, s + chunk), n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter,
-             board, dist, k) for k, s in enumerate(range(0, n_events, chunk))]
+             board, dist, k, rot_amp) for k, s in enumerate(range(0, n_events, chunk))]
     if workers > 1 and len(jobs) > 1:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
@@ -204,7 +204,7 @@ def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001
     P = np.concatenate([p[3] for p in parts])
     out = dict(t=T, x=X, y=Y, p=P, width=width, height=height)
     if return_truth:
-        out.update(camera=Camera(width, height), trajectory=Trajectory(seed, board, dist), board=board)
+        out.update(camera=Camera(width, height), trajectory=Trajectory(seed, board, dist, rot_amp), board=board)
     return out
 
 

@@ -168,6 +168,52 @@ int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, 
 int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, void *d_out,
                        double *h_out, double *cost);
 
+/* ---- a12: the LM step around the GPU normal equations (EventCalibSpline::optimize, src/EventCalibSpline.cpp:197-247) ---- */
+typedef struct {
+    int32_t max_iterations;        /* 50 (Ceres default; BASELINE config C4) */
+    int32_t jacobi_scaling;        /* 1 */
+    int32_t fixed_iterations;      /* != 0: convergence tests off, exactly max_iterations LM iterations (benchmark C4) */
+    int32_t reserved;
+    double function_tolerance;     /* 1e-10 (EventCalibSpline.cpp:239-240) */
+    double gradient_tolerance;     /* 1e-10 */
+    double parameter_tolerance;    /* 1e-8 */
+    double initial_radius, max_radius, min_radius;      /* 1e4, 1e16, 1e-32 */
+    double min_relative_decrease;  /* 1e-3 */
+    double min_lm_diagonal, max_lm_diagonal;            /* 1e-6, 1e32 */
+} ecb_lm_options;
+
+typedef struct {
+    int32_t iterations, successful_steps, termination, reserved;
+    double initial_cost, final_cost, gradient_max_norm, radius;
+} ecb_lm_summary;
+
+#define ECB_LM_RUNNING 0
+#define ECB_LM_NO_CONVERGENCE 2       /* max_iterations reached */
+#define ECB_LM_FUNCTION_TOLERANCE 3
+#define ECB_LM_GRADIENT_TOLERANCE 4
+#define ECB_LM_PARAMETER_TOLERANCE 5
+#define ECB_LM_MIN_RADIUS 6
+#define ECB_LM_FAILURE 7
+
+typedef struct ecb_lm ecb_lm;
+void ecb_lm_default_options(ecb_lm_options *o);
+/* Host-only LM state machine (no CUDA): the caller evaluates, possibly all-reducing the packed normal equations
+ * across GPUs in between.   begin(x, packed) -> { propose(candidate) -> [caller: cost(candidate)] -> feedback(cost)
+ *   -> 1: accepted, caller evaluates packed at the candidate -> update(packed) | 0: rejected } until != RUNNING */
+ecb_lm *ecb_lm_create(int n_splines, const int32_t *n_cp, const ecb_lm_options *opt);
+void ecb_lm_destroy(ecb_lm *lm);
+int ecb_lm_dimension(const ecb_lm *lm);
+int ecb_lm_begin(ecb_lm *lm, const double *intrinsics, const double *rot_cp, const double *trans_cp, const double *packed);
+int ecb_lm_propose(ecb_lm *lm, double *cand_intrinsics, double *cand_rot_cp, double *cand_trans_cp);
+int ecb_lm_feedback(ecb_lm *lm, double candidate_cost);
+int ecb_lm_update(ecb_lm *lm, const double *packed);
+int ecb_lm_state(const ecb_lm *lm, double *intrinsics, double *rot_cp, double *trans_cp, ecb_lm_summary *summary);
+/* rows of (cost, gradient_max_norm, radius, accepted) per recorded evaluation; returns the row count */
+int ecb_lm_trace(const ecb_lm *lm, double *out, int cap_rows);
+/* single-GPU driver of the whole loop; parameters are updated in place */
+int ecb_calibrate(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, double *intrinsics, double *rot_cp, double *trans_cp,
+                  const ecb_lm_options *opt, ecb_lm_summary *summary, double *trace, int trace_rows);
+
 #ifdef __cplusplus
 }
 #endif
