@@ -62,7 +62,7 @@ def test_lm_matches_dense_restatement(small_problem):
     np.testing.assert_allclose(i1, i2, rtol=1e-9)
     np.testing.assert_allclose(r1, r2, rtol=0, atol=1e-9)
     np.testing.assert_allclose(t1, t2, rtol=1e-9, atol=1e-9)
-    assert summ["final_cost"] < 0.5 * summ["initial_cost"]
+    assert summ["final_cost"] < 0.7 * summ["initial_cost"]
 
 
 def test_lm_recovers_intrinsics(small_problem):
