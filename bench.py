@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "events/sec (detection: window+dedupe+DBSCAN+circle fit)"
+METRIC = "events/sec (detection+residual eval)"
 UNIT = "events/s"
 WIDTH, HEIGHT = 346, 260
 WINDOW = 1.5e-3
@@ -113,29 +113,46 @@ class ClockSampler:
 
 
 def cpu_reference_rate(ev, win, rthr, budget_s=12.0, threads=None):
-    """Reference CPU path (verbatim reference DBSCAN from oracle/_ref + restated glue; oracle port if _ref is
-    absent) on a bounded sample of the workload's windows, threaded like the reference
-    (hardware_concurrency()-2 std::threads over windows, eventCameraCalib.cpp:172-190)."""
+    """Reference CPU path on a bounded sample of the workload's windows, threaded like the reference
+    (hardware_concurrency()-2 std::threads over windows, eventCameraCalib.cpp:172-190; Ceres num_threads = hw-2,
+    EventCalibSpline.cpp:242):  detection = verbatim reference DBSCAN from oracle/_ref + restated glue (oracle port if
+    _ref is absent);  residual evaluation = association + one dual-number (Jet<37>) Jacobian evaluation with dense
+    per-span J^T J + one cost-only evaluation (oracle/ecb_oracle_cost.cpp)."""
     import oracle
+    from eventcalib_b200 import calib_problem, synth
     oracle.build()
     kind = "reference" if oracle.have_ref() else "port"
     hw = os.cpu_count() or 4
     threads = threads or max(1, hw - 2)
     kw = dict(eps=4.0, minS=2, clusterMin=5, knn_num=3, fitCircle=1, Rthr=rthr, rows_cols=36, ref=True)
-    # calibrate on a few windows, then size the sample for ~budget_s of wall time
+    # calibrate on a few windows, then size the sample for ~budget_s of wall time (detection is ~half of it)
     probe = win[: min(len(win), 4 * threads)]
     t0 = time.perf_counter()
     _, nev, _ = oracle.frontend_windows(ev["t"], ev["x"], ev["y"], ev["p"], probe, threads=threads, **kw)
     dt = max(time.perf_counter() - t0, 1e-6)
     rate = nev / dt
-    n_s = int(min(len(win), max(len(probe), rate * budget_s / max(nev / len(probe), 1))))
+    n_s = int(min(len(win), max(len(probe), 0.4 * rate * budget_s / max(nev / len(probe), 1))))
     sample = win[:n_s]
     t0 = time.perf_counter()
     cand, nev, _ = oracle.frontend_windows(ev["t"], ev["x"], ev["y"], ev["p"], sample, threads=threads, **kw)
-    dt = time.perf_counter() - t0
+    dt_det = time.perf_counter() - t0
+    # residual evaluation of the same events
+    hi = int(np.searchsorted(ev["t"], sample[-1, 1], side="right"))
+    cam, board = synth.Camera(WIDTH, HEIGHT), synth.Board()
+    seed = int(round((ev["t"][0] - 5.0) / max(len(ev["t"]) / RATE, 1e-9)))
+    pb = calib_problem.build_from_truth(cam, synth.Trajectory(1002 + seed, board, 78.0), board, float(ev["t"][0]),
+                                        float(ev["t"][hi - 1]))
+    P = oracle.CostProblem([pb["n_cp"]], [pb["knots"]], pb["radius"], pb["huber"])
+    t0 = time.perf_counter()
+    P.associate(ev["t"][:hi], ev["x"][:hi], ev["y"][:hi], pb["kf_t"], pb["circles"], pb["landmarks"], pb["step"])
+    P.eval_mt(pb["intrinsics"], pb["rot_cp"], pb["trans_cp"], threads)
+    dt_res = time.perf_counter() - t0
+    dt = dt_det + dt_res
     return dict(value=nev / dt, unit=UNIT, cores=threads, kind=kind, seconds=dt,
-                sample="first %d of %d windows (%d events), %d std::threads of %d host cores; %s" % (
-                    n_s, len(win), nev, threads, hw,
+                detection_events_per_s=nev / dt_det, residual_eval_events_per_s=nev / dt_res,
+                sample="first %d of %d windows (%d events, %d residuals), %d std::threads of %d host cores; detection: %s; "
+                       "residual eval: single-thread association + Jet<37> Jacobian evaluation + cost-only evaluation (port)" % (
+                    n_s, len(win), nev, P.n_residuals, threads, hw,
                     "verbatim reference DBSCAN + restated glue (oracle/_ref)" if kind == "reference" else "oracle port")), cand
 
 
@@ -166,14 +183,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def build_cost_problem(ev_truth, world, n_events):
+    """Global calibration problem: one spline segment per rank's time slice (EventCalibSpline splits the map into
+    segments at gaps, EventCalibSpline.cpp:319-348); every rank knows all segments, holds only its own residuals."""
+    from eventcalib_b200 import calib_problem, synth
+    cam, board = ev_truth["camera"], ev_truth["board"]
+    dur = n_events / RATE
+    segs = []
+    for r in range(world):
+        traj = synth.Trajectory(1002 + r, board, 78.0)
+        segs.append(calib_problem.build_from_truth(cam, traj, board, 5.0 + r * dur + 0.5 / RATE, 5.0 + (r + 1) * dur - 0.5 / RATE,
+                                                   seed=r))
+    return segs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--events", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lm-iters", type=int, default=50, help="LM iterations of the C4 side measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -203,20 +235,52 @@ def main():
     d_raw = torch.empty(n * 25 + 16, dtype=torch.uint8, device="cuda")
     d_raw[: n * 25].copy_(pinned, non_blocking=False)
 
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream shared by torch (copies, NCCL, timing events) and the library's kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = ecb.Context(local, stream.cuda_stream)
     ctx.set_sensor(WIDTH, HEIGHT)
     prm, rthr = frontend_params()
 
+    # residual evaluation: key frames / circles / spline segments from the ground truth (host-side initialisation is
+    # outside the hot path); rank r owns segment r
+    segs = build_cost_problem(dict(camera=synth.Camera(WIDTH, HEIGHT), board=synth.Board()), world, n)
+    mine = segs[rank]
+    n_cp = [sg["n_cp"] for sg in segs]
+    ctx.cost_setup(n_cp, [sg["knots"] for sg in segs], mine["radius"], mine["huber"])
+    intr = mine["intrinsics"]
+    rot = np.concatenate([sg["rot_cp"] for sg in segs])
+    trans = np.concatenate([sg["trans_cp"] for sg in segs])
+    ctx.load_events_device(d_raw.data_ptr(), n)
+    n_res = ctx.cost_associate(mine["kf_t"], mine["circles"], mine["landmarks"], mine["step"])
+    lay = ctx.cost_layout()
+    d_ne = torch.zeros(lay["out_doubles"], dtype=torch.float64, device="cuda")
+    h_ne = torch.empty(lay["out_doubles"], dtype=torch.float64, pin_memory=True)
+    d_cost = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def residual_eval():
+        """one LM iteration's worth of evaluation: association + J^T J / J^T r (+ all-reduce) + cost-only"""
+        ctx.cost_associate(mine["kf_t"], mine["circles"], mine["landmarks"], mine["step"])
+        ctx.cost_normal_eq(intr, rot, trans, d_out=d_ne.data_ptr(), host=False)
+        if world > 1:
+            dist.all_reduce(d_ne)
+        c = ctx.cost_eval(intr, rot, trans)
+        if world > 1:
+            d_cost[0] = c
+            dist.all_reduce(d_cost)
+
     def step_device():
         ctx.load_events_device(d_raw.data_ptr(), n)
         ctx.frontend_run(win, prm)
+        residual_eval()
 
     def step_e2e():
         ctx.load_events_ptr(pinned.data_ptr(), n)
         ctx.frontend_run(win, prm)
+        residual_eval()
         s = ctx.summary()
         c = ctx.candidates(48)
+        h_ne.copy_(d_ne, non_blocking=False)
         return s, c
 
     def barrier():
@@ -245,7 +309,6 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(step_device, args.steps)
     launches = ctx.launches - l0
-    clocks = sampler.stop() if sampler else None
     value = world * n * args.steps / (ms * 1e-3)
 
     # per-kernel durations, measured live with CUDA events on the launching stream (separate pass)
@@ -262,36 +325,104 @@ def main():
     s, c = step_e2e()
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
     e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
-    h2d = n * 25 + win.nbytes
-    d2h = s.nbytes + c.nbytes
+    h2d = n * 25 + win.nbytes + (9 + 7 * len(rot)) * 8 * 2
+    d2h = s.nbytes + c.nbytes + h_ne.numel() * 8
+
+    # C4 side measurement: fixed number of LM iterations (normal equations + all-reduce + replicated host solve)
+    lm_info = None
+    if args.lm_iters > 0:
+        lm = ecb.LmState(n_cp, ecb.lm_options(max_iterations=args.lm_iters, fixed_iterations=1))
+        barrier()
+        t0 = time.perf_counter()
+
+        def packed_at(i, r, t):
+            ctx.cost_normal_eq(i, r, t, d_out=d_ne.data_ptr(), host=False)
+            if world > 1:
+                dist.all_reduce(d_ne)
+            h_ne.copy_(d_ne, non_blocking=False)
+            return h_ne.numpy()
+
+        def cost_at(i, r, t):
+            cc = ctx.cost_eval(i, r, t)
+            if world > 1:
+                d_cost[0] = cc
+                dist.all_reduce(d_cost)
+                cc = float(d_cost.item())
+            return cc
+
+        st = lm.begin(intr, rot, trans, packed_at(intr, rot, trans))
+        n_eval = 1
+        while st == 0:
+            st, ci, cr, ct = lm.propose()
+            if st != 0:
+                break
+            fb = lm.feedback(cost_at(ci, cr, ct))
+            if fb == 1:
+                st = lm.update(packed_at(ci, cr, ct))
+                n_eval += 1
+            elif fb == 0:
+                st = 0
+            else:
+                st = fb
+        barrier()
+        lm_s = time.perf_counter() - t0
+        fi, _, _, summ = lm.state()
+        lm_info = {"iterations": summ["iterations"], "successful_steps": summ["successful_steps"], "seconds": lm_s,
+                   "s_per_iteration": lm_s / max(1, summ["iterations"]), "jacobian_evaluations": n_eval,
+                   "initial_cost": summ["initial_cost"], "final_cost": summ["final_cost"], "termination": summ["termination"],
+                   "residuals_all_gpus": None, "dimension": 9 + 6 * len(rot)}
+        if world > 1:
+            t = torch.tensor([float(n_res)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t)
+            lm_info["residuals_all_gpus"] = int(t.item())
+        else:
+            lm_info["residuals_all_gpus"] = int(n_res)
 
     if rank == 0:
         hbm, which = peaks()
         npts = int(s["n_points"].sum())
-        # algorithmic bytes per launch of each kernel
-        algo = {"ingest": n * 37.0, "window": n * 4.0 + npts * 8.0, "cluster": npts * 12.0, "pair": npts * 8.0}
+        # algorithmic bytes / flops per launch of each kernel (Kernels)
+        algo = {"ingest": n * 37.0, "window": n * 4.0 + npts * 8.0, "cluster": npts * 12.0, "pair": npts * 8.0,
+                "assoc": n * 12.0 * 2 + n_res * 60.0, "normal_eq": n_res * 76.0, "cost": n_res * 76.0}
+        flops = {"normal_eq": n_res * 2.0e3, "cost": n_res * 150.0}
+        tot = sum(stage.values())
+        kernels = {}
+        for k in stage:
+            kernels[k] = {"ms": stage[k], "share": stage[k] / tot, "algo_gbs": algo[k] / (stage[k] * 1e-3) / 1e9 if k in algo else None}
+            if k in flops:
+                kernels[k]["algo_tflops"] = flops[k] / (stage[k] * 1e-3) / 1e12
         dom = max((k for k in stage if k in algo), key=lambda k: stage[k])
-        kernels = {k: {"ms": stage[k], "share": stage[k] / sum(stage.values()),
-                       "algo_gbs": algo[k] / (stage[k] * 1e-3) / 1e9 if k in algo else None} for k in stage}
         achieved = algo[dom] / (stage[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                     "frac": achieved / hbm, "traffic": None, "peak_source": which,
                     "path_frac": (value / world) * ALGO_BYTES_PER_EVENT / 1e9 / hbm,
-                    "note": "achieved = algorithmic bytes of the dominant kernel / its CUDA-event duration; "
-                            "path_frac = whole-path 29 B/event x events/s / peak", "kernels": kernels}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "note": "achieved = algorithmic bytes of the dominant kernel / its CUDA-event duration (DESIGN.md); "
+                            "path_frac = whole-path 29 B/event x events/s / peak; the dominant kernels are shared-memory / "
+                            "issue bound, not HBM bound (profiles/)", "kernels": kernels}
+        if "normal_eq" in stage:
+            roofline["cost_kernel"] = {"bound": "tensor", "kernel": "k_normal_eq (FP64 DMMA)", "unit": "TFLOP/s",
+                                       "achieved": flops["normal_eq"] / (stage["normal_eq"] * 1e-3) / 1e12, "peak": 37.0,
+                                       "frac": flops["normal_eq"] / (stage["normal_eq"] * 1e-3) / 1e12 / 37.0,
+                                       "peak_source": "measured FP64 DMMA m8n8k4 on this pool's B200 (profiles/r1_fp64_peak.txt)"}
+        line = {"metric": "events/sec (detection+residual eval)", "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int32 pixels / f64 fit", "data": "synthetic",
+                "dtype": "int32 pixels / f64 fit + f64 residuals", "data": "synthetic",
                 "config": {"workload": "C2 per GPU: synthetic %d-event DAVIS346 (346x260) circle-grid stream, %d tiling "
-                                       "windows of 1.5 ms, DBSCAN eps 4 minPts 2 + cluster filter + circle fit (fitCircle 1)"
-                                       % (n, len(win)),
-                           "events_per_gpu": n, "windows_per_gpu": int(len(win)), "parallelism": "windows sharded x%d" % world,
+                                       "windows of 1.5 ms, DBSCAN eps 4 minPts 2 + cluster filter + circle fit (fitCircle 1), "
+                                       "then residual evaluation of the same events (association + J^T J/J^T r + cost, "
+                                       "all-reduce when N>1)" % (n, len(win)),
+                           "events_per_gpu": n, "windows_per_gpu": int(len(win)), "residuals_per_gpu": int(n_res),
+                           "control_points": int(len(rot)), "parallelism": "windows / spline segments sharded x%d" % world,
                            "l2": "inputs larger than L2 (%.0f MB of records per step)" % (n * 25 / 1e6),
                            "found_circles_per_window": float(s["n_candidates"].mean())},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)}}
+        if lm_info:
+            line["lm"] = lm_info
         if not args.no_cpu and world == 1:
             cb, _ = cpu_reference_rate(ev, win, rthr)
             cb.pop("seconds", None)

@@ -10,9 +10,13 @@ import numpy as np
 from . import spline, synth
 
 
-def build(ev, step=5e-4, kf_every=None, seed=0, intr_noise=0.02, pose_noise=(0.002, 0.05), max_cp=None):
-    cam, traj, board = ev["camera"], ev["trajectory"], ev["board"]
-    t0, t1 = float(ev["t"][0]), float(ev["t"][-1])
+def build(ev, **kw):
+    """Problem for a stream generated with return_truth=True."""
+    return build_from_truth(ev["camera"], ev["trajectory"], ev["board"], float(ev["t"][0]), float(ev["t"][-1]), **kw)
+
+
+def build_from_truth(cam, traj, board, t0, t1, step=5e-4, kf_every=None, seed=0, intr_noise=0.02, pose_noise=(0.002, 0.05),
+                     max_cp=None):
     kf_every = kf_every or 8 * step          # len 3 step + frameGap 5 step (eventCameraCalib.cpp:168-169)
     kf_t = np.arange(t0 + 2 * step, t1 - 2 * step, kf_every)
     K = len(kf_t)

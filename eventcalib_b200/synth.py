@@ -149,9 +149,9 @@ def project(cam: Camera, R, tw, Xw):
 
 
 def _gen_chunk(args):
-    (s, e, n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter, board, dist, k, rot_amp) = args
+    (s, e, n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter, board, dist, k, rot_amp, traj_seed) = args
     cam = Camera(width, height)
-    traj = Trajectory(seed, board, dist, rot_amp)
+    traj = Trajectory(traj_seed, board, dist, rot_amp)
     centres = board.centres()
     rng = np.random.default_rng([seed, k])
     dt = duration / n_events
@@ -184,14 +184,16 @@ def _gen_chunk(args):
 
 
 def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001, noise_frac=0.05, flip_frac=0.0,
-                jitter=0.7, board: Board = None, dist=None, chunk=1 << 19, return_truth=False, workers=1, rot_amp=None):
+                jitter=0.7, board: Board = None, dist=None, chunk=1 << 19, return_truth=False, workers=1, rot_amp=None, traj_seed=None):
     """Returns dict(t, x, y, p) float64/uint8 arrays (time sorted, integer-valued pixel coordinates).
     Deterministic in (seed, n_events, chunk) — independent of `workers` (processes used to generate chunks)."""
     board = board or Board()
     if dist is None:
         dist = 78.0
+    if traj_seed is None:
+        traj_seed = seed
     jobs = [(s, min(n_events, s + chunk), n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter,
-             board, dist, k, rot_amp) for k, s in enumerate(range(0, n_events, chunk))]
+             board, dist, k, rot_amp, traj_seed) for k, s in enumerate(range(0, n_events, chunk))]
     if workers > 1 and len(jobs) > 1:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
@@ -204,7 +206,7 @@ def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001
     P = np.concatenate([p[3] for p in parts])
     out = dict(t=T, x=X, y=Y, p=P, width=width, height=height)
     if return_truth:
-        out.update(camera=Camera(width, height), trajectory=Trajectory(seed, board, dist, rot_amp), board=board)
+        out.update(camera=Camera(width, height), trajectory=Trajectory(traj_seed, board, dist, rot_amp), board=board)
     return out
 
 

@@ -305,6 +305,14 @@ class CostProblem:
         a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans)]
         return self.lib.orc_cost(self.h, _p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp))
 
+    def eval_mt(self, intr, rot, trans, threads):
+        """CPU baseline: one Jacobian evaluation + one cost-only evaluation on `threads` std::threads."""
+        a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans)]
+        self.lib.orc_eval_mt.restype = C.c_double
+        c2 = C.c_double(0)
+        c = self.lib.orc_eval_mt(self.h, _p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), C.c_int(threads), C.byref(c2))
+        return c, c2.value
+
     def normal_eq(self, intr, rot, trans, want_rows=False):
         a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans)]
         H = np.zeros((self.n_spans, 33, 33))

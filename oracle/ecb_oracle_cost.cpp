@@ -433,6 +433,58 @@ double orc_normal_eq(void *h, const double *intr, const double *rot, const doubl
     return cost;
 }
 
+// multi-threaded evaluation for the CPU baseline (Ceres: options.num_threads = hardware_concurrency() - 2,
+// EventCalibSpline.cpp:242): one Jacobian evaluation (normal equations) + one cost-only evaluation.
+}  // extern "C"
+#include <thread>
+extern "C" double orc_eval_mt(void *h, const double *intr, const double *rot, const double *trans, int threads, double *cost_only) {
+    Problem &p = *(Problem *) h;
+    const int ns = p.total_spans();
+    const size_t n = p.span.size();
+    if (threads < 1) threads = 1;
+    std::vector<std::vector<double>> H(threads), G(threads);
+    std::vector<double> cost(threads, 0.0), cost2(threads, 0.0);
+    auto work = [&](int t) {
+        H[t].assign((size_t) ns * 1089, 0.0);
+        G[t].assign((size_t) ns * 33, 0.0);
+        const size_t b = n * t / threads, e = n * (t + 1) / threads;
+        for (size_t k = b; k < e; ++k) {
+            double r, J[33];
+            cost[t] += eval_block(p, k, intr, rot, trans, &r, J);
+            double *B = H[t].data() + (size_t) p.span[k] * 1089, *g = G[t].data() + (size_t) p.span[k] * 33;
+            for (int i = 0; i < 33; ++i) {
+                for (int j = 0; j < 33; ++j) B[33 * i + j] += J[i] * J[j];
+                g[i] += J[i] * r;
+            }
+        }
+        // cost-only pass (Evaluate without Jacobians: plain doubles)
+        for (size_t k = b; k < e; ++k) {
+            const int c0 = p.cp0[k];
+            const double *rcp[4], *tcp[4];
+            for (int j = 0; j < 4; ++j) {
+                rcp[j] = rot + 4 * (c0 + j);
+                tcp[j] = trans + 3 * (c0 + j);
+            }
+            const double *bb = &p.basis[4 * k];
+            double r = residual<double>(intr, rcp, tcp, &p.obs[2 * k], &p.lm[3 * k], p.radius, bb, bb);
+            const double s = r * r, a2 = p.huber * p.huber;
+            cost2[t] += 0.5 * (s > a2 ? 2 * p.huber * std::sqrt(s) - a2 : s);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    double c = 0, c2 = 0;
+    for (int t = 0; t < threads; ++t) {
+        c += cost[t];
+        c2 += cost2[t];
+    }
+    if (cost_only) *cost_only = c2;
+    return c;
+}
+extern "C" {
+
 // EigenQuaternionParameterization::Plus (x_plus = [sin|d|/|d| d, cos|d|] (x) x), Eigen product order  [external: Ceres]
 void orc_quat_plus(const double *x, const double *d, double *out) {
     const double nd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
