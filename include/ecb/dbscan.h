@@ -1,0 +1,108 @@
+// Drop-in for the reference's `dbscan.h` (DB/include/dbscan.h:42-113): same class name, template signature, `Run`
+// arguments, return codes and public result members — the work is done by the CUDA library through the C ABI.
+//
+//   reference:  template<typename T, typename Float> class DBSCAN final;            dbscan.h:42-43
+//               int Run(TVector* V, const uint dim, const Float eps, const uint min, const DistanceFunc& = ...)   :67-68
+//               returns 0 SUCCESS / 1 FAILED when V->size()<1 || dim<1 || min<1, never throws                       :121-123
+//               public: std::vector<std::vector<uint>> Clusters; std::vector<uint> Noise;                            :92-93
+//
+// Differences: only dim == 2 with integer-valued, distinct points is supported by the device path
+// (that is the reference's only instantiation, CirclesEventFrame.cpp:66-70) — anything else returns FAILED and
+// `last_error()` says why; `Clusters[c]` lists its members in ascending pid (the reference: BFS pop order); cluster
+// ids, membership and Noise are bit-exact.  `disfunc` is accepted and ignored exactly like the reference's kd-tree build.
+// Thread model: one lazily created context per host thread (the reference runs Run() on hardware_concurrency()-2 threads).
+#ifndef ECB_DBSCAN_H
+#define ECB_DBSCAN_H
+
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../eventcalib_b200.h"
+
+#if __has_include(<Eigen/StdVector>)
+#include <Eigen/Eigen>
+#include <Eigen/StdVector>
+#define ECB_ALLOC(T) Eigen::aligned_allocator<T>
+#else
+#define ECB_ALLOC(T) std::allocator<T>
+#endif
+
+typedef unsigned int uint;
+
+namespace ecb {
+struct CtxDeleter {
+    void operator()(ecb_ctx *c) const { ecb_ctx_destroy(c); }
+};
+// per-thread context on device ECB_DEVICE (default 0)
+inline ecb_ctx *thread_context() {
+    static thread_local std::unique_ptr<ecb_ctx, CtxDeleter> ctx;
+    if (!ctx) {
+        ecb_ctx *c = nullptr;
+        const char *d = getenv("ECB_DEVICE");
+        if (ecb_ctx_create(d ? atoi(d) : 0, nullptr, &c) == ECB_OK) ctx.reset(c);
+    }
+    return ctx.get();
+}
+}  // namespace ecb
+
+template <typename T, typename Float>
+class DBSCAN final {
+    enum ERROR_TYPE { SUCCESS = 0, FAILED, COUNT };
+    using TVector = std::vector<T, ECB_ALLOC(T)>;
+    using DistanceFunc = std::function<Float(const T &, const T &)>;
+
+public:
+    DBSCAN() {}
+    ~DBSCAN() {}
+
+    int Run(TVector *V, const uint dim, const Float eps, const uint min,
+            const DistanceFunc &disfunc = [](const T &, const T &) -> Float { return 0; }) {
+        (void) disfunc;
+        if (V->size() < 1) return ERROR_TYPE::FAILED;
+        if (dim < 1) return ERROR_TYPE::FAILED;
+        if (min < 1) return ERROR_TYPE::FAILED;
+        Clusters.clear();
+        Noise.clear();
+        if (dim != 2) {
+            err_ = "device DBSCAN supports dim == 2 only";
+            return ERROR_TYPE::FAILED;
+        }
+        ecb_ctx *ctx = ecb::thread_context();
+        if (!ctx) {
+            err_ = "no CUDA device (there is no CPU fallback)";
+            return ERROR_TYPE::FAILED;
+        }
+        const int n = (int) V->size();
+        std::vector<double> xy(2 * (size_t) n);
+        for (int i = 0; i < n; ++i) {
+            xy[2 * i] = (double) (*V)[i][0];
+            xy[2 * i + 1] = (double) (*V)[i][1];
+        }
+        std::vector<int32_t> labels((size_t) n);
+        int32_t nc = 0;
+        const int rc = ecb_dbscan_run(ctx, xy.data(), n, (double) eps, min, labels.data(), &nc);
+        if (rc != ECB_OK) {
+            err_ = ecb_last_error(ctx);
+            return ERROR_TYPE::FAILED;
+        }
+        Clusters.assign((size_t) nc, std::vector<uint>());
+        for (int i = 0; i < n; ++i) {
+            if (labels[i] >= 0) Clusters[(size_t) labels[i]].push_back((uint) i);
+            else Noise.push_back((uint) i);
+        }
+        return ERROR_TYPE::SUCCESS;
+    }
+
+    const std::string &last_error() const { return err_; }
+
+public:
+    std::vector<std::vector<uint>> Clusters;
+    std::vector<uint> Noise;
+
+private:
+    std::string err_;
+};
+
+#endif  // ECB_DBSCAN_H

@@ -1,0 +1,266 @@
+// C++ façade of the event front end and the spline calibration over the C ABI, mirroring the reference's classes
+// (names, argument meaning, error behaviour) without its Eigen / OpenCV / Ceres dependencies:
+//
+//   opengv2::EventContainer        EV/include/opengv2/event/EventContainer.hpp:15-30   (time-ordered event store)
+//   opengv2::CirclePatternParameters  ECC/include/.../parameters.hpp:12-27
+//   opengv2::CirclesEventFrame     ECC/include/.../CirclesEventFrame.hpp:21-95: Params, ctor(container, duration, pattern,
+//                                  params), bool extractFeatures(), eventsNum(), findCenter(p), fitCircle(...)
+//   opengv2::EventCalibSpline      ECC/include/.../EventCalibSpline.hpp:17-357: optimize(), intrinsics OFFSET_* enum
+//
+// The batched entry point the reference lacks — many windows per launch — is ecb::FrontEnd below; the per-frame class
+// is kept so that the reference's MultiProcess loop (ECC/test/eventCameraCalib.cpp:34-97) compiles unchanged against it.
+// What is NOT here yet: the grid ordering of candidates (findCirclesGrid) and rectifyFeatures —
+// extractFeatures() therefore returns the candidate circles unordered and reports success when at least rows*cols
+// candidates were found.
+#ifndef ECB_EVENT_CALIB_HPP
+#define ECB_EVENT_CALIB_HPP
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../eventcalib_b200.h"
+#include "dbscan.h"
+
+namespace opengv2 {
+
+struct Vec2 {
+    double v[2];
+    double &operator[](int i) { return v[i]; }
+    const double &operator[](int i) const { return v[i]; }
+};
+
+// the reference's 25-byte record (Event.hpp:36-47), packed
+#pragma pack(push, 1)
+struct EventRecord {
+    double t, x, y;
+    uint8_t polarity;
+};
+#pragma pack(pop)
+static_assert(sizeof(EventRecord) == 25, "reference record is 25 bytes");
+
+struct CirclePatternParameters {
+    typedef std::shared_ptr<CirclePatternParameters> Ptr;
+    bool isAsymmetric = true;
+    int rows = 9, cols = 4;
+    double circleRadius = 1.75, squareSize = 5.5;
+};
+
+// Time-ordered events resident on the device (replaces std::multimap<double, Event_loc_pol>, EventContainer.hpp:26)
+struct EventContainer {
+    typedef std::shared_ptr<EventContainer> Ptr;
+    ecb_ctx *ctx = nullptr;
+    int width = 0, height = 0;
+    int64_t size = 0;
+    double firstTime = 0, lastTime = 0;
+
+    EventContainer(int device, int w, int h) : width(w), height(h) {
+        if (ecb_ctx_create(device, nullptr, &ctx) != ECB_OK) throw std::runtime_error("ecb: no usable CUDA device");
+        if (ecb_set_sensor(ctx, w, h) != ECB_OK) throw std::invalid_argument(ecb_last_error(ctx));
+    }
+    ~EventContainer() { ecb_ctx_destroy(ctx); }
+    EventContainer(const EventContainer &) = delete;
+    EventContainer &operator=(const EventContainer &) = delete;
+
+    // records: time-sorted reference records (the caller applies StartTime / EndTime like eventCameraCalib.cpp:154-163)
+    void load(const EventRecord *records, int64_t n) {
+        if (ecb_load_events_host(ctx, records, n) != ECB_OK) throw std::invalid_argument(ecb_last_error(ctx));
+        size = n;
+        if (n > 0) {
+            firstTime = records[0].t;
+            lastTime = records[n - 1].t;
+        }
+    }
+};
+
+struct CalibCircleLite {
+    Vec2 center;
+    double radius;
+    int pCluster, nCluster;
+};
+
+// ---- batched front end: all windows of a piece in one launch ----
+class FrontEnd {
+public:
+    struct Params {  // CirclesEventFrame::Params (CirclesEventFrame.cpp:35-48)
+        double dbscan_eps = 4;
+        int dbscan_startMinSample = 2;
+        int clusterMinSample = 5;
+        int knn_num = 3;
+        bool fitCircle = false;
+    };
+    FrontEnd(EventContainer::Ptr c, CirclePatternParameters::Ptr pattern, Params p) : c_(c), pattern_(pattern), p_(p) {
+        // circleRadiusThreshold_ (CirclesEventFrame.cpp:16-33)
+        const double W = c->width, H = c->height;
+        const double c2 = pattern->isAsymmetric ? 2.0 * pattern->cols : (double) pattern->cols;
+        rthr_ = std::min(std::max(W, H) / std::max((double) pattern->rows, c2), std::min(W, H) / std::min((double) pattern->rows, c2)) /
+                pattern->squareSize * pattern->circleRadius * 1.5;
+    }
+    // windows: closed intervals [first, second] (EventFrame.cpp:14-15)
+    void run(const std::vector<std::pair<double, double>> &windows) {
+        ecb_frontend_params fp;
+        std::memset(&fp, 0, sizeof fp);
+        fp.dbscan_eps = p_.dbscan_eps;
+        fp.dbscan_min_pts = (uint32_t) p_.dbscan_startMinSample;
+        fp.cluster_min = (uint32_t) p_.clusterMinSample;
+        fp.knn_num = p_.knn_num;
+        fp.fit_circle = p_.fitCircle ? 1 : 0;
+        fp.radius_threshold = rthr_;
+        fp.rows_cols = (uint32_t) (pattern_->rows * pattern_->cols);
+        std::vector<double> w(2 * windows.size());
+        for (size_t i = 0; i < windows.size(); ++i) {
+            w[2 * i] = windows[i].first;
+            w[2 * i + 1] = windows[i].second;
+        }
+        if (ecb_frontend_run(c_->ctx, w.data(), (int) windows.size(), &fp) != ECB_OK)
+            throw std::runtime_error(ecb_last_error(c_->ctx));
+        summary_.resize(windows.size());
+        cand_.assign(windows.size() * kMaxCand * 5, 0.0);
+        if (!windows.empty()) {
+            ecb_frontend_summary(c_->ctx, summary_.data(), (int) windows.size());
+            ecb_frontend_candidates(c_->ctx, cand_.data(), kMaxCand);
+        }
+    }
+    const ecb_window_summary &summary(size_t w) const { return summary_[w]; }
+    int eventsNum(size_t w) const { return summary_[w].n_points[0] + summary_[w].n_points[1]; }
+    std::vector<CalibCircleLite> candidates(size_t w) const {
+        std::vector<CalibCircleLite> out;
+        for (int k = 0; k < summary_[w].n_candidates && k < kMaxCand; ++k) {
+            const double *c = &cand_[(w * kMaxCand + k) * 5];
+            out.push_back(CalibCircleLite{{{c[2], c[3]}}, c[4], (int) c[0], (int) c[1]});
+        }
+        return out;
+    }
+    double circleRadiusThreshold() const { return rthr_; }
+    static constexpr int kMaxCand = 128;
+
+private:
+    EventContainer::Ptr c_;
+    CirclePatternParameters::Ptr pattern_;
+    Params p_;
+    double rthr_;
+    std::vector<ecb_window_summary> summary_;
+    std::vector<double> cand_;
+};
+
+// ---- per-frame class with the reference's interface ----
+class CirclesEventFrame {
+public:
+    typedef FrontEnd::Params Params;
+    CirclesEventFrame(EventContainer::Ptr container, const std::pair<double, double> &duration,
+                      CirclePatternParameters::Ptr pattern, Params params = Params())
+        : fe_(container, pattern, params), duration_(duration), pattern_(pattern) {
+        fe_.run({duration_});  // the EventFrame ctor does the window / dedupe / cancel work (EventFrame.cpp:10-36)
+    }
+    bool extractFeatures() {  // CirclesEventFrame.cpp:61-359 up to the grid ordering
+        const ecb_window_summary &s = fe_.summary(0);
+        if (s.n_points[0] == 0 || s.n_points[1] == 0) return false;  // :62-64
+        features_ = fe_.candidates(0);
+        return (int) features_.size() >= pattern_->rows * pattern_->cols;
+    }
+    int eventsNum() const { return fe_.eventsNum(0); }
+    const std::vector<CalibCircleLite> &features() const { return features_; }
+    // CirclesEventFrame.hpp:50-65: nearest circle, accepted iff | ||p-c|| - r | < 5 px; returns the feature index or -1
+    int findCenter(const Vec2 &p) const {
+        int best = -1;
+        double bd = 0;
+        for (size_t i = 0; i < features_.size(); ++i) {
+            const double dx = p[0] - features_[i].center[0], dy = p[1] - features_[i].center[1], d2 = dx * dx + dy * dy;
+            if (best < 0 || d2 < bd) {
+                best = (int) i;
+                bd = d2;
+            }
+        }
+        if (best < 0) return -1;
+        return std::abs(std::sqrt(bd) - features_[(size_t) best].radius) < 5 ? best : -1;
+    }
+
+private:
+    FrontEnd fe_;
+    std::pair<double, double> duration_;
+    CirclePatternParameters::Ptr pattern_;
+    std::vector<CalibCircleLite> features_;
+};
+
+// ---- spline calibration: EventCalibSpline::optimize on the GPU ----
+class EventCalibSpline {
+public:
+    enum {  // EventCalibSpline.hpp:24-34
+        OFFSET_FOCAL_LENGTH_X, OFFSET_FOCAL_LENGTH_Y, OFFSET_PRINCIPAL_POINT_X, OFFSET_PRINCIPAL_POINT_Y,
+        OFFSET_K1, OFFSET_K2, OFFSET_K3, OFFSET_K4, OFFSET_K5,
+    };
+    struct Segment {            // one spline (EventCalibSpline.cpp:63-91)
+        std::vector<double> knots;      // n_cp + 4, clamped cubic
+        std::vector<double> rot_cp;     // n_cp x (x,y,z,w)
+        std::vector<double> trans_cp;   // n_cp x 3
+    };
+    struct KeyFrame {
+        double timeStamp;
+        std::vector<std::array<double, 3>> circles;  // (cx, cy, r) per board point; r < 0: absent
+    };
+    EventCalibSpline(EventContainer::Ptr events, std::vector<Segment> segments, std::array<double, 9> intrinsics,
+                     double motionTimeStep, double circleRadius)
+        : ev_(events), seg_(std::move(segments)), intr_(intrinsics), step_(motionTimeStep), radius_(circleRadius) {
+        if (seg_.empty()) throw std::logic_error("sampleSets not filtered");  // EventCalibSpline.cpp:78-80
+        std::vector<double> kn;
+        for (auto &s : seg_) {
+            n_cp_.push_back((int32_t) (s.rot_cp.size() / 4));
+            kn.insert(kn.end(), s.knots.begin(), s.knots.end());
+        }
+        if (ecb_cost_setup(ev_->ctx, (int) seg_.size(), n_cp_.data(), kn.data(), radius_, 0.2 * radius_) != ECB_OK)
+            throw std::logic_error(ecb_last_error(ev_->ctx));  // HuberLoss(0.2 r), EventCalibSpline.cpp:197
+    }
+    // association loop, EventCalibSpline.cpp:157-192; landmarks: board points (EventCalibIni.cpp:99-113)
+    int64_t associate(const std::vector<KeyFrame> &kf, const std::vector<std::array<double, 3>> &landmarks) {
+        const int nc = (int) landmarks.size();
+        std::vector<double> t(kf.size()), c(kf.size() * nc * 3);
+        for (size_t i = 0; i < kf.size(); ++i) {
+            t[i] = kf[i].timeStamp;
+            for (int q = 0; q < nc; ++q)
+                for (int a = 0; a < 3; ++a) c[(i * nc + q) * 3 + a] = q < (int) kf[i].circles.size() ? kf[i].circles[q][a] : -1.0;
+        }
+        int64_t n = 0;
+        if (ecb_cost_associate(ev_->ctx, t.data(), c.data(), (int) kf.size(), nc, &landmarks[0][0], step_, &n) != ECB_OK)
+            throw std::runtime_error(ecb_last_error(ev_->ctx));
+        return n;
+    }
+    bool optimize(ecb_lm_summary *summary = nullptr) {  // EventCalibSpline.cpp:115-251
+        std::vector<double> rot, trans;
+        for (auto &s : seg_) {
+            rot.insert(rot.end(), s.rot_cp.begin(), s.rot_cp.end());
+            trans.insert(trans.end(), s.trans_cp.begin(), s.trans_cp.end());
+        }
+        ecb_lm_options opt;
+        ecb_lm_default_options(&opt);
+        ecb_lm_summary sum;
+        if (ecb_calibrate(ev_->ctx, (int) seg_.size(), n_cp_.data(), intr_.data(), rot.data(), trans.data(), &opt, &sum, nullptr, 0) != ECB_OK)
+            return false;
+        size_t ro = 0, to = 0;
+        for (auto &s : seg_) {
+            std::copy(rot.begin() + ro, rot.begin() + ro + s.rot_cp.size(), s.rot_cp.begin());
+            std::copy(trans.begin() + to, trans.begin() + to + s.trans_cp.size(), s.trans_cp.begin());
+            ro += s.rot_cp.size();
+            to += s.trans_cp.size();
+        }
+        if (summary) *summary = sum;
+        return true;
+    }
+    const std::array<double, 9> &intrinsics() const { return intr_; }
+    const std::vector<Segment> &segments() const { return seg_; }
+
+private:
+    EventContainer::Ptr ev_;
+    std::vector<Segment> seg_;
+    std::vector<int32_t> n_cp_;
+    std::array<double, 9> intr_;
+    double step_, radius_;
+};
+
+}  // namespace opengv2
+#endif  // ECB_EVENT_CALIB_HPP

@@ -1,0 +1,78 @@
+"""The C++ host side over the C ABI: CLI argument / error behaviour (CPU) and, on the GPU, the façade self-test and a
+full CLI run on a synthetic .bin with the reference's config keys (parameter/event_calibration/example.yaml)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "eventcalib_b200", "host")
+CLI = os.path.join(HOST, "unit_test_eventCameraCalib")
+
+YAML = """%YAML:1.0
+# same keys as the reference's parameter/event_calibration/example.yaml
+StartTime: 5
+EndTime: 10
+MotionTimeStep: 5e-4
+FrameEventNumThreshold: 4000
+Camera.width: 346
+Camera.height: 260
+Is_Pattern_Asymmetric: 1
+BoardSize_Rows: 9
+BoardSize_Cols: 4
+Square_Size: 5.5
+Circles_Radius: 1.75
+dbscan_eps: 4
+dbscan_startMinSample: 2
+clusterMinSample: 5
+knn_num: 3
+fitCircle: 0
+useSO3: 0
+reduceMap: 0
+Viewer.Facing: [ 1,0,0,0,1,0,0,0,1 ]
+"""
+
+
+@pytest.fixture(scope="module")
+def built():
+    import eventcalib_b200.build as b
+    b.build()
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    return CLI
+
+
+def test_usage_and_missing_settings(built, tmp_path):
+    r = subprocess.run([built], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage: ./unit_test_eventCameraCalib settingFilePath binFilePath SavePath" in r.stderr
+    r = subprocess.run([built, "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1
+    r = subprocess.run([built, str(tmp_path / "nope.yaml"), "x.bin", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 255 and "Failed to open settings file at:" in r.stderr   # exit(-1), eventCameraCalib.cpp:115-118
+
+
+@pytest.mark.gpu
+def test_facade_selftest(built):
+    r = subprocess.run([os.path.join(HOST, "test_facade")], capture_output=True, text=True)
+    assert r.returncode == 0 and "facade ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_on_synthetic_stream(built, tmp_path):
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(200000, 346, 260, t0=5.0, duration=0.1, seed=1001)
+    # a few events before StartTime must be skipped by the loader
+    pre = synth.make_stream(1000, 346, 260, t0=4.0, duration=0.01, seed=1)
+    full = {k: np.concatenate([pre[k], ev[k]]) for k in "txyp"}
+    synth.write_bin(str(tmp_path / "ev.bin"), full)
+    (tmp_path / "cfg.yaml").write_text(YAML)
+    save = tmp_path / "out"
+    r = subprocess.run([built, str(tmp_path / "cfg.yaml"), str(tmp_path / "ev.bin"), str(save)], capture_output=True, text=True,
+                       stdin=subprocess.DEVNULL, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Events from 5 second to" in r.stdout and "frames in Map." in r.stdout and "press Enter to exit..." in r.stdout
+    frames = int([l for l in r.stdout.splitlines() if l.endswith("frames in Map.")][0].split()[0])
+    assert frames >= 20
+    cand = np.loadtxt(str(save / "candidates.txt"))
+    assert cand.shape[1] == 5 and len(np.unique(cand[:, 0])) == frames
+    assert np.all((cand[:, 4] > 4) & (cand[:, 4] < 12))      # circle radii in pixels
