@@ -75,4 +75,4 @@ def test_cli_on_synthetic_stream(built, tmp_path):
     assert frames >= 20
     cand = np.loadtxt(str(save / "candidates.txt"))
     assert cand.shape[1] == 5 and len(np.unique(cand[:, 0])) == frames
-    assert np.all((cand[:, 4] > 4) & (cand[:, 4] < 12))      # circle radii in pixels
+    assert np.all((cand[:, 4] > 1) & (cand[:, 4] < 16))      # circle radii in pixels (< circleRadiusThreshold)
