@@ -305,6 +305,7 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     pa.n_win = n_win;
     pa.max_k = max_k;
     pa.cand_stride = ctx->cand_stride;
+    pa.smem_cap = (int) max_n;
     pa.fit_circle = params->fit_circle;
     pa.knn_num = params->knn_num < 1 ? 1 : params->knn_num;
     pa.rows_cols = params->rows_cols;

@@ -16,16 +16,23 @@
 //      (CirclesEventFrame.cpp:364-404) and the median-by-norm member (CirclesEventFrame.cpp:137-147)
 //
 // HBM traffic per point: 4 B pixel read + 4 B label write + 4 B member write; everything else is on-chip.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "ecb_cluster.cuh"
 
 namespace {
 
 template <typename RankT>
 struct Smem {
-    uint32_t *U, *FX, *FY, *C;
+    uint32_t *U, *C;
     RankT *wrank;
     uint32_t *r_pix, *r_por, *r_lab, *r_kd, *r_st;
+    uint8_t *r_flag;
 };
+
+constexpr int KD_PT = 6;  // points per thread kept in registers during the kd rounds
 
 __device__ __forceinline__ uint32_t find_root(volatile uint32_t *parent, uint32_t a) {
     uint32_t p = parent[a];
@@ -56,16 +63,14 @@ template <typename RankT>
 __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a) {
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ uint32_t ws[33];
-    __shared__ uint32_t s_pb, s_status, s_tmp[4];
+    __shared__ uint32_t s_pb, s_status;
     __shared__ int32_t k_raw[ECB_MAXK_LIMIT], k_size[ECB_MAXK_LIMIT], k_off[ECB_MAXK_LIMIT + 1];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     const int PW = a.PW, PH = a.PH, E = a.E, NW = PW * PH;
     Smem<RankT> s;
     s.U = smem_raw;
-    s.FX = s.U + NW;
-    s.FY = s.FX + NW;
-    s.C = s.FY + NW;
+    s.C = s.U + NW;
     s.wrank = reinterpret_cast<RankT *>(s.C + NW);
     uint32_t *arr = a.arrays_in_smem
                         ? (s.C + NW + (NW * sizeof(RankT) + 3) / 4)
@@ -76,6 +81,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
     s.r_lab = arr + 2 * NC;
     s.r_kd = arr + 3 * NC;  // 2*NC words
     s.r_st = arr + 5 * NC;
+    s.r_flag = reinterpret_cast<uint8_t *>(arr + 6 * NC);  // NC bytes, indexed by rank: kd tie flags (bit0 x, bit1 y)
 
     for (;;) {
         __syncthreads();
@@ -92,7 +98,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         int32_t *glab = a.labels[d.pol] + d.off;
 
         // ---- 0. clear planes -----------------------------------------------------------------
-        for (int i = tid; i < 4 * NW; i += nthr) s.U[i] = 0;
+        for (int i = tid; i < 2 * NW; i += nthr) s.U[i] = 0;
         __syncthreads();
         // ---- 1. occupancy bitmap ---------------------------------------------------------------
         for (int pid = tid; pid < n; pid += nthr) {
@@ -138,43 +144,82 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
             if (loc != ECB_NONE) s.r_por[rank_of(loc & 0xFFFF, loc >> 16)] = pid;
         }
         // ---- 4. kd insertion-order emulation -> tie flags ---------------------------------------
-        uint32_t *child = s.r_kd, *state = s.r_st;
-        const uint32_t DONE = 0x3FFFFFFFu;
+        // NOTE: the root is pid 0 like kd_insert's first insertion.
+        uint32_t *child = s.r_kd;
         for (int i = tid; i < 2 * n; i += nthr) child[i] = ECB_NONE;
-        for (int pid = tid; pid < n; pid += nthr) state[pid] = (pid == 0 || s.r_pix[pid] == ECB_NONE) ? DONE : 0u;
-        // NOTE: the root is pid 0 like kd_insert's first insertion; an out-of-range pid 0 is not supported
-        __syncthreads();
-        for (int round = 0;; ++round) {
-            const int dsh = (round & 1) ? 16 : 0;
-            bool any = false;
-            for (int pid = tid; pid < n; pid += nthr) {
-                uint32_t st = state[pid];
-                uint32_t cur = st & DONE;
-                if (cur == DONE) continue;
-                any = true;
-                uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
-                if (ci == ca) state[pid] = st | (0x40000000u << (round & 1));
-                atomicMin(&child[2 * cur + (ci < ca ? 0 : 1)], (uint32_t) pid);
-            }
-            if (!__syncthreads_or(any)) break;
-            for (int pid = tid; pid < n; pid += nthr) {
-                uint32_t st = state[pid];
-                uint32_t cur = st & DONE;
-                if (cur == DONE) continue;
-                uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
-                uint32_t c = child[2 * cur + (ci < ca ? 0 : 1)];
-                state[pid] = (st & 0xC0000000u) | (c == (uint32_t) pid ? DONE : c);
+        if (n <= KD_PT * nthr) {
+            // fast path: each thread keeps its <= KD_PT points (pixel, current node, flags) in registers
+            uint32_t mypix[KD_PT], cur[KD_PT], fl[KD_PT];
+#pragma unroll
+            for (int k = 0; k < KD_PT; ++k) {
+                const int pid = tid + k * nthr;
+                mypix[k] = pid < n ? s.r_pix[pid] : ECB_NONE;
+                cur[k] = (pid == 0 || mypix[k] == ECB_NONE) ? ECB_NONE : 0u;
+                fl[k] = 0;
             }
             __syncthreads();
-        }
-        for (int pid = tid; pid < n; pid += nthr) {
-            uint32_t st = state[pid], loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
-            int x = loc & 0xFFFF, y = loc >> 16;
-            if (st & 0x40000000u) atomicOr(&s.FX[y * PW + (x >> 5)], 1u << (x & 31));
-            if (st & 0x80000000u) atomicOr(&s.FY[y * PW + (x >> 5)], 1u << (x & 31));
+            for (int round = 0;; ++round) {
+                const int dsh = (round & 1) ? 16 : 0;
+                bool any = false;
+                uint32_t slot[KD_PT];
+#pragma unroll
+                for (int k = 0; k < KD_PT; ++k) {
+                    if (cur[k] == ECB_NONE) continue;
+                    any = true;
+                    const uint32_t ci = (mypix[k] >> dsh) & 0xFFFF, ca = (s.r_pix[cur[k]] >> dsh) & 0xFFFF;
+                    if (ci == ca) fl[k] |= 1u << (round & 1);
+                    slot[k] = 2 * cur[k] + (ci < ca ? 0 : 1);
+                    atomicMin(&child[slot[k]], (uint32_t) (tid + k * nthr));
+                }
+                if (!__syncthreads_or(any)) break;
+#pragma unroll
+                for (int k = 0; k < KD_PT; ++k) {
+                    if (cur[k] == ECB_NONE) continue;
+                    const uint32_t c = child[slot[k]];
+                    cur[k] = c == (uint32_t) (tid + k * nthr) ? ECB_NONE : c;
+                }
+                // no barrier needed here: a child slot is written only in the round in which its parent is reached,
+                // and all points that reach a node do so in the same round
+            }
+#pragma unroll
+            for (int k = 0; k < KD_PT; ++k)
+                if (mypix[k] != ECB_NONE) s.r_flag[rank_of(mypix[k] & 0xFFFF, mypix[k] >> 16)] = (uint8_t) fl[k];
+        } else {
+            uint32_t *state = s.r_st;
+            const uint32_t DONE = 0x3FFFFFFFu;
+            for (int pid = tid; pid < n; pid += nthr) state[pid] = (pid == 0 || s.r_pix[pid] == ECB_NONE) ? DONE : 0u;
+            __syncthreads();
+            for (int round = 0;; ++round) {
+                const int dsh = (round & 1) ? 16 : 0;
+                bool any = false;
+                for (int pid = tid; pid < n; pid += nthr) {
+                    uint32_t st = state[pid];
+                    uint32_t cur = st & DONE;
+                    if (cur == DONE) continue;
+                    any = true;
+                    uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
+                    if (ci == ca) state[pid] = st | (0x40000000u << (round & 1));
+                    atomicMin(&child[2 * cur + (ci < ca ? 0 : 1)], (uint32_t) pid);
+                }
+                if (!__syncthreads_or(any)) break;
+                for (int pid = tid; pid < n; pid += nthr) {
+                    uint32_t st = state[pid];
+                    uint32_t cur = st & DONE;
+                    if (cur == DONE) continue;
+                    uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
+                    uint32_t c = child[2 * cur + (ci < ca ? 0 : 1)];
+                    state[pid] = (st & 0xC0000000u) | (c == (uint32_t) pid ? DONE : c);
+                }
+                __syncthreads();
+            }
+            for (int pid = tid; pid < n; pid += nthr) {
+                const uint32_t loc = s.r_pix[pid];
+                if (loc != ECB_NONE) s.r_flag[rank_of(loc & 0xFFFF, loc >> 16)] = (uint8_t) (state[pid] >> 30);
+            }
         }
         __syncthreads();
+        // tie flag of the (occupied) pixel (x,y): bit0 = FX, bit1 = FY
+        auto flag_of = [&](int x, int y) -> uint32_t { return s.r_flag[rank_of(x, y)]; };
         // ---- 5. neighbour count, core flag -----------------------------------------------------------
         const int ei = a.eps_int;
         for (int pid = tid; pid < n; pid += nthr) {
@@ -186,9 +231,9 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 const int w = a.halfw[dy < 0 ? -dy : dy];
                 cnt += __popc(row_bits(s.U + (y + dy) * PW, x - w, 2 * w + 1));
             }
-            if (ei > 0) {
-                cnt -= (int) (test_bit(s.U + y * PW, x + ei) & test_bit(s.FX + y * PW, x + ei));
-                cnt -= (int) (test_bit(s.U + (y + ei) * PW, x) & test_bit(s.FY + (y + ei) * PW, x));
+            if (ei > 0) {  // neighbours the kd query misses (kdtree.cpp:166-171)
+                if (test_bit(s.U + y * PW, x + ei)) cnt -= (int) (flag_of(x + ei, y) & 1u);
+                if (test_bit(s.U + (y + ei) * PW, x)) cnt -= (int) ((flag_of(x, y + ei) >> 1) & 1u);
             }
             if (cnt >= (int) a.min_pts) atomicOr(&s.C[y * PW + (x >> 5)], 1u << (x & 31));
         }
@@ -198,7 +243,11 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
             glabel[r] = ECB_NONE;
         }
         __syncthreads();
-        // ---- 6. union-find over mutual core edges (half-plane enumeration) ----------------------------
+        // ---- 6. union-find over mutual core edges -------------------------------------------------------
+        // Half-plane enumeration.  Inside one bitmap row, core pixels less than eps apart are always mutually adjacent
+        // (the tie rule only concerns distance exactly eps), so it suffices to unite q with the FIRST pixel of every
+        // run (gap < eps) inside the row segment; the run itself is chained by its own dy = 0 unions.
+        const int gap = (ei > 0 ? ei : E + 1) - 1;  // pixels whose distance is <= gap are unconditionally adjacent in-row
         for (int pid = tid; pid < n; pid += nthr) {
             uint32_t loc = s.r_pix[pid];
             if (loc == ECB_NONE) continue;
@@ -211,13 +260,20 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 const int len = dy == 0 ? w : 2 * w + 1;
                 if (len <= 0) continue;
                 uint32_t bits = row_bits(s.C + (y + dy) * PW, xs, len);
+                if (dy == 0) {
+                    bits &= (uint32_t) -(int32_t) bits;  // nearest right neighbour only; farther ones chain through it
+                } else {
+                    uint32_t lower = 0;
+                    for (int g = 1; g <= gap; ++g) lower |= bits << g;
+                    bits &= ~lower;  // first pixel of every run
+                }
                 while (bits) {
                     const int b = __ffs(bits) - 1;
                     bits &= bits - 1;
                     const int nx = xs + b, ny = y + dy;
-                    if (ei > 0) {  // q -> p missed by the kd query: the pair is a one-way edge p -> q
-                        if (dy == 0 && nx - x == ei && test_bit(s.FX + ny * PW, nx)) continue;
-                        if (dy == ei && nx == x && test_bit(s.FY + ny * PW, nx)) continue;
+                    if (ei > 0) {  // q -> p missed by the kd query: the pair is a one-way edge p -> q (handled in 7)
+                        if (dy == 0 && nx - x == ei && (flag_of(nx, ny) & 1u)) continue;
+                        if (dy == ei && nx == x && (flag_of(nx, ny) & 2u)) continue;
                     }
                     unite(parent, rq, rank_of(nx, ny));
                 }
@@ -228,51 +284,47 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         int n_core_local = 0;
         for (int pid = tid; pid < n; pid += nthr) {
             uint32_t loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
-            const int x = loc & 0xFFFF, y = loc >> 16;
-            if (!test_bit(s.C + y * PW, x)) continue;
-            ++n_core_local;
-            const uint32_t r = rank_of(x, y);
-            const uint32_t root = find_root(parent, r);
-            atomicMin(&glabel[root], (uint32_t) pid);
+            uint32_t root = ECB_NONE;
+            if (loc != ECB_NONE) {
+                const int x = loc & 0xFFFF, y = loc >> 16;
+                if (test_bit(s.C + y * PW, x)) {
+                    ++n_core_local;
+                    root = find_root(parent, rank_of(x, y));
+                    atomicMin(&glabel[root], (uint32_t) pid);
+                }
+            }
+            s.r_lab[pid] = root;  // stash: root rank of the point's group (ECB_NONE for non-core)
         }
         __syncthreads();
-        for (int pid = tid; pid < n; pid += nthr) {  // full flatten (all unions are done)
-            uint32_t loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
-            const int x = loc & 0xFFFF, y = loc >> 16;
-            if (!test_bit(s.C + y * PW, x)) continue;
-            const uint32_t r = rank_of(x, y);
-            uint32_t root = r;
-            while (parent[root] != root) root = parent[root];
-            s.r_lab[pid] = root;  // stash; parent[] itself is rewritten after the barrier
-        }
-        __syncthreads();
-        for (int pid = tid; pid < n; pid += nthr) {
-            uint32_t loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
-            const int x = loc & 0xFFFF, y = loc >> 16;
-            if (!test_bit(s.C + y * PW, x)) continue;
-            parent[rank_of(x, y)] = s.r_lab[pid];
+        for (int pid = tid; pid < n; pid += nthr) {  // full flatten: parent[rank] = root for every core point
+            const uint32_t root = s.r_lab[pid];
+            if (root == ECB_NONE) continue;
+            const uint32_t loc = s.r_pix[pid];
+            parent[rank_of(loc & 0xFFFF, loc >> 16)] = root;
         }
         __syncthreads();
         if (ei > 0) {
             for (;;) {
                 bool changed = false;
                 for (int pid = tid; pid < n; pid += nthr) {
-                    uint32_t loc = s.r_pix[pid];
-                    if (loc == ECB_NONE) continue;
+                    const uint32_t gq = s.r_lab[pid];
+                    if (gq == ECB_NONE) continue;
+                    const uint32_t loc = s.r_pix[pid];
                     const int x = loc & 0xFFFF, y = loc >> 16;
-                    if (!test_bit(s.C + y * PW, x)) continue;
-                    const uint32_t gq = parent[rank_of(x, y)];
                     // p = q + eps*e_x with FX(p): edge p -> q only
-                    if (test_bit(s.C + y * PW, x + ei) && test_bit(s.FX + y * PW, x + ei)) {
-                        uint32_t lp = ((volatile uint32_t *) glabel)[parent[rank_of(x + ei, y)]];
-                        if (lp < atomicMin(&glabel[gq], lp)) changed = true;
+                    if (test_bit(s.C + y * PW, x + ei)) {
+                        const uint32_t rp = rank_of(x + ei, y);
+                        if (s.r_flag[rp] & 1u) {
+                            uint32_t lp = ((volatile uint32_t *) glabel)[parent[rp]];
+                            if (lp < atomicMin(&glabel[gq], lp)) changed = true;
+                        }
                     }
-                    if (test_bit(s.C + (y + ei) * PW, x) && test_bit(s.FY + (y + ei) * PW, x)) {
-                        uint32_t lp = ((volatile uint32_t *) glabel)[parent[rank_of(x, y + ei)]];
-                        if (lp < atomicMin(&glabel[gq], lp)) changed = true;
+                    if (test_bit(s.C + (y + ei) * PW, x)) {
+                        const uint32_t rp = rank_of(x, y + ei);
+                        if (s.r_flag[rp] & 2u) {
+                            uint32_t lp = ((volatile uint32_t *) glabel)[parent[rp]];
+                            if (lp < atomicMin(&glabel[gq], lp)) changed = true;
+                        }
                     }
                 }
                 if (!__syncthreads_or(changed)) break;
@@ -284,16 +336,11 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         for (int i = tid; i < nw32; i += nthr) seedmask[i] = 0;
         __syncthreads();
         for (int pid = tid; pid < n; pid += nthr) {
-            uint32_t loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
-            const int x = loc & 0xFFFF, y = loc >> 16;
-            if (!test_bit(s.C + y * PW, x)) continue;
-            const uint32_t r = rank_of(x, y);
-            if (parent[r] != r) continue;  // roots only
-            const uint32_t lab = glabel[r];
-            // the group is a seed iff its final label is one of its own members (nothing smaller reached it)
-            const uint32_t ll = s.r_pix[lab];
-            if (parent[rank_of(ll & 0xFFFF, ll >> 16)] == r) atomicOr(&seedmask[lab >> 5], 1u << (lab & 31));
+            const uint32_t g = s.r_lab[pid];
+            if (g == ECB_NONE) continue;
+            // a group is a seed iff its final label is one of its own members (nothing smaller reached it);
+            // the member with pid == glabel[g] marks it
+            if (glabel[g] == (uint32_t) pid) atomicOr(&seedmask[pid >> 5], 1u << (pid & 31));
         }
         __syncthreads();
         uint32_t n_clusters;
@@ -310,14 +357,11 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         }
         __syncthreads();
         for (int pid = tid; pid < n; pid += nthr) {
-            uint32_t loc = s.r_pix[pid];
+            const uint32_t g = s.r_lab[pid];
             int32_t lab = -1;
-            if (loc != ECB_NONE) {
-                const int x = loc & 0xFFFF, y = loc >> 16;
-                if (test_bit(s.C + y * PW, x)) {
-                    const uint32_t seed = glabel[parent[rank_of(x, y)]];
-                    lab = (int32_t) (seedpref[seed >> 5] + __popc(seedmask[seed >> 5] & ((1u << (seed & 31)) - 1u)));
-                }
+            if (g != ECB_NONE) {
+                const uint32_t seed = glabel[g];
+                lab = (int32_t) (seedpref[seed >> 5] + __popc(seedmask[seed >> 5] & ((1u << (seed & 31)) - 1u)));
             }
             s.r_lab[pid] = (uint32_t) lab;
             glab[pid] = lab;
@@ -369,18 +413,74 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         uint32_t *members = s.r_st;  // seedmask/seedpref are dead
         uint32_t *gmem = a.kmem[d.pol] + d.off;
         KeptCluster *kt = a.ktab + (size_t) pb * a.max_k;
+        if (n_kept > 0) {
+            // Ordered member lists (ascending pid inside every cluster) without scanning all points once per cluster:
+            // each warp owns a contiguous pid range; pass A counts its members per kept cluster, a scan over the warps
+            // turns the counts into start positions, pass B places.  Counters live in the (now dead) rank->pid array.
+            const int L = (((n + nwarp - 1) / nwarp) + 31) & ~31;  // pids per warp, multiple of 32
+            const int p0 = wid * L, p1 = min(n, p0 + L);
+            auto kept_of = [&](int pid) -> int {
+                if (pid >= p1) return -1;
+                const int32_t lab = (int32_t) s.r_lab[pid];
+                if (lab < 0) return -1;
+                const uint32_t ki = keptidx[lab];
+                return (ki != ECB_NONE && ki < n_kept) ? (int) ki : -1;
+            };
+            if ((int) n_kept * nwarp <= NC) {
+                uint32_t *cnt = s.r_por;
+                for (int i = tid; i < (int) n_kept * nwarp; i += nthr) cnt[i] = 0;
+                __syncthreads();
+                uint32_t *mycnt = cnt + wid * n_kept;
+                for (int c = p0; c < p1; c += 32) {
+                    const int kidx = kept_of(c + lane);
+                    const uint32_t peers = __match_any_sync(0xffffffffu, kidx);
+                    if (kidx >= 0 && (peers & ((1u << lane) - 1u)) == 0) mycnt[kidx] += __popc(peers);
+                    __syncwarp();
+                }
+                __syncthreads();
+                for (int k = tid; k < (int) n_kept; k += nthr) {
+                    uint32_t run = 0;
+                    for (int w = 0; w < nwarp; ++w) {
+                        const uint32_t t = cnt[w * n_kept + k];
+                        cnt[w * n_kept + k] = run;
+                        run += t;
+                    }
+                }
+                __syncthreads();
+                for (int c = p0; c < p1; c += 32) {
+                    const int pid = c + lane;
+                    const int kidx = kept_of(pid);
+                    const uint32_t peers = __match_any_sync(0xffffffffu, kidx);
+                    const int rk = __popc(peers & ((1u << lane) - 1u));
+                    uint32_t base = 0;
+                    if (kidx >= 0) {
+                        base = mycnt[kidx];
+                        members[k_off[kidx] + base + rk] = pid;
+                    }
+                    __syncwarp();
+                    if (kidx >= 0 && rk == 0) mycnt[kidx] = base + __popc(peers);
+                    __syncwarp();
+                }
+            } else {
+                // many kept clusters: one warp per cluster scans the labels (O(n_kept * n / 32))
+                for (int k = wid; k < (int) n_kept; k += nwarp) {
+                    const int32_t cid = k_raw[k];
+                    const int base = k_off[k];
+                    int pos = 0;
+                    for (int st = 0; st < n; st += 32) {
+                        const int pid = st + lane;
+                        const bool m = pid < n && (int32_t) s.r_lab[pid] == cid;
+                        const uint32_t ball = __ballot_sync(0xffffffffu, m);
+                        if (m) members[base + pos + __popc(ball & ((1u << lane) - 1u))] = pid;
+                        pos += __popc(ball);
+                    }
+                }
+            }
+        }
+        __syncthreads();
         for (int k = wid; k < (int) n_kept; k += nwarp) {
             const int32_t cid = k_raw[k];
             const int base = k_off[k], sz = k_size[k];
-            int pos = 0;
-            for (int st = 0; st < n; st += 32) {
-                const int pid = st + lane;
-                const bool m = pid < n && (int32_t) s.r_lab[pid] == cid;
-                const uint32_t ball = __ballot_sync(0xffffffffu, m);
-                if (m) members[base + pos + __popc(ball & ((1u << lane) - 1u))] = pid;
-                pos += __popc(ball);
-            }
-            __syncwarp();
             long long S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             int med = -1;
             for (int i = lane; i < sz; i += 32) {
@@ -447,8 +547,8 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
 
 size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, bool arrays_in_smem, bool rank32) {
     size_t NW = (size_t) PW * PH;
-    size_t b = 4 * NW * 4 + ((NW * (rank32 ? 4 : 2) + 3) / 4) * 4;
-    if (arrays_in_smem) b += (size_t) 6 * n_cap * 4;
+    size_t b = 2 * NW * 4 + ((NW * (rank32 ? 4 : 2) + 3) / 4) * 4;
+    if (arrays_in_smem) b += (size_t) 6 * n_cap * 4 + (((size_t) n_cap + 3) / 4) * 4;
     return b;
 }
 
@@ -464,19 +564,21 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     size_t with_arrays = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, true, rank32);
     a.arrays_in_smem = with_arrays <= limit;  // else the per-point arrays live in per-CTA L2 scratch
     size_t smem = a.arrays_in_smem ? with_arrays : planes;
+    int threads = ECB_CL_THREADS;
+    if (const char *e = getenv("ECB_CL_THREADS")) threads = std::max(64, std::min(ECB_CL_THREADS, atoi(e) & ~31));
     int per_sm = 1;
     if (rank32) {
         ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint32_t>, ECB_CL_THREADS, smem));
+        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint32_t>, threads, smem));
     } else {
         ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint16_t>, ECB_CL_THREADS, smem));
+        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint16_t>, threads, smem));
     }
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_prob) grid = a.n_prob;
     if (!a.arrays_in_smem) {
-        a.gscratch_stride = (size_t) 6 * a.n_cap;
+        a.gscratch_stride = (size_t) 6 * a.n_cap + (a.n_cap + 3) / 4;
         int rc = ecb_reserve(ctx, ctx->scratch, (size_t) grid * a.gscratch_stride * 4);
         if (rc) return rc;
         a.gscratch = (uint32_t *) ctx->scratch.p;
@@ -484,9 +586,9 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     ECB_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, 4, ctx->stream));
     ECB_PROF_BEGIN(ctx, ECB_STAGE_CLUSTER);
     if (rank32)
-        k_cluster<uint32_t><<<grid, ECB_CL_THREADS, smem, ctx->stream>>>(a);
+        k_cluster<uint32_t><<<grid, threads, smem, ctx->stream>>>(a);
     else
-        k_cluster<uint16_t><<<grid, ECB_CL_THREADS, smem, ctx->stream>>>(a);
+        k_cluster<uint16_t><<<grid, threads, smem, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_CLUSTER);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_cluster launch");

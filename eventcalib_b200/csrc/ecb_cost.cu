@@ -40,7 +40,7 @@ struct CostState {
     DevBuf d_knots, d_knot_off, d_ncp, d_cp_off, d_span_off;
     DevBuf obs, lm, tt, spl, basis, cp0, span;        // residual records (SoA)
     DevBuf span_start, items, part, out, params, cost_part, flags;
-    DevBuf ev_flag, ev_cnt, kf_t, kf_circ, lm_tab, sel_event, sel_circle;
+    DevBuf ev_flag, ev_cnt, ev_tag, kf_t, kf_circ, lm_tab, sel_event, sel_circle;
     std::vector<int64_t> h_span_start;
 };
 
@@ -330,13 +330,16 @@ __device__ __forceinline__ int assoc_one(const AssocArgs &a, int64_t i, int *spl
 
 constexpr int AS_THREADS = 256;
 
-__global__ void __launch_bounds__(AS_THREADS) k_assoc_count(const AssocArgs a, uint32_t *__restrict__ block_cnt) {
+// pass 1: decide every event once, remember the decision in a 16-bit tag (0 = no residual, else spline<<8 | circle+1)
+__global__ void __launch_bounds__(AS_THREADS) k_assoc_count(const AssocArgs a, uint16_t *__restrict__ tag,
+                                                           uint32_t *__restrict__ block_cnt) {
     __shared__ uint32_t ws[33];
     const int64_t i = (int64_t) blockIdx.x * AS_THREADS + threadIdx.x;
-    int s;
-    const bool ok = i < a.n_ev && assoc_one(a, i, &s) >= 0;
+    int s = 0;
+    const int bi = i < a.n_ev ? assoc_one(a, i, &s) : -1;
+    if (i < a.n_ev) tag[i] = bi >= 0 ? (uint16_t) ((s << 8) | (bi + 1)) : (uint16_t) 0;
     uint32_t tot;
-    block_excl_scan(ok ? 1u : 0u, ws, &tot);
+    block_excl_scan(bi >= 0 ? 1u : 0u, ws, &tot);
     if (threadIdx.x == 0) block_cnt[blockIdx.x] = tot;
 }
 
@@ -358,21 +361,22 @@ __global__ void k_scan_blocks(uint32_t *cnt, int n, int64_t *off, int64_t *total
     if (threadIdx.x == 0) *total = run;
 }
 
-__global__ void __launch_bounds__(AS_THREADS) k_assoc_write(const AssocArgs a, const int64_t *__restrict__ block_off,
+// pass 2: ordered compaction of the tagged events into residual records (pure streaming)
+__global__ void __launch_bounds__(AS_THREADS) k_assoc_write(const AssocArgs a, const uint16_t *__restrict__ tag,
+                                                           const int64_t *__restrict__ block_off,
                                                            double *__restrict__ obs, double *__restrict__ lm,
                                                            double *__restrict__ tt, int *__restrict__ spl,
                                                            int64_t *__restrict__ sel_event, int *__restrict__ sel_circle) {
     __shared__ uint32_t ws[33];
     const int64_t i = (int64_t) blockIdx.x * AS_THREADS + threadIdx.x;
-    int s = 0;
-    const int bi = i < a.n_ev ? assoc_one(a, i, &s) : -1;
+    const uint32_t tg = i < a.n_ev ? tag[i] : 0u;
     uint32_t tot;
-    const uint32_t ex = block_excl_scan(bi >= 0 ? 1u : 0u, ws, &tot);
-    if (bi >= 0) {
+    const uint32_t ex = block_excl_scan(tg ? 1u : 0u, ws, &tot);
+    if (tg) {
+        const int bi = (int) (tg & 0xFF) - 1, s = (int) (tg >> 8);
         const int64_t k = block_off[blockIdx.x] + ex;
         const uint32_t e = a.ev_xyp[i];
-        obs[2 * k] = (double) ECB_PIX_X(e);
-        obs[2 * k + 1] = (double) ECB_PIX_Y(e);
+        reinterpret_cast<double2 *>(obs)[k] = make_double2((double) ECB_PIX_X(e), (double) ECB_PIX_Y(e));
         lm[3 * k] = a.lm_tab[3 * bi];
         lm[3 * k + 1] = a.lm_tab[3 * bi + 1];
         lm[3 * k + 2] = a.lm_tab[3 * bi + 2];
@@ -454,7 +458,7 @@ void ecb_cost_free(ecb_ctx *ctx) {
     CostState *st = (CostState *) ctx->cost;
     DevBuf *bufs[] = {&st->d_knots, &st->d_knot_off, &st->d_ncp, &st->d_cp_off, &st->d_span_off, &st->obs, &st->lm, &st->tt,
                       &st->spl, &st->basis, &st->cp0, &st->span, &st->span_start, &st->items, &st->part, &st->out, &st->params,
-                      &st->cost_part, &st->flags, &st->ev_flag, &st->ev_cnt, &st->kf_t, &st->kf_circ, &st->lm_tab,
+                      &st->cost_part, &st->flags, &st->ev_flag, &st->ev_cnt, &st->ev_tag, &st->kf_t, &st->kf_circ, &st->lm_tab,
                       &st->sel_event, &st->sel_circle};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -548,7 +552,9 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if ((rc = ecb_reserve(ctx, st->kf_t, (size_t) n_keyframes * 8))) return rc;
     if ((rc = ecb_reserve(ctx, st->kf_circ, (size_t) n_keyframes * n_circles * 24))) return rc;
     if ((rc = ecb_reserve(ctx, st->lm_tab, (size_t) n_circles * 24))) return rc;
+    if (n_circles > 254 || st->n_splines > 255) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "more than 254 circles or 255 spline segments");
     if ((rc = ecb_reserve(ctx, st->ev_cnt, (size_t) nb * 4 + 16))) return rc;
+    if ((rc = ecb_reserve(ctx, st->ev_tag, (size_t) n * 2 + 16))) return rc;
     if ((rc = ecb_reserve(ctx, st->ev_flag, (size_t) nb * 8 + 16))) return rc;
     ECB_CUDA(ctx, cudaMemcpyAsync(st->kf_t.p, kf_time, (size_t) n_keyframes * 8, cudaMemcpyHostToDevice, ctx->stream));
     ECB_CUDA(ctx, cudaMemcpyAsync(st->kf_circ.p, kf_circles, (size_t) n_keyframes * n_circles * 24, cudaMemcpyHostToDevice, ctx->stream));
@@ -568,7 +574,7 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     a.n_circ = n_circles;
     a.gate2 = 5 * motion_time_step * 5 * motion_time_step;  // EventCalibSpline.cpp:168
     ECB_PROF_BEGIN(ctx, ECB_STAGE_ASSOC);
-    k_assoc_count<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (uint32_t *) st->ev_cnt.p);
+    k_assoc_count<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (uint16_t *) st->ev_tag.p, (uint32_t *) st->ev_cnt.p);
     ECB_LAUNCHED(ctx);
     int64_t *d_total = (int64_t *) st->ev_flag.p + nb;
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>((uint32_t *) st->ev_cnt.p, nb, (int64_t *) st->ev_flag.p, d_total);
@@ -583,7 +589,7 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if ((rc = ecb_reserve(ctx, st->spl, nn * 4))) return rc;
     if ((rc = ecb_reserve(ctx, st->sel_event, nn * 8))) return rc;
     if ((rc = ecb_reserve(ctx, st->sel_circle, nn * 4))) return rc;
-    k_assoc_write<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (const int64_t *) st->ev_flag.p, (double *) st->obs.p, (double *) st->lm.p,
+    k_assoc_write<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (const uint16_t *) st->ev_tag.p, (const int64_t *) st->ev_flag.p, (double *) st->obs.p, (double *) st->lm.p,
                                                       (double *) st->tt.p, (int *) st->spl.p, (int64_t *) st->sel_event.p,
                                                       (int *) st->sel_circle.p);
     ECB_LAUNCHED(ctx);

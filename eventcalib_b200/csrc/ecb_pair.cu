@@ -75,10 +75,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // sum over the members of |‖p-c‖ - r|   (CirclesEventFrame.cpp:209-214,300-305)
+// DIRECT: `mem` already holds the members' packed pixels (staged in shared memory); else it holds pids into `pts`
+template <bool DIRECT>
 __device__ double warp_abs_dev(const uint32_t *pts, const uint32_t *mem, int sz, double cx, double cy, double r) {
     double s = 0;
     for (int i = threadIdx.x & 31; i < sz; i += 32) {
-        const uint32_t p = pts[mem[i]];
+        const uint32_t p = DIRECT ? mem[i] : pts[mem[i]];
         const double dx = (double) ECB_PIX_X(p) - cx, dy = (double) ECB_PIX_Y(p) - cy;
         s += fabs(sqrt(dx * dx + dy * dy) - r);
     }
@@ -108,7 +110,9 @@ __device__ void warp_knn(const int *mx, const int *my, int n, int qx, int qy, in
     }
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(PAIR_THREADS) k_pair(const PairArgs a) {
+    extern __shared__ __align__(16) uint32_t sm_pix[];  // DIRECT: member pixels of both polarities
     __shared__ int mx[2][ECB_MAXK_LIMIT], my[2][ECB_MAXK_LIMIT];
     __shared__ int acc_ni[ECB_MAXK_LIMIT];
     __shared__ double acc_c[ECB_MAXK_LIMIT][3];
@@ -131,9 +135,20 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair(const PairArgs a) {
             acc_ni[i] = -1;
         }
         __syncthreads();
-        const bool enough = dn.n > 0 && dp.n > 0 && (uint32_t) nkp >= a.rows_cols && (uint32_t) nkn >= a.rows_cols;
+        const bool enough0 = dn.n > 0 && dp.n > 0 && (uint32_t) nkp >= a.rows_cols && (uint32_t) nkn >= a.rows_cols;
+        const bool enough = enough0;
         const uint32_t *ptsP = a.pts[1] + dp.off, *ptsN = a.pts[0] + dn.off;
         const uint32_t *memP = a.kmem[1] + dp.off, *memN = a.kmem[0] + dn.off;
+        if (DIRECT && enough0) {
+            // stage the kept clusters' member pixels once (coalesced list read, gathered pixel read), then every
+            // fit-error loop runs out of shared memory
+            const int totP = nkp ? kp[nkp - 1].mem_off + kp[nkp - 1].size : 0, totN = nkn ? kn[nkn - 1].mem_off + kn[nkn - 1].size : 0;
+            for (int i = tid; i < totN; i += PAIR_THREADS) sm_pix[i] = ptsN[memN[i]];
+            for (int i = tid; i < totP; i += PAIR_THREADS) sm_pix[a.smem_cap + i] = ptsP[memP[i]];
+            memN = sm_pix;
+            memP = sm_pix + a.smem_cap;
+            __syncthreads();
+        }
         const double gate = 4 * a.rthr * a.rthr;
         if (enough) {
             for (int pi = wid; pi < nkp; pi += nwarp) {
@@ -149,9 +164,9 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair(const PairArgs a) {
                     const double cx = (px + qx) / 2, cy = (py + qy) / 2;
                     const double ddx = px - qx, ddy = py - qy;
                     const double r = sqrt(ddx * ddx + ddy * ddy) / 2;
-                    double e = warp_abs_dev(ptsP, memP + kp[pi].mem_off, kp[pi].size, cx, cy, r);
+                    double e = warp_abs_dev<DIRECT>(ptsP, memP + kp[pi].mem_off, kp[pi].size, cx, cy, r);
                     // the reference accumulates + members then - members into one sum
-                    e += warp_abs_dev(ptsN, memN + kn[n0].mem_off, kn[n0].size, cx, cy, r);
+                    e += warp_abs_dev<DIRECT>(ptsN, memN + kn[n0].mem_off, kn[n0].size, cx, cy, r);
                     e /= (double) (kp[pi].size + kn[n0].size) * r;
                     if (e < 10 / r && lane == 0) {
                         acc_ni[pi] = n0;
@@ -178,8 +193,8 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair(const PairArgs a) {
                         const double ddx = (double) mx[1][p] - (double) mx[0][n], ddy = (double) my[1][p] - (double) my[0][n];
                         const double approx = sqrt(ddx * ddx + ddy * ddy) / 2;
                         if (r > a.rthr || r > 2 * approx) return DBL_MAX;
-                        double e = warp_abs_dev(ptsP, memP + kp[p].mem_off, kp[p].size, cx, cy, r);
-                        e += warp_abs_dev(ptsN, memN + kn[n].mem_off, kn[n].size, cx, cy, r);
+                        double e = warp_abs_dev<DIRECT>(ptsP, memP + kp[p].mem_off, kp[p].size, cx, cy, r);
+                        e += warp_abs_dev<DIRECT>(ptsN, memN + kn[n].mem_off, kn[n].size, cx, cy, r);
                         return e / ((double) (kp[p].size + kn[n].size) * r);
                     };
                     for (int j = 0; j < real; ++j) ferr[j] = fit_pair(pi, nidx[j], fcx[j], fcy[j], fr[j]);
@@ -282,8 +297,16 @@ __global__ void k_fit(const double *__restrict__ xy, const int64_t *__restrict__
 int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     if (a.n_win <= 0) return ECB_OK;
     int grid = a.n_win < ctx->sm_count * 8 ? a.n_win : ctx->sm_count * 8;
+    // stage member pixels in shared memory when both polarities of the largest window fit
+    const size_t smem = (size_t) 2 * a.smem_cap * 4;
+    const bool direct = a.smem_cap > 0 && smem <= 96 * 1024;
     ECB_PROF_BEGIN(ctx, ECB_STAGE_PAIR);
-    k_pair<<<grid, PAIR_THREADS, 0, ctx->stream>>>(a);
+    if (direct) {
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        k_pair<true><<<grid, PAIR_THREADS, smem, ctx->stream>>>(a);
+    } else {
+        k_pair<false><<<grid, PAIR_THREADS, 0, ctx->stream>>>(a);
+    }
     ECB_PROF_END(ctx, ECB_STAGE_PAIR);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_pair launch");

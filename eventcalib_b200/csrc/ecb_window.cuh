@@ -23,6 +23,7 @@ struct PairArgs {
     ecb_window_summary *summary;
     double *cand;             // [n_win][cand_stride][5]
     int n_win, max_k, cand_stride;
+    int smem_cap;             // max points of any problem (capacity of the shared-memory member staging), 0 = off
     int fit_circle, knn_num;
     uint32_t rows_cols;
     double rthr;
