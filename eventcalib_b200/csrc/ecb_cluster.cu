@@ -28,11 +28,11 @@ template <typename RankT>
 struct Smem {
     uint32_t *U, *C;
     RankT *wrank;
-    uint32_t *r_pix, *r_por, *r_lab, *r_kd, *r_st;
+    uint32_t *r_pix, *r_lab, *r_kd, *r_st;
     uint8_t *r_flag;
 };
 
-constexpr int KD_PT = 6;  // points per thread kept in registers during the kd rounds
+constexpr int KD_PT = 3;  // points per thread kept in registers during the kd rounds
 
 __device__ __forceinline__ uint32_t find_root(volatile uint32_t *parent, uint32_t a) {
     uint32_t p = parent[a];
@@ -77,11 +77,10 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                         : (a.gscratch + (size_t) blockIdx.x * a.gscratch_stride);
     const int NC = a.n_cap;
     s.r_pix = arr;
-    s.r_por = arr + NC;
-    s.r_lab = arr + 2 * NC;
-    s.r_kd = arr + 3 * NC;  // 2*NC words
-    s.r_st = arr + 5 * NC;
-    s.r_flag = reinterpret_cast<uint8_t *>(arr + 6 * NC);  // NC bytes, indexed by rank: kd tie flags (bit0 x, bit1 y)
+    s.r_lab = arr + NC;
+    s.r_kd = arr + 2 * NC;  // 2*NC words
+    s.r_st = arr + 4 * NC;
+    s.r_flag = reinterpret_cast<uint8_t *>(arr + 5 * NC);  // NC bytes, indexed by rank: kd tie flags (bit0 x, bit1 y)
 
     for (;;) {
         __syncthreads();
@@ -138,11 +137,6 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
             const int w = y * PW + (x >> 5);
             return (uint32_t) s.wrank[w] + __popc(s.U[w] & ((1u << (x & 31)) - 1u));
         };
-        // ---- 3. rank -> pid ----------------------------------------------------------------------
-        for (int pid = tid; pid < n; pid += nthr) {
-            uint32_t loc = s.r_pix[pid];
-            if (loc != ECB_NONE) s.r_por[rank_of(loc & 0xFFFF, loc >> 16)] = pid;
-        }
         // ---- 4. kd insertion-order emulation -> tie flags ---------------------------------------
         // NOTE: the root is pid 0 like kd_insert's first insertion.
         uint32_t *child = s.r_kd;
@@ -248,35 +242,42 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         // (the tie rule only concerns distance exactly eps), so it suffices to unite q with the FIRST pixel of every
         // run (gap < eps) inside the row segment; the run itself is chained by its own dy = 0 unions.
         const int gap = (ei > 0 ? ei : E + 1) - 1;  // pixels whose distance is <= gap are unconditionally adjacent in-row
-        for (int pid = tid; pid < n; pid += nthr) {
-            uint32_t loc = s.r_pix[pid];
+        // work item = (point, row offset): <= 2 unions each, so lanes of a warp stay balanced
+        for (int item = tid; item < n * (E + 1); item += nthr) {
+            const int pid = item / (E + 1), dy = item - pid * (E + 1);
+            const uint32_t loc = s.r_pix[pid];
             if (loc == ECB_NONE) continue;
             const int x = loc & 0xFFFF, y = loc >> 16;
             if (!test_bit(s.C + y * PW, x)) continue;
+            const int w = a.halfw[dy];
+            const int xs = dy == 0 ? x + 1 : x - w;
+            const int len = dy == 0 ? w : 2 * w + 1;
+            if (len <= 0) continue;
+            uint32_t bits = row_bits(s.C + (y + dy) * PW, xs, len);
+            if (!bits) continue;
+            if (dy == 0) {
+                bits &= (uint32_t) -(int32_t) bits;  // nearest right neighbour only; farther ones chain through it
+            } else {
+                // lower = OR of (bits << 1 .. bits << gap), by doubling; the first pixel of every run survives
+                uint32_t sm = bits;  // OR of shifts 0..k
+                for (int k = 0; k < gap - 1;) {
+                    const int add = min(k + 1, gap - 1 - k);
+                    sm |= sm << add;
+                    k += add;
+                }
+                const uint32_t lower = gap > 0 ? sm << 1 : 0u;
+                bits &= ~lower;
+            }
             const uint32_t rq = rank_of(x, y);
-            for (int dy = 0; dy <= E; ++dy) {
-                const int w = a.halfw[dy];
-                const int xs = dy == 0 ? x + 1 : x - w;
-                const int len = dy == 0 ? w : 2 * w + 1;
-                if (len <= 0) continue;
-                uint32_t bits = row_bits(s.C + (y + dy) * PW, xs, len);
-                if (dy == 0) {
-                    bits &= (uint32_t) -(int32_t) bits;  // nearest right neighbour only; farther ones chain through it
-                } else {
-                    uint32_t lower = 0;
-                    for (int g = 1; g <= gap; ++g) lower |= bits << g;
-                    bits &= ~lower;  // first pixel of every run
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int nx = xs + b, ny = y + dy;
+                if (ei > 0) {  // q -> p missed by the kd query: the pair is a one-way edge p -> q (handled in 7)
+                    if (dy == 0 && nx - x == ei && (flag_of(nx, ny) & 1u)) continue;
+                    if (dy == ei && nx == x && (flag_of(nx, ny) & 2u)) continue;
                 }
-                while (bits) {
-                    const int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int nx = xs + b, ny = y + dy;
-                    if (ei > 0) {  // q -> p missed by the kd query: the pair is a one-way edge p -> q (handled in 7)
-                        if (dy == 0 && nx - x == ei && (flag_of(nx, ny) & 1u)) continue;
-                        if (dy == ei && nx == x && (flag_of(nx, ny) & 2u)) continue;
-                    }
-                    unite(parent, rq, rank_of(nx, ny));
-                }
+                unite(parent, rq, rank_of(nx, ny));
             }
         }
         __syncthreads();
@@ -368,8 +369,8 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         }
         __syncthreads();
         // ---- 9. cluster sizes, size filter, member lists, moments, medians ----------------------------
-        uint32_t *csize = s.r_kd, *keptidx = s.r_kd + NC;
         const int nc = (int) n_clusters;
+        uint32_t *csize = s.r_kd, *keptidx = s.r_kd + nc;  // nc <= n <= NC; the rest of r_kd is scratch
         for (int i = tid; i < nc; i += nthr) csize[i] = 0;
         __syncthreads();
         for (int pid = tid; pid < n; pid += nthr) {
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         if (n_kept > 0) {
             // Ordered member lists (ascending pid inside every cluster) without scanning all points once per cluster:
             // each warp owns a contiguous pid range; pass A counts its members per kept cluster, a scan over the warps
-            // turns the counts into start positions, pass B places.  Counters live in the (now dead) rank->pid array.
+            // turns the counts into start positions, pass B places.  Counters live in the free tail of r_kd.
             const int L = (((n + nwarp - 1) / nwarp) + 31) & ~31;  // pids per warp, multiple of 32
             const int p0 = wid * L, p1 = min(n, p0 + L);
             auto kept_of = [&](int pid) -> int {
@@ -426,8 +427,8 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 const uint32_t ki = keptidx[lab];
                 return (ki != ECB_NONE && ki < n_kept) ? (int) ki : -1;
             };
-            if ((int) n_kept * nwarp <= NC) {
-                uint32_t *cnt = s.r_por;
+            if ((int) n_kept * nwarp <= 2 * NC - 2 * nc) {
+                uint32_t *cnt = s.r_kd + 2 * nc;
                 for (int i = tid; i < (int) n_kept * nwarp; i += nthr) cnt[i] = 0;
                 __syncthreads();
                 uint32_t *mycnt = cnt + wid * n_kept;
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
 size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, bool arrays_in_smem, bool rank32) {
     size_t NW = (size_t) PW * PH;
     size_t b = 2 * NW * 4 + ((NW * (rank32 ? 4 : 2) + 3) / 4) * 4;
-    if (arrays_in_smem) b += (size_t) 6 * n_cap * 4 + (((size_t) n_cap + 3) / 4) * 4;
+    if (arrays_in_smem) b += (size_t) 5 * n_cap * 4 + (((size_t) n_cap + 3) / 4) * 4;
     return b;
 }
 
@@ -578,7 +579,7 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_prob) grid = a.n_prob;
     if (!a.arrays_in_smem) {
-        a.gscratch_stride = (size_t) 6 * a.n_cap + (a.n_cap + 3) / 4;
+        a.gscratch_stride = (size_t) 5 * a.n_cap + (a.n_cap + 3) / 4;
         int rc = ecb_reserve(ctx, ctx->scratch, (size_t) grid * a.gscratch_stride * 4);
         if (rc) return rc;
         a.gscratch = (uint32_t *) ctx->scratch.p;
