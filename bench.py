@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--events", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--slices", type=int, default=4, help="time slices (contexts/streams/host threads) of the e2e pipeline")
     ap.add_argument("--lm-iters", type=int, default=50, help="LM iterations of the C4 side measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -274,14 +275,60 @@ def main():
         ctx.frontend_run(win, prm)
         residual_eval()
 
+    # ---- end to end from host buffers: S time slices, each with its own context / stream / host thread, so the H2D copy
+    # of slice k+1 overlaps the kernels of slice k (the C ABI is re-entrant per context; ctypes releases the GIL).
+    from concurrent.futures import ThreadPoolExecutor
+    from eventcalib_b200 import sharding
+    S = max(1, args.slices)
+    slices = []
+    for j in range(S):
+        w0, w1 = sharding.window_shard(len(win), j, S)
+        lo = int(np.searchsorted(ev["t"], win[w0, 0], side="left")) if j > 0 else 0
+        slices.append(dict(w0=w0, w1=w1, lo=lo))
+    for j in range(S):
+        sl = slices[j]
+        sl["hi"] = slices[j + 1]["lo"] if j + 1 < S else n
+        sl["ctx"] = ecb.Context(local)          # own non-blocking stream
+        sl["ctx"].set_sensor(WIDTH, HEIGHT)
+        sl["ctx"].cost_setup(n_cp, [sg["knots"] for sg in segs], mine["radius"], mine["huber"])
+        ta, tb = ev["t"][sl["lo"]], ev["t"][sl["hi"] - 1]
+        m = (mine["kf_t"] > ta - 6 * mine["step"]) & (mine["kf_t"] < tb + 6 * mine["step"])
+        sl["kf_t"], sl["circles"] = mine["kf_t"][m].copy(), mine["circles"][m].copy()
+    d_parts = torch.zeros(S, lay["out_doubles"], dtype=torch.float64, device="cuda")
+    pool = ThreadPoolExecutor(S)
+
+    trace = os.environ.get("ECB_BENCH_TRACE")
+    t_origin = [0.0]
+
+    def slice_work(j):
+        sl = slices[j]
+        c = sl["ctx"]
+        tm = [time.perf_counter()]
+        c.load_events_ptr(pinned.data_ptr() + sl["lo"] * 25, sl["hi"] - sl["lo"])
+        tm.append(time.perf_counter())
+        c.frontend_run(win[sl["w0"]:sl["w1"]], prm)
+        tm.append(time.perf_counter())
+        c.cost_associate(sl["kf_t"], sl["circles"], mine["landmarks"], mine["step"])
+        c.cost_normal_eq(intr, rot, trans, d_out=d_parts[j].data_ptr(), host=False)
+        cost = c.cost_eval(intr, rot, trans)       # synchronises the slice's stream
+        tm.append(time.perf_counter())
+        out = c.summary(), c.candidates(48), cost
+        tm.append(time.perf_counter())
+        if trace:
+            sys.stderr.write("slice %d: start %.2f load_end %.2f frontend_end %.2f cost_end %.2f fetch_end %.2f ms\n" % (
+                (j,) + tuple((x - t_origin[0]) * 1e3 for x in tm)))
+        return out
+
     def step_e2e():
-        ctx.load_events_ptr(pinned.data_ptr(), n)
-        ctx.frontend_run(win, prm)
-        residual_eval()
-        s = ctx.summary()
-        c = ctx.candidates(48)
+        t_origin[0] = time.perf_counter()
+        res = list(pool.map(slice_work, range(S)))
+        torch.sum(d_parts, dim=0, out=d_ne)
+        if world > 1:
+            dist.all_reduce(d_ne)
+            d_cost[0] = sum(r[2] for r in res)
+            dist.all_reduce(d_cost)
         h_ne.copy_(d_ne, non_blocking=False)
-        return s, c
+        return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
 
     def barrier():
         if world > 1:
@@ -420,7 +467,8 @@ def main():
                            "found_circles_per_window": float(s["n_candidates"].mean())},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h)}}
+                        "d2h_bytes_per_step": int(d2h), "pipeline": "%d time slices, one context/stream/host thread each "
+                        "(H2D of slice k+1 overlaps the kernels of slice k)" % S}}
         if lm_info:
             line["lm"] = lm_info
         if not args.no_cpu and world == 1:
@@ -431,6 +479,9 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    pool.shutdown()
+    for sl in slices:
+        sl["ctx"].close()
     ctx.close()
 
 

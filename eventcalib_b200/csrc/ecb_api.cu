@@ -43,8 +43,25 @@ static int reserve_pinned(ecb_ctx *ctx, size_t bytes) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     ctx->pinned = nullptr;
     ctx->pinned_cap = 0;
+    bytes += bytes / 4 + 4096;
     ECB_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
     ctx->pinned_cap = bytes;
+    return ECB_OK;
+}
+
+// Device -> host copy + stream synchronisation through the context's pinned staging buffer: a cudaMemcpyAsync into
+// pageable memory takes the driver's slow staged path and serialises against other threads' transfers.
+int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "stream synchronize");
+    if (bytes > ((size_t) 256 << 20)) {
+        ECB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "device to host copy");
+    }
+    int rc = reserve_pinned(ctx, bytes);
+    if (rc) return rc;
+    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(dst, ctx->pinned, bytes);
     return ECB_OK;
 }
 
@@ -151,8 +168,7 @@ static int unpack_events(ecb_ctx *ctx, const void *d_raw, int64_t n) {
     ECB_CUDA(ctx, cudaMemsetAsync(ctx->ev_flag.p, 0, 16, ctx->stream));
     if ((rc = ecb_launch_ingest(ctx, d_raw, n))) return rc;
     uint32_t flag = 0;
-    ECB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->ev_flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ecb_d2h(ctx, &flag, ctx->ev_flag.p, 4))) return rc;
     ctx->n_events = n;
     if (flag & 2u) {
         ctx->n_events = 0;
@@ -225,8 +241,7 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     if ((rc = ecb_launch_bounds(ctx, (const double *) ctx->win_t.p, n_win, (int64_t *) ctx->win_lohi.p))) return rc;
     ctx->h_lohi.resize((size_t) 2 * n_win);
     ctx->h_ptoff.resize((size_t) n_win);
-    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->h_lohi.data(), ctx->win_lohi.p, (size_t) n_win * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ecb_d2h(ctx, ctx->h_lohi.data(), ctx->win_lohi.p, (size_t) n_win * 16))) return rc;
     int64_t total = 0, max_cnt = 0;
     for (int w = 0; w < n_win; ++w) {
         int64_t cnt = std::max<int64_t>(0, ctx->h_lohi[2 * w + 1] - ctx->h_lohi[2 * w]);
@@ -269,8 +284,7 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     ECB_CUDA(ctx, cudaMemsetAsync(ctx->status.p, 0, 64, ctx->stream));
     if ((rc = ecb_launch_window(ctx, wa))) return rc;
     uint32_t max_n = 0;
-    ECB_CUDA(ctx, cudaMemcpyAsync(&max_n, wa.max_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ecb_d2h(ctx, &max_n, wa.max_n, 4))) return rc;
 
     ca.prob = (const ProbDesc *) ctx->db_dims.p;
     ca.n_prob = 2 * n_win;
@@ -319,9 +333,7 @@ int ecb_frontend_summary(ecb_ctx *ctx, ecb_window_summary *out, int n_win) {
     if (!ctx || !out) return ECB_ERR_ARG;
     if (n_win > ctx->n_win) n_win = ctx->n_win;
     cudaSetDevice(ctx->device);
-    ECB_CUDA(ctx, cudaMemcpyAsync(out, ctx->summary.p, (size_t) n_win * sizeof(ecb_window_summary), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "summary copy");
+    return ecb_d2h(ctx, out, ctx->summary.p, (size_t) n_win * sizeof(ecb_window_summary));
 }
 
 int64_t ecb_frontend_total_points(ecb_ctx *ctx, int polarity) {
@@ -353,9 +365,15 @@ int ecb_frontend_candidates(ecb_ctx *ctx, double *out, int max_cand) {
     if (ctx->n_win <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no front-end results");
     cudaSetDevice(ctx->device);
     const int k = std::min(max_cand, ctx->cand_stride);
-    ECB_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t) max_cand * 40, ctx->cand.p, (size_t) ctx->cand_stride * 40, (size_t) k * 40,
+    const size_t bytes = (size_t) ctx->n_win * k * 40;
+    int rc = reserve_pinned(ctx, bytes);
+    if (rc) return rc;
+    ECB_CUDA(ctx, cudaMemcpy2DAsync(ctx->pinned, (size_t) k * 40, ctx->cand.p, (size_t) ctx->cand_stride * 40, (size_t) k * 40,
                                     (size_t) ctx->n_win, cudaMemcpyDeviceToHost, ctx->stream));
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "candidate copy");
+    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int w = 0; w < ctx->n_win; ++w)
+        memcpy(out + (size_t) w * max_cand * 5, (const char *) ctx->pinned + (size_t) w * k * 40, (size_t) k * 40);
+    return ECB_OK;
 }
 
 int ecb_frontend_clusters(ecb_ctx *ctx, int window, int polarity, int32_t *raw_id, int32_t *size, int32_t *median_pid,

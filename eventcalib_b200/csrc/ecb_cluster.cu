@@ -237,27 +237,47 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
             glabel[r] = ECB_NONE;
         }
         __syncthreads();
-        // ---- 6. union-find over mutual core edges -------------------------------------------------------
-        // Half-plane enumeration.  Inside one bitmap row, core pixels less than eps apart are always mutually adjacent
-        // (the tie rule only concerns distance exactly eps), so it suffices to unite q with the FIRST pixel of every
-        // run (gap < eps) inside the row segment; the run itself is chained by its own dy = 0 unions.
+        // ---- 6. connected components over mutual core edges ---------------------------------------------
+        // Inside one bitmap row, core pixels less than eps apart are always mutually adjacent (the tie rule only concerns
+        // distance exactly eps).  6a: every core pixel points straight at the first pixel of its in-row run (gaps <= gap),
+        // found with bit scans — no atomics, depth-1 trees.  6b/6c: runs are then united across rows (and across an
+        // exact-eps in-row gap) with a lock-free union-find whose chains start at run heads.
         const int gap = (ei > 0 ? ei : E + 1) - 1;  // pixels whose distance is <= gap are unconditionally adjacent in-row
-        // work item = (point, row offset): <= 2 unions each, so lanes of a warp stay balanced
-        for (int item = tid; item < n * (E + 1); item += nthr) {
-            const int pid = item / (E + 1), dy = item - pid * (E + 1);
+        for (int pid = tid; pid < n; pid += nthr) {
             const uint32_t loc = s.r_pix[pid];
             if (loc == ECB_NONE) continue;
             const int x = loc & 0xFFFF, y = loc >> 16;
             if (!test_bit(s.C + y * PW, x)) continue;
+            int p = x;
+            if (gap > 0)
+                for (;;) {  // hop to the farthest core pixel within `gap` to the left until there is none
+                    const uint32_t wbits = row_bits(s.C + y * PW, p - gap, gap);
+                    if (!wbits) break;
+                    p = p - gap + (__ffs(wbits) - 1);
+                }
+            if (p != x) parent[rank_of(x, y)] = rank_of(p, y);
+        }
+        __syncthreads();
+        // work item = (core pixel, row offset dy): dy = 0 handles the exact-eps in-row link of run heads, dy >= 1 unites the
+        // pixel's run with the first pixel of every run inside the eps-disc segment of row y + dy
+        for (int dy = 0; dy <= E; ++dy)
+        for (int pid = tid; pid < n; pid += nthr) {
+            const uint32_t loc = s.r_pix[pid];
+            if (loc == ECB_NONE) continue;
+            const int x = loc & 0xFFFF, y = loc >> 16;
+            if (!test_bit(s.C + y * PW, x)) continue;
+            if (dy == 0) {
+                // q = p - eps*e_x with nothing in between: mutual unless the kd query misses q -> p (FX(p))
+                if (ei > 0 && test_bit(s.C + y * PW, x + ei) && !row_bits(s.C + y * PW, x + 1, ei - 1) &&
+                    !(flag_of(x + ei, y) & 1u))
+                    unite(parent, rank_of(x, y), rank_of(x + ei, y));
+                continue;
+            }
             const int w = a.halfw[dy];
-            const int xs = dy == 0 ? x + 1 : x - w;
-            const int len = dy == 0 ? w : 2 * w + 1;
-            if (len <= 0) continue;
+            const int xs = x - w, len = 2 * w + 1;
             uint32_t bits = row_bits(s.C + (y + dy) * PW, xs, len);
             if (!bits) continue;
-            if (dy == 0) {
-                bits &= (uint32_t) -(int32_t) bits;  // nearest right neighbour only; farther ones chain through it
-            } else {
+            {
                 // lower = OR of (bits << 1 .. bits << gap), by doubling; the first pixel of every run survives
                 uint32_t sm = bits;  // OR of shifts 0..k
                 for (int k = 0; k < gap - 1;) {
@@ -273,10 +293,8 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
                 const int nx = xs + b, ny = y + dy;
-                if (ei > 0) {  // q -> p missed by the kd query: the pair is a one-way edge p -> q (handled in 7)
-                    if (dy == 0 && nx - x == ei && (flag_of(nx, ny) & 1u)) continue;
-                    if (dy == ei && nx == x && (flag_of(nx, ny) & 2u)) continue;
-                }
+                // q -> p missed by the kd query: the pair is a one-way edge p -> q (handled in 7)
+                if (ei > 0 && dy == ei && nx == x && (flag_of(nx, ny) & 2u)) continue;
                 unite(parent, rq, rank_of(nx, ny));
             }
         }
@@ -484,6 +502,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
             const int base = k_off[k], sz = k_size[k];
             long long S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             int med = -1;
+            uint32_t *mnorm = s.r_kd;  // csize / keptidx are dead: squared norms of the members, same indexing as `members`
             for (int i = lane; i < sz; i += 32) {
                 const uint32_t pid = members[base + i];
                 gmem[base + i] = pid;
@@ -498,17 +517,17 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 S[6] += y * y * y;
                 S[7] += x * y * y;
                 S[8] += x * x * y;
-                // rank of (norm^2, pid) among the members
-                const unsigned long long key = ((unsigned long long) (x * x + y * y) << 32) | pid;
+                mnorm[base + i] = (uint32_t) (x * x + y * y);
+            }
+            __syncwarp();
+            for (int i = lane; i < sz; i += 32) {  // rank of (norm^2, pid) among the members; slot sz/2 is the median
+                const uint32_t ni = mnorm[base + i], pi = members[base + i];
                 int cnt = 0;
                 for (int j = 0; j < sz; ++j) {
-                    const uint32_t pj = members[base + j];
-                    const uint32_t lj = s.r_pix[pj];
-                    const long long xj = (int) (lj & 0xFFFF) - E + d.x0, yj = (int) (lj >> 16) - E + d.y0;
-                    const unsigned long long kj = ((unsigned long long) (xj * xj + yj * yj) << 32) | pj;
-                    cnt += kj < key;
+                    const uint32_t nj = mnorm[base + j], pj = members[base + j];
+                    cnt += (nj < ni) || (nj == ni && pj < pi);
                 }
-                if (cnt == sz / 2) med = (int) pid;
+                if (cnt == sz / 2) med = (int) pi;
             }
 #pragma unroll
             for (int q = 0; q < 9; ++q)
@@ -557,7 +576,9 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     if (a.n_prob <= 0) return ECB_OK;
     const bool rank32 = max_n >= 65535;
     a.n_cap = max_n < 64 ? 64 : max_n;
-    const size_t limit = (size_t) ctx->smem_optin - 9 * 1024;  // static shared + reserve
+    // static shared + reserve; also the (constant) dynamic-smem attribute value, so that concurrent launches from several
+    // host threads with different sizes cannot race on cudaFuncSetAttribute
+    const size_t limit = (size_t) ctx->smem_optin - 9 * 1024;
     size_t planes = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, false, rank32);
     if (planes > limit)
         return ecb_fail(ctx, ECB_ERR_UNSUPPORTED,
@@ -569,10 +590,10 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     if (const char *e = getenv("ECB_CL_THREADS")) threads = std::max(64, std::min(ECB_CL_THREADS, atoi(e) & ~31));
     int per_sm = 1;
     if (rank32) {
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit));
         ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint32_t>, threads, smem));
     } else {
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit));
         ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint16_t>, threads, smem));
     }
     if (per_sm < 1) per_sm = 1;

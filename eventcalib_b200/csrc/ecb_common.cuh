@@ -60,6 +60,7 @@ struct ecb_ctx {
 int ecb_fail(ecb_ctx *ctx, int code, const char *fmt, ...);
 int ecb_reserve(ecb_ctx *ctx, DevBuf &b, size_t bytes);
 int ecb_check(ecb_ctx *ctx, cudaError_t e, const char *what);
+int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes);  // pinned-staged copy + stream sync
 #define ECB_CUDA(ctx, call)                                   \
     do {                                                      \
         int _rc = ecb_check((ctx), (call), #call);            \

@@ -409,10 +409,14 @@ int prepare_records(ecb_ctx *ctx, CostState *st) {
                                                                            (int64_t *) st->span_start.p);
     ECB_LAUNCHED(ctx);
     uint32_t flag = 0;
-    ECB_CUDA(ctx, cudaMemcpyAsync(&flag, st->flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaMemcpyAsync(st->h_span_start.data(), st->span_start.p, (size_t) (st->total_spans + 1) * 8,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ECB_CUDA(ctx, cudaMemcpyAsync((int64_t *) st->span_start.p + st->total_spans + 1, st->flags.p, 4, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));  // one staged copy for both
+    {
+        std::vector<int64_t> tmp((size_t) st->total_spans + 2);
+        if ((rc = ecb_d2h(ctx, tmp.data(), st->span_start.p, tmp.size() * 8))) return rc;
+        std::copy(tmp.begin(), tmp.begin() + st->total_spans + 1, st->h_span_start.begin());
+        flag = (uint32_t) (tmp[(size_t) st->total_spans + 1] & 0xFFFFFFFF);
+    }
     if (flag & 1u) return ecb_fail(ctx, ECB_ERR_ARG, "a residual's time stamp lies outside its spline's knot range");
     if (flag & 2u) return ecb_fail(ctx, ECB_ERR_ARG, "residual records must be ordered by (spline, time)");
     // work items: chunks of <= CHUNK residuals inside one span (fixed => deterministic reduction order)
@@ -580,8 +584,7 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>((uint32_t *) st->ev_cnt.p, nb, (int64_t *) st->ev_flag.p, d_total);
     ECB_LAUNCHED(ctx);
     int64_t total = 0;
-    ECB_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ecb_d2h(ctx, &total, d_total, 8))) return rc;
     const size_t nn = (size_t) std::max<int64_t>(total, 1);
     if ((rc = ecb_reserve(ctx, st->obs, nn * 16))) return rc;
     if ((rc = ecb_reserve(ctx, st->lm, nn * 24))) return rc;
@@ -630,8 +633,7 @@ int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, 
     k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->cost_part.p, grid, 1, 0, (double *) st->cost_part.p + 4000);
     ECB_LAUNCHED(ctx);
     ECB_PROF_END(ctx, ECB_STAGE_COST);
-    ECB_CUDA(ctx, cudaMemcpyAsync(cost, (double *) st->cost_part.p + 4000, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "cost evaluation");
+    return ecb_d2h(ctx, cost, (double *) st->cost_part.p + 4000, 8);
 }
 
 // Packed result (device or host): per span s  [H 33x33 full symmetric | g 33], then [cost, 0].
@@ -661,7 +663,7 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
         a.huber = st->huber;
         a.part = (double *) st->part.p;
         const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)  /* constant */);
         int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * 2);
         ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
         k_normal_eq<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
@@ -675,9 +677,12 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
         ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);
         if ((rc = ecb_check(ctx, cudaGetLastError(), "normal equation kernels"))) return rc;
     }
-    if (h_out) ECB_CUDA(ctx, cudaMemcpyAsync(h_out, out, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cost) ECB_CUDA(ctx, cudaMemcpyAsync(cost, out + (size_t) st->total_spans * OUT_STRIDE, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (h_out || cost) return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "normal equation copy");
+    if (h_out) {
+        if ((rc = ecb_d2h(ctx, h_out, out, n_out * 8))) return rc;
+        if (cost) *cost = h_out[(size_t) st->total_spans * OUT_STRIDE];
+    } else if (cost) {
+        return ecb_d2h(ctx, cost, out + (size_t) st->total_spans * OUT_STRIDE, 8);
+    }
     return ECB_OK;
 }
 

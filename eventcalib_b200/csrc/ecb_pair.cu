@@ -302,7 +302,7 @@ int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     const bool direct = a.smem_cap > 0 && smem <= 96 * 1024;
     ECB_PROF_BEGIN(ctx, ECB_STAGE_PAIR);
     if (direct) {
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)  /* constant: race-free */);
         k_pair<true><<<grid, PAIR_THREADS, smem, ctx->stream>>>(a);
     } else {
         k_pair<false><<<grid, PAIR_THREADS, 0, ctx->stream>>>(a);

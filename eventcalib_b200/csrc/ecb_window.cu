@@ -241,7 +241,7 @@ int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a) {
     if (smem > (size_t) ctx->smem_optin - 12 * 1024)
         return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "sensor %dx%d needs %zu B of shared memory for the window bitmaps", a.W,
                         a.H, smem);
-    ECB_CUDA(ctx, cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    ECB_CUDA(ctx, cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - 12 * 1024)  /* constant: race-free */);
     int per_sm = 1;
     ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_window, WIN_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
