@@ -14,6 +14,8 @@
 //                   CUDA-core register-tiled SYRK.  tcgen05 has no f64 kind.
 //   k_reduce_*      fixed-order reduction of the per-work-item partials -> run-to-run identical J^T J / J^T r / cost
 //   k_cost          cost-only evaluation (LM step acceptance)
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -146,7 +148,8 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(NE_THREADS, 2) k_normal_eq(const NeArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) {
     extern __shared__ __align__(16) double sm_tiles[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *tile = sm_tiles + (size_t) wid * TILE_ROWS * TILE_LD;
@@ -663,10 +666,15 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
         a.huber = st->huber;
         a.part = (double *) st->part.p;
         const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)  /* constant */);
-        int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * 2);
+        static const int variant = getenv("ECB_NE_VARIANT") ? atoi(getenv("ECB_NE_VARIANT")) : 2;
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * (variant == 1 ? 1 : 2));
         ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
-        k_normal_eq<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
+        if (variant == 1)
+            k_normal_eq<1><<<grid, NE_THREADS, smem, ctx->stream>>>(a);
+        else
+            k_normal_eq<2><<<grid, NE_THREADS, smem, ctx->stream>>>(a);
         ECB_LAUNCHED(ctx);
         const int *item_start = (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
         k_reduce_spans<<<st->total_spans, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start, st->total_spans, out);

@@ -111,7 +111,7 @@ __device__ void warp_knn(const int *mx, const int *my, int n, int qx, int qy, in
 }
 
 template <bool DIRECT>
-__global__ void __launch_bounds__(PAIR_THREADS) k_pair(const PairArgs a) {
+__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) uint32_t sm_pix[];  // DIRECT: member pixels of both polarities
     __shared__ int mx[2][ECB_MAXK_LIMIT], my[2][ECB_MAXK_LIMIT];
     __shared__ int acc_ni[ECB_MAXK_LIMIT];
