@@ -26,9 +26,10 @@ namespace {
 
 constexpr int NE_THREADS = 256;            // 8 warps
 constexpr int NE_WARPS = NE_THREADS / 32;
-constexpr int TILE_ROWS = 40, TILE_LD = 36;  // [param][residual], LD % 16 == 4 -> conflict-free fragment loads
-constexpr int N_TILES = 15;                 // upper 8x8 tiles of the 40x40 Gram matrix
-constexpr int PART_STRIDE = N_TILES * 64 + 8;  // per work item: 15 tiles + cost (+pad)
+constexpr int TILE_ROWS = 34, TILE_LD = 36;  // [param | r][residual], LD % 16 == 4 -> conflict-free fragment loads
+constexpr int N_TILES = 10;                 // upper 8x8 DMMA tiles of the leading 32x32 block of the 34x34 Gram matrix
+// per work item: 10 tiles | row 32 (32) | row 33 = J^T r (32) | H[32][32], g[32], sum r^2, cost
+constexpr int PART_E32 = N_TILES * 64, PART_E33 = PART_E32 + 32, PART_SC = PART_E33 + 32, PART_STRIDE = PART_SC + 8;
 constexpr int CHUNK = 2048;                 // residuals per work item
 constexpr int OUT_STRIDE = 33 * 33 + 33;    // per span: H (full symmetric) | g
 
@@ -154,15 +155,17 @@ __global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *tile = sm_tiles + (size_t) wid * TILE_ROWS * TILE_LD;
     const int g = lane >> 2, t = lane & 3;
-    for (int r = 34; r < TILE_ROWS; ++r) tile[r * TILE_LD + lane] = 0.0;  // padding rows stay zero
     const double *intr = a.params, *rot = a.params + 9, *trans = a.params + 9 + 4 * (size_t) a.total_cp;
     const int gw = blockIdx.x * NE_WARPS + wid, nw = gridDim.x * NE_WARPS;
     for (int it = gw; it < a.n_items; it += nw) {
         const Item item = a.items[it];
+        // Gram matrix of [J | r] (34 columns): the leading 32x32 block on the FP64 tensor pipe (10 upper 8x8 tiles),
+        // rows 32 (last parameter) and 33 (r) with plain DFMAs — padding 34 -> 40 would waste 5 of 15 DMMA tiles
         double acc[N_TILES][2];
 #pragma unroll
         for (int i = 0; i < N_TILES; ++i) acc[i][0] = acc[i][1] = 0.0;
-        double cost = 0.0;
+        double e32 = 0.0, e33 = 0.0;            // lane j: sum_k J_k[32] J_k[j], sum_k r_k J_k[j]
+        double s3232 = 0.0, s3233 = 0.0, s3333 = 0.0, cost = 0.0;  // per-lane partials over its own residuals
         for (int64_t base = item.begin; base < item.end; base += 32) {
             const int64_t k = base + lane;
             double res = 0.0;
@@ -184,28 +187,54 @@ __global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) 
             }
             tile[33 * TILE_LD + lane] = res;
             __syncwarp();
+            {
+                const double x32 = tile[32 * TILE_LD + lane];
+                s3232 += x32 * x32;
+                s3233 += x32 * res;
+                s3333 += res * res;
+            }
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-                double f[5];
+                double f[4];
 #pragma unroll
-                for (int G = 0; G < 5; ++G) f[G] = tile[(8 * G + g) * TILE_LD + 4 * ks + t];
+                for (int G = 0; G < 4; ++G) f[G] = tile[(8 * G + g) * TILE_LD + 4 * ks + t];
                 int ti = 0;
 #pragma unroll
-                for (int I = 0; I < 5; ++I)
+                for (int I = 0; I < 4; ++I)
 #pragma unroll
-                    for (int Jt = I; Jt < 5; ++Jt) {
+                    for (int Jt = I; Jt < 4; ++Jt) {
                         dmma(acc[ti][0], acc[ti][1], f[I], f[Jt]);
                         ++ti;
                     }
+                // rows 32 / 33: lane j accumulates column j; residual index rotated per lane group -> conflict-free loads
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int kk = (4 * ks + q + (lane >> 2)) & 31;
+                    const double aj = tile[lane * TILE_LD + kk];
+                    e32 += aj * tile[32 * TILE_LD + kk];
+                    e33 += aj * tile[33 * TILE_LD + kk];
+                }
             }
         }
         // partial of this work item
         double *p = a.part + (size_t) it * PART_STRIDE;
 #pragma unroll
         for (int ti = 0; ti < N_TILES; ++ti) reinterpret_cast<double2 *>(p + ti * 64)[lane] = make_double2(acc[ti][0], acc[ti][1]);
+        p[PART_E32 + lane] = e32;
+        p[PART_E33 + lane] = e33;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-        if (lane == 0) p[N_TILES * 64] = cost;
+        for (int o = 16; o > 0; o >>= 1) {
+            cost += __shfl_xor_sync(0xffffffffu, cost, o);
+            s3232 += __shfl_xor_sync(0xffffffffu, s3232, o);
+            s3233 += __shfl_xor_sync(0xffffffffu, s3233, o);
+            s3333 += __shfl_xor_sync(0xffffffffu, s3333, o);
+        }
+        if (lane == 0) {
+            p[PART_SC + 0] = s3232;
+            p[PART_SC + 1] = s3233;
+            p[PART_SC + 2] = s3333;
+            p[PART_SC + 3] = cost;
+        }
     }
 }
 
@@ -216,24 +245,32 @@ __global__ void k_reduce_spans(const double *__restrict__ part, const int *__res
     if (s >= n_spans) return;
     const int i0 = item_start[s], i1 = item_start[s + 1];
     double *o = out + (size_t) s * OUT_STRIDE;
-    for (int e = threadIdx.x; e < N_TILES * 64; e += blockDim.x) {
+    for (int e = threadIdx.x; e < PART_SC + 2; e += blockDim.x) {
         double v = 0.0;
         for (int it = i0; it < i1; ++it) v += part[(size_t) it * PART_STRIDE + e];
-        const int ti = e >> 6, r = (e >> 3) & 7, c = e & 7;
-        int I = 0, rem = ti;  // tile index -> (I, Jt), I <= Jt over 5 groups
-        while (rem >= 5 - I) {
-            rem -= 5 - I;
-            ++I;
-        }
-        const int Jt = I + rem;
-        const int i = 8 * I + r, j = 8 * Jt + c;
-        if (i < 33 && j < 33) {
+        if (e < PART_E32) {
+            const int ti = e >> 6, r = (e >> 3) & 7, c = e & 7;
+            int I = 0, rem = ti;  // tile index -> (I, Jt), I <= Jt over 4 groups
+            while (rem >= 4 - I) {
+                rem -= 4 - I;
+                ++I;
+            }
+            const int Jt = I + rem;
+            const int i = 8 * I + r, j = 8 * Jt + c;
             if (I != Jt || i <= j) {
                 o[i * 33 + j] = v;
                 o[j * 33 + i] = v;
             }
-        } else if (i < 33 && j == 33) {
-            o[1089 + i] = v;
+        } else if (e < PART_E33) {
+            const int j = e - PART_E32;
+            o[32 * 33 + j] = v;
+            o[j * 33 + 32] = v;
+        } else if (e < PART_SC) {
+            o[1089 + (e - PART_E33)] = v;
+        } else if (e == PART_SC) {
+            o[32 * 33 + 32] = v;
+        } else {
+            o[1089 + 32] = v;
         }
     }
 }
@@ -333,7 +370,21 @@ __device__ __forceinline__ int assoc_one(const AssocArgs &a, int64_t i, int *spl
 
 constexpr int AS_THREADS = 256;
 
+// nearest key frame in time, ties -> the earlier frame (1-NN over the stamps, EventCalibSpline.cpp:166)
+__device__ __forceinline__ int nearest_kf(const double *kf_t, int K, double u) {
+    int lo = 0, hi = K;
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (kf_t[m] < u) lo = m + 1; else hi = m;
+    }
+    int best = lo < K ? lo : K - 1;
+    if (lo > 0 && (lo >= K || (u - kf_t[lo - 1]) <= (kf_t[lo] - u))) best = lo - 1;
+    return best;
+}
+
 // pass 1: decide every event once, remember the decision in a 16-bit tag (0 = no residual, else spline<<8 | circle+1)
+// (a shared-memory / FP32-preselect variant of this kernel measured slower on B200 — 1.45 vs 1.20 ms per 20 M events —
+//  the 36 FP64 distance evaluations per event are not the bottleneck)
 __global__ void __launch_bounds__(AS_THREADS) k_assoc_count(const AssocArgs a, uint16_t *__restrict__ tag,
                                                            uint32_t *__restrict__ block_cnt) {
     __shared__ uint32_t ws[33];
@@ -679,7 +730,7 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
         const int *item_start = (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
         k_reduce_spans<<<st->total_spans, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start, st->total_spans, out);
         ECB_LAUNCHED(ctx);
-        k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, N_TILES * 64,
+        k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, PART_SC + 3,
                                                   out + (size_t) st->total_spans * OUT_STRIDE);
         ECB_LAUNCHED(ctx);
         ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);

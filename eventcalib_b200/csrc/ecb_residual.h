@@ -37,21 +37,23 @@ ECB_HD EcbResidualOut ecb_residual(const double *intr, const double *Q, const do
     double q2 = b[0] * Q[2] + b[1] * Q[6] + b[2] * Q[10] + b[3] * Q[14];
     double q3 = b[0] * Q[3] + b[1] * Q[7] + b[2] * Q[11] + b[3] * Q[15];
     const double nz = sqrt((q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3));
-    const double inz = 1.0 / nz;
-    q0 /= nz; q1 /= nz; q2 /= nz; q3 /= nz;  // x y z w
+    const double inz = 1.0 / nz;  // one reciprocal instead of four divisions (differs from Eigen's /= by <= 1 ulp)
+    q0 *= inz; q1 *= inz; q2 *= inz; q3 *= inz;  // x y z w
     const double t0 = b[0] * T[0] + b[1] * T[3] + b[2] * T[6] + b[3] * T[9];
     const double t1 = b[0] * T[1] + b[1] * T[4] + b[2] * T[7] + b[3] * T[10];
     const double t2 = b[0] * T[2] + b[1] * T[5] + b[2] * T[8] + b[3] * T[11];
     // unDistort (:36-63)
     const double fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
-    const double x = (ou - cx) / fx, y = (ov - cy) / fy;
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    const double x = (ou - cx) * ifx, y = (ov - cy) * ify;
     const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2, r10 = r8 * r2;
     const double s = 1.0 + intr[4] * r2 + intr[5] * r4 + intr[6] * r6 + intr[7] * r8 + intr[8] * r10;
     const double X0 = x * s, X1 = y * s;  // X2 = 1
     // third row of R(q) and the ray-plane depth (:213-223)
     const double R30 = 2.0 * (q0 * q2 - q3 * q1), R31 = 2.0 * (q1 * q2 + q3 * q0), R32 = 1.0 - 2.0 * (q0 * q0 + q1 * q1);
     const double den = R30 * X0 + R31 * X1 + R32;
-    const double lam = -t2 / den;
+    const double iden = 1.0 / den;
+    const double lam = -t2 * iden;
     const double v0 = lam * X0, v1 = lam * X1, v2 = lam;
     // Xw = q * v + t  (Eigen: uv = 2 q.vec x v; v + w uv + q.vec x uv)  (:224-226)
     const double uv0 = 2.0 * (q1 * v2 - q2 * v1), uv1 = 2.0 * (q2 * v0 - q0 * v2), uv2 = 2.0 * (q0 * v1 - q1 * v0);
@@ -75,16 +77,17 @@ ECB_HD EcbResidualOut ecb_residual(const double *intr, const double *Q, const do
     o.raw = r;
     if (!WANT_JAC) return o;
 
-    const double w0 = d0 / nrm, w1 = d1 / nrm, w2 = d2 / nrm;
+    const double inrm = 1.0 / nrm;
+    const double w0 = d0 * inrm, w1 = d1 * inrm, w2 = d2 * inrm;
     // f(q, X) = rotated un-scaled ray; a = w . f(q,X)
     const double ux0 = 2.0 * (q1 - q2 * X1), ux1 = 2.0 * (q2 * X0 - q0), ux2 = 2.0 * (q0 * X1 - q1 * X0);
     const double f0 = X0 + q3 * ux0 + (q1 * ux2 - q2 * ux1);
     const double f1 = X1 + q3 * ux1 + (q2 * ux0 - q0 * ux2);
     const double f2 = 1.0 + q3 * ux2 + (q0 * ux1 - q1 * ux0);
     const double a = w0 * f0 + w1 * f1 + w2 * f2;
-    const double c1 = -a * lam / den;
+    const double c1 = -a * lam * iden;
     // translation gradient
-    const double gt0 = w0, gt1 = w1, gt2 = w2 - a / den;
+    const double gt0 = w0, gt1 = w1, gt2 = w2 - a * iden;
     // m = R^T w  (rotation by the conjugate): w + 2 qw (w x u) + 2 u x (u x w)
     const double wu0 = w1 * q2 - w2 * q1, wu1 = w2 * q0 - w0 * q2, wu2 = w0 * q1 - w1 * q0;  // w x u
     // u x (u x w) = -(u x (w x u))
@@ -96,10 +99,10 @@ ECB_HD EcbResidualOut ecb_residual(const double *intr, const double *Q, const do
     const double Gx = gX0 * (s + 2.0 * x * x * sp) + gX1 * (2.0 * x * y * sp);
     const double Gy = gX0 * (2.0 * x * y * sp) + gX1 * (s + 2.0 * y * y * sp);
     const double dot = gX0 * x + gX1 * y;
-    J[0 * JS] = sr * (-Gx * x / fx);
-    J[1 * JS] = sr * (-Gy * y / fy);
-    J[2 * JS] = sr * (-Gx / fx);
-    J[3 * JS] = sr * (-Gy / fy);
+    J[0 * JS] = sr * (-Gx * x * ifx);
+    J[1 * JS] = sr * (-Gy * y * ify);
+    J[2 * JS] = sr * (-Gx * ifx);
+    J[3 * JS] = sr * (-Gy * ify);
     J[4 * JS] = sr * dot * r2;
     J[5 * JS] = sr * dot * r4;
     J[6 * JS] = sr * dot * r6;
