@@ -56,11 +56,11 @@ def make_workload(n_events, rank):
     return ev, win
 
 
-def frontend_params():
+def frontend_params(order_mode=0):
     import eventcalib_b200 as ecb
     rthr = ecb.radius_threshold(WIDTH, HEIGHT, 9, 4, True, 5.5, 1.75)
     return ecb.default_params(eps=4.0, min_pts=2, cluster_min=5, knn_num=3, fit_circle=1, radius_threshold=rthr,
-                              rows_cols=36), rthr
+                              rows_cols=36, order_mode=order_mode), rthr
 
 
 class ClockSampler:
@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--events", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--slices", type=int, default=4, help="time slices (contexts/streams/host threads) of the e2e pipeline")
+    ap.add_argument("--order-mode", type=int, default=0, help="pid order: 0 first arrival, 1 libstdc++ unordered_set order")
     ap.add_argument("--lm-iters", type=int, default=50, help="LM iterations of the C4 side measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -241,7 +242,7 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = ecb.Context(local, stream.cuda_stream)
     ctx.set_sensor(WIDTH, HEIGHT)
-    prm, rthr = frontend_params()
+    prm, rthr = frontend_params(args.order_mode)
 
     # residual evaluation: key frames / circles / spline segments from the ground truth (host-side initialisation is
     # outside the hot path); rank r owns segment r

@@ -180,13 +180,13 @@ class Context:
     def synchronize(self):
         self._chk(self.lib.ecb_synchronize(self.h))
 
-    STAGES = ["ingest", "bounds", "window", "cluster", "pair", "assoc", "normal_eq", "cost"]
+    STAGES = ["ingest", "bounds", "window", "cluster", "pair", "assoc", "normal_eq", "cost", "order"]
 
     def set_profiling(self, on=True):
         self._chk(self.lib.ecb_set_profiling(self.h, int(on)))
 
     def stage_ms(self):
-        out = np.zeros(8, np.float32)
+        out = np.zeros(len(self.STAGES), np.float32)
         self._chk(self.lib.ecb_stage_ms(self.h, _ptr(out)))
         return dict(zip(self.STAGES, out.tolist()))
 

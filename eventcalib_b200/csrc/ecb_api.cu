@@ -61,8 +61,46 @@ int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (rc) return rc;
     ECB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->up_off = 0;  // every staged upload has been pulled
     memcpy(dst, ctx->pinned, bytes);
     return ECB_OK;
+}
+
+__global__ void k_pull(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t words, size_t bytes) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t) gridDim.x * blockDim.x)
+        dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x < (bytes & 3))
+        ((uint8_t *) dst)[words * 4 + threadIdx.x] = ((const uint8_t *) src)[words * 4 + threadIdx.x];
+}
+
+int ecb_h2d(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return ECB_OK;
+    if (bytes > ((size_t) 8 << 20) || ((uintptr_t) dst & 3u))
+        return ecb_check(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "host to device copy");
+    const size_t need = (bytes + 255) & ~(size_t) 255;
+    if (ctx->up_off + need > ctx->up_cap) {
+        // everything staged so far must have been pulled before the region is reused (or replaced)
+        ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->up_off = 0;
+        if (need > ctx->up_cap) {
+            if (ctx->up) cudaFreeHost(ctx->up);
+            ctx->up = nullptr;
+            ctx->up_cap = 0;
+            const size_t cap = std::max(need * 2, (size_t) 2 << 20);
+            ECB_CUDA(ctx, cudaHostAlloc(&ctx->up, cap, cudaHostAllocMapped));
+            ctx->up_cap = cap;
+        }
+    }
+    char *stage = (char *) ctx->up + ctx->up_off;
+    ctx->up_off += need;
+    memcpy(stage, src, bytes);
+    void *dstage = nullptr;
+    ECB_CUDA(ctx, cudaHostGetDevicePointer(&dstage, stage, 0));
+    const size_t words = bytes >> 2;
+    const int grid = (int) std::min<size_t>((words + 255) / 256 + 1, 128);
+    k_pull<<<grid, 256, 0, ctx->stream>>>((uint32_t *) dst, (const uint32_t *) dstage, words, bytes);
+    ECB_LAUNCHED(ctx);
+    return ecb_check(ctx, cudaGetLastError(), "k_pull launch");
 }
 
 extern "C" {
@@ -114,6 +152,7 @@ void ecb_ctx_destroy(ecb_ctx *c) {
         for (int j = 0; j < 2; ++j)
             if (c->pev[i][j]) cudaEventDestroy(c->pev[i][j]);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->up) cudaFreeHost(c->up);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -221,7 +260,8 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     if (!ctx || !params || (n_win > 0 && !windows) || n_win < 0) return ECB_ERR_ARG;
     if (ctx->n_events <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no events loaded");
     if (params->dbscan_min_pts < 1) return ecb_fail(ctx, ECB_FAILED, "min_pts < 1 (DBSCAN::Run returns FAILED)");
-    if (params->order_mode != 0) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "order_mode %d not available", params->order_mode);
+    if (params->order_mode != 0 && params->order_mode != 1)
+        return ecb_fail(ctx, ECB_ERR_ARG, "order_mode %d unknown", params->order_mode);
     cudaSetDevice(ctx->device);
     int rc;
     ctx->fp = *params;
@@ -237,7 +277,7 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     if ((rc = ecb_reserve(ctx, ctx->win_t, (size_t) n_win * 16))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->win_lohi, (size_t) n_win * 16))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->win_ptoff, (size_t) n_win * 8))) return rc;
-    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->win_t.p, windows, (size_t) n_win * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ecb_h2d(ctx, ctx->win_t.p, windows, (size_t) n_win * 16))) return rc;
     if ((rc = ecb_launch_bounds(ctx, (const double *) ctx->win_t.p, n_win, (int64_t *) ctx->win_lohi.p))) return rc;
     ctx->h_lohi.resize((size_t) 2 * n_win);
     ctx->h_ptoff.resize((size_t) n_win);
@@ -251,7 +291,7 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     }
     if (max_cnt > 0x3FFFFFFF) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "window with %lld events", (long long) max_cnt);
     ctx->total_points = total;
-    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->win_ptoff.p, ctx->h_ptoff.data(), (size_t) n_win * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ecb_h2d(ctx, ctx->win_ptoff.p, ctx->h_ptoff.data(), (size_t) n_win * 8))) return rc;
 
     const size_t slots = (size_t) std::max<int64_t>(total, 1);
     if ((rc = ecb_reserve(ctx, ctx->arrive, 2 * slots * 4))) return rc;
@@ -281,10 +321,24 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     wa.W = ctx->width;
     wa.H = ctx->height;
     wa.max_n = (uint32_t *) ctx->status.p + 4;
+    wa.order_mode = params->order_mode;
     ECB_CUDA(ctx, cudaMemsetAsync(ctx->status.p, 0, 64, ctx->stream));
     if ((rc = ecb_launch_window(ctx, wa))) return rc;
-    uint32_t max_n = 0;
-    if ((rc = ecb_d2h(ctx, &max_n, wa.max_n, 4))) return rc;
+    uint32_t max_nm[2] = {0, 0};
+    if ((rc = ecb_d2h(ctx, max_nm, wa.max_n, 8))) return rc;
+    const uint32_t max_n = max_nm[0];
+    if (params->order_mode == 1) {  // pid order = iteration order of the reference's unordered_sets
+        OrderArgs oa;
+        memset(&oa, 0, sizeof oa);
+        oa.prob = (const ProbDesc *) ctx->db_dims.p;
+        oa.n_prob = 2 * n_win;
+        oa.work_counter = (unsigned *) ctx->status.p;
+        for (int p = 0; p < 2; ++p) {
+            oa.arrive[p] = wa.arrive[p];
+            oa.pts[p] = wa.pts[p];
+        }
+        if ((rc = ecb_launch_order(ctx, oa, (int) max_nm[1]))) return rc;
+    }
 
     ca.prob = (const ProbDesc *) ctx->db_dims.p;
     ca.n_prob = 2 * n_win;

@@ -50,9 +50,11 @@ struct ecb_ctx {
     DevBuf db_pix, db_off, db_labels, db_hdr, db_scratch, db_dims, db_hdr_b, db_ktab, db_counter;
     // fit
     DevBuf fit_in, fit_off, fit_out;
-    // pinned staging
+    // pinned staging (device -> host), and mapped pinned staging the device pulls small uploads from
     void *pinned = nullptr;
     size_t pinned_cap = 0;
+    void *up = nullptr;
+    size_t up_cap = 0, up_off = 0;
     // cost evaluation (ecb_cost.cu)
     void *cost = nullptr;
 };
@@ -61,6 +63,9 @@ int ecb_fail(ecb_ctx *ctx, int code, const char *fmt, ...);
 int ecb_reserve(ecb_ctx *ctx, DevBuf &b, size_t bytes);
 int ecb_check(ecb_ctx *ctx, cudaError_t e, const char *what);
 int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes);  // pinned-staged copy + stream sync
+// Small host -> device upload that does not touch the copy engines: the data is staged in mapped pinned memory and a
+// kernel on the context stream pulls it over PCIe, so it cannot queue behind another context's bulk record upload.
+int ecb_h2d(ecb_ctx *ctx, void *dst, const void *src, size_t bytes);
 #define ECB_CUDA(ctx, call)                                   \
     do {                                                      \
         int _rc = ecb_check((ctx), (call), #call);            \

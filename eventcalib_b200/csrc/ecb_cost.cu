@@ -489,11 +489,8 @@ int prepare_records(ecb_ctx *ctx, CostState *st) {
     if ((rc = ecb_reserve(ctx, st->out, ((size_t) st->total_spans * OUT_STRIDE + 8) * 8))) return rc;
     if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
     if (!items.empty())
-        ECB_CUDA(ctx, cudaMemcpyAsync(st->items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
-    ECB_CUDA(ctx, cudaMemcpyAsync((char *) st->items.p + ni * sizeof(Item), item_start.data(), item_start.size() * 4,
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return ECB_OK;
+        if ((rc = ecb_h2d(ctx, st->items.p, items.data(), items.size() * sizeof(Item)))) return rc;
+    return ecb_h2d(ctx, (char *) st->items.p + ni * sizeof(Item), item_start.data(), item_start.size() * 4);  // staged: no sync needed
 }
 
 int upload_params(ecb_ctx *ctx, CostState *st, const double *intr, const double *rot, const double *trans) {
@@ -501,10 +498,9 @@ int upload_params(ecb_ctx *ctx, CostState *st, const double *intr, const double 
     const size_t C = (size_t) st->total_cp;
     if ((rc = ecb_reserve(ctx, st->params, (9 + 7 * C) * 8))) return rc;
     double *p = (double *) st->params.p;
-    ECB_CUDA(ctx, cudaMemcpyAsync(p, intr, 72, cudaMemcpyHostToDevice, ctx->stream));
-    ECB_CUDA(ctx, cudaMemcpyAsync(p + 9, rot, 32 * C, cudaMemcpyHostToDevice, ctx->stream));
-    ECB_CUDA(ctx, cudaMemcpyAsync(p + 9 + 4 * C, trans, 24 * C, cudaMemcpyHostToDevice, ctx->stream));
-    return ECB_OK;
+    if ((rc = ecb_h2d(ctx, p, intr, 72))) return rc;
+    if ((rc = ecb_h2d(ctx, p + 9, rot, 32 * C))) return rc;
+    return ecb_h2d(ctx, p + 9 + 4 * C, trans, 24 * C);
 }
 
 }  // namespace
@@ -614,9 +610,9 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if ((rc = ecb_reserve(ctx, st->ev_cnt, (size_t) nb * 4 + 16))) return rc;
     if ((rc = ecb_reserve(ctx, st->ev_tag, (size_t) n * 2 + 16))) return rc;
     if ((rc = ecb_reserve(ctx, st->ev_flag, (size_t) nb * 8 + 16))) return rc;
-    ECB_CUDA(ctx, cudaMemcpyAsync(st->kf_t.p, kf_time, (size_t) n_keyframes * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ECB_CUDA(ctx, cudaMemcpyAsync(st->kf_circ.p, kf_circles, (size_t) n_keyframes * n_circles * 24, cudaMemcpyHostToDevice, ctx->stream));
-    ECB_CUDA(ctx, cudaMemcpyAsync(st->lm_tab.p, landmarks_xyz, (size_t) n_circles * 24, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ecb_h2d(ctx, st->kf_t.p, kf_time, (size_t) n_keyframes * 8))) return rc;
+    if ((rc = ecb_h2d(ctx, st->kf_circ.p, kf_circles, (size_t) n_keyframes * n_circles * 24))) return rc;
+    if ((rc = ecb_h2d(ctx, st->lm_tab.p, landmarks_xyz, (size_t) n_circles * 24))) return rc;
     AssocArgs a;
     a.ev_t = (const double *) ctx->ev_t.p;
     a.ev_xyp = (const uint32_t *) ctx->ev_xyp.p;

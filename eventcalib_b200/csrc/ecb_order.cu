@@ -1,0 +1,227 @@
+// k_uset_order — the pid order the reference hands to DBSCAN::Run.
+//
+// EventFrame::EventFrame (event/src/EventFrame.cpp:12-35) inserts the window's pixels, in time order, into one
+// std::unordered_set<Vector2d, EigenMatrixHash> per polarity (hash: core/utility/include/opengv2/utility/utility.hpp:38-51
+// = boost hash_combine over std::hash<double>), erases the pixels present in both sets and copies the sets to
+// positiveEvents_/negativeEvents_ in ITERATION order.  That order is a pure function of the insertion sequence and of
+// libstdc++'s hashtable policy (external: libstdc++ hashtable.h _M_insert_bucket_begin / _M_rehash_aux, hashtable_c++0x.cc
+// prime policy; g++ 13):
+//   * a node goes to the FRONT of its bucket's run if the bucket is occupied, else to the front of the whole list;
+//   * inserting the (B+1)-th element into B buckets first rehashes to the next policy prime (13, 29, 59, 127, ...),
+//     re-inserting the nodes in current list order by the same rule;
+//   * erase keeps the relative order of the remaining nodes.
+// So one "stage" (a rehash followed by the insertions up to the next rehash) maps the sequence S = old list order ++ new
+// arrivals to:  buckets in DESCENDING order of their first position in S, inside a bucket DESCENDING position in S.
+// That is a grouping, not a sequential process: atomicMin gives the first position, an atomicExch chain the bucket's
+// members, a suffix scan over the bucket heads the run starts.  Stage sizes grow geometrically, so the whole emulation
+// costs about two passes over the final set.  Checked against the real std::unordered_set (oracle/, tests/golden/uset_order.npz).
+//
+// One CTA per (window, polarity); all arrays in shared memory when they fit, else in per-CTA L2 scratch.
+#include "ecb_window.cuh"
+
+namespace {
+
+constexpr int ORD_THREADS = 256;
+constexpr int ORD_NSTAGE = 17;
+__constant__ uint32_t c_prime[ORD_NSTAGE] = {13,    29,     59,     127,    257,    541,     1109,   2357,   5087,
+                                             10273, 20753,  42043,  85229,  172933, 351061,  712697, 1447153};
+static const uint32_t h_prime[ORD_NSTAGE] = {13,    29,     59,     127,    257,    541,     1109,   2357,   5087,
+                                             10273, 20753,  42043,  85229,  172933, 351061,  712697, 1447153};
+
+// std::hash<double> of libstdc++: 0 for +-0.0, else _Hash_bytes(&v, 8, 0xc70f6907) (64-bit murmur variant)
+__device__ __forceinline__ uint64_t hash_double(double v) {
+    if (v == 0.0) return 0;
+    const uint64_t mul = (0xc6a4a793ull << 32) + 0x5bd1e995ull;
+    uint64_t h = 0xc70f6907ull ^ (8ull * mul);
+    uint64_t d = (uint64_t) __double_as_longlong(v) * mul;
+    d ^= d >> 47;
+    d *= mul;
+    h ^= d;
+    h *= mul;
+    h ^= h >> 47;
+    h *= mul;
+    h ^= h >> 47;
+    return h;
+}
+
+// EigenMatrixHash<Vector2d> (utility.hpp:38-51)
+__device__ __forceinline__ uint64_t hash_pixel(uint32_t pix) {
+    uint64_t seed = 0;
+    seed ^= hash_double((double) ECB_PIX_X(pix)) + 0x9e3779b9ull + (seed << 6) + (seed >> 2);
+    seed ^= hash_double((double) ECB_PIX_Y(pix)) + 0x9e3779b9ull + (seed << 6) + (seed >> 2);
+    return seed;
+}
+
+// h % c_prime[stage] with compile-time divisors (the stage is uniform across the CTA)
+__device__ __forceinline__ uint32_t bucket_of(uint64_t h, int stage) {
+    switch (stage) {
+        case 0: return (uint32_t) (h % 13ull);
+        case 1: return (uint32_t) (h % 29ull);
+        case 2: return (uint32_t) (h % 59ull);
+        case 3: return (uint32_t) (h % 127ull);
+        case 4: return (uint32_t) (h % 257ull);
+        case 5: return (uint32_t) (h % 541ull);
+        case 6: return (uint32_t) (h % 1109ull);
+        case 7: return (uint32_t) (h % 2357ull);
+        case 8: return (uint32_t) (h % 5087ull);
+        case 9: return (uint32_t) (h % 10273ull);
+        case 10: return (uint32_t) (h % 20753ull);
+        case 11: return (uint32_t) (h % 42043ull);
+        case 12: return (uint32_t) (h % 85229ull);
+        case 13: return (uint32_t) (h % 172933ull);
+        case 14: return (uint32_t) (h % 351061ull);
+        case 15: return (uint32_t) (h % 712697ull);
+        default: return (uint32_t) (h % 1447153ull);
+    }
+}
+
+__global__ void __launch_bounds__(ORD_THREADS) k_uset_order(const OrderArgs a) {
+    extern __shared__ __align__(16) uint32_t smo[];
+    __shared__ uint32_t ws[33];
+    __shared__ uint32_t s_pb;
+    const int tid = threadIdx.x, nthr = ORD_THREADS, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
+    uint32_t *base = a.arrays_in_smem ? smo : a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
+    const int MC = a.m_cap, BC = a.b_cap;
+    uint32_t *cur = base, *nxtL = base + MC;       // ping-pong order lists (arrival indices)
+    uint32_t *chain = base + 2 * MC;               // next position in the bucket's chain
+    uint32_t *bk = base + 3 * MC;                  // bucket of position p (bit 31: p is the bucket's first position)
+    uint32_t *first = base + 4 * MC;               // [BC] first position, then the run start of the bucket
+    uint32_t *head = first + BC;                   // [BC] chain head
+    uint32_t *cnt = head + BC;                     // [BC] bucket size
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_pb = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const uint32_t pb = s_pb;
+        if (pb >= (uint32_t) a.n_prob) break;
+        const ProbDesc d = a.prob[pb];
+        const int m = d.pad0;  // arrival count = size of the set before the +/- cancellation
+        const uint32_t *arr = a.arrive[d.pol] + d.off;
+        uint32_t *dst = a.pts[d.pol] + d.off;
+        if (m <= 0) continue;
+
+        for (int stage = 0;; ++stage) {
+            const int B = (int) c_prime[stage];
+            const int prevN = stage ? (int) c_prime[stage - 1] : 0;
+            const int newN = min(m, B);
+            for (int b = tid; b < B; b += nthr) {
+                first[b] = ECB_NONE;
+                head[b] = ECB_NONE;
+                cnt[b] = 0;
+            }
+            __syncthreads();
+            // A: bucket of every position of S = (old list order) ++ (new arrivals), first position, chains, sizes
+            for (int p = tid; p < newN; p += nthr) {
+                const uint32_t e = p < prevN ? cur[p] : (uint32_t) p;
+                if (p >= prevN) cur[p] = e;
+                const uint32_t b = bucket_of(hash_pixel(arr[e] & 0x3FFFFFFFu), stage);
+                bk[p] = b;
+                atomicMin(&first[b], (uint32_t) p);
+                chain[p] = atomicExch(&head[b], (uint32_t) p);
+                atomicAdd(&cnt[b], 1u);
+            }
+            __syncthreads();
+            // B: run starts = suffix sum of the bucket sizes over the head positions (descending first position).
+            // Warp w owns positions [w*L, (w+1)*L), lanes interleaved.
+            const int L = (((newN + nwarp - 1) / nwarp) + 31) & ~31;
+            const int p0 = wid * L, p1 = min(newN, p0 + L);
+            uint32_t wsum = 0;
+            for (int c = p0; c < p1; c += 32) {
+                const int p = c + lane;
+                uint32_t hs = 0;
+                if (p < p1) {
+                    const uint32_t b = bk[p];
+                    if (first[b] == (uint32_t) p) {
+                        hs = cnt[b];
+                        bk[p] = b | 0x80000000u;
+                    }
+                }
+                wsum += hs;
+            }
+            for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+            if (lane == 0) ws[wid] = wsum;
+            __syncthreads();  // also orders all reads of first[] == p before the overwrite below
+            uint32_t carry = 0;
+            for (int w = wid + 1; w < nwarp; ++w) carry += ws[w];
+            for (int c = ((p1 - p0 + 31) & ~31) - 32 + p0; c >= p0; c -= 32) {
+                const int p = c + lane;
+                uint32_t hs = 0, b = 0;
+                if (p < p1) {
+                    b = bk[p];
+                    if (b & 0x80000000u) hs = cnt[b & 0x7FFFFFFFu];
+                }
+                // exclusive suffix sum inside the warp (lanes above)
+                uint32_t inc = hs;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_down_sync(0xffffffffu, inc, o);
+                    if (lane + o < 32) inc += t;
+                }
+                if (hs) first[b & 0x7FFFFFFFu] = carry + inc - hs;
+                carry += __shfl_sync(0xffffffffu, inc, 0);
+            }
+            __syncthreads();
+            // C: place — inside the run, descending position
+            for (int p = tid; p < newN; p += nthr) {
+                const uint32_t b = bk[p] & 0x7FFFFFFFu;
+                uint32_t g = 0;
+                for (uint32_t q = head[b]; q != ECB_NONE; q = chain[q]) g += q > (uint32_t) p;
+                nxtL[first[b] + g] = cur[p];
+            }
+            __syncthreads();
+            uint32_t *t = cur;
+            cur = nxtL;
+            nxtL = t;
+            if (m <= B) break;
+        }
+        // survivors of the +/- cancellation (bit 31 of the arrival word), in iteration order
+        uint32_t run = 0;
+        for (int c0 = 0; c0 < m; c0 += nthr) {
+            const int i = c0 + tid;
+            uint32_t p = 0;
+            bool keep = false;
+            if (i < m) {
+                p = arr[cur[i]];
+                keep = !(p & 0x80000000u);
+            }
+            uint32_t tot;
+            const uint32_t ex = block_excl_scan(keep ? 1u : 0u, ws, &tot);
+            if (keep) dst[run + ex] = p;
+            run += tot;
+        }
+    }
+}
+
+}  // namespace
+
+int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
+    if (a.n_prob <= 0 || max_m <= 0) return ECB_OK;
+    if (max_m > (int) h_prime[ORD_NSTAGE - 1]) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "window with %d distinct pixels", max_m);
+    int st = 0;
+    while ((int) h_prime[st] < max_m) ++st;
+    a.m_cap = (max_m + 3) & ~3;
+    a.b_cap = ((int) h_prime[st] + 3) & ~3;
+    const size_t words = (size_t) 4 * a.m_cap + (size_t) 3 * a.b_cap;
+    const size_t limit = (size_t) ctx->smem_optin - 2 * 1024;
+    a.arrays_in_smem = words * 4 <= limit;
+    const size_t smem = a.arrays_in_smem ? words * 4 : 0;
+    ECB_CUDA(ctx, cudaFuncSetAttribute(k_uset_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
+    int per_sm = 1;
+    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_uset_order, ORD_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = ctx->sm_count * per_sm;
+    if (grid > a.n_prob) grid = a.n_prob;
+    if (!a.arrays_in_smem) {
+        a.gscratch_stride = words;
+        int rc = ecb_reserve(ctx, ctx->scratch, (size_t) grid * words * 4);
+        if (rc) return rc;
+        a.gscratch = (uint32_t *) ctx->scratch.p;
+    }
+    ECB_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, 4, ctx->stream));
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_ORDER);
+    k_uset_order<<<grid, ORD_THREADS, smem, ctx->stream>>>(a);
+    ECB_PROF_END(ctx, ECB_STAGE_ORDER);
+    ECB_LAUNCHED(ctx);
+    return ecb_check(ctx, cudaGetLastError(), "k_uset_order launch");
+}

@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window(const WindowArgs a) {
             __syncthreads();
         }
         // ---- +/- cancellation and pid order -------------------------------------------------------
-        // order_mode 0: pid = arrival order of the surviving pixels.  (order_mode 1 reorders `arrive`
-        // beforehand into the libstdc++ iteration order — k_uset_order — and re-runs this compaction.)
+        // order_mode 0: pid = arrival order of the surviving pixels.  order_mode 1: only mark the cancelled pixels;
+        // k_uset_order (ecb_order.cu) emits the survivors in the libstdc++ iteration order.
         for (int pol = 0; pol < 2; ++pol) {
             const uint32_t m = base[pol];
             const uint32_t *other = plane[pol ^ 1];
@@ -189,7 +189,11 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window(const WindowArgs a) {
                 }
                 uint32_t tot;
                 const uint32_t ex = block_excl_scan(keep ? 1u : 0u, ws, &tot);
-                if (keep) dst[run + ex] = p;
+                if (a.order_mode == 1) {
+                    if (i < m && !keep) arr[pol][i] = p | 0x80000000u;  // cancelled; k_uset_order compacts in set order
+                } else if (keep) {
+                    dst[run + ex] = p;
+                }
                 run += tot;
             }
             if (tid == 0) {
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window(const WindowArgs a) {
                 d.pad1 = 0;
                 a.prob[2 * w + pol] = d;
                 atomicMax(a.max_n, run);
+                atomicMax(a.max_n + 1, m);
             }
         }
     }

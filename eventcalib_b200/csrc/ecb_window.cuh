@@ -9,8 +9,22 @@ struct WindowArgs {
     uint32_t *arrive[2];      // distinct pixels per polarity in first-arrival order (before cancellation)
     uint32_t *pts[2];         // surviving pixels in pid order
     ProbDesc *prob;           // [2*n_win] clustering problems (index 2*w+pol)
-    uint32_t *max_n;          // device word: max points of any problem (sizes the cluster kernel's arrays)
+    uint32_t *max_n;          // device words: [0] max points of any problem (sizes the cluster kernel's arrays),
+                              //               [1] max distinct pixels before cancellation (sizes k_uset_order)
     int n_win, W, H, RW;
+    int order_mode;           // 1: mark cancelled pixels in `arrive` (bit 31) for k_uset_order instead of compacting
+};
+
+// k_uset_order (ecb_order.cu): libstdc++ unordered_set iteration order of every (window, polarity) pixel set
+struct OrderArgs {
+    const ProbDesc *prob;     // pad0 = arrival count
+    int n_prob;
+    unsigned *work_counter;
+    const uint32_t *arrive[2];
+    uint32_t *pts[2];
+    uint32_t *gscratch;
+    size_t gscratch_stride;
+    int arrays_in_smem, m_cap, b_cap;
 };
 
 struct PairArgs {
@@ -32,5 +46,6 @@ struct PairArgs {
 int ecb_launch_ingest(ecb_ctx *ctx, const void *d_raw, int64_t n);
 int ecb_launch_bounds(ecb_ctx *ctx, const double *d_win, int n_win, int64_t *d_lohi);
 int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a);
+int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m);
 int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a);
 int ecb_launch_fit(ecb_ctx *ctx, const double *d_xy, const int64_t *d_off, int n_sets, double *d_out);

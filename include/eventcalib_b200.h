@@ -64,7 +64,8 @@ int ecb_synchronize(ecb_ctx *ctx);
 #define ECB_STAGE_ASSOC 5
 #define ECB_STAGE_NORMAL_EQ 6
 #define ECB_STAGE_COST 7
-#define ECB_N_STAGES 8
+#define ECB_STAGE_ORDER 8
+#define ECB_N_STAGES 9
 int ecb_set_profiling(ecb_ctx *ctx, int on);
 int ecb_stage_ms(ecb_ctx *ctx, float *out);
 const char *ecb_version(void);

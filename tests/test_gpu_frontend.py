@@ -1,7 +1,7 @@
 """Parity of the batched CUDA front end (ecb_load_events + ecb_frontend_run) with the oracle.
 
 Per window: event range, per-polarity pixel sets after dedupe and +/- cancellation (EventFrame.cpp:10-36),
-pid order (order_mode 0 = first arrival), DBSCAN labels bit-exact, kept clusters, medians, candidate pairs
+pid order (order_mode 0 = first arrival, order_mode 1 = the reference's libstdc++ unordered_set iteration order), DBSCAN labels bit-exact, kept clusters, medians, candidate pairs
 exact and circle centres / radii within 1e-9 relative (CirclesEventFrame.cpp:61-312,361-415).
 """
 import numpy as np
@@ -29,14 +29,15 @@ def _first_arrival(ev, lo, hi, pol):
     return np.array(out, np.float64).reshape(-1, 2)
 
 
-def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4.0, min_pts=2):
+def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4.0, min_pts=2, order_mode=0):
     import eventcalib_b200 as ecb
     from eventcalib_b200 import synth
     ctx.set_sensor(width, height)
     n = ctx.load_events(synth.to_records(ev))
     assert n == len(ev["t"])
     rthr = ecb.radius_threshold(width, height, 9, 4, True, 5.5, 1.75)
-    prm = ecb.default_params(eps=eps, min_pts=min_pts, fit_circle=fit_circle, radius_threshold=rthr)
+    prm = ecb.default_params(eps=eps, min_pts=min_pts, fit_circle=fit_circle, radius_threshold=rthr,
+                             order_mode=order_mode)
     ctx.frontend_run(windows, prm)
     summ = ctx.summary()
     pts = [ctx.points(0), ctx.points(1)]
@@ -53,7 +54,10 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
             xy = pts[pol][0][o:o + k]
             assert k == len(ref_set)
             assert set(map(tuple, xy.tolist())) == set(map(tuple, ref_set.tolist()))
-            assert np.array_equal(xy, _first_arrival(ev, lo, hi, pol))
+            if order_mode == 1:   # the reference's own pid order: iteration order of the real std::unordered_set
+                assert np.array_equal(xy, ref_set), "pid order differs from the libstdc++ set order, window %d" % w
+            else:
+                assert np.array_equal(xy, _first_arrival(ev, lo, hi, pol))
             V.append(xy)
         r = oracle_mod.extract(V[1], V[0], eps=eps, minS=min_pts, fitCircle=fit_circle, Rthr=rthr, canonical_median=True)
         for pol, key in ((0, "n"), (1, "p")):
@@ -74,12 +78,13 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
     return n_cand_total
 
 
+@pytest.mark.parametrize("order_mode", [0, 1])
 @pytest.mark.parametrize("fit_circle", [0, 1])
-def test_davis346_windows(ctx, oracle_mod, fit_circle):
+def test_davis346_windows(ctx, oracle_mod, fit_circle, order_mode):
     from eventcalib_b200 import synth
     ev = synth.make_stream(120000, 346, 260, t0=5.0, duration=0.06, seed=1001)
     win = synth.tiling_windows(5.0, 5.06, 1.5e-3)
-    total = _check_stream(ctx, oracle_mod, ev, win, 346, 260, fit_circle)
+    total = _check_stream(ctx, oracle_mod, ev, win, 346, 260, fit_circle, order_mode=order_mode)
     assert total > 30 * len(win)  # the synthetic board is found in (almost) every window
 
 
@@ -88,6 +93,16 @@ def test_overlapping_and_empty_windows(ctx, oracle_mod):
     ev = synth.make_stream(40000, 346, 260, t0=5.0, duration=0.02, seed=7)
     win = np.array([[5.0, 5.0015], [5.0005, 5.003], [4.0, 4.5], [5.019, 9.0], [5.002, 5.002], [5.0, 5.02]])
     _check_stream(ctx, oracle_mod, ev, win, 346, 260, 0)
+    _check_stream(ctx, oracle_mod, ev, win, 346, 260, 0, order_mode=1)
+
+
+def test_set_order_window_sizes(ctx, oracle_mod):
+    """libstdc++ order emulation across every rehash boundary (13, 29, 59, ... buckets): windows of growing length."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(60000, 346, 260, t0=5.0, duration=0.03, seed=11, noise_frac=0.3)
+    lens = [2e-6, 5e-6, 8e-6, 1.5e-5, 3e-5, 6e-5, 1.3e-4, 2.7e-4, 5.5e-4, 1.1e-3, 2.3e-3, 5e-3, 1e-2, 3e-2]
+    win = np.array([[5.0 + 1e-4 * k, 5.0 + 1e-4 * k + L] for k, L in enumerate(lens)])
+    _check_stream(ctx, oracle_mod, ev, win, 346, 260, 1, order_mode=1)
 
 
 def test_vga_large_windows(ctx, oracle_mod):
@@ -95,6 +110,7 @@ def test_vga_large_windows(ctx, oracle_mod):
     ev = synth.make_stream(300000, 640, 480, t0=0.0, duration=0.03, seed=1003)
     win = synth.tiling_windows(0.0, 0.03, 10e-3)
     _check_stream(ctx, oracle_mod, ev, win, 640, 480, 1)
+    _check_stream(ctx, oracle_mod, ev, win, 640, 480, 1, order_mode=1)
 
 
 def test_eps_minpts_sweep(ctx, oracle_mod):
