@@ -56,11 +56,11 @@ def make_workload(n_events, rank):
     return ev, win
 
 
-def frontend_params(order_mode=0):
+def frontend_params(order_mode=1, median_mode=1):
     import eventcalib_b200 as ecb
     rthr = ecb.radius_threshold(WIDTH, HEIGHT, 9, 4, True, 5.5, 1.75)
     return ecb.default_params(eps=4.0, min_pts=2, cluster_min=5, knn_num=3, fit_circle=1, radius_threshold=rthr,
-                              rows_cols=36, order_mode=order_mode), rthr
+                              rows_cols=36, order_mode=order_mode, median_mode=median_mode), rthr
 
 
 class ClockSampler:
@@ -206,7 +206,8 @@ def main():
     ap.add_argument("--events", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--slices", type=int, default=4, help="time slices (contexts/streams/host threads) of the e2e pipeline")
-    ap.add_argument("--order-mode", type=int, default=0, help="pid order: 0 first arrival, 1 libstdc++ unordered_set order")
+    ap.add_argument("--order-mode", type=int, default=1, help="pid order: 0 first arrival, 1 libstdc++ unordered_set order (the reference's)")
+    ap.add_argument("--median-mode", type=int, default=1, help="cluster centre: 0 canonical, 1 std::nth_element over BFS order (the reference's)")
     ap.add_argument("--lm-iters", type=int, default=50, help="LM iterations of the C4 side measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -242,7 +243,7 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = ecb.Context(local, stream.cuda_stream)
     ctx.set_sensor(WIDTH, HEIGHT)
-    prm, rthr = frontend_params(args.order_mode)
+    prm, rthr = frontend_params(args.order_mode, args.median_mode)
 
     # residual evaluation: key frames / circles / spline segments from the ground truth (host-side initialisation is
     # outside the hot path); rank r owns segment r
@@ -296,6 +297,9 @@ def main():
         m = (mine["kf_t"] > ta - 6 * mine["step"]) & (mine["kf_t"] < tb + 6 * mine["step"])
         sl["kf_t"], sl["circles"] = mine["kf_t"][m].copy(), mine["circles"][m].copy()
     d_parts = torch.zeros(S, lay["out_doubles"], dtype=torch.float64, device="cuda")
+    # caller-owned host result buffers: every slice writes its windows' summaries / candidate circles in place
+    h_summ = np.zeros(len(win), ecb.SUMMARY_DTYPE)
+    h_cand = np.zeros((len(win), 48, 5))
     pool = ThreadPoolExecutor(S)
 
     trace = os.environ.get("ECB_BENCH_TRACE")
@@ -313,7 +317,7 @@ def main():
         c.cost_normal_eq(intr, rot, trans, d_out=d_parts[j].data_ptr(), host=False)
         cost = c.cost_eval(intr, rot, trans)       # synchronises the slice's stream
         tm.append(time.perf_counter())
-        out = c.summary(), c.candidates(48), cost
+        out = c.summary(out=h_summ[sl["w0"]:sl["w1"]]), c.candidates(48, out=h_cand[sl["w0"]:sl["w1"]]), cost
         tm.append(time.perf_counter())
         if trace:
             sys.stderr.write("slice %d: start %.2f load_end %.2f frontend_end %.2f cost_end %.2f fetch_end %.2f ms\n" % (
@@ -329,7 +333,7 @@ def main():
             d_cost[0] = sum(r[2] for r in res)
             dist.all_reduce(d_cost)
         h_ne.copy_(d_ne, non_blocking=False)
-        return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+        return h_summ, h_cand
 
     def barrier():
         if world > 1:
@@ -433,6 +437,7 @@ def main():
         npts = int(s["n_points"].sum())
         # algorithmic bytes / flops per launch of each kernel (Kernels)
         algo = {"ingest": n * 37.0, "window": n * 4.0 + npts * 8.0, "cluster": npts * 12.0, "pair": npts * 8.0,
+                "order": npts * 8.0,
                 "assoc": n * 12.0 * 2 + n_res * 60.0, "normal_eq": n_res * 76.0, "cost": n_res * 76.0}
         flops = {"normal_eq": n_res * 2.0e3, "cost": n_res * 150.0}
         tot = sum(stage.values())

@@ -26,7 +26,7 @@ class FrontendParams(C.Structure):
     _fields_ = [("dbscan_eps", C.c_double), ("dbscan_min_pts", C.c_uint32), ("cluster_min", C.c_uint32),
                 ("knn_num", C.c_int32), ("fit_circle", C.c_int32), ("radius_threshold", C.c_double),
                 ("rows_cols", C.c_uint32), ("order_mode", C.c_int32), ("max_clusters", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("median_mode", C.c_uint32)]
 
 
 class LmOptions(C.Structure):
@@ -58,6 +58,7 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_set_sensor", "ecb_load_events_host", "ecb_load_events_device", "ecb_num_events", "ecb_frontend_run",
            "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
            "ecb_frontend_clusters", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
+           "ecb_dbscan_run_ordered", "ecb_dbscan_run_batch_ordered",
            "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_layout",
            "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq", "ecb_lm_default_options", "ecb_lm_create",
            "ecb_lm_destroy", "ecb_lm_dimension", "ecb_lm_begin", "ecb_lm_propose", "ecb_lm_feedback", "ecb_lm_update",
@@ -99,6 +100,8 @@ def load_library():
     lib.ecb_frontend_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
     lib.ecb_dbscan_run.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32)]
     lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
+    lib.ecb_dbscan_run_ordered.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32), vp, vp]
+    lib.ecb_dbscan_run_batch_ordered.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp, vp, vp]
     lib.ecb_fit_circles.argtypes = [vp, vp, vp, i32, vp]
     lib.ecb_set_profiling.argtypes = [vp, i32]
     lib.ecb_stage_ms.argtypes = [vp, vp]
@@ -132,10 +135,11 @@ def _ptr(a):
 
 
 def default_params(eps=4.0, min_pts=2, cluster_min=5, knn_num=3, fit_circle=0, radius_threshold=15.511363636363637,
-                   rows_cols=36, order_mode=0, max_clusters=128):
-    """CirclesEventFrame::Params defaults + parameter/event_calibration/example.yaml."""
+                   rows_cols=36, order_mode=0, max_clusters=128, median_mode=0):
+    """CirclesEventFrame::Params defaults + parameter/event_calibration/example.yaml.
+    order_mode=1, median_mode=1 reproduce the reference's pid order and std::nth_element medians."""
     return FrontendParams(eps, min_pts, cluster_min, knn_num, fit_circle, radius_threshold, rows_cols, order_mode,
-                          max_clusters, 0)
+                          max_clusters, median_mode)
 
 
 def radius_threshold(width, height, rows, cols, asymmetric, square, radius):
@@ -180,7 +184,7 @@ class Context:
     def synchronize(self):
         self._chk(self.lib.ecb_synchronize(self.h))
 
-    STAGES = ["ingest", "bounds", "window", "cluster", "pair", "assoc", "normal_eq", "cost", "order"]
+    STAGES = ["ingest", "bounds", "window", "cluster", "pair", "assoc", "normal_eq", "cost", "order", "bfs"]
 
     def set_profiling(self, on=True):
         self._chk(self.lib.ecb_set_profiling(self.h, int(on)))
@@ -217,8 +221,11 @@ class Context:
         self._chk(self.lib.ecb_frontend_run(self.h, _ptr(win), len(win), C.byref(params)))
         self.n_win = len(win)
 
-    def summary(self):
-        out = np.zeros(self.n_win, SUMMARY_DTYPE)
+    def summary(self, out=None):
+        """per-window summaries; `out` (optional): a caller-owned SUMMARY_DTYPE array of n_win entries to fill"""
+        if out is None:
+            out = np.zeros(self.n_win, SUMMARY_DTYPE)
+        assert out.dtype == SUMMARY_DTYPE and out.flags.c_contiguous and len(out) == self.n_win
         if self.n_win:
             self._chk(self.lib.ecb_frontend_summary(self.h, _ptr(out), self.n_win))
         return out
@@ -230,8 +237,10 @@ class Context:
         self._chk(self.lib.ecb_frontend_points(self.h, polarity, _ptr(xy), _ptr(lab)))
         return xy[:n], lab[:n]
 
-    def candidates(self, max_cand=64):
-        out = np.zeros((self.n_win, max_cand, 5))
+    def candidates(self, max_cand=64, out=None):
+        if out is None:
+            out = np.zeros((self.n_win, max_cand, 5))
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.n_win, max_cand, 5)
         if self.n_win:
             self._chk(self.lib.ecb_frontend_candidates(self.h, _ptr(out), max_cand))
         return out
@@ -255,6 +264,40 @@ class Context:
             return FAILED, labels[:0], 0
         self._chk(rc)
         return OK, labels[:n], nc.value
+
+    def dbscan_ordered(self, xy, eps, min_pts):
+        """DBSCAN::Run with `Clusters` as ordered lists (the reference's member order) and `Noise`."""
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        n = len(xy)
+        labels = np.full(max(n, 1), -1, np.int32)
+        sizes = np.zeros(max(n, 1), np.int32)
+        members = np.zeros(max(n, 1), np.uint32)
+        nc = C.c_int32(0)
+        rc = self.lib.ecb_dbscan_run_ordered(self.h, _ptr(xy), n, float(eps), int(min_pts), _ptr(labels), C.byref(nc),
+                                             _ptr(sizes), _ptr(members))
+        if rc == FAILED:
+            return FAILED, labels[:0], [], labels[:0]
+        self._chk(rc)
+        off = np.concatenate([[0], np.cumsum(sizes[:nc.value])])
+        clusters = [members[off[c]:off[c + 1]].copy() for c in range(nc.value)]
+        return OK, labels[:n], clusters, np.nonzero(labels[:n] < 0)[0].astype(np.uint32)
+
+    def dbscan_batch_ordered(self, xy, offsets, eps, min_pts):
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, np.int64)
+        k = len(off) - 1
+        labels = np.full(max(len(xy), 1), -1, np.int32)
+        sizes = np.zeros(max(len(xy), 1), np.int32)
+        members = np.zeros(max(len(xy), 1), np.uint32)
+        nc = np.zeros(max(k, 1), np.int32)
+        st = np.zeros(max(k, 1), np.uint32)
+        self._chk(self.lib.ecb_dbscan_run_batch_ordered(self.h, _ptr(xy), _ptr(off), k, float(eps), int(min_pts),
+                                                        _ptr(labels), _ptr(nc), _ptr(st), _ptr(sizes), _ptr(members)))
+        out = []
+        for j in range(k):
+            o = np.concatenate([[0], np.cumsum(sizes[off[j]:off[j] + nc[j]])]) + off[j]
+            out.append([members[o[c]:o[c + 1]].copy() for c in range(nc[j])])
+        return labels[:len(xy)], nc[:k], st[:k], out
 
     def dbscan_batch(self, xy, offsets, eps, min_pts):
         xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)

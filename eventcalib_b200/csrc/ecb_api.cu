@@ -145,7 +145,8 @@ void ecb_ctx_destroy(ecb_ctx *c) {
     DevBuf *bufs[] = {&c->ev_raw, &c->ev_t, &c->ev_xyp, &c->ev_flag, &c->win_t, &c->win_lohi, &c->win_ptoff, &c->summary,
                       &c->arrive, &c->pts[0], &c->pts[1], &c->labels[0], &c->labels[1], &c->scratch, &c->ktab, &c->kmem,
                       &c->cand, &c->status, &c->db_pix, &c->db_off, &c->db_labels, &c->db_hdr, &c->db_scratch, &c->db_dims,
-                      &c->fit_in, &c->fit_off, &c->fit_out, &c->db_hdr_b, &c->db_ktab, &c->db_counter};
+                      &c->fit_in, &c->fit_off, &c->fit_out, &c->db_hdr_b, &c->db_ktab, &c->db_counter, &c->kd_tree, &c->bfs_key,
+                      &c->bfs_items, &c->bfs_front, &c->bfs_tab};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < ECB_N_STAGES; ++i)
@@ -262,6 +263,7 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     if (params->dbscan_min_pts < 1) return ecb_fail(ctx, ECB_FAILED, "min_pts < 1 (DBSCAN::Run returns FAILED)");
     if (params->order_mode != 0 && params->order_mode != 1)
         return ecb_fail(ctx, ECB_ERR_ARG, "order_mode %d unknown", params->order_mode);
+    if (params->median_mode > 1) return ecb_fail(ctx, ECB_ERR_ARG, "median_mode %u unknown", params->median_mode);
     cudaSetDevice(ctx->device);
     int rc;
     ctx->fp = *params;
@@ -357,7 +359,48 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     ca.PH = ca.H + 2 * ca.E;
     ca.min_pts = params->dbscan_min_pts;
     ca.cluster_min = params->cluster_min;
+    const bool exact = params->median_mode == 1;
+    int bfs_cap = 0;
+    if (exact) {  // reference-exact medians: export the kd-tree, queue the clusters whose median norm is tied
+        bfs_cap = (int) std::min<size_t>((size_t) 2 * n_win * max_k, 2 * slots / std::max<uint32_t>(params->cluster_min, 1u) + 16);
+        if ((rc = ecb_reserve(ctx, ctx->kd_tree, 6 * slots * 4))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->bfs_key, 2 * slots * 8))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->bfs_items, (size_t) bfs_cap * sizeof(BfsItem) + 16))) return rc;
+        ca.exact_order = 1;
+        for (int p = 0; p < 2; ++p) {
+            ca.kd_left[p] = (uint32_t *) ctx->kd_tree.p + (size_t) (3 * p) * slots;
+            ca.kd_right[p] = (uint32_t *) ctx->kd_tree.p + (size_t) (3 * p + 1) * slots;
+            ca.kd_parent[p] = (uint32_t *) ctx->kd_tree.p + (size_t) (3 * p + 2) * slots;
+        }
+        ca.bfs_items = (BfsItem *) ((char *) ctx->bfs_items.p + 16);
+        ca.bfs_count = (unsigned *) ctx->bfs_items.p;
+        ca.bfs_cap = bfs_cap;
+        ECB_CUDA(ctx, cudaMemsetAsync(ctx->bfs_items.p, 0, 16, ctx->stream));
+    }
     if ((rc = ecb_launch_cluster(ctx, ca, (int) max_n))) return rc;
+    if (exact) {
+        BfsArgs ba;
+        memset(&ba, 0, sizeof ba);
+        ba.items = ca.bfs_items;
+        ba.count = ca.bfs_count;
+        ba.max_items = bfs_cap;
+        ba.prob = ca.prob;
+        for (int p = 0; p < 2; ++p) {
+            ba.pix[p] = ca.pix[p];
+            ba.labels[p] = ca.labels[p];
+            ba.kd_left[p] = ca.kd_left[p];
+            ba.kd_right[p] = ca.kd_right[p];
+            ba.kd_parent[p] = ca.kd_parent[p];
+            ba.members[p] = ca.kmem[p];
+            ba.scratch[p] = wa.arrive[p];  // the arrival lists are dead by now
+            ba.key[p] = (unsigned long long *) ctx->bfs_key.p + (size_t) p * slots;
+        }
+        ba.init_keys = 1;
+        ba.ktab = ca.ktab;
+        ba.max_k = max_k;
+        ba.eps = params->dbscan_eps;
+        if ((rc = ecb_launch_bfs(ctx, ba))) return rc;
+    }
 
     PairArgs pa;
     pa.prob = ca.prob;
@@ -460,9 +503,11 @@ int ecb_frontend_device_ptrs(ecb_ctx *ctx, void **d_summary, void **d_candidates
 }
 
 // ------------------------------------------------------------------------- DBSCAN::Run boundary ----
-int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
-                         uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status) {
+static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
+                        uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status, int32_t *cluster_sizes,
+                        uint32_t *members) {
     if (!ctx || !offsets || n_problems < 0 || (!xy && n_problems > 0)) return ECB_ERR_ARG;
+    const bool ordered = cluster_sizes && members;
     if (min_pts < 1) return ecb_fail(ctx, ECB_FAILED, "min < 1 (dbscan.h:123)");
     cudaSetDevice(ctx->device);
     int rc;
@@ -533,7 +578,51 @@ int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets,
     ca.PH = ca.H + 2 * ca.E;
     ca.min_pts = min_pts;
     ca.cluster_min = 0x7FFFFFFF;  // no kept-cluster tables on this path
+    if (ordered) {
+        if ((rc = ecb_reserve(ctx, ctx->kd_tree, 3 * slots * 4))) return rc;
+        ca.exact_order = 1;
+        ca.kd_left[0] = ca.kd_left[1] = (uint32_t *) ctx->kd_tree.p;
+        ca.kd_right[0] = ca.kd_right[1] = (uint32_t *) ctx->kd_tree.p + slots;
+        ca.kd_parent[0] = ca.kd_parent[1] = (uint32_t *) ctx->kd_tree.p + 2 * slots;
+        ca.bfs_count = (unsigned *) ctx->db_counter.p + 4;  // unused by k_cluster here (no kept clusters), must be valid
+        ca.bfs_cap = 0;
+    }
     if ((rc = ecb_launch_cluster(ctx, ca, max_n))) return rc;
+    if (ordered) {
+        // every cluster -> one work item; member lists of problem k at members[offsets[k] + offset of the cluster]
+        if ((rc = ecb_reserve(ctx, ctx->bfs_key, slots * 8))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->bfs_items, slots * sizeof(BfsItem) + 16))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->bfs_front, slots * 4))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->bfs_tab, 3 * slots * 4))) return rc;
+        ECB_CUDA(ctx, cudaMemsetAsync(ctx->bfs_key.p, 0xFF, slots * 8, ctx->stream));
+        ECB_CUDA(ctx, cudaMemsetAsync(ctx->bfs_items.p, 0, 16, ctx->stream));
+        uint32_t *csize = (uint32_t *) ctx->bfs_tab.p, *cseed = csize + slots, *coff = cseed + slots;
+        BfsItem *items = (BfsItem *) ((char *) ctx->bfs_items.p + 16);
+        if ((rc = ecb_launch_bfs_all_items(ctx, ca.prob, ca.hdr, n_problems, ca.labels[0], csize, cseed, coff, items,
+                                           (unsigned *) ctx->bfs_items.p, (int) slots)))
+            return rc;
+        BfsArgs ba;
+        memset(&ba, 0, sizeof ba);
+        ba.items = items;
+        ba.count = (const unsigned *) ctx->bfs_items.p;
+        ba.max_items = (int) slots;
+        ba.prob = ca.prob;
+        for (int p = 0; p < 2; ++p) {
+            ba.pix[p] = ca.pix[0];
+            ba.labels[p] = ca.labels[0];
+            ba.kd_left[p] = ca.kd_left[0];
+            ba.kd_right[p] = ca.kd_right[0];
+            ba.kd_parent[p] = ca.kd_parent[0];
+            ba.members[p] = (uint32_t *) ctx->db_scratch.p;
+            ba.scratch[p] = (uint32_t *) ctx->bfs_front.p;
+            ba.key[p] = (unsigned long long *) ctx->bfs_key.p;
+        }
+        ba.init_keys = 0;
+        ba.eps = eps;
+        if ((rc = ecb_launch_bfs(ctx, ba))) return rc;
+        ECB_CUDA(ctx, cudaMemcpyAsync(members, ctx->db_scratch.p, (size_t) total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ECB_CUDA(ctx, cudaMemcpyAsync(cluster_sizes, csize, (size_t) total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     std::vector<ProbHdr> hdr((size_t) n_problems);
     if (labels) ECB_CUDA(ctx, cudaMemcpyAsync(labels, ctx->db_labels.p, (size_t) total * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ECB_CUDA(ctx, cudaMemcpyAsync(hdr.data(), ctx->db_hdr_b.p, (size_t) n_problems * sizeof(ProbHdr), cudaMemcpyDeviceToHost,
@@ -546,6 +635,26 @@ int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets,
             return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "problem %d holds duplicate points (the reference path never does)", k);
     }
     return ECB_OK;
+}
+
+int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
+                         uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status) {
+    return dbscan_batch(ctx, xy, offsets, n_problems, eps, min_pts, labels, n_clusters, status, nullptr, nullptr);
+}
+
+int ecb_dbscan_run_batch_ordered(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
+                                 uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status,
+                                 int32_t *cluster_sizes, uint32_t *members) {
+    if (!cluster_sizes || !members) return ECB_ERR_ARG;
+    return dbscan_batch(ctx, xy, offsets, n_problems, eps, min_pts, labels, n_clusters, status, cluster_sizes, members);
+}
+
+int ecb_dbscan_run_ordered(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t min_pts, int32_t *labels,
+                           int32_t *n_clusters, int32_t *cluster_sizes, uint32_t *members) {
+    if (!ctx || !cluster_sizes || !members) return ECB_ERR_ARG;
+    if (n < 1 || min_pts < 1) return ECB_FAILED;  // dbscan.h:121-123
+    const int64_t off[2] = {0, n};
+    return dbscan_batch(ctx, xy, off, 1, eps, min_pts, labels, n_clusters, nullptr, cluster_sizes, members);
 }
 
 int ecb_dbscan_run(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t min_pts, int32_t *labels,

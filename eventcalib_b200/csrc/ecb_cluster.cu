@@ -69,12 +69,12 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     const int PW = a.PW, PH = a.PH, E = a.E, NW = PW * PH;
     Smem<RankT> s;
-    s.U = smem_raw;
+    const int plane_words = 2 * NW + (int) ((NW * sizeof(RankT) + 3) / 4);
+    uint32_t *gs = a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
+    s.U = a.planes_in_smem ? smem_raw : gs;
     s.C = s.U + NW;
     s.wrank = reinterpret_cast<RankT *>(s.C + NW);
-    uint32_t *arr = a.arrays_in_smem
-                        ? (s.C + NW + (NW * sizeof(RankT) + 3) / 4)
-                        : (a.gscratch + (size_t) blockIdx.x * a.gscratch_stride);
+    uint32_t *arr = a.arrays_in_smem ? (s.U + plane_words) : (a.planes_in_smem ? gs : gs + plane_words);
     const int NC = a.n_cap;
     s.r_pix = arr;
     s.r_lab = arr + NC;
@@ -170,7 +170,12 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 for (int k = 0; k < KD_PT; ++k) {
                     if (cur[k] == ECB_NONE) continue;
                     const uint32_t c = child[slot[k]];
-                    cur[k] = c == (uint32_t) (tid + k * nthr) ? ECB_NONE : c;
+                    if (c == (uint32_t) (tid + k * nthr)) {
+                        if (a.exact_order) a.kd_parent[d.pol][d.off + tid + k * nthr] = cur[k];
+                        cur[k] = ECB_NONE;
+                    } else {
+                        cur[k] = c;
+                    }
                 }
                 // no barrier needed here: a child slot is written only in the round in which its parent is reached,
                 // and all points that reach a node do so in the same round
@@ -202,6 +207,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                     if (cur == DONE) continue;
                     uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
                     uint32_t c = child[2 * cur + (ci < ca ? 0 : 1)];
+                    if (a.exact_order && c == (uint32_t) pid) a.kd_parent[d.pol][d.off + pid] = cur;
                     state[pid] = (st & 0xC0000000u) | (c == (uint32_t) pid ? DONE : c);
                 }
                 __syncthreads();
@@ -212,6 +218,14 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
             }
         }
         __syncthreads();
+        if (a.exact_order) {  // the emulated tree itself, for the member-order pass
+            uint32_t *gl = a.kd_left[d.pol] + d.off, *gr = a.kd_right[d.pol] + d.off;
+            for (int pid = tid; pid < n; pid += nthr) {
+                gl[pid] = child[2 * pid];
+                gr[pid] = child[2 * pid + 1];
+            }
+            if (tid == 0 && n > 0) a.kd_parent[d.pol][d.off] = ECB_NONE;
+        }
         // tie flag of the (occupied) pixel (x,y): bit0 = FX, bit1 = FY
         auto flag_of = [&](int x, int y) -> uint32_t { return s.r_flag[rank_of(x, y)]; };
         // ---- 5. neighbour count, core flag -----------------------------------------------------------
@@ -520,14 +534,32 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 mnorm[base + i] = (uint32_t) (x * x + y * y);
             }
             __syncwarp();
+            bool tie = false;
             for (int i = lane; i < sz; i += 32) {  // rank of (norm^2, pid) among the members; slot sz/2 is the median
                 const uint32_t ni = mnorm[base + i], pi = members[base + i];
-                int cnt = 0;
+                int cnt = 0, eq = 0;
                 for (int j = 0; j < sz; ++j) {
                     const uint32_t nj = mnorm[base + j], pj = members[base + j];
                     cnt += (nj < ni) || (nj == ni && pj < pi);
+                    eq += nj == ni;
                 }
-                if (cnt == sz / 2) med = (int) pi;
+                if (cnt == sz / 2) {
+                    med = (int) pi;
+                    tie = eq > 1;  // std::nth_element's pick among equal norms depends on the member order
+                }
+            }
+            if (a.exact_order && __any_sync(0xffffffffu, tie) && lane == 0) {
+                const unsigned slot = atomicAdd(a.bfs_count, 1u);
+                if (slot < (unsigned) a.bfs_cap) {
+                    BfsItem it;
+                    it.pb = (int32_t) pb;
+                    it.cid = cid;
+                    it.seed = (int32_t) members[base];  // ascending pid list: the seed is its first entry
+                    it.size = sz;
+                    it.mem_off = base;
+                    it.kept = k;
+                    a.bfs_items[slot] = it;
+                }
             }
 #pragma unroll
             for (int q = 0; q < 9; ++q)
@@ -580,12 +612,11 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     // host threads with different sizes cannot race on cudaFuncSetAttribute
     const size_t limit = (size_t) ctx->smem_optin - 9 * 1024;
     size_t planes = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, false, rank32);
-    if (planes > limit)
-        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED,
-                        "bitmap of %dx%d px (+eps border) needs %zu B shared memory, limit %zu", a.W, a.H, planes, limit);
     size_t with_arrays = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, true, rank32);
+    // sensors whose bit planes exceed one CTA's shared memory (e.g. 1280x720) run with the planes in per-CTA L2 scratch
+    a.planes_in_smem = planes <= limit;
     a.arrays_in_smem = with_arrays <= limit;  // else the per-point arrays live in per-CTA L2 scratch
-    size_t smem = a.arrays_in_smem ? with_arrays : planes;
+    size_t smem = a.arrays_in_smem ? with_arrays : (a.planes_in_smem ? planes : 0);
     int threads = ECB_CL_THREADS;
     if (const char *e = getenv("ECB_CL_THREADS")) threads = std::max(64, std::min(ECB_CL_THREADS, atoi(e) & ~31));
     int per_sm = 1;
@@ -600,7 +631,7 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_prob) grid = a.n_prob;
     if (!a.arrays_in_smem) {
-        a.gscratch_stride = (size_t) 5 * a.n_cap + (a.n_cap + 3) / 4;
+        a.gscratch_stride = (size_t) 5 * a.n_cap + (a.n_cap + 3) / 4 + (a.planes_in_smem ? 0 : (planes + 3) / 4);
         int rc = ecb_reserve(ctx, ctx->scratch, (size_t) grid * a.gscratch_stride * 4);
         if (rc) return rc;
         a.gscratch = (uint32_t *) ctx->scratch.p;

@@ -30,6 +30,16 @@ struct KeptCluster {
     double m[9];       // Sx Sy Sxx Syy Sxy Sxxx Syyy Sxyy Sxxy (exact integers)
 };
 
+// one cluster whose members must be put in the reference's BFS pop order (k_bfs_order, ecb_bfs.cu)
+struct BfsItem {
+    int32_t pb;        // problem
+    int32_t cid;       // raw cluster id (label)
+    int32_t seed;      // lowest pid of the cluster = the point Run() started it from
+    int32_t size;
+    int32_t mem_off;   // offset of the member list inside the problem's member slice
+    int32_t kept;      // index into the problem's KeptCluster table whose median is to be re-selected, or -1
+};
+
 struct ClusterArgs {
     const ProbDesc *prob;
     int n_prob;
@@ -43,12 +53,41 @@ struct ClusterArgs {
     uint32_t *gscratch;         // per-CTA global scratch when the per-point arrays do not fit shared memory
     size_t gscratch_stride;     // words per CTA
     int arrays_in_smem;
+    int planes_in_smem;         // 0: sensor too large for one CTA's shared memory, the bit planes live in the L2 scratch too
     int n_cap;                  // region size (>= max n over the batch, >= 64)
     int W, H, E, PW, PH;        // bitmap: W x H pixels, E = floor(eps) padding, PW words per padded row, PH rows
     int eps_int;                // eps if it is an integer (the kd tie rule can fire), else -1
     uint32_t min_pts, cluster_min;
     int8_t halfw[ECB_MAX_EPS + 1];  // half width of the eps-disc at |dy|
+    // exact-order mode: the emulated kd-tree is exported (left / right / parent pid per point slot, same indexing as
+    // pix[pol]) and every kept cluster whose median norm is tied is queued for k_bfs_order
+    int exact_order;
+    uint32_t *kd_left[2], *kd_right[2], *kd_parent[2];
+    BfsItem *bfs_items;
+    unsigned *bfs_count;
+    int bfs_cap;
+};
+
+struct BfsArgs {
+    const BfsItem *items;
+    const unsigned *count;      // device: number of items
+    int max_items;
+    const ProbDesc *prob;
+    const uint32_t *pix[2];
+    const int32_t *labels[2];
+    const uint32_t *kd_left[2], *kd_right[2], *kd_parent[2];
+    uint32_t *members[2];       // in: nothing required / out: member pids in BFS pop order at [off + mem_off, +size)
+    uint32_t *scratch[2];       // same layout as members: unsorted frontier
+    unsigned long long *key[2]; // per point slot
+    int init_keys;              // 1: keys of the cluster's members are initialised here from the (ascending) member list
+    KeptCluster *ktab;          // may be null
+    int max_k;
+    double eps;
 };
 
 size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, bool arrays_in_smem, bool rank32);
 int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n);
+int ecb_launch_bfs(ecb_ctx *ctx, BfsArgs &a);
+// every cluster of every problem -> BfsItem (ecb_dbscan_run_ordered): csize/cseed/coff are per point slot (index off + cid)
+int ecb_launch_bfs_all_items(ecb_ctx *ctx, const ProbDesc *prob, const ProbHdr *hdr, int n_prob, const int32_t *labels,
+                             uint32_t *csize, uint32_t *cseed, uint32_t *coff, BfsItem *items, unsigned *count, int cap);

@@ -46,6 +46,8 @@ struct ecb_ctx {
     std::vector<int64_t> h_lohi, h_ptoff;
     int64_t total_points = 0;
     int cand_stride = 0;
+    // exact member order / medians (ecb_bfs.cu): exported kd-tree, claim keys, work items, frontier scratch
+    DevBuf kd_tree, bfs_key, bfs_items, bfs_front, bfs_tab;
     // dbscan boundary
     DevBuf db_pix, db_off, db_labels, db_hdr, db_scratch, db_dims, db_hdr_b, db_ktab, db_counter;
     // fit

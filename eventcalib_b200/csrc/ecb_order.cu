@@ -14,7 +14,7 @@
 // arrivals to:  buckets in DESCENDING order of their first position in S, inside a bucket DESCENDING position in S.
 // That is a grouping, not a sequential process: atomicMin gives the first position, an atomicExch chain the bucket's
 // members, a suffix scan over the bucket heads the run starts.  Stage sizes grow geometrically, so the whole emulation
-// costs about two passes over the final set.  Checked against the real std::unordered_set (oracle/, tests/golden/uset_order.npz).
+// costs about two passes over the final set.  Checked against the real std::unordered_set in tests/test_gpu_frontend.py.
 //
 // One CTA per (window, polarity); all arrays in shared memory when they fit, else in per-CTA L2 scratch.
 #include "ecb_window.cuh"

@@ -108,13 +108,14 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window(const WindowArgs a) {
     __shared__ uint32_t hash[WIN_HASH];
     const int tid = threadIdx.x, nthr = WIN_THREADS;
     const int RW = a.RW, NWp = RW * a.H;
-    uint32_t *plane[2] = {smw, smw + NWp};
+    uint32_t *pl0 = a.gplanes ? a.gplanes + (size_t) blockIdx.x * 2 * NWp : smw;
+    uint32_t *plane[2] = {pl0, pl0 + NWp};
 
     for (int w = blockIdx.x; w < a.n_win; w += gridDim.x) {
         const int64_t lo = a.lohi[2 * w], hi = max(a.lohi[2 * w + 1], a.lohi[2 * w]);
         const int64_t off = a.ptoff[w];
         __syncthreads();
-        for (int i = tid; i < 2 * NWp; i += nthr) smw[i] = 0;
+        for (int i = tid; i < 2 * NWp; i += nthr) pl0[i] = 0;
         for (int i = tid; i < WIN_HASH; i += nthr) hash[i] = ECB_NONE;
         __syncthreads();
         uint32_t base[2] = {0, 0};  // arrival counts so far (uniform across the block)
@@ -243,15 +244,21 @@ int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a) {
     if (a.n_win <= 0) return ECB_OK;
     a.RW = (a.W + 31) >> 5;
     size_t smem = (size_t) 2 * a.RW * a.H * 4;
-    if (smem > (size_t) ctx->smem_optin - 12 * 1024)
-        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "sensor %dx%d needs %zu B of shared memory for the window bitmaps", a.W,
-                        a.H, smem);
-    ECB_CUDA(ctx, cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - 12 * 1024)  /* constant: race-free */);
+    const size_t limit = (size_t) ctx->smem_optin - 12 * 1024;
+    const bool gpl = smem > limit;  // large sensors: planes in per-CTA L2 scratch
+    if (gpl) smem = 0;
+    ECB_CUDA(ctx, cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
     int per_sm = 1;
     ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_window, WIN_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_win) grid = a.n_win;
+    a.gplanes = nullptr;
+    if (gpl) {
+        int rc = ecb_reserve(ctx, ctx->scratch, (size_t) grid * 2 * a.RW * a.H * 4);
+        if (rc) return rc;
+        a.gplanes = (uint32_t *) ctx->scratch.p;
+    }
     ECB_PROF_BEGIN(ctx, ECB_STAGE_WINDOW);
     k_window<<<grid, WIN_THREADS, smem, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_WINDOW);

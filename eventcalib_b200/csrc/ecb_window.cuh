@@ -12,6 +12,7 @@ struct WindowArgs {
     uint32_t *max_n;          // device words: [0] max points of any problem (sizes the cluster kernel's arrays),
                               //               [1] max distinct pixels before cancellation (sizes k_uset_order)
     int n_win, W, H, RW;
+    uint32_t *gplanes;        // per-CTA bit planes in L2 scratch when they exceed shared memory (else NULL)
     int order_mode;           // 1: mark cancelled pixels in `arrive` (bit 31) for k_uset_order instead of compacting
 };
 

@@ -8,8 +8,8 @@
 //
 // Differences: only dim == 2 with integer-valued, distinct points is supported by the device path
 // (that is the reference's only instantiation, CirclesEventFrame.cpp:66-70) — anything else returns FAILED and
-// `last_error()` says why; `Clusters[c]` lists its members in ascending pid (the reference: BFS pop order); cluster
-// ids, membership and Noise are bit-exact.  `disfunc` is accepted and ignored exactly like the reference's kd-tree build.
+// `last_error()` says why.  `Clusters` (discovery order, members in the reference's BFS pop order) and `Noise` are
+// identical to the reference's as ordered lists.  `disfunc` is accepted and ignored exactly like the reference's kd-tree build.
 // Thread model: one lazily created context per host thread (the reference runs Run() on hardware_concurrency()-2 threads).
 #ifndef ECB_DBSCAN_H
 #define ECB_DBSCAN_H
@@ -80,18 +80,23 @@ public:
             xy[2 * i] = (double) (*V)[i][0];
             xy[2 * i + 1] = (double) (*V)[i][1];
         }
-        std::vector<int32_t> labels((size_t) n);
+        std::vector<int32_t> labels((size_t) n), sizes((size_t) n);
+        std::vector<uint32_t> members((size_t) n);
         int32_t nc = 0;
-        const int rc = ecb_dbscan_run(ctx, xy.data(), n, (double) eps, min, labels.data(), &nc);
+        const int rc = ecb_dbscan_run_ordered(ctx, xy.data(), n, (double) eps, min, labels.data(), &nc, sizes.data(),
+                                              members.data());
         if (rc != ECB_OK) {
             err_ = ecb_last_error(ctx);
             return ERROR_TYPE::FAILED;
         }
         Clusters.assign((size_t) nc, std::vector<uint>());
-        for (int i = 0; i < n; ++i) {
-            if (labels[i] >= 0) Clusters[(size_t) labels[i]].push_back((uint) i);
-            else Noise.push_back((uint) i);
+        size_t at = 0;
+        for (int c = 0; c < nc; ++c) {  // members already in the reference's order (dbscan.h:229-259)
+            Clusters[(size_t) c].assign(members.begin() + at, members.begin() + at + (size_t) sizes[(size_t) c]);
+            at += (size_t) sizes[(size_t) c];
         }
+        for (int i = 0; i < n; ++i)
+            if (labels[i] < 0) Noise.push_back((uint) i);
         return ERROR_TYPE::SUCCESS;
     }
 

@@ -65,7 +65,8 @@ int ecb_synchronize(ecb_ctx *ctx);
 #define ECB_STAGE_NORMAL_EQ 6
 #define ECB_STAGE_COST 7
 #define ECB_STAGE_ORDER 8
-#define ECB_N_STAGES 9
+#define ECB_STAGE_BFS 9
+#define ECB_N_STAGES 10
 int ecb_set_profiling(ecb_ctx *ctx, int on);
 int ecb_stage_ms(ecb_ctx *ctx, float *out);
 const char *ecb_version(void);
@@ -94,7 +95,10 @@ typedef struct {
     int32_t order_mode;         /* 0: pid = first-arrival order; 1: libstdc++ unordered_set iteration order
                                    (the reference's order, EventFrame.cpp:12-35) */
     uint32_t max_clusters;      /* kept-cluster table capacity per (window,polarity); 0 -> 128 */
-    uint32_t reserved;
+    uint32_t median_mode;       /* cluster centre = member with the median norm (CirclesEventFrame.cpp:137-147):
+                                   0: slot size/2 of the members sorted by (norm, pid) — order independent;
+                                   1: the reference's pick: std::nth_element (libstdc++) over the members in DBSCAN's
+                                      BFS pop order — differs from 0 only when several members share the median norm */
 } ecb_frontend_params;
 
 typedef struct {
@@ -135,6 +139,18 @@ int ecb_dbscan_run(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t m
  * (optional) receives ECB_PB_* bits per problem */
 int ecb_dbscan_run_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
                          uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status);
+
+/* Same, plus `Clusters` as the reference builds them (dbscan.h:92,143-162,229-259): cluster c (discovery order) holds
+ * cluster_sizes[c] members, listed consecutively in `members` in the reference's order (the seed, then core points in
+ * the order expandCluster's FIFO pops them; neighbours enumerated like kd_nearest_range does).  Noise = the pids with
+ * label -1, ascending.  cluster_sizes and members need room for n entries. */
+int ecb_dbscan_run_ordered(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t min_pts, int32_t *labels,
+                           int32_t *n_clusters, int32_t *cluster_sizes, uint32_t *members);
+/* batch form: problem k's sizes start at cluster_sizes[offsets[k]] (n_clusters[k] entries) and its member lists at
+ * members[offsets[k]] (one entry per core point) */
+int ecb_dbscan_run_batch_ordered(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
+                                 uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status,
+                                 int32_t *cluster_sizes, uint32_t *members);
 
 /* ---- a5: batched circle fit ---------------------------------------------------------------------- */
 /* set k = points xy[offsets[k]..offsets[k+1]) (union of a + and a - index set); out[k] = cx, cy, r */

@@ -82,3 +82,42 @@ def test_unsupported_inputs_fail_loudly(ctx):
         ctx.dbscan(np.array([[0.5, 1.0], [2.0, 3.0]]), 4, 2)
     with pytest.raises(ecb.EcbError):
         ctx.dbscan(np.array([[1.0, 1.0], [1.0, 1.0]]), 4, 2)  # duplicates
+
+
+@pytest.mark.parametrize("eps,minpts", [(4, 2), (2, 2), (3, 3), (6, 5), (4, 1), (2.5, 2)])
+def test_ordered_clusters_equal_the_reference_lists(ctx, oracle_mod, eps, minpts):
+    """`Clusters` as ORDERED lists (BFS pop order, kd result-list neighbour order; dbscan.h:229-259, kdtree.cpp:148-179,
+    469-486) and `Noise`, against the unmodified reference DBSCAN compiled in oracle/_ref (the restated oracle when the
+    prebuilt reference library is absent)."""
+    ref_fn = oracle_mod.ref_dbscan if oracle_mod.have_ref() else oracle_mod.dbscan
+    rng = np.random.default_rng(1000 + int(eps * 10) + minpts)
+    for it in range(10):
+        n = int(rng.integers(1, 2500))
+        W = int(rng.integers(12, 120))
+        pts = _rand_points(rng, n, W, W)
+        ref = ref_fn(pts, eps, minpts)
+        rc, lab, clusters, noise = ctx.dbscan_ordered(pts, eps, minpts)
+        assert rc == 0 and np.array_equal(lab, ref["labels"])
+        assert len(clusters) == len(ref["clusters"])
+        for c, (g, r) in enumerate(zip(clusters, ref["clusters"])):
+            assert np.array_equal(g, r), "cluster %d member order differs (n=%d W=%d)" % (c, len(pts), W)
+        assert np.array_equal(noise, ref["noise"])
+
+
+def test_ordered_circle_frames_and_batch(ctx, oracle_mod):
+    from eventcalib_b200 import synth
+    ref_fn = oracle_mod.ref_dbscan if oracle_mod.have_ref() else oracle_mod.dbscan
+    ev = synth.make_stream(30000, 346, 260, t0=5.0, duration=0.015, seed=21)
+    sets = []
+    for w in synth.tiling_windows(5.0, 5.015, 1.5e-3):
+        P, N, _, _ = oracle_mod.event_frame(ev["t"], ev["x"], ev["y"], ev["p"], w[0], w[1])
+        sets += [P, N]
+    off = np.concatenate([[0], np.cumsum([len(s) for s in sets])])
+    lab, nc, st, clusters = ctx.dbscan_batch_ordered(np.concatenate(sets), off, 4, 2)
+    assert (st == 0).all()
+    for k, pts in enumerate(sets):
+        ref = ref_fn(pts, 4, 2)
+        assert np.array_equal(lab[off[k]:off[k + 1]], ref["labels"])
+        assert len(clusters[k]) == len(ref["clusters"])
+        for g, r in zip(clusters[k], ref["clusters"]):
+            assert np.array_equal(g, r)

@@ -29,7 +29,8 @@ def _first_arrival(ev, lo, hi, pol):
     return np.array(out, np.float64).reshape(-1, 2)
 
 
-def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4.0, min_pts=2, order_mode=0):
+def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4.0, min_pts=2, order_mode=0,
+                  median_mode=0):
     import eventcalib_b200 as ecb
     from eventcalib_b200 import synth
     ctx.set_sensor(width, height)
@@ -37,7 +38,7 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
     assert n == len(ev["t"])
     rthr = ecb.radius_threshold(width, height, 9, 4, True, 5.5, 1.75)
     prm = ecb.default_params(eps=eps, min_pts=min_pts, fit_circle=fit_circle, radius_threshold=rthr,
-                             order_mode=order_mode)
+                             order_mode=order_mode, median_mode=median_mode)
     ctx.frontend_run(windows, prm)
     summ = ctx.summary()
     pts = [ctx.points(0), ctx.points(1)]
@@ -59,7 +60,9 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
             else:
                 assert np.array_equal(xy, _first_arrival(ev, lo, hi, pol))
             V.append(xy)
-        r = oracle_mod.extract(V[1], V[0], eps=eps, minS=min_pts, fitCircle=fit_circle, Rthr=rthr, canonical_median=True)
+        # median_mode 1: the oracle runs the real std::nth_element over the BFS-ordered member lists, like the reference
+        r = oracle_mod.extract(V[1], V[0], eps=eps, minS=min_pts, fitCircle=fit_circle, Rthr=rthr,
+                               canonical_median=(median_mode == 0))
         for pol, key in ((0, "n"), (1, "p")):
             o, k = int(s["point_offset"][pol]), int(s["n_points"][pol])
             assert np.array_equal(pts[pol][1][o:o + k], r[key + "_labels"]), "labels differ window %d pol %d" % (w, pol)
@@ -88,6 +91,25 @@ def test_davis346_windows(ctx, oracle_mod, fit_circle, order_mode):
     assert total > 30 * len(win)  # the synthetic board is found in (almost) every window
 
 
+@pytest.mark.parametrize("fit_circle", [0, 1])
+def test_reference_exact_mode(ctx, oracle_mod, fit_circle):
+    """order_mode 1 + median_mode 1: the reference's own pid order (libstdc++ unordered_set) and its own cluster centres
+    (std::nth_element over DBSCAN's BFS-ordered member lists) — no documented deviation left on this path."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(240000, 346, 260, t0=5.0, duration=0.12, seed=1001)
+    win = synth.tiling_windows(5.0, 5.12, 1.5e-3)
+    total = _check_stream(ctx, oracle_mod, ev, win, 346, 260, fit_circle, order_mode=1, median_mode=1)
+    assert total > 30 * len(win)
+    # the tie clusters are really there: the canonical medians differ somewhere on this stream
+    import eventcalib_b200 as ecb
+    rthr = ecb.radius_threshold(346, 260, 9, 4, True, 5.5, 1.75)
+    meds = []
+    for mm in (0, 1):
+        ctx.frontend_run(win, ecb.default_params(fit_circle=fit_circle, radius_threshold=rthr, order_mode=1, median_mode=mm))
+        meds.append(np.concatenate([ctx.clusters(w, pol)[2] for w in range(len(win)) for pol in (0, 1)]))
+    assert len(meds[0]) == len(meds[1]) and (meds[0] != meds[1]).any()
+
+
 def test_overlapping_and_empty_windows(ctx, oracle_mod):
     from eventcalib_b200 import synth
     ev = synth.make_stream(40000, 346, 260, t0=5.0, duration=0.02, seed=7)
@@ -110,7 +132,18 @@ def test_vga_large_windows(ctx, oracle_mod):
     ev = synth.make_stream(300000, 640, 480, t0=0.0, duration=0.03, seed=1003)
     win = synth.tiling_windows(0.0, 0.03, 10e-3)
     _check_stream(ctx, oracle_mod, ev, win, 640, 480, 1)
-    _check_stream(ctx, oracle_mod, ev, win, 640, 480, 1, order_mode=1)
+    _check_stream(ctx, oracle_mod, ev, win, 640, 480, 1, order_mode=1, median_mode=1)
+
+
+def test_hd_sensor_noise_sweep(ctx, oracle_mod):
+    """BASELINE config C5 in miniature: 1280x720, polarity noise, 1 ms windows, eps / minPts sweep.  The bit planes of
+    this sensor exceed one CTA's shared memory, so the kernels run them from per-CTA L2 scratch."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(200000, 1280, 720, t0=0.0, duration=0.002, seed=1005, noise_frac=0.2, flip_frac=0.05)
+    win = synth.tiling_windows(0.0, 0.002, 1e-3)
+    _check_stream(ctx, oracle_mod, ev, win, 1280, 720, 1, order_mode=1, median_mode=1)
+    for eps, mp in ((2, 2), (3, 5), (6, 3), (8, 8)):
+        _check_stream(ctx, oracle_mod, ev, win, 1280, 720, 0, eps=float(eps), min_pts=mp)
 
 
 def test_eps_minpts_sweep(ctx, oracle_mod):
