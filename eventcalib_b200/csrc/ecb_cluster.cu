@@ -170,12 +170,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 for (int k = 0; k < KD_PT; ++k) {
                     if (cur[k] == ECB_NONE) continue;
                     const uint32_t c = child[slot[k]];
-                    if (c == (uint32_t) (tid + k * nthr)) {
-                        if (a.exact_order) a.kd_parent[d.pol][d.off + tid + k * nthr] = cur[k];
-                        cur[k] = ECB_NONE;
-                    } else {
-                        cur[k] = c;
-                    }
+                    cur[k] = c == (uint32_t) (tid + k * nthr) ? ECB_NONE : c;
                 }
                 // no barrier needed here: a child slot is written only in the round in which its parent is reached,
                 // and all points that reach a node do so in the same round
@@ -207,7 +202,6 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                     if (cur == DONE) continue;
                     uint32_t ci = (s.r_pix[pid] >> dsh) & 0xFFFF, ca = (s.r_pix[cur] >> dsh) & 0xFFFF;
                     uint32_t c = child[2 * cur + (ci < ca ? 0 : 1)];
-                    if (a.exact_order && c == (uint32_t) pid) a.kd_parent[d.pol][d.off + pid] = cur;
                     state[pid] = (st & 0xC0000000u) | (c == (uint32_t) pid ? DONE : c);
                 }
                 __syncthreads();
@@ -220,11 +214,15 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
         __syncthreads();
         if (a.exact_order) {  // the emulated tree itself, for the member-order pass
             uint32_t *gl = a.kd_left[d.pol] + d.off, *gr = a.kd_right[d.pol] + d.off;
+            uint32_t *gp = a.kd_parent[d.pol] + d.off;
             for (int pid = tid; pid < n; pid += nthr) {
-                gl[pid] = child[2 * pid];
-                gr[pid] = child[2 * pid + 1];
+                const uint32_t l = child[2 * pid], r = child[2 * pid + 1];
+                gl[pid] = l;
+                gr[pid] = r;
+                if (l != ECB_NONE) gp[l] = (uint32_t) pid;
+                if (r != ECB_NONE) gp[r] = (uint32_t) pid;
             }
-            if (tid == 0 && n > 0) a.kd_parent[d.pol][d.off] = ECB_NONE;
+            if (tid == 0 && n > 0) gp[0] = ECB_NONE;
         }
         // tie flag of the (occupied) pixel (x,y): bit0 = FX, bit1 = FY
         auto flag_of = [&](int x, int y) -> uint32_t { return s.r_flag[rank_of(x, y)]; };
@@ -272,44 +270,62 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
             if (p != x) parent[rank_of(x, y)] = rank_of(p, y);
         }
         __syncthreads();
-        // work item = (core pixel, row offset dy): dy = 0 handles the exact-eps in-row link of run heads, dy >= 1 unites the
-        // pixel's run with the first pixel of every run inside the eps-disc segment of row y + dy
-        for (int dy = 0; dy <= E; ++dy)
-        for (int pid = tid; pid < n; pid += nthr) {
-            const uint32_t loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
-            const int x = loc & 0xFFFF, y = loc >> 16;
-            if (!test_bit(s.C + y * PW, x)) continue;
-            if (dy == 0) {
-                // q = p - eps*e_x with nothing in between: mutual unless the kd query misses q -> p (FX(p))
-                if (ei > 0 && test_bit(s.C + y * PW, x + ei) && !row_bits(s.C + y * PW, x + 1, ei - 1) &&
-                    !(flag_of(x + ei, y) & 1u))
-                    unite(parent, rank_of(x, y), rank_of(x + ei, y));
-                continue;
-            }
-            const int w = a.halfw[dy];
-            const int xs = x - w, len = 2 * w + 1;
-            uint32_t bits = row_bits(s.C + (y + dy) * PW, xs, len);
-            if (!bits) continue;
-            {
-                // lower = OR of (bits << 1 .. bits << gap), by doubling; the first pixel of every run survives
-                uint32_t sm = bits;  // OR of shifts 0..k
+        // 6b/6c work item = core pixel.  Every pixel tests its exact-eps in-row link (dy = 0); the inter-row unions are done
+        // by the FIRST pixel of every sub-run of its bitmap word only (sub-run = core pixels of the word with gaps <= gap),
+        // so an adjacent (sub-run, run) pair is united once instead of once per pixel pair: the sub-run is dilated by the
+        // half width of the eps-disc at dy and intersected with row y + dy, and the first pixel of every run in the
+        // intersection is united with the sub-run's first pixel.  dy = eps (half width 0): pixel pairs in the same column,
+        // minus the ones the kd query misses (one-way edges, see 7).
+        {
+            auto smear = [&](uint64_t v) -> uint64_t {  // OR of (v << 1 .. v << gap)
+                uint64_t sm = v;
                 for (int k = 0; k < gap - 1;) {
                     const int add = min(k + 1, gap - 1 - k);
                     sm |= sm << add;
                     k += add;
                 }
-                const uint32_t lower = gap > 0 ? sm << 1 : 0u;
-                bits &= ~lower;
-            }
-            const uint32_t rq = rank_of(x, y);
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int nx = xs + b, ny = y + dy;
-                // q -> p missed by the kd query: the pair is a one-way edge p -> q (handled in 7)
-                if (ei > 0 && dy == ei && nx == x && (flag_of(nx, ny) & 2u)) continue;
-                unite(parent, rq, rank_of(nx, ny));
+                return gap > 0 ? sm << 1 : 0ull;
+            };
+            for (int pid = tid; pid < n; pid += nthr) {
+                const uint32_t loc = s.r_pix[pid];
+                if (loc == ECB_NONE) continue;
+                const int x = loc & 0xFFFF, y = loc >> 16;
+                const int j = x >> 5, f = x & 31;
+                const uint32_t *crow = s.C + y * PW;
+                const uint32_t src = crow[j];
+                if (!((src >> f) & 1u)) continue;
+                // q = p - eps*e_x with nothing in between: mutual unless the kd query misses q -> p (FX(p))
+                if (ei > 0 && test_bit(crow, x + ei) && !row_bits(crow, x + 1, ei - 1) && !(flag_of(x + ei, y) & 1u))
+                    unite(parent, rank_of(x, y), rank_of(x + ei, y));
+                const uint32_t F = src & ~(uint32_t) smear(src);  // first pixel of every sub-run of the word
+                if (!((F >> f) & 1u)) continue;
+                const uint32_t Fup = f < 31 ? F >> (f + 1) : 0u;  // next sub-run start above f
+                const uint32_t upto = Fup ? ((1u << (f + __ffs(Fup))) - 1u) : 0xFFFFFFFFu;
+                const uint64_t S64 = (uint64_t) (src & upto & ~((1u << f) - 1u)) << 16;
+                const uint32_t rf = rank_of(x, y);
+                for (int dy = 1; dy <= E; ++dy) {
+                    const int w = a.halfw[dy];
+                    const uint32_t *tr = crow + dy * PW + j;  // word j of row y + dy
+                    const uint32_t T0 = j > 0 ? tr[-1] : 0u, T1 = tr[0], T2 = j + 1 < PW ? tr[1] : 0u;
+                    if (!(T0 | T1 | T2)) continue;
+                    const uint64_t Tw = ((uint64_t) T0 >> 16) | ((uint64_t) T1 << 16) | ((uint64_t) T2 << 48);  // bit k = pixel 32j-16+k
+                    uint64_t d64 = S64 >> w;  // bits >= 16 - w >= 1
+                    for (int k = 0; k < 2 * w;) {  // OR of shifts 0..2w: the sub-run dilated by w (top bit <= 47 + w)
+                        const int add = min(k + 1, 2 * w - k);
+                        d64 |= d64 << add;
+                        k += add;
+                    }
+                    uint64_t hits = d64 & Tw;
+                    if (!hits) continue;
+                    if (dy != ei) hits &= ~smear(hits);  // first pixel of every run of the intersection
+                    while (hits) {
+                        const int nx = 32 * j - 16 + (__ffsll((long long) hits) - 1);
+                        hits &= hits - 1;
+                        // dy = eps: q -> p missed by the kd query: the pair is a one-way edge p -> q (handled in 7)
+                        if (dy == ei && (flag_of(nx, y + dy) & 2u)) continue;
+                        unite(parent, rf, rank_of(nx, y + dy));
+                    }
+                }
             }
         }
         __syncthreads();
