@@ -59,22 +59,30 @@ __device__ __forceinline__ void unite(uint32_t *parent, uint32_t a, uint32_t b) 
     }
 }
 
-template <typename RankT>
-__global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a) {
+// SM = true: bit planes AND per-point arrays live in shared memory — every pointer below is then derived from the
+// shared array alone, so the compiler emits LDS / STS / ATOMS with 32-bit addresses instead of generic accesses.
+template <typename RankT, bool SM>
+__global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs a) {
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ uint32_t ws[33];
-    __shared__ uint32_t s_pb, s_status;
+    __shared__ uint32_t s_pb, s_status, s_chunk;
     __shared__ int32_t k_raw[ECB_MAXK_LIMIT], k_size[ECB_MAXK_LIMIT], k_off[ECB_MAXK_LIMIT + 1];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     const int PW = a.PW, PH = a.PH, E = a.E, NW = PW * PH;
     Smem<RankT> s;
     const int plane_words = 2 * NW + (int) ((NW * sizeof(RankT) + 3) / 4);
-    uint32_t *gs = a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
-    s.U = a.planes_in_smem ? smem_raw : gs;
+    uint32_t *arr;
+    if constexpr (SM) {
+        s.U = smem_raw;
+        arr = smem_raw + plane_words;
+    } else {
+        uint32_t *gs = a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
+        s.U = a.planes_in_smem ? smem_raw : gs;
+        arr = a.planes_in_smem ? gs : gs + plane_words;
+    }
     s.C = s.U + NW;
     s.wrank = reinterpret_cast<RankT *>(s.C + NW);
-    uint32_t *arr = a.arrays_in_smem ? (s.U + plane_words) : (a.planes_in_smem ? gs : gs + plane_words);
     const int NC = a.n_cap;
     s.r_pix = arr;
     s.r_lab = arr + NC;
@@ -269,6 +277,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 }
             if (p != x) parent[rank_of(x, y)] = rank_of(p, y);
         }
+        if (tid == 0) s_chunk = 0;
         __syncthreads();
         // 6b/6c work item = core pixel.  Every pixel tests its exact-eps in-row link (dy = 0); the inter-row unions are done
         // by the FIRST pixel of every sub-run of its bitmap word only (sub-run = core pixels of the word with gaps <= gap),
@@ -286,30 +295,60 @@ __global__ void __launch_bounds__(ECB_CL_THREADS) k_cluster(const ClusterArgs a)
                 }
                 return gap > 0 ? sm << 1 : 0ull;
             };
-            for (int pid = tid; pid < n; pid += nthr) {
-                const uint32_t loc = s.r_pix[pid];
-                if (loc == ECB_NONE) continue;
-                const int x = loc & 0xFFFF, y = loc >> 16;
-                const int j = x >> 5, f = x & 31;
-                const uint32_t *crow = s.C + y * PW;
-                const uint32_t src = crow[j];
-                if (!((src >> f) & 1u)) continue;
-                // q = p - eps*e_x with nothing in between: mutual unless the kd query misses q -> p (FX(p))
-                if (ei > 0 && test_bit(crow, x + ei) && !row_bits(crow, x + 1, ei - 1) && !(flag_of(x + ei, y) & 1u))
-                    unite(parent, rank_of(x, y), rank_of(x + ei, y));
-                const uint32_t F = src & ~(uint32_t) smear(src);  // first pixel of every sub-run of the word
-                if (!((F >> f) & 1u)) continue;
-                const uint32_t Fup = f < 31 ? F >> (f + 1) : 0u;  // next sub-run start above f
-                const uint32_t upto = Fup ? ((1u << (f + __ffs(Fup))) - 1u) : 0xFFFFFFFFu;
-                const uint64_t S64 = (uint64_t) (src & upto & ~((1u << f) - 1u)) << 16;
-                const uint32_t rf = rank_of(x, y);
-                for (int dy = 1; dy <= E; ++dy) {
+            // Load balance: warps draw chunks of 32 pids from a shared counter, and inside a warp the (sub-run head, dy) pairs
+            // of the chunk are dealt out evenly to the lanes (the union cost per pair varies a lot).
+            const uint32_t invE = (65536u + (uint32_t) E - 1u) / (uint32_t) E;  // it / E == (it * invE) >> 16 for it < 512
+            for (;;) {
+                int base = 0;
+                if (lane == 0) base = (int) atomicAdd(&s_chunk, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) break;
+                const int pid = base + lane;
+                bool head = false;
+                uint32_t h_xy = 0, h_sub = 0, h_rf = 0;
+                if (pid < n) {
+                    const uint32_t loc = s.r_pix[pid];
+                    if (loc != ECB_NONE) {
+                        const int x = loc & 0xFFFF, y = loc >> 16;
+                        const int j = x >> 5, f = x & 31;
+                        const uint32_t *crow = s.C + y * PW;
+                        const uint32_t src = crow[j];
+                        if ((src >> f) & 1u) {
+                            // q = p - eps*e_x with nothing in between: mutual unless the kd query misses q -> p (FX(p))
+                            if (ei > 0 && test_bit(crow, x + ei) && !row_bits(crow, x + 1, ei - 1) &&
+                                !(flag_of(x + ei, y) & 1u))
+                                unite(parent, rank_of(x, y), rank_of(x + ei, y));
+                            const uint32_t F = src & ~(uint32_t) smear(src);  // first pixel of every sub-run of the word
+                            if ((F >> f) & 1u) {
+                                const uint32_t Fup = f < 31 ? F >> (f + 1) : 0u;  // next sub-run start above f
+                                const uint32_t upto = Fup ? ((1u << (f + __ffs(Fup))) - 1u) : 0xFFFFFFFFu;
+                                head = true;
+                                h_xy = loc;
+                                h_sub = src & upto & ~((1u << f) - 1u);
+                                h_rf = rank_of(x, y);
+                            }
+                        }
+                    }
+                }
+                const uint32_t hm = __ballot_sync(0xffffffffu, head);
+                const int n_it = __popc(hm) * E;
+                for (int it0 = 0; it0 < n_it; it0 += 32) {
+                    const int it = it0 + lane;
+                    const bool act = it < n_it;
+                    const int hi = act ? (int) (((uint32_t) it * invE) >> 16) : 0;
+                    const int dy = it - hi * E + 1;
+                    const int owner = (int) __fns(hm, 0, hi + 1);
+                    const uint32_t loc = __shfl_sync(0xffffffffu, h_xy, owner);
+                    const uint32_t sub = __shfl_sync(0xffffffffu, h_sub, owner);
+                    const uint32_t rf = __shfl_sync(0xffffffffu, h_rf, owner);
+                    if (!act) continue;
+                    const int x = loc & 0xFFFF, y = loc >> 16, j = x >> 5;
                     const int w = a.halfw[dy];
-                    const uint32_t *tr = crow + dy * PW + j;  // word j of row y + dy
+                    const uint32_t *tr = s.C + (y + dy) * PW + j;  // word j of row y + dy
                     const uint32_t T0 = j > 0 ? tr[-1] : 0u, T1 = tr[0], T2 = j + 1 < PW ? tr[1] : 0u;
                     if (!(T0 | T1 | T2)) continue;
                     const uint64_t Tw = ((uint64_t) T0 >> 16) | ((uint64_t) T1 << 16) | ((uint64_t) T2 << 48);  // bit k = pixel 32j-16+k
-                    uint64_t d64 = S64 >> w;  // bits >= 16 - w >= 1
+                    uint64_t d64 = ((uint64_t) sub << 16) >> w;  // bits >= 16 - w >= 1
                     for (int k = 0; k < 2 * w;) {  // OR of shifts 0..2w: the sub-run dilated by w (top bit <= 47 + w)
                         const int add = min(k + 1, 2 * w - k);
                         d64 |= d64 << add;
@@ -636,13 +675,10 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     int threads = ECB_CL_THREADS;
     if (const char *e = getenv("ECB_CL_THREADS")) threads = std::max(64, std::min(ECB_CL_THREADS, atoi(e) & ~31));
     int per_sm = 1;
-    if (rank32) {
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit));
-        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint32_t>, threads, smem));
-    } else {
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_cluster<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit));
-        ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cluster<uint16_t>, threads, smem));
-    }
+    void (*kern)(const ClusterArgs) = rank32 ? (a.arrays_in_smem ? k_cluster<uint32_t, true> : k_cluster<uint32_t, false>)
+                                             : (a.arrays_in_smem ? k_cluster<uint16_t, true> : k_cluster<uint16_t, false>);
+    ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit));
+    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_prob) grid = a.n_prob;
@@ -654,10 +690,7 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     }
     ECB_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, 4, ctx->stream));
     ECB_PROF_BEGIN(ctx, ECB_STAGE_CLUSTER);
-    if (rank32)
-        k_cluster<uint32_t><<<grid, threads, smem, ctx->stream>>>(a);
-    else
-        k_cluster<uint16_t><<<grid, threads, smem, ctx->stream>>>(a);
+    kern<<<grid, threads, smem, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_CLUSTER);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_cluster launch");
