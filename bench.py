@@ -450,10 +450,21 @@ def main():
         achieved = algo[dom] / (stage[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                     "frac": achieved / hbm, "traffic": None, "peak_source": which,
+                    "algorithmic_bytes_per_launch": algo[dom],
                     "path_frac": (value / world) * ALGO_BYTES_PER_EVENT / 1e9 / hbm,
                     "note": "achieved = algorithmic bytes of the dominant kernel / its CUDA-event duration (DESIGN.md); "
                             "path_frac = whole-path 29 B/event x events/s / peak; the dominant kernels are shared-memory / "
                             "issue bound, not HBM bound (profiles/)", "kernels": kernels}
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), scaled to this
+        # run's event count when it differs
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            k = tr["kernels"].get("k_" + dom)
+            if k:
+                roofline["traffic"] = (k["dram_bytes_read"] + k["dram_bytes_write"]) * (n / float(tr["events"]))
+                roofline["traffic_source"] = tr["source"] + ("" if n == tr["events"] else " (scaled from %d events)" % tr["events"])
+        except Exception:
+            pass
         if "normal_eq" in stage:
             roofline["cost_kernel"] = {"bound": "tensor", "kernel": "k_normal_eq (FP64 DMMA)", "unit": "TFLOP/s",
                                        "achieved": flops["normal_eq"] / (stage["normal_eq"] * 1e-3) / 1e12, "peak": 37.0,
@@ -464,9 +475,11 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32 pixels / f64 fit + f64 residuals", "data": "synthetic",
                 "config": {"workload": "C2 per GPU: synthetic %d-event DAVIS346 (346x260) circle-grid stream, %d tiling "
-                                       "windows of 1.5 ms, DBSCAN eps 4 minPts 2 + cluster filter + circle fit (fitCircle 1), "
-                                       "then residual evaluation of the same events (association + J^T J/J^T r + cost, "
-                                       "all-reduce when N>1)" % (n, len(win)),
+                                       "windows of 1.5 ms, DBSCAN eps 4 minPts 2 + cluster filter + circle fit (fitCircle 1; pid order %s, "
+                                       "cluster centres %s), then residual evaluation of the same events (association + "
+                                       "J^T J/J^T r + cost, all-reduce when N>1)" % (
+                                           n, len(win), "= libstdc++ unordered_set order like the reference" if args.order_mode == 1 else "= first arrival",
+                                           "= std::nth_element over BFS-ordered members like the reference" if args.median_mode == 1 else "canonical"),
                            "events_per_gpu": n, "windows_per_gpu": int(len(win)), "residuals_per_gpu": int(n_res),
                            "control_points": int(len(rot)), "parallelism": "windows / spline segments sharded x%d" % world,
                            "l2": "inputs larger than L2 (%.0f MB of records per step)" % (n * 25 / 1e6),

@@ -75,12 +75,16 @@ __device__ __forceinline__ uint32_t bucket_of(uint64_t h, int stage) {
     }
 }
 
+// SM: arrays in shared memory (pointers derived from the shared array only -> LDS/STS/ATOMS), else per-CTA L2 scratch
+template <bool SM>
 __global__ void __launch_bounds__(ORD_THREADS) k_uset_order(const OrderArgs a) {
     extern __shared__ __align__(16) uint32_t smo[];
     __shared__ uint32_t ws[33];
     __shared__ uint32_t s_pb;
     const int tid = threadIdx.x, nthr = ORD_THREADS, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
-    uint32_t *base = a.arrays_in_smem ? smo : a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
+    uint32_t *base;
+    if constexpr (SM) base = smo;
+    else base = a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
     const int MC = a.m_cap, BC = a.b_cap;
     uint32_t *cur = base, *nxtL = base + MC;       // ping-pong order lists (arrival indices)
     uint32_t *chain = base + 2 * MC;               // next position in the bucket's chain
@@ -97,8 +101,8 @@ __global__ void __launch_bounds__(ORD_THREADS) k_uset_order(const OrderArgs a) {
         if (pb >= (uint32_t) a.n_prob) break;
         const ProbDesc d = a.prob[pb];
         const int m = d.pad0;  // arrival count = size of the set before the +/- cancellation
-        const uint32_t *arr = a.arrive[d.pol] + d.off;
-        uint32_t *dst = a.pts[d.pol] + d.off;
+        const uint32_t *arr = (d.pol ? a.arrive[1] : a.arrive[0]) + d.off;
+        uint32_t *dst = (d.pol ? a.pts[1] : a.pts[0]) + d.off;
         if (m <= 0) continue;
 
         for (int stage = 0;; ++stage) {
@@ -206,9 +210,10 @@ int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
     const size_t limit = (size_t) ctx->smem_optin - 2 * 1024;
     a.arrays_in_smem = words * 4 <= limit;
     const size_t smem = a.arrays_in_smem ? words * 4 : 0;
-    ECB_CUDA(ctx, cudaFuncSetAttribute(k_uset_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
+    void (*kern)(const OrderArgs) = a.arrays_in_smem ? k_uset_order<true> : k_uset_order<false>;
+    ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
     int per_sm = 1;
-    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_uset_order, ORD_THREADS, smem));
+    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ORD_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_prob) grid = a.n_prob;
@@ -220,7 +225,7 @@ int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
     }
     ECB_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, 4, ctx->stream));
     ECB_PROF_BEGIN(ctx, ECB_STAGE_ORDER);
-    k_uset_order<<<grid, ORD_THREADS, smem, ctx->stream>>>(a);
+    kern<<<grid, ORD_THREADS, smem, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_ORDER);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_uset_order launch");

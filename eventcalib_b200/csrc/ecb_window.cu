@@ -102,13 +102,16 @@ __global__ void k_bounds(const double *__restrict__ t, int64_t n, const double *
 constexpr int WIN_THREADS = 512;
 constexpr int WIN_HASH = 2048;
 
+template <bool SM>  // SM: bit planes in shared memory, else in per-CTA L2 scratch (large sensors)
 __global__ void __launch_bounds__(WIN_THREADS) k_window(const WindowArgs a) {
     extern __shared__ __align__(16) uint32_t smw[];
     __shared__ uint32_t ws[33];
     __shared__ uint32_t hash[WIN_HASH];
     const int tid = threadIdx.x, nthr = WIN_THREADS;
     const int RW = a.RW, NWp = RW * a.H;
-    uint32_t *pl0 = a.gplanes ? a.gplanes + (size_t) blockIdx.x * 2 * NWp : smw;
+    uint32_t *pl0;
+    if constexpr (SM) pl0 = smw;
+    else pl0 = a.gplanes + (size_t) blockIdx.x * 2 * NWp;
     uint32_t *plane[2] = {pl0, pl0 + NWp};
 
     for (int w = blockIdx.x; w < a.n_win; w += gridDim.x) {
@@ -247,9 +250,10 @@ int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a) {
     const size_t limit = (size_t) ctx->smem_optin - 12 * 1024;
     const bool gpl = smem > limit;  // large sensors: planes in per-CTA L2 scratch
     if (gpl) smem = 0;
-    ECB_CUDA(ctx, cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
+    void (*kern)(const WindowArgs) = gpl ? k_window<false> : k_window<true>;
+    ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
     int per_sm = 1;
-    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_window, WIN_THREADS, smem));
+    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WIN_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_win) grid = a.n_win;
@@ -260,7 +264,7 @@ int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a) {
         a.gplanes = (uint32_t *) ctx->scratch.p;
     }
     ECB_PROF_BEGIN(ctx, ECB_STAGE_WINDOW);
-    k_window<<<grid, WIN_THREADS, smem, ctx->stream>>>(a);
+    kern<<<grid, WIN_THREADS, smem, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_WINDOW);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_window launch");
