@@ -113,6 +113,8 @@ public:
         fp.fit_circle = p_.fitCircle ? 1 : 0;
         fp.radius_threshold = rthr_;
         fp.rows_cols = (uint32_t) (pattern_->rows * pattern_->cols);
+        fp.order_mode = 1;   // pid order = iteration order of EventFrame's unordered_sets (EventFrame.cpp:12-35)
+        fp.median_mode = 1;  // cluster centre = std::nth_element's pick over the BFS-ordered members (CirclesEventFrame.cpp:137-147)
         std::vector<double> w(2 * windows.size());
         for (size_t i = 0; i < windows.size(); ++i) {
             w[2 * i] = windows[i].first;
