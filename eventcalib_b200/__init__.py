@@ -57,7 +57,7 @@ assert SUMMARY_DTYPE.itemsize == C.sizeof(WindowSummary)
 SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_count", "ecb_synchronize", "ecb_version",
            "ecb_set_sensor", "ecb_load_events_host", "ecb_load_events_device", "ecb_num_events", "ecb_frontend_run",
            "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
-           "ecb_frontend_clusters", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
+           "ecb_frontend_clusters", "ecb_frontend_rectify", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
            "ecb_dbscan_run_ordered", "ecb_dbscan_run_batch_ordered",
            "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_layout",
            "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq", "ecb_lm_default_options", "ecb_lm_create",
@@ -98,6 +98,7 @@ def load_library():
     lib.ecb_frontend_candidates.argtypes = [vp, vp, i32]
     lib.ecb_frontend_clusters.argtypes = [vp, i32, i32, vp, vp, vp, i32]
     lib.ecb_frontend_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
+    lib.ecb_frontend_rectify.argtypes = [vp, vp, i32, i32, vp, dbl, i32, i32, i32, vp, vp]
     lib.ecb_dbscan_run.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32)]
     lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
     lib.ecb_dbscan_run_ordered.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32), vp, vp]
@@ -244,6 +245,18 @@ class Context:
         if self.n_win:
             self._chk(self.lib.ecb_frontend_candidates(self.h, _ptr(out), max_cand))
         return out
+
+    def rectify(self, window_index, image_points, rows=9, cols=4, asymmetric=True, inlier_threshold=3.0):
+        """rectifyFeatures for frames of the last front-end run; image_points [n_frames][n_circles][5][2]"""
+        wi = np.ascontiguousarray(window_index, np.int32)
+        img = np.ascontiguousarray(image_points, np.float64)
+        nf, nc = img.shape[0], img.shape[1]
+        assert img.shape == (nf, nc, 5, 2) and len(wi) == nf
+        out = np.zeros((max(nf, 1), nc, 3))
+        ok = np.zeros(max(nf, 1), np.int32)
+        self._chk(self.lib.ecb_frontend_rectify(self.h, _ptr(wi), nf, nc, _ptr(img), float(inlier_threshold), rows, cols,
+                                                int(asymmetric), _ptr(out), _ptr(ok)))
+        return out[:nf], ok[:nf]
 
     def clusters(self, window, polarity, cap=512):
         raw = np.zeros(cap, np.int32)

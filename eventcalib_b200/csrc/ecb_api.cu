@@ -494,6 +494,68 @@ int ecb_frontend_clusters(ecb_ctx *ctx, int window, int polarity, int32_t *raw_i
     return n;
 }
 
+int ecb_frontend_rectify(ecb_ctx *ctx, const int32_t *window_index, int n_frames, int n_circles,
+                         const double *image_points, double inlier_threshold, int rows, int cols, int asymmetric,
+                         double *out, int32_t *frame_ok) {
+    if (!ctx || n_frames < 0 || n_circles < 1 || (n_frames > 0 && (!window_index || !image_points || !out))) return ECB_ERR_ARG;
+    if (ctx->n_win <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no front-end results");
+    if (n_frames == 0) return ECB_OK;
+    for (int i = 0; i < n_frames; ++i)
+        if (window_index[i] < 0 || window_index[i] >= ctx->n_win)
+            return ecb_fail(ctx, ECB_ERR_ARG, "frame %d: window index %d outside the last run's %d windows", i, window_index[i], ctx->n_win);
+    cudaSetDevice(ctx->device);
+    int rc;
+    const size_t items = (size_t) n_frames * n_circles;
+    if ((rc = ecb_reserve(ctx, ctx->fit_in, items * 80 + (size_t) n_frames * 4 + 16))) return rc;
+    if ((rc = ecb_reserve(ctx, ctx->fit_out, items * 24))) return rc;
+    double *d_img = (double *) ctx->fit_in.p;
+    int32_t *d_win = (int32_t *) (d_img + items * 10);
+    if ((rc = ecb_h2d(ctx, d_img, image_points, items * 80))) return rc;
+    if ((rc = ecb_h2d(ctx, d_win, window_index, (size_t) n_frames * 4))) return rc;
+    PairArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.prob = (const ProbDesc *) ctx->db_dims.p;
+    pa.hdr = (const ProbHdr *) ctx->db_hdr.p;
+    pa.ktab = (const KeptCluster *) ctx->ktab.p;
+    const int32_t *labels[2];
+    for (int p = 0; p < 2; ++p) {
+        pa.pts[p] = (const uint32_t *) ctx->pts[p].p;
+        labels[p] = (const int32_t *) ctx->labels[p].p;
+    }
+    pa.max_k = ctx->cand_stride;
+    if ((rc = ecb_launch_rectify(ctx, d_win, n_frames, n_circles, d_img, (double *) ctx->fit_out.p, pa, labels, inlier_threshold)))
+        return rc;
+    if ((rc = ecb_d2h(ctx, out, ctx->fit_out.p, items * 24))) return rc;
+    if (frame_ok) {  // :585-609 (host: a few dozen integer operations per frame)
+        auto on_edge = [&](int e, int i) -> bool {
+            const int step = (asymmetric ? 2 : 1) * cols;
+            if (e == 0) return i < cols;
+            if (e == 1) return i >= (rows - 1) * cols && i < rows * cols;
+            if (e == 2) return i < rows * cols && i % step == 0;
+            const int first = asymmetric ? 2 * cols - 1 : cols - 1;
+            return i >= first && i < rows * cols && (i - first) % step == 0;
+        };
+        int size_[4] = {0, 0, 0, 0};
+        for (int e = 0; e < 4; ++e)
+            for (int i = 0; i < rows * cols; ++i) size_[e] += on_edge(e, i);
+        for (int f = 0; f < n_frames; ++f) {
+            int score[4] = {0, 0, 0, 0}, counter = 0;
+            for (int i = 0; i < n_circles; ++i)
+                if (out[((size_t) f * n_circles + i) * 3 + 2] < 0) {
+                    for (int e = 0; e < 4; ++e) score[e] += on_edge(e, i);
+                    ++counter;
+                }
+            int okf = 1;
+            if (!ctx->fp.fit_circle)
+                for (int e = 0; e < 4; ++e)
+                    if (score[e] >= size_[e] - 1) okf = 0;
+            if (counter >= 0.2 * (cols * rows)) okf = 0;
+            frame_ok[f] = okf;
+        }
+    }
+    return ECB_OK;
+}
+
 int ecb_frontend_device_ptrs(ecb_ctx *ctx, void **d_summary, void **d_candidates, int *cand_stride) {
     if (!ctx) return ECB_ERR_ARG;
     if (d_summary) *d_summary = ctx->summary.p;

@@ -262,6 +262,110 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
     }
 }
 
+// k_rectify — CirclesEventFrame::rectifyFeatures (CirclesEventFrame.cpp:417-576) for every (kept frame, board circle): one
+// warp per circle.  img = the projected centre and four quadrant points of the circle (cv::projectPoints stays with the
+// caller, :449): radius search over the window's points (nanoflann radiusSearch: d2 < R2), quadrant-wise +-3 px band
+// (:484-519), expansion of the inliers to their whole kept DBSCAN clusters (:522-555; here: a bit mask over the kept-cluster
+// table, whose exact integer moments are simply added), Kasa fit (:563-566) and the two sanity gates (:568-574).
+struct RectifyArgs {
+    const int32_t *win;       // [n_frames] window index of the last front-end run
+    int n_frames, n_feat;
+    const double *img;        // [n_frames][n_feat][5][2]
+    double *out;              // [n_frames][n_feat][3]: cx, cy, r (r < 0: feature deleted)
+    const ProbDesc *prob;
+    const ProbHdr *hdr;
+    const KeptCluster *ktab;
+    const uint32_t *pts[2];
+    const int32_t *labels[2];
+    int max_k;
+    double W, H, thr;
+};
+
+constexpr int RECT_WARPS = 4;
+
+__global__ void __launch_bounds__(RECT_WARPS * 32) k_rectify(const RectifyArgs a) {
+    __shared__ uint32_t mask[RECT_WARPS][2][ECB_MAXK_LIMIT / 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int item = blockIdx.x * RECT_WARPS + wib;
+    if (item >= a.n_frames * a.n_feat) return;
+    const int fr = item / a.n_feat;
+    const double *ip = a.img + (size_t) item * 10;
+    double *o = a.out + (size_t) item * 3;
+    const int w = a.win[fr];
+    bool ok = !(ip[0] >= a.W || ip[1] >= a.H || ip[0] < 0 || ip[1] < 0);  // :459-463
+    double radius[4], maxRadius = 0;
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+        const double dx = ip[2 * i] - ip[0], dy = ip[2 * i + 1] - ip[1];
+        radius[i - 1] = sqrt(dx * dx + dy * dy);
+        if (radius[i - 1] > maxRadius) maxRadius = radius[i - 1];
+    }
+    const double R2 = (maxRadius + a.thr) * (maxRadius + a.thr);
+    for (int i = lane; i < 2 * (ECB_MAXK_LIMIT / 32); i += 32) (&mask[wib][0][0])[i] = 0;
+    __syncwarp();
+    double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt[2] = {0, 0};
+    for (int pol = 1; pol >= 0 && ok; --pol) {  // + first like the reference (sums are exact integers anyway)
+        const ProbDesc d = a.prob[2 * w + pol];
+        const int nk = a.hdr[2 * w + pol].n_kept;
+        const KeptCluster *kt = a.ktab + (size_t) (2 * w + pol) * a.max_k;
+        const uint32_t *pts = a.pts[pol] + d.off;
+        const int32_t *lab = a.labels[pol] + d.off;
+        for (int i = lane; i < d.n; i += 32) {
+            const uint32_t p = pts[i];
+            const double dx = (double) ECB_PIX_X(p) - ip[0], dy = (double) ECB_PIX_Y(p) - ip[1];
+            const double d2 = dx * dx + dy * dy;
+            if (!(d2 < R2)) continue;
+            const double distance = sqrt(d2);
+            int idx = 0;
+            if (dx >= 0 && dy >= 0) idx = 0;
+            else if (dx >= 0 && dy <= 0) idx = 1;
+            else if (dx <= 0 && dy <= 0) idx = 2;
+            else if (dx <= 0 && dy >= 0) idx = 3;
+            const double rq = idx == 0 ? radius[0] : idx == 1 ? radius[1] : idx == 2 ? radius[2] : radius[3];
+            if (!(fabs(distance - rq) <= a.thr)) continue;
+            const int32_t l = lab[i];
+            if (l < 0) continue;
+            int lo = 0, hi = nk;  // kept clusters are listed in ascending raw id
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (kt[mid].raw_id < l) lo = mid + 1; else hi = mid;
+            }
+            if (lo < nk && kt[lo].raw_id == l) atomicOr(&mask[wib][pol][lo >> 5], 1u << (lo & 31));
+        }
+        __syncwarp();
+        for (int k = lane; k < nk; k += 32)
+            if ((mask[wib][pol][k >> 5] >> (k & 31)) & 1u) {
+                cnt[pol] += kt[k].size;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) m[q] += kt[k].m[q];
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) m[q] = warp_sum(m[q]);
+    for (int pol = 0; pol < 2; ++pol)
+        for (int off = 16; off > 0; off >>= 1) cnt[pol] += __shfl_xor_sync(0xffffffffu, cnt[pol], off);
+    if (cnt[0] < 5 || cnt[1] < 5) ok = false;  // :558-561
+    double cx = 0, cy = 0, r = -1;
+    if (ok) {
+        fit_from_moments(m, (double) (cnt[0] + cnt[1]), cx, cy, r);
+        // median of the four quadrant radii = what std::nth_element leaves in slot 2 (:568)
+        double s0 = radius[0], s1 = radius[1], s2 = radius[2], s3 = radius[3], t;
+        if (s0 > s1) { t = s0; s0 = s1; s1 = t; }
+        if (s2 > s3) { t = s2; s2 = s3; s3 = t; }
+        if (s0 > s2) { t = s0; s0 = s2; s2 = t; }
+        if (s1 > s3) { t = s1; s1 = s3; s3 = t; }
+        if (s1 > s2) { t = s1; s1 = s2; s2 = t; }
+        const double ex = cx - ip[0], ey = cy - ip[1];
+        if (sqrt(ex * ex + ey * ey) > 2 * a.thr || fabs(r - s2) > 1.5 * a.thr) ok = false;  // :570-574
+    }
+    if (lane == 0) {
+        o[0] = ok ? cx : 0.0;
+        o[1] = ok ? cy : 0.0;
+        o[2] = ok ? r : -1.0;
+    }
+}
+
 // batched fit of explicit point sets: one warp per set (ecb_fit_circles)
 __global__ void k_fit(const double *__restrict__ xy, const int64_t *__restrict__ off, int n_sets, double *__restrict__ out) {
     const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -318,4 +422,30 @@ int ecb_launch_fit(ecb_ctx *ctx, const double *d_xy, const int64_t *d_off, int n
     k_fit<<<(n_sets * 32 + thr - 1) / thr, thr, 0, ctx->stream>>>(d_xy, d_off, n_sets, d_out);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_fit launch");
+}
+
+int ecb_launch_rectify(ecb_ctx *ctx, const int32_t *d_win, int n_frames, int n_feat, const double *d_img, double *d_out,
+                       const PairArgs &pa, const int32_t *const labels[2], double thr) {
+    if (n_frames <= 0 || n_feat <= 0) return ECB_OK;
+    RectifyArgs a;
+    a.win = d_win;
+    a.n_frames = n_frames;
+    a.n_feat = n_feat;
+    a.img = d_img;
+    a.out = d_out;
+    a.prob = pa.prob;
+    a.hdr = pa.hdr;
+    a.ktab = pa.ktab;
+    for (int p = 0; p < 2; ++p) {
+        a.pts[p] = pa.pts[p];
+        a.labels[p] = labels[p];
+    }
+    a.max_k = pa.max_k;
+    a.W = ctx->width;
+    a.H = ctx->height;
+    a.thr = thr;
+    const int items = n_frames * n_feat;
+    k_rectify<<<(items + RECT_WARPS - 1) / RECT_WARPS, RECT_WARPS * 32, 0, ctx->stream>>>(a);
+    ECB_LAUNCHED(ctx);
+    return ecb_check(ctx, cudaGetLastError(), "k_rectify launch");
 }

@@ -49,4 +49,6 @@ int ecb_launch_bounds(ecb_ctx *ctx, const double *d_win, int n_win, int64_t *d_l
 int ecb_launch_window(ecb_ctx *ctx, WindowArgs &a);
 int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m);
 int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a);
+int ecb_launch_rectify(ecb_ctx *ctx, const int32_t *d_win, int n_frames, int n_feat, const double *d_img, double *d_out,
+                       const PairArgs &pa, const int32_t *const labels[2], double thr);
 int ecb_launch_fit(ecb_ctx *ctx, const double *d_xy, const int64_t *d_off, int n_sets, double *d_out);

@@ -140,6 +140,7 @@ public:
         return out;
     }
     double circleRadiusThreshold() const { return rthr_; }
+    ecb_ctx *context() const { return c_->ctx; }
     static constexpr int kMaxCand = 128;
 
 private:
@@ -165,6 +166,30 @@ public:
         if (s.n_points[0] == 0 || s.n_points[1] == 0) return false;  // :62-64
         features_ = fe_.candidates(0);
         return (int) features_.size() >= pattern_->rows * pattern_->cols;
+    }
+    // rectifyFeatures (CirclesEventFrame.cpp:417-609).  The reference projects every feature's landmark and four quadrant
+    // points with cv::projectPoints (:431-456) from (outlierIdxs, Rcw, tcw); that projection needs the OpenCV initialisation
+    // and stays with the caller, who passes the 5 image points per feature (board order).  Radius search, quadrant band,
+    // cluster expansion, refit and the gates run batched on the GPU; deleted features are erased like :585-594.
+    bool rectifyFeatures(const std::vector<std::array<Vec2, 5>> &imagePoints) {
+        const int n = (int) imagePoints.size();
+        std::vector<double> img((size_t) n * 10), out((size_t) n * 3);
+        for (int k = 0; k < n; ++k)
+            for (int i = 0; i < 5; ++i) {
+                img[(size_t) k * 10 + 2 * i] = imagePoints[(size_t) k][(size_t) i][0];
+                img[(size_t) k * 10 + 2 * i + 1] = imagePoints[(size_t) k][(size_t) i][1];
+            }
+        const int32_t w = 0;
+        int32_t ok = 0;
+        if (ecb_frontend_rectify(fe_.context(), &w, 1, n, img.data(), 3.0, pattern_->rows, pattern_->cols,
+                                 pattern_->isAsymmetric ? 1 : 0, out.data(), &ok) != ECB_OK)
+            return false;
+        std::vector<CalibCircleLite> kept;
+        for (int k = 0; k < n; ++k)
+            if (out[(size_t) k * 3 + 2] >= 0)
+                kept.push_back(CalibCircleLite{{{out[(size_t) k * 3], out[(size_t) k * 3 + 1]}}, out[(size_t) k * 3 + 2], -1, -1});
+        features_ = kept;
+        return ok != 0;
     }
     int eventsNum() const { return fe_.eventsNum(0); }
     const std::vector<CalibCircleLite> &features() const { return features_; }

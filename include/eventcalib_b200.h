@@ -126,6 +126,16 @@ int ecb_frontend_candidates(ecb_ctx *ctx, double *out, int max_cand);
 /* kept-cluster table of one window/polarity: raw cluster id, size, median pid  (each up to cap entries) */
 int ecb_frontend_clusters(ecb_ctx *ctx, int window, int polarity, int32_t *raw_id, int32_t *size,
                           int32_t *median_pid, int cap);
+/* a6: CirclesEventFrame::rectifyFeatures (CirclesEventFrame.cpp:417-609) for n_frames windows of the last run, batched over
+ * frames x board circles.  image_points[n_frames][n_circles][5][2]: the projected circle centre and its four quadrant
+ * points (:431-456; cv::projectPoints stays on the caller's side, it needs the OpenCV initialisation).  Per circle: radius
+ * search over the window's points, quadrant-wise +-inlier_threshold band, expansion to whole DBSCAN clusters, circle fit,
+ * sanity gates.  out[n_frames][n_circles][3] = rectified cx, cy, r (r < 0: feature deleted, :461,:560,:573);
+ * frame_ok[n_frames] (optional) = the frame verdict of :585-609 (edge scores — skipped when fit_circle — and the 20 % rule)
+ * for a rows x cols (a)symmetric pattern.  inlier_threshold is 3 px in the reference (:475). */
+int ecb_frontend_rectify(ecb_ctx *ctx, const int32_t *window_index, int n_frames, int n_circles,
+                         const double *image_points, double inlier_threshold, int rows, int cols, int asymmetric,
+                         double *out, int32_t *frame_ok);
 /* device pointers of the results of the last run (for callers that keep working on the GPU) */
 int ecb_frontend_device_ptrs(ecb_ctx *ctx, void **d_summary, void **d_candidates, int *cand_stride);
 

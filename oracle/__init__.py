@@ -188,6 +188,20 @@ def extract(pxy, nxy, eps=4.0, minS=2, clusterMin=5, knn_num=3, fitCircle=0, Rth
                 cand=cand[:info[5]].copy())
 
 
+def rectify(pxy, nxy, img, W, H, eps=4.0, minS=2, clusterMin=5, rows=9, cols=4, asym=True, fitCircle=0):
+    """rectifyFeatures (CirclesEventFrame.cpp:417-609) on explicit point sets; img [n_feat][5][2] projected points.
+    Returns (out [n_feat][3] = cx, cy, r with r < 0 for deleted features, frame verdict)."""
+    pxy = np.ascontiguousarray(pxy, np.float64).reshape(-1, 2)
+    nxy = np.ascontiguousarray(nxy, np.float64).reshape(-1, 2)
+    img = np.ascontiguousarray(img, np.float64)
+    nf = img.shape[0]
+    out = np.zeros((nf, 3))
+    ok = port().orc_rectify(_p(pxy, _dp), C.c_int(len(pxy)), _p(nxy, _dp), C.c_int(len(nxy)), C.c_double(eps),
+                            C.c_uint(minS), C.c_uint(clusterMin), _p(img, _dp), C.c_int(nf), C.c_double(W), C.c_double(H),
+                            C.c_int(rows), C.c_int(cols), C.c_int(int(asym)), C.c_int(fitCircle), _p(out, _dp))
+    return out, int(ok)
+
+
 def frontend_windows(t, x, y, pol, windows, eps=4.0, minS=2, clusterMin=5, knn_num=3, fitCircle=0, Rthr=15.51,
                      rows_cols=36, threads=1, ref=True):
     """CPU baseline: reference-shaped front end over a list of windows with `threads` std::threads.

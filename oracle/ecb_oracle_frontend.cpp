@@ -559,6 +559,104 @@ int orc_extract(const double *pxy, int np, const double *nxy, int nn, double eps
     return 0;
 }
 
+}  // extern "C"
+
+// ---- rectifyFeatures ----
+// CirclesEventFrame::rectifyFeatures, CirclesEventFrame.cpp:417-609, from the projected image points on (cv::projectPoints
+// at :449 is the caller's, like in the reference it needs the OpenCV initialisation): img = n_feat x 5 x 2 doubles
+// (centre, then the four quadrant points of :434-440).  out = n_feat x 3 (cx, cy, r); r < 0: feature deleted.
+// Returns the frame verdict (:596-609): 1 keep, 0 drop.  std::pow(x, 2) is evaluated as x*x.
+static int rectify(const FrameResult &f, const double *img, int n_feat, double W, double H, int rows, int cols, int asym,
+                   int fitCircleFlag, double *out) {
+    const double inlierThreshold = 3;
+    std::vector<int> pS2S(f.pos.size(), -1), nS2S(f.neg.size(), -1);  // :523-534 (each sample is in at most one cluster)
+    for (size_t i = 0; i < f.pcl.size(); ++i)
+        for (unsigned j : f.pcl[i]) pS2S[j] = (int) i;
+    for (size_t i = 0; i < f.ncl.size(); ++i)
+        for (unsigned j : f.ncl[i]) nS2S[j] = (int) i;
+    std::vector<char> gone((size_t) n_feat, 0);
+    for (int k = 0; k < n_feat; ++k) {
+        const double *ip = img + (size_t) k * 10;
+        double *o = out + 3 * (size_t) k;
+        o[0] = o[1] = 0;
+        o[2] = -1;
+        gone[(size_t) k] = 1;
+        if (ip[0] >= W || ip[1] >= H || ip[0] < 0 || ip[1] < 0) continue;  // :459-463
+        double radius[4], maxRadius = 0;
+        for (int i = 1; i < 5; ++i) {  // :465-473
+            const double dx = ip[2 * i] - ip[0], dy = ip[2 * i + 1] - ip[1];
+            radius[i - 1] = std::sqrt(dx * dx + dy * dy);
+            if (radius[i - 1] > maxRadius) maxRadius = radius[i - 1];
+        }
+        const double R2 = (maxRadius + inlierThreshold) * (maxRadius + inlierThreshold);
+        std::set<unsigned> pSet, nSet;
+        auto collect = [&](const std::vector<P2> &pts, const std::vector<int> &s2s, std::set<unsigned> &sets) {
+            for (size_t i = 0; i < pts.size(); ++i) {  // radiusSearch: d2 < R2 (nanoflann RadiusResultSet) :476-481
+                const double dx = pts[i].x - ip[0], dy = pts[i].y - ip[1];
+                const double d2 = dx * dx + dy * dy;
+                if (!(d2 < R2)) continue;
+                const double distance = std::sqrt(d2);
+                int idx = 0;  // :487-497
+                if (dx >= 0 && dy >= 0) idx = 0;
+                else if (dx >= 0 && dy <= 0) idx = 1;
+                else if (dx <= 0 && dy <= 0) idx = 2;
+                else if (dx <= 0 && dy >= 0) idx = 3;
+                if (std::abs(distance - radius[idx]) <= inlierThreshold && s2s[i] >= 0) sets.insert((unsigned) s2s[i]);  // :499-501,536-543
+            }
+        };
+        collect(f.pos, pS2S, pSet);
+        collect(f.neg, nS2S, nSet);
+        std::vector<unsigned> pAll, nAll;  // :544-555
+        for (unsigned c : pSet) pAll.insert(pAll.end(), f.pcl[c].begin(), f.pcl[c].end());
+        for (unsigned c : nSet) nAll.insert(nAll.end(), f.ncl[c].begin(), f.ncl[c].end());
+        if (pAll.size() < 5 || nAll.size() < 5) continue;  // :558-561
+        double c[2], r;
+        fit_circle(f.pos, f.neg, pAll, nAll, c, r);  // :563-566
+        std::nth_element(radius, radius + 2, radius + 4);  // :568
+        const double ex = c[0] - ip[0], ey = c[1] - ip[1];
+        if (std::sqrt(ex * ex + ey * ey) > 2 * inlierThreshold || std::abs(r - radius[2]) > 1.5 * inlierThreshold) continue;  // :570-574
+        o[0] = c[0];
+        o[1] = c[1];
+        o[2] = r;
+        gone[(size_t) k] = 0;
+    }
+    // edge scores and the 20 % rule :585-609
+    int score[4] = {0, 0, 0, 0}, size_[4] = {0, 0, 0, 0}, counter = 0;
+    auto on_edge = [&](int e, int i) -> bool {
+        const int step = (asym ? 2 : 1) * cols;
+        if (e == 0) return i < cols;
+        if (e == 1) return i >= (rows - 1) * cols && i < rows * cols;
+        if (e == 2) return i < rows * cols && i % step == 0;
+        const int first = asym ? 2 * cols - 1 : cols - 1;
+        return i >= first && i < rows * cols && (i - first) % step == 0;
+    };
+    for (int e = 0; e < 4; ++e)
+        for (int i = 0; i < rows * cols; ++i) size_[e] += on_edge(e, i);
+    for (int i = 0; i < n_feat; ++i)
+        if (gone[(size_t) i]) {
+            for (int e = 0; e < 4; ++e) score[e] += on_edge(e, i);
+            ++counter;
+        }
+    if (!fitCircleFlag)
+        for (int e = 0; e < 4; ++e)
+            if (score[e] >= size_[e] - 1) return 0;
+    if (counter >= 0.2 * (cols * rows)) return 0;
+    return 1;
+}
+
+extern "C" int orc_rectify(const double *pxy, int np, const double *nxy, int nn, double eps, unsigned minS, unsigned clusterMin,
+                           const double *img, int n_feat, double W, double H, int rows, int cols, int asym, int fitCircleFlag,
+                           double *out) {
+    FrameResult f;
+    f.pos.resize(np);
+    f.neg.resize(nn);
+    for (int i = 0; i < np; ++i) f.pos[i] = {pxy[2 * i], pxy[2 * i + 1]};
+    for (int i = 0; i < nn; ++i) f.neg[i] = {nxy[2 * i], nxy[2 * i + 1]};
+    extract(f, eps, minS, clusterMin, 1, 0, 1e30, 0xFFFFFFFFu, true);  // DBSCAN + the clusterMinSample filter only
+    return rectify(f, img, n_feat, W, H, rows, cols, asym, fitCircleFlag, out);
+}
+
+extern "C" {
 // ---- CPU baseline: the reference-shaped front end over a list of windows, `threads` std::threads ----
 // (event/src/EventFrame.cpp:10-36 + CirclesEventFrame.cpp:61-312, worker model of
 //  event_camera_calib/test/eventCameraCalib.cpp:172-190).  Returns total candidates found; n_events_out =

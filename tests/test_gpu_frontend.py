@@ -185,3 +185,55 @@ def test_fit_circles_api(ctx, oracle_mod):
     off = np.concatenate([[0], np.cumsum([len(s) for s in sets])])
     out = ctx.fit_circles(np.concatenate(sets), off)
     np.testing.assert_allclose(out, np.array(ref), rtol=RTOL)
+
+
+def _image_points(truth, t_mid, shift=(0.0, 0.0), scale=1.0):
+    """projected circle centre + four quadrant points (CirclesEventFrame.cpp:431-456) through the ground-truth camera,
+    rounded to float like cv::projectPoints' Point2f output"""
+    from eventcalib_b200 import synth
+    board, cam, traj = truth["board"], truth["camera"], truth["trajectory"]
+    c = board.centres()
+    k = board.radius / np.sqrt(2) * scale
+    offs = np.array([[0, 0, 0], [k, k, 0], [k, -k, 0], [-k, -k, 0], [-k, k, 0]])
+    X = (c[:, None, :] + offs[None, :, :]).reshape(-1, 3)
+    R, tw = traj.pose(np.full(len(X), t_mid))
+    u, v = synth.project(cam, R, tw, X)
+    img = np.stack([u + shift[0], v + shift[1]], axis=1).reshape(len(c), 5, 2)
+    return img.astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("fit_circle", [0, 1])
+def test_rectify_features(ctx, oracle_mod, fit_circle):
+    """a6 rectifyFeatures (CirclesEventFrame.cpp:417-609) batched over frames x circles: rectified centres / radii within
+    1e-9 of the oracle, deleted features and frame verdicts identical; good, shifted and mis-scaled projections."""
+    import eventcalib_b200 as ecb
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(90000, 346, 260, t0=5.0, duration=0.045, seed=31, return_truth=True)
+    win = synth.tiling_windows(5.0, 5.045, 1.5e-3)
+    ctx.set_sensor(346, 260)
+    ctx.load_events(synth.to_records(ev))
+    rthr = ecb.radius_threshold(346, 260, 9, 4, True, 5.5, 1.75)
+    ctx.frontend_run(win, ecb.default_params(fit_circle=fit_circle, radius_threshold=rthr, order_mode=1, median_mode=1))
+    summ = ctx.summary()
+    pts = [ctx.points(0), ctx.points(1)]
+    frames = np.arange(len(win), dtype=np.int32)
+    imgs = []
+    for w in frames:
+        mid = 0.5 * (win[w, 0] + win[w, 1])
+        variant = w % 5
+        shift = {0: (0, 0), 1: (0.4, -0.3), 2: (7.0, 2.0), 3: (0, 0), 4: (-2.5, 1.5)}[variant]
+        imgs.append(_image_points(ev, mid, shift=shift, scale=1.6 if variant == 3 else 1.0))
+    imgs = np.array(imgs)
+    imgs[7, 3, 0] = [-4.0, 10.0]      # a centre outside the image
+    out, ok = ctx.rectify(frames, imgs)
+    n_alive = 0
+    for w in frames:
+        s = summ[w]
+        V = [pts[pol][0][int(s["point_offset"][pol]):int(s["point_offset"][pol]) + int(s["n_points"][pol])] for pol in (0, 1)]
+        ref, ref_ok = oracle_mod.rectify(V[1], V[0], imgs[w], 346, 260, fitCircle=fit_circle)
+        assert np.array_equal(out[w, :, 2] < 0, ref[:, 2] < 0), "deleted features differ, frame %d" % w
+        alive = ref[:, 2] >= 0
+        n_alive += int(alive.sum())
+        np.testing.assert_allclose(out[w][alive], ref[alive], rtol=RTOL, atol=0)
+        assert ok[w] == ref_ok
+    assert n_alive > 10 * len(win) and (ok == 1).any() and (ok == 0).any()

@@ -87,3 +87,25 @@ def test_frontend_finds_the_board(oracle_mod):
         assert os.path.getsize(f.name) == 25 * len(ev["t"])
         back = synth.read_bin(f.name)
         assert all(np.array_equal(back[k], ev[k]) for k in "txyp")
+
+
+def test_rectify_features_oracle_sanity(oracle_mod):
+    """rectifyFeatures restatement (CirclesEventFrame.cpp:417-609): with projections through the ground-truth camera the
+    rectified circles land on the projected centres and the frame is kept; shifted projections delete features."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(6000, 346, 260, t0=5.0, duration=0.003, seed=5, return_truth=True)
+    P, N, _, _ = oracle_mod.event_frame(ev["t"], ev["x"], ev["y"], ev["p"], 5.0, 5.0015)
+    board, cam, traj = ev["board"], ev["camera"], ev["trajectory"]
+    c = board.centres()
+    k = board.radius / np.sqrt(2)
+    offs = np.array([[0, 0, 0], [k, k, 0], [k, -k, 0], [-k, -k, 0], [-k, k, 0]])
+    X = (c[:, None, :] + offs[None, :, :]).reshape(-1, 3)
+    R, tw = traj.pose(np.full(len(X), 5.00075))
+    u, v = synth.project(cam, R, tw, X)
+    img = np.stack([u, v], 1).reshape(36, 5, 2)
+    out, ok = oracle_mod.rectify(P, N, img, 346, 260)
+    alive = out[:, 2] >= 0
+    assert ok == 1 and alive.sum() >= 32
+    assert np.abs(out[alive, :2] - img[alive, 0]).max() < 1.5
+    out2, ok2 = oracle_mod.rectify(P, N, img + 9.0, 346, 260)
+    assert ok2 == 0 and (out2[:, 2] < 0).sum() > 20
