@@ -31,7 +31,7 @@ class FrontendParams(C.Structure):
 
 class LmOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("jacobi_scaling", C.c_int32), ("fixed_iterations", C.c_int32),
-                ("reserved", C.c_int32), ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("rotation_model", C.c_int32), ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
                 ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double), ("max_radius", C.c_double),
                 ("min_radius", C.c_double), ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
                 ("max_lm_diagonal", C.c_double)]
@@ -59,7 +59,7 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
            "ecb_frontend_clusters", "ecb_frontend_rectify", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
            "ecb_dbscan_run_ordered", "ecb_dbscan_run_batch_ordered",
-           "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_layout",
+           "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_set_rotation_model", "ecb_cost_layout",
            "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq", "ecb_lm_default_options", "ecb_lm_create",
            "ecb_lm_destroy", "ecb_lm_dimension", "ecb_lm_begin", "ecb_lm_propose", "ecb_lm_feedback", "ecb_lm_update",
            "ecb_lm_state", "ecb_lm_trace", "ecb_calibrate"]
@@ -99,6 +99,7 @@ def load_library():
     lib.ecb_frontend_clusters.argtypes = [vp, i32, i32, vp, vp, vp, i32]
     lib.ecb_frontend_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
     lib.ecb_frontend_rectify.argtypes = [vp, vp, i32, i32, vp, dbl, i32, i32, i32, vp, vp]
+    lib.ecb_cost_set_rotation_model.argtypes = [vp, i32]
     lib.ecb_dbscan_run.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32)]
     lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
     lib.ecb_dbscan_run_ordered.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32), vp, vp]
@@ -338,6 +339,10 @@ class Context:
                                   if isinstance(knots, (list, tuple)) else knots, np.float64)
         assert len(kn) == int(n_cp.sum()) + 4 * len(n_cp)
         self._chk(self.lib.ecb_cost_setup(self.h, len(n_cp), _ptr(n_cp), _ptr(kn), float(radius), float(huber)))
+
+    def cost_set_rotation_model(self, use_so3):
+        """0: normalised quaternion spline (useSO3: 0); 1: cumulative SO(3) spline + LocalParameterizationSO3 (useSO3: 1)"""
+        self._chk(self.lib.ecb_cost_set_rotation_model(self.h, int(use_so3)))
 
     def cost_layout(self):
         cp, sp = C.c_int32(), C.c_int32()

@@ -20,7 +20,7 @@
 #include <vector>
 
 #include "ecb_common.cuh"
-#include "ecb_residual.h"
+#include "ecb_residual_so3.h"
 
 namespace {
 
@@ -38,6 +38,7 @@ struct CostState {
     std::vector<int> n_cp, cp_off, span_off, knot_off;
     std::vector<double> knots;
     double radius = 1.75, huber = 0.35;
+    int so3 = 0;  // rotation model: 0 normalised quaternion spline (useSO3: 0), 1 cumulative SO(3) spline (useSO3: 1)
     int64_t n_res = 0;
     int n_items = 0;
     DevBuf d_knots, d_knot_off, d_ncp, d_cp_off, d_span_off;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-template <int MINB>
+template <int MINB, bool SO3>
 __global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) {
     extern __shared__ __align__(16) double sm_tiles[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -176,9 +177,13 @@ __global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) 
                 const double b[4] = {b4.x, b4.y, b4.z, b4.w};
                 const double2 o = reinterpret_cast<const double2 *>(a.obs)[k];
                 // the Jacobian is scattered straight into column `lane` of the shared tile (no register array)
-                const EcbResidualOut r = ecb_residual<true, TILE_LD>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x,
-                                                                     o.y, a.lm[3 * k], a.lm[3 * k + 1], a.lm[3 * k + 2],
-                                                                     a.radius, a.huber, tile + lane);
+                const EcbResidualOut r =
+                    SO3 ? ecb_residual_so3<true, TILE_LD>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y,
+                                                          a.lm[3 * k], a.lm[3 * k + 1], a.lm[3 * k + 2], a.radius, a.huber,
+                                                          tile + lane)
+                        : ecb_residual<true, TILE_LD>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y,
+                                                      a.lm[3 * k], a.lm[3 * k + 1], a.lm[3 * k + 2], a.radius, a.huber,
+                                                      tile + lane);
                 res = r.res;
                 cost += r.cost;
             } else {
@@ -289,6 +294,7 @@ __global__ void k_reduce_cost(const double *__restrict__ part, int n, int stride
     if (threadIdx.x == 0) *out = sh[0];
 }
 
+template <bool SO3>
 __global__ void __launch_bounds__(256) k_cost(const double *__restrict__ obs, const double *__restrict__ lm,
                                              const double *__restrict__ basis, const int *__restrict__ cp0, int64_t n,
                                              const double *__restrict__ params, int total_cp, double radius, double huber,
@@ -301,8 +307,10 @@ __global__ void __launch_bounds__(256) k_cost(const double *__restrict__ obs, co
         const double4 b4 = reinterpret_cast<const double4 *>(basis)[k];
         const double b[4] = {b4.x, b4.y, b4.z, b4.w};
         const double2 o = reinterpret_cast<const double2 *>(obs)[k];
-        c += ecb_residual<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, lm[3 * k], lm[3 * k + 1],
-                                 lm[3 * k + 2], radius, huber, nullptr).cost;
+        c += SO3 ? ecb_residual_so3<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, lm[3 * k],
+                                           lm[3 * k + 1], lm[3 * k + 2], radius, huber, nullptr).cost
+                 : ecb_residual<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, lm[3 * k],
+                                       lm[3 * k + 1], lm[3 * k + 2], radius, huber, nullptr).cost;
     }
     sh[threadIdx.x] = c;
     __syncthreads();
@@ -561,6 +569,13 @@ int ecb_cost_setup(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const doubl
     return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "cost setup");
 }
 
+int ecb_cost_set_rotation_model(ecb_ctx *ctx, int use_so3) {
+    if (!ctx || !ctx->cost) return ecb_fail(ctx, ECB_ERR_STATE, "ecb_cost_setup first");
+    if (use_so3 != 0 && use_so3 != 1) return ECB_ERR_ARG;
+    ((CostState *) ctx->cost)->so3 = use_so3;
+    return ECB_OK;
+}
+
 int ecb_cost_layout(ecb_ctx *ctx, int32_t *total_cp, int32_t *total_spans, int64_t *n_residuals, int64_t *out_doubles) {
     if (!ctx || !ctx->cost) return ECB_ERR_STATE;
     CostState *st = (CostState *) ctx->cost;
@@ -676,7 +691,7 @@ int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, 
     if (st->n_res == 0) return ECB_OK;
     int grid = (int) std::min<int64_t>((st->n_res + 255) / 256, (int64_t) ctx->sm_count * 8);
     ECB_PROF_BEGIN(ctx, ECB_STAGE_COST);
-    k_cost<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p, (const double *) st->basis.p,
+    (st->so3 ? k_cost<true> : k_cost<false>)<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p, (const double *) st->basis.p,
                                           (const int *) st->cp0.p, st->n_res, (const double *) st->params.p, st->total_cp,
                                           st->radius, st->huber, (double *) st->cost_part.p);
     ECB_LAUNCHED(ctx);
@@ -714,14 +729,11 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
         a.part = (double *) st->part.p;
         const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
         static const int variant = getenv("ECB_NE_VARIANT") ? atoi(getenv("ECB_NE_VARIANT")) : 2;
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_normal_eq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * (variant == 1 ? 1 : 2));
+        void (*kern)(const NeArgs) = st->so3 ? k_normal_eq<1, true> : (variant == 1 ? k_normal_eq<1, false> : k_normal_eq<2, false>);
+        ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * ((variant == 1 || st->so3) ? 1 : 2));
         ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
-        if (variant == 1)
-            k_normal_eq<1><<<grid, NE_THREADS, smem, ctx->stream>>>(a);
-        else
-            k_normal_eq<2><<<grid, NE_THREADS, smem, ctx->stream>>>(a);
+        kern<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
         ECB_LAUNCHED(ctx);
         const int *item_start = (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
         k_reduce_spans<<<st->total_spans, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start, st->total_spans, out);

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "ecb_common.cuh"
+#include "ecb_so3.h"
 
 namespace {
 
@@ -189,7 +190,8 @@ struct ecb_lm {
         otr.resize(3 * (size_t) C);
         for (int i = 0; i < 9; ++i) oi[i] = intr[i] + d[6 * C + i];
         for (int c = 0; c < C; ++c) {
-            quat_plus(&rot[4 * c], &d[6 * c], &orot[4 * c]);
+            if (opt.rotation_model == 1) ecb_so3::plus(&rot[4 * c], &d[6 * c], &orot[4 * c]);  // LocalParameterizationSO3::Plus
+            else quat_plus(&rot[4 * c], &d[6 * c], &orot[4 * c]);
             for (int k = 0; k < 3; ++k) otr[3 * c + k] = trans[3 * c + k] + d[6 * c + 3 + k];
         }
     }
@@ -251,7 +253,7 @@ void ecb_lm_default_options(ecb_lm_options *o) {
     o->max_lm_diagonal = 1e32;
     o->jacobi_scaling = 1;
     o->fixed_iterations = 0;
-    o->reserved = 0;
+    o->rotation_model = 0;
 }
 
 ecb_lm *ecb_lm_create(int n_splines, const int32_t *n_cp, const ecb_lm_options *opt) {

@@ -231,9 +231,11 @@ public:
         double timeStamp;
         std::vector<std::array<double, 3>> circles;  // (cx, cy, r) per board point; r < 0: absent
     };
+    // useSO3 (eventCameraCalib.cpp:204-209): false = CalibReprojectionError (normalised quaternion spline), true =
+    // CalibReprojectionError_SO3 (cumulative SO(3) spline, LocalParameterizationSO3); rot_cp are x,y,z,w coefficients either way
     EventCalibSpline(EventContainer::Ptr events, std::vector<Segment> segments, std::array<double, 9> intrinsics,
-                     double motionTimeStep, double circleRadius)
-        : ev_(events), seg_(std::move(segments)), intr_(intrinsics), step_(motionTimeStep), radius_(circleRadius) {
+                     double motionTimeStep, double circleRadius, bool useSO3 = false)
+        : ev_(events), seg_(std::move(segments)), intr_(intrinsics), step_(motionTimeStep), radius_(circleRadius), useSO3_(useSO3) {
         if (seg_.empty()) throw std::logic_error("sampleSets not filtered");  // EventCalibSpline.cpp:78-80
         std::vector<double> kn;
         for (auto &s : seg_) {
@@ -242,6 +244,7 @@ public:
         }
         if (ecb_cost_setup(ev_->ctx, (int) seg_.size(), n_cp_.data(), kn.data(), radius_, 0.2 * radius_) != ECB_OK)
             throw std::logic_error(ecb_last_error(ev_->ctx));  // HuberLoss(0.2 r), EventCalibSpline.cpp:197
+        ecb_cost_set_rotation_model(ev_->ctx, useSO3_ ? 1 : 0);
     }
     // association loop, EventCalibSpline.cpp:157-192; landmarks: board points (EventCalibIni.cpp:99-113)
     int64_t associate(const std::vector<KeyFrame> &kf, const std::vector<std::array<double, 3>> &landmarks) {
@@ -265,6 +268,7 @@ public:
         }
         ecb_lm_options opt;
         ecb_lm_default_options(&opt);
+        opt.rotation_model = useSO3_ ? 1 : 0;
         ecb_lm_summary sum;
         if (ecb_calibrate(ev_->ctx, (int) seg_.size(), n_cp_.data(), intr_.data(), rot.data(), trans.data(), &opt, &sum, nullptr, 0) != ECB_OK)
             return false;
@@ -287,6 +291,7 @@ private:
     std::vector<int32_t> n_cp_;
     std::array<double, 9> intr_;
     double step_, radius_;
+    bool useSO3_ = false;
 };
 
 }  // namespace opengv2

@@ -173,6 +173,12 @@ int ecb_fit_circles(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int 
  * huber_delta = 0.2 * circle_radius in the reference (:197). */
 int ecb_cost_setup(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const double *knots, double circle_radius,
                    double huber_delta);
+/* Rotation model of the residual blocks (the reference's `useSO3` switch, eventCameraCalib.cpp:204-209):
+ *   0 (default) CalibReprojectionError      — normalised quaternion B-spline, EigenQuaternionParameterization (hpp:158-250)
+ *   1           CalibReprojectionError_SO3 — cumulative SO(3) B-spline R0 * prod exp(beta_j log(R_{j-1}^-1 R_j)) with
+ *               LocalParameterizationSO3 (hpp:65-156, BsplineSO3.hpp:190-221); rot_cp are then Sophus::SO3d coefficients (x,y,z,w)
+ * Also selects the Plus operation of the host LM step (ecb_lm_options.rotation_model must match). */
+int ecb_cost_set_rotation_model(ecb_ctx *ctx, int use_so3);
 /* total control points, total span blocks (sum of n_cp-3), residual count, doubles in the packed result */
 int ecb_cost_layout(ecb_ctx *ctx, int32_t *total_cp, int32_t *total_spans, int64_t *n_residuals, int64_t *out_doubles);
 /* Residual blocks from the loaded events (association loop of optimize(), :157-192, with findCenter,
@@ -200,7 +206,7 @@ typedef struct {
     int32_t max_iterations;        /* 50 (Ceres default; BASELINE config C4) */
     int32_t jacobi_scaling;        /* 1 */
     int32_t fixed_iterations;      /* != 0: convergence tests off, exactly max_iterations LM iterations (benchmark C4) */
-    int32_t reserved;
+    int32_t rotation_model;        /* 0: x+ = dq(delta) * x (EigenQuaternionParameterization); 1: x+ = x * exp(delta) (LocalParameterizationSO3) */
     double function_tolerance;     /* 1e-10 (EventCalibSpline.cpp:239-240) */
     double gradient_tolerance;     /* 1e-10 */
     double parameter_tolerance;    /* 1e-8 */

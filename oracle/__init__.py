@@ -260,6 +260,32 @@ def residual_jac(intr, rcp, tcp, obs, lm, radius, b):
     return r, jac
 
 
+def residual_jac_so3(intr, Q, T, obs, lm, radius, basis):
+    """CalibReprojectionError_SO3 on Jet<37>: value and 1x37 ambient Jacobian (intrinsics | 4x4 SO3 coeffs | 4x3 translations)"""
+    a = [np.ascontiguousarray(v, np.float64) for v in (intr, Q, T, obs, lm, basis)]
+    jac = np.zeros(37)
+    lib = port()
+    lib.orc_residual_jac_so3.restype = C.c_double
+    r = lib.orc_residual_jac_so3(_p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), _p(a[3], _dp), _p(a[4], _dp), C.c_double(radius),
+                                 _p(a[5], _dp), _p(jac, _dp))
+    return r, jac
+
+
+def so3_plus(x, d):
+    x = np.ascontiguousarray(x, np.float64)
+    d = np.ascontiguousarray(d, np.float64)
+    out = np.zeros(4)
+    port().orc_so3_plus(_p(x, _dp), _p(d, _dp), _p(out, _dp))
+    return out
+
+
+def so3_plus_jacobian(x):
+    x = np.ascontiguousarray(x, np.float64)
+    J = np.zeros(12)
+    port().orc_so3_plus_jacobian(_p(x, _dp), _p(J, _dp))
+    return J.reshape(4, 3)
+
+
 def quat_plus(x, d):
     x = np.ascontiguousarray(x, np.float64)
     d = np.ascontiguousarray(d, np.float64)
@@ -271,7 +297,7 @@ def quat_plus(x, d):
 class CostProblem:
     """Oracle of the cost path: association, cost, per-span normal equations (oracle/ecb_oracle_cost.cpp)."""
 
-    def __init__(self, n_cp, knots_list, radius=1.75, huber=0.35):
+    def __init__(self, n_cp, knots_list, radius=1.75, huber=0.35, so3=False):
         self.lib = port()
         self.lib.orc_problem_create.restype = C.c_void_p
         self.lib.orc_cost.restype = C.c_double
@@ -283,6 +309,7 @@ class CostProblem:
         self.h = C.c_void_p(self.lib.orc_problem_create(C.c_int(len(ncp)), _p(ncp, _ip), _p(kn, _dp), C.c_double(radius),
                                                         C.c_double(huber)))
         self.n_spans = int(self.lib.orc_problem_num_spans(self.h))
+        self.lib.orc_problem_set_so3(self.h, C.c_int(int(so3)))   # useSO3: CalibReprojectionError_SO3
 
     def __del__(self):
         try:

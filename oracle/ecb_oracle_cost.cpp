@@ -107,6 +107,33 @@ template <int NP> Jet<NP> jsqrt(const Jet<NP> &f) {
     return h;
 }
 inline double jsqrt(double f) { return std::sqrt(f); }
+// ceres/jet.h: sin, cos, atan
+template <int NP> Jet<NP> jsin(const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = std::sin(f.a);
+    const double c = std::cos(f.a);
+    for (int i = 0; i < NP; ++i) h.v[i] = c * f.v[i];
+    return h;
+}
+template <int NP> Jet<NP> jcos(const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = std::cos(f.a);
+    const double sn = -std::sin(f.a);
+    for (int i = 0; i < NP; ++i) h.v[i] = sn * f.v[i];
+    return h;
+}
+template <int NP> Jet<NP> jatan(const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = std::atan(f.a);
+    const double t = 1.0 / (1.0 + f.a * f.a);
+    for (int i = 0; i < NP; ++i) h.v[i] = t * f.v[i];
+    return h;
+}
+inline double jsin(double f) { return std::sin(f); }
+inline double jcos(double f) { return std::cos(f); }
+inline double jatan(double f) { return std::atan(f); }
+template <int NP> double jval(const Jet<NP> &f) { return f.a; }
+inline double jval(double f) { return f; }
 
 // ---------------------------------------------------------------- the residual ----
 // EventCalibSpline.hpp:36-63
@@ -156,11 +183,103 @@ T residual(const T *intr, const T *const r_cp[4], const T *const t_cp[4], const 
     return jsqrt(d[0] * d[0] + (d[1] * d[1] + d[2] * d[2])) - radius;
 }
 
+// ---- Sophus::SO3 pieces used by CalibReprojectionError_SO3  [external: Sophus 1.x so3.hpp, NOT in /root/reference] ----
+// storage = Eigen quaternion coefficients x y z w
+template <class T> void so3_mul(const T a[4], const T b[4], T r[4]) {  // SO3::operator*
+    r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+template <class T> void so3_inverse(const T a[4], T r[4]) {  // conjugate
+    r[0] = -a[0];
+    r[1] = -a[1];
+    r[2] = -a[2];
+    r[3] = a[3];
+}
+template <class T> void so3_log(const T q[4], T t[3]) {  // SO3::logAndTheta
+    const double eps = 1e-10;  // Sophus::Constants<double>::epsilon()
+    T squared_n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    T w = q[3];
+    T two_atan_nbyw_by_n;
+    if (jval(squared_n) < eps * eps) {
+        T squared_w = w * w;
+        two_atan_nbyw_by_n = T(2.0) / w - T(2.0 / 3.0) * (squared_n) / (w * squared_w);
+    } else {
+        T n = jsqrt(squared_n);
+        if (std::abs(jval(w)) < eps) {
+            two_atan_nbyw_by_n = T(jval(w) > 0 ? M_PI : -M_PI) / n;
+        } else {
+            two_atan_nbyw_by_n = T(2.0) * jatan(n / w) / n;
+        }
+    }
+    for (int c = 0; c < 3; ++c) t[c] = two_atan_nbyw_by_n * q[c];
+}
+template <class T> void so3_exp(const T o[3], T q[4]) {  // SO3::expAndTheta
+    const double eps = 1e-10;
+    T theta_sq = o[0] * o[0] + o[1] * o[1] + o[2] * o[2];
+    T imag, real;
+    if (jval(theta_sq) < eps * eps) {
+        T theta_po4 = theta_sq * theta_sq;
+        imag = T(0.5) - T(1.0 / 48.0) * theta_sq + T(1.0 / 3840.0) * theta_po4;
+        real = T(1.0) - T(1.0 / 8.0) * theta_sq + T(1.0 / 384.0) * theta_po4;
+    } else {
+        T theta = jsqrt(theta_sq);
+        T half = T(0.5) * theta;
+        imag = jsin(half) / theta;
+        real = jcos(half);
+    }
+    for (int c = 0; c < 3; ++c) q[c] = imag * o[c];
+    q[3] = real;
+}
+
+// CalibReprojectionError_SO3::operator(), EventCalibSpline.hpp:78-140.  rb: cumulative basis beta_1..3, tb: basis N_0..3
+template <class T>
+T residual_so3(const T *intr, const T *const r_cp[4], const T *const t_cp[4], const double obs[2], const double lm[3],
+               double radius, const double rb[3], const double tb[4]) {
+    T q[4] = {r_cp[0][0], r_cp[0][1], r_cp[0][2], r_cp[0][3]};  // Qwb = r_cp0            (:100)
+    for (int j = 1; j < 4; ++j) {                                 // Qwb *= exp(b_j log(r_cp{j-1}^-1 r_cp{j}))   (:101-103)
+        T inv[4], rel[4], lg[3], ex[4], nq[4];
+        so3_inverse(r_cp[j - 1], inv);
+        so3_mul(inv, r_cp[j], rel);
+        so3_log(rel, lg);
+        for (int c = 0; c < 3; ++c) lg[c] = rb[j - 1] * lg[c];
+        so3_exp(lg, ex);
+        so3_mul(q, ex, nq);
+        for (int c = 0; c < 4; ++c) q[c] = nq[c];
+    }
+    T tw[3];
+    for (int c = 0; c < 3; ++c) tw[c] = tb[0] * t_cp[0][c] + tb[1] * t_cp[1][c] + tb[2] * t_cp[2][c] + tb[3] * t_cp[3][c];
+    T Xc[3];
+    undistort(intr[0], intr[1], intr[2], intr[3], intr[4], intr[5], intr[6], intr[7], intr[8], obs, Xc);
+    const T &qx = q[0], &qy = q[1], &qz = q[2], &qw = q[3];
+    T tx = 2. * qx, ty = 2. * qy, tz = 2. * qz;
+    T twx = tx * qw, twy = ty * qw, txx = tx * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy;
+    T R2[3] = {txz - twy, tyz + twx, 1.0 - (txx + tyy)};
+    T depth = -tw[2] / (R2[0] * Xc[0] + (R2[1] * Xc[1] + R2[2] * Xc[2]));
+    for (int c = 0; c < 3; ++c) Xc[c] = Xc[c] * depth;
+    T uv[3] = {qy * Xc[2] - qz * Xc[1], qz * Xc[0] - qx * Xc[2], qx * Xc[1] - qy * Xc[0]};
+    for (int c = 0; c < 3; ++c) uv[c] = uv[c] + uv[c];
+    T cr[3] = {qy * uv[2] - qz * uv[1], qz * uv[0] - qx * uv[2], qx * uv[1] - qy * uv[0]};
+    T d[3];
+    for (int c = 0; c < 3; ++c) d[c] = ((Xc[c] + qw * uv[c]) + cr[c] + tw[c]) - lm[c];
+    return jsqrt(d[0] * d[0] + (d[1] * d[1] + d[2] * d[2])) - radius;
+}
+
+// Sophus SO3::Dx_this_mul_exp_x_at_0 (4x3, row major; rows x y z w) = Jacobian of LocalParameterizationSO3 (BsplineSO3.hpp:209-217)
+void so3_plus_jacobian(const double *x, double J[12]) {
+    const double c = 0.5;
+    J[0] = c * x[3];  J[1] = -c * x[2]; J[2] = c * x[1];
+    J[3] = c * x[2];  J[4] = c * x[3];  J[5] = -c * x[0];
+    J[6] = -c * x[1]; J[7] = c * x[0];  J[8] = c * x[3];
+    J[9] = -c * x[0]; J[10] = -c * x[1]; J[11] = -c * x[2];
+}
+
 typedef Jet<37> J37;
 
 // residual + 1x37 ambient Jacobian: [intrinsics 9 | r_cp0..3 (4 each) | t_cp0..3 (3 each)]
 double residual_jac(const double *intr, const double *const rcp[4], const double *const tcp[4], const double obs[2],
-                    const double lm[3], double radius, const double rb[4], const double tb[4], double jac[37]) {
+                    const double lm[3], double radius, const double rb[4], const double tb[4], double jac[37], bool so3 = false) {
     std::vector<J37> P(37);
     for (int i = 0; i < 9; ++i) P[i].a = intr[i];
     for (int j = 0; j < 4; ++j)
@@ -170,7 +289,16 @@ double residual_jac(const double *intr, const double *const rcp[4], const double
     for (int i = 0; i < 37; ++i) P[i].v[i] = 1.0;
     const J37 *r4[4] = {&P[9], &P[13], &P[17], &P[21]};
     const J37 *t4[4] = {&P[25], &P[28], &P[31], &P[34]};
-    J37 r = residual<J37>(P.data(), r4, t4, obs, lm, radius, rb, tb);
+    J37 r;
+    if (so3) {  // cumulative basis of BsplineSO3::derBasisFuns (BsplineSO3.cpp:88-92)
+        double beta[3];
+        beta[2] = rb[3];
+        beta[1] = beta[2] + rb[2];
+        beta[0] = beta[1] + rb[1];
+        r = residual_so3<J37>(P.data(), r4, t4, obs, lm, radius, beta, tb);
+    } else {
+        r = residual<J37>(P.data(), r4, t4, obs, lm, radius, rb, tb);
+    }
     std::memcpy(jac, r.v, sizeof(double) * 37);
     return r.a;
 }
@@ -190,6 +318,7 @@ struct Problem {
     std::vector<int> span_off;       // offset of each spline's first span block (n_cp-3 spans per spline)
     std::vector<std::vector<double>> knots;
     double radius = 1.75, huber = 0.35;
+    bool so3 = false;  // useSO3: CalibReprojectionError_SO3 + LocalParameterizationSO3
     // residual records
     std::vector<double> obs, lm, basis;
     std::vector<int> span;    // global span block index
@@ -210,11 +339,12 @@ double eval_block(const Problem &p, size_t k, const double *intr, const double *
     }
     double jac[37];
     const double *b = &p.basis[4 * k];
-    double r = residual_jac(intr, rcp, tcp, &p.obs[2 * k], &p.lm[3 * k], p.radius, b, b, jac);
+    double r = residual_jac(intr, rcp, tcp, &p.obs[2 * k], &p.lm[3 * k], p.radius, b, b, jac, p.so3);
     for (int i = 0; i < 9; ++i) J33[i] = jac[i];
     for (int j = 0; j < 4; ++j) {  // J_local = J_global(1x4) * PlusJacobian(4x3)
         double PJ[12];
-        quat_plus_jacobian(rcp[j], PJ);
+        if (p.so3) so3_plus_jacobian(rcp[j], PJ);
+        else quat_plus_jacobian(rcp[j], PJ);
         for (int c = 0; c < 3; ++c) {
             double s = 0;
             for (int a = 0; a < 4; ++a) s += jac[9 + 4 * j + a] * PJ[3 * a + c];
@@ -305,6 +435,14 @@ double orc_residual_jac(const double *intr, const double *rcp16, const double *t
     return residual_jac(intr, r4, t4, obs, lm, radius, basis, basis, jac37);
 }
 
+// same for CalibReprojectionError_SO3 (basis = the 4 values N; the cumulative rotation basis is derived from them)
+double orc_residual_jac_so3(const double *intr, const double *rcp16, const double *tcp12, const double *obs, const double *lm,
+                            double radius, const double *basis, double *jac37) {
+    const double *r4[4] = {rcp16, rcp16 + 4, rcp16 + 8, rcp16 + 12}, *t4[4] = {tcp12, tcp12 + 3, tcp12 + 6, tcp12 + 9};
+    return residual_jac(intr, r4, t4, obs, lm, radius, basis, basis, jac37, true);
+}
+void orc_so3_plus_jacobian(const double *x, double *J12) { so3_plus_jacobian(x, J12); }
+
 // ---- problem handle ----
 void *orc_problem_create(int n_splines, const int *n_cp, const double *knots_concat, double radius, double huber) {
     Problem *p = new Problem();
@@ -325,6 +463,13 @@ void *orc_problem_create(int n_splines, const int *n_cp, const double *knots_con
     return p;
 }
 void orc_problem_free(void *h) { delete (Problem *) h; }
+void orc_problem_set_so3(void *h, int so3) { ((Problem *) h)->so3 = so3 != 0; }
+// LocalParameterizationSO3::Plus: T * exp(delta)
+void orc_so3_plus(const double *x, const double *d, double *out) {
+    double e[4];
+    so3_exp<double>(d, e);
+    so3_mul<double>(x, e, out);
+}
 
 // explicit residual records: obs (2), landmark (3), time, spline index. Basis / span computed like optimize() :173-179
 void orc_problem_set_residuals(void *h, const double *obs, const double *lm, const double *t, const int *spline, int64_t n) {

@@ -35,18 +35,22 @@ def assemble(H, g, maps, D):
     return A, b
 
 
+SO3 = [False]   # set by solve(so3=...): LocalParameterizationSO3::Plus (T * exp(delta)) instead of the quaternion Plus
+
+
 def plus(intr, rot, trans, d):
     C = len(rot)
     ni = intr + d[:9]
     nr = np.zeros_like(rot)
     nt = np.zeros_like(trans)
     for c in range(C):
-        nr[c] = oracle.quat_plus(rot[c], d[9 + 6 * c: 9 + 6 * c + 3])
+        nr[c] = (oracle.so3_plus if SO3[0] else oracle.quat_plus)(rot[c], d[9 + 6 * c: 9 + 6 * c + 3])
         nt[c] = trans[c] + d[9 + 6 * c + 3: 9 + 6 * c + 6]
     return ni, nr, nt
 
 
-def solve(P, n_cp_list, intr, rot, trans, max_iterations=50, ftol=1e-10, gtol=1e-10, ptol=1e-8, fixed=False):
+def solve(P, n_cp_list, intr, rot, trans, max_iterations=50, ftol=1e-10, gtol=1e-10, ptol=1e-8, fixed=False, so3=False):
+    SO3[0] = bool(so3)
     maps, C = _index_map(n_cp_list)
     D = 9 + 6 * C
     intr, rot, trans = np.array(intr, float), np.array(rot, float).reshape(C, 4), np.array(trans, float).reshape(C, 3)

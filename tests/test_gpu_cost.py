@@ -99,3 +99,33 @@ def test_rejects_unordered_residuals(ctx):
         ctx.cost_set_residuals(np.zeros((2, 2)), np.zeros((2, 3)), np.array([0.5, 0.2]), np.zeros(2))
     with pytest.raises(ecb.EcbError):
         ctx.cost_set_residuals(np.zeros((1, 2)), np.zeros((1, 3)), np.array([1.5]), np.zeros(1))
+
+
+def test_so3_variant_normal_equations(ctx, oracle_mod, problem):
+    """a11: CalibReprojectionError_SO3 + LocalParameterizationSO3 (EventCalibSpline.hpp:65-156) — cost, J^T J, J^T r of the
+    same residual set against the oracle's Jet<37> evaluation, 1e-9 relative"""
+    ev, pb, P, n, oe, oc = problem
+    Ps = oracle_mod.CostProblem([pb["n_cp"]], [pb["knots"]], pb["radius"], pb["huber"], so3=True)
+    Ps.associate(ev["t"], ev["x"], ev["y"], pb["kf_t"], pb["circles"], pb["landmarks"], pb["step"])
+    rot = pb["rot_cp"].reshape(-1, 4)
+    rot = rot / np.linalg.norm(rot, axis=1, keepdims=True)   # Sophus::SO3d control points are unit quaternions
+    x = (pb["intrinsics"], rot, pb["trans_cp"])
+    from eventcalib_b200 import synth
+    ctx.set_sensor(346, 260)                 # earlier tests re-used the context for other residual sets
+    ctx.load_events(synth.to_records(ev))
+    ctx.cost_setup([pb["n_cp"]], [pb["knots"]], pb["radius"], pb["huber"])
+    assert ctx.cost_associate(pb["kf_t"], pb["circles"], pb["landmarks"], pb["step"]) == Ps.n_residuals
+    ctx.cost_set_rotation_model(1)
+    try:
+        c_ref, H_ref, g_ref = Ps.normal_eq(*x)
+        c, H, g = ctx.cost_normal_eq(*x)
+        assert abs(ctx.cost_eval(*x) - c_ref) <= RTOL * c_ref
+        assert abs(c - c_ref) <= RTOL * c_ref
+        for s in range(H.shape[0]):
+            np.testing.assert_allclose(H[s], H_ref[s], rtol=0, atol=RTOL * np.abs(H_ref[s]).max())
+            np.testing.assert_allclose(g[s], g_ref[s], rtol=0, atol=RTOL * np.abs(g_ref[s]).max())
+        # a different function from the quaternion-spline variant
+        c_q, _, _ = P.normal_eq(*x)
+        assert abs(c_q - c_ref) > 1e-6 * c_ref
+    finally:
+        ctx.cost_set_rotation_model(0)

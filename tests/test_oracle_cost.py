@@ -155,3 +155,110 @@ def test_association_and_normal_equations_consistency(oracle_mod):
         m = sp == s
         np.testing.assert_allclose(H[s], J[m].T @ J[m], rtol=1e-12, atol=1e-9)
         np.testing.assert_allclose(g[s], J[m].T @ r[m], rtol=1e-12, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------- SO(3) variant ----
+def _so3_case(rng):
+    intr, Q, T, b, obs, lm = _case(rng)
+    Q = Q / np.linalg.norm(Q, axis=1, keepdims=True)      # Sophus::SO3d control points are unit quaternions
+    return intr, np.ascontiguousarray(Q), np.ascontiguousarray(T), b, obs, lm
+
+
+def _so3_value_scipy(intr, Q, T, b, obs, lm):
+    """independent evaluation of CalibReprojectionError_SO3 (EventCalibSpline.hpp:78-140) with scipy rotations"""
+    from scipy.spatial.transform import Rotation as Rot
+    beta = [b[1] + b[2] + b[3], b[2] + b[3], b[3]]
+    R = [Rot.from_quat(q) for q in Q]
+    Rw = R[0]
+    for j in range(1, 4):
+        Rw = Rw * Rot.from_rotvec(beta[j - 1] * (R[j - 1].inv() * R[j]).as_rotvec())
+    tw = sum(b[j] * T[j] for j in range(4))
+    fx, fy, cx, cy = intr[:4]
+    x, y = (obs[0] - cx) / fx, (obs[1] - cy) / fy
+    r2 = x * x + y * y
+    s = 1 + sum(intr[4 + i] * r2 ** (i + 1) for i in range(5))
+    Xc = np.array([x * s, y * s, 1.0])
+    M = Rw.as_matrix()
+    depth = -tw[2] / (M[2] @ Xc)
+    Xw = M @ (depth * Xc) + tw
+    return np.linalg.norm(Xw - lm) - 1.75
+
+
+def test_so3_residual_oracle_against_scipy_and_finite_differences(oracle_mod):
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(17)
+    for it in range(40):
+        intr, Q, T, b, obs, lm = _so3_case(rng)
+        r, jac = oracle_mod.residual_jac_so3(intr, Q, T, obs, lm, 1.75, b)
+        ref = _so3_value_scipy(intr, Q, T, b, obs, lm)
+        assert abs(r - ref) <= 1e-10 * max(1.0, abs(ref))
+        # tangent-space derivative along T_j * exp(delta): ambient Jacobian x Dx_this_mul_exp_x_at_0 vs central differences
+        for j in range(4):
+            Jl = jac[9 + 4 * j: 13 + 4 * j] @ oracle_mod.so3_plus_jacobian(Q[j])
+            for k in range(3):
+                h = 1e-6
+                vals = []
+                for sgn in (1, -1):
+                    d = np.zeros(3)
+                    d[k] = sgn * h
+                    Q2 = Q.copy()
+                    Q2[j] = (Rot.from_quat(Q[j]) * Rot.from_rotvec(d)).as_quat()
+                    if np.dot(Q2[j], Q[j]) < 0:
+                        Q2[j] = -Q2[j]
+                    vals.append(_so3_value_scipy(intr, Q2, T, b, obs, lm))
+                fd = (vals[0] - vals[1]) / (2 * h)
+                assert abs(fd - Jl[k]) <= 2e-6 * max(1.0, abs(Jl[k]))
+        # LocalParameterizationSO3::Plus
+        d = rng.normal(0, 0.2, 3)
+        want = (Rot.from_quat(Q[0]) * Rot.from_rotvec(d)).as_quat()
+        got = oracle_mod.so3_plus(Q[0], d)
+        assert min(np.abs(got - want).max(), np.abs(got + want).max()) < 1e-14
+
+
+def test_so3_tangent_jacobian_matches_dual_numbers(oracle_mod):
+    """product header (ecb_residual_so3.h: 3-partial duals along the tangent) vs the oracle (Jet<37> in the ambient space
+    times Sophus' Dx_this_mul_exp_x_at_0, what Ceres does with LocalParameterizationSO3) — incl. small relative rotations
+    that take the Taylor branches of Sophus exp / log"""
+    so = os.path.join(ROOT, "tests", "_build", "libresid_host.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so,
+                           os.path.join(ROOT, "tests", "helpers", "residual_host.cpp")])
+    h = C.CDLL(so)
+    h.host_residual_so3.restype = C.c_double
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for it in range(400):
+        intr, Q, T, b, obs, lm = _so3_case(rng)
+        if it % 3 == 0:
+            obs = obs + rng.normal(0, 25, 2)
+        if it % 7 == 0:
+            Q[2] = Q[1]                       # identical neighbours: log / exp small-angle branches
+        if it % 11 == 0:
+            Q[1] = -Q[1]                      # the double cover: same rotation, opposite sign
+        r, jac = oracle_mod.residual_jac_so3(intr, Q, T, obs, lm, 1.75, b)
+        J = np.zeros(33)
+        cost, raw = C.c_double(), C.c_double()
+        res = h.host_residual_so3(P(intr), P(Q), P(T), P(b), P(obs), P(lm), C.c_double(1.75), C.c_double(0.35), P(J),
+                                  C.byref(cost), C.byref(raw))
+        Jr = np.zeros(33)
+        Jr[:9] = jac[:9]
+        for j in range(4):
+            Jr[9 + 3 * j: 12 + 3 * j] = jac[9 + 4 * j: 13 + 4 * j] @ oracle_mod.so3_plus_jacobian(Q[j])
+        Jr[21:] = jac[25:]
+        s = r * r
+        rho1 = 1.0 if s <= 0.35 ** 2 else 0.35 / np.sqrt(s)
+        rho = s if s <= 0.35 ** 2 else 2 * 0.35 * np.sqrt(s) - 0.35 ** 2
+        Jr *= np.sqrt(rho1)
+        worst = max(worst, np.abs(J - Jr).max() / np.abs(Jr).max(), abs(raw.value - r) / max(abs(r), 1e-9))
+        assert abs(cost.value - 0.5 * rho) <= 1e-12 * max(rho, 1e-12)
+    assert worst < 1e-10
+    # Plus
+    h.host_so3_plus.restype = None
+    for it in range(20):
+        x = rng.normal(size=4)
+        x /= np.linalg.norm(x)
+        d = rng.normal(0, 10.0 ** rng.uniform(-12, 0), 3)
+        out = np.zeros(4)
+        h.host_so3_plus(P(x), P(d), P(out))
+        assert np.abs(out - oracle_mod.so3_plus(x, d)).max() < 1e-15
