@@ -17,7 +17,8 @@ constexpr int PAIR_THREADS = 256;
 constexpr int KNN_MAX = 8;
 
 // Eigen PartialPivLU<Matrix3d>::solve, unblocked, first-max pivot [external: Eigen, not in /root/reference]
-__device__ void lu_solve3(double A[3][3], const double b_in[3], double x[3]) {
+// (kept out of line, like warp_abs_dev / warp_knn: k_pair inlined was 180 KB of SASS and stalled on instruction fetch)
+__device__ __noinline__ void lu_solve3(double A[3][3], const double b_in[3], double x[3]) {
     int perm[3] = {0, 1, 2};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -77,7 +78,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // sum over the members of |‖p-c‖ - r|   (CirclesEventFrame.cpp:209-214,300-305)
 // DIRECT: `mem` already holds the members' packed pixels (staged in shared memory); else it holds pids into `pts`
 template <bool DIRECT>
-__device__ double warp_abs_dev(const uint32_t *pts, const uint32_t *mem, int sz, double cx, double cy, double r) {
+__device__ __noinline__ double warp_abs_dev(const uint32_t *pts, const uint32_t *mem, int sz, double cx, double cy, double r) {
     double s = 0;
     for (int i = threadIdx.x & 31; i < sz; i += 32) {
         const uint32_t p = DIRECT ? mem[i] : pts[mem[i]];
@@ -88,7 +89,7 @@ __device__ double warp_abs_dev(const uint32_t *pts, const uint32_t *mem, int sz,
 }
 
 // k nearest medians (ascending squared distance, ties by index), warp cooperative
-__device__ void warp_knn(const int *mx, const int *my, int n, int qx, int qy, int k, int *idx, unsigned long long *d2) {
+__device__ __noinline__ void warp_knn(const int *mx, const int *my, int n, int qx, int qy, int k, int *idx, unsigned long long *d2) {
     unsigned long long last = 0;
     bool first = true;
     for (int j = 0; j < k; ++j) {
@@ -110,7 +111,7 @@ __device__ void warp_knn(const int *mx, const int *my, int n, int qx, int qy, in
     }
 }
 
-template <bool DIRECT>
+template <bool DIRECT, bool FIT>
 __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) uint32_t sm_pix[];  // DIRECT: member pixels of both polarities
     __shared__ int mx[2][ECB_MAXK_LIMIT], my[2][ECB_MAXK_LIMIT];
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
             for (int pi = wid; pi < nkp; pi += nwarp) {
                 int nidx[KNN_MAX], pidx[KNN_MAX];
                 unsigned long long d2[KNN_MAX];
-                if (!a.fit_circle) {  // CirclesEventFrame.cpp:282-312
+                if (!FIT) {  // CirclesEventFrame.cpp:282-312
                     warp_knn(mx[0], my[0], nkn, mx[1][pi], my[1][pi], 1, nidx, d2);
                     if ((double) d2[0] > gate) continue;
                     const int n0 = nidx[0];
@@ -405,12 +406,10 @@ int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     const size_t smem = (size_t) 2 * a.smem_cap * 4;
     const bool direct = a.smem_cap > 0 && smem <= 96 * 1024;
     ECB_PROF_BEGIN(ctx, ECB_STAGE_PAIR);
-    if (direct) {
-        ECB_CUDA(ctx, cudaFuncSetAttribute(k_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)  /* constant: race-free */);
-        k_pair<true><<<grid, PAIR_THREADS, smem, ctx->stream>>>(a);
-    } else {
-        k_pair<false><<<grid, PAIR_THREADS, 0, ctx->stream>>>(a);
-    }
+    void (*kern)(const PairArgs) = direct ? (a.fit_circle ? k_pair<true, true> : k_pair<true, false>)
+                                          : (a.fit_circle ? k_pair<false, true> : k_pair<false, false>);
+    ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)  /* constant: race-free */);
+    kern<<<grid, PAIR_THREADS, direct ? smem : 0, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_PAIR);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_pair launch");
