@@ -566,6 +566,11 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             }
         }
         __syncthreads();
+        // median keys fit one word when norm^2 * 2^bits(pid) < 2^32 (DAVIS346: 18 + 12 bits)
+        const int pbits = 32 - __clz(max(n - 1, 1));
+        const unsigned long long maxn2 = (unsigned long long) (a.W - 1 + d.x0) * (a.W - 1 + d.x0) +
+                                         (unsigned long long) (a.H - 1 + d.y0) * (a.H - 1 + d.y0);
+        const bool key32 = pbits < 32 && maxn2 < (1ull << (32 - pbits));
         for (int k = wid; k < (int) n_kept; k += nwarp) {
             const int32_t cid = k_raw[k];
             const int base = k_off[k], sz = k_size[k];
@@ -590,17 +595,37 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             }
             __syncwarp();
             bool tie = false;
-            for (int i = lane; i < sz; i += 32) {  // rank of (norm^2, pid) among the members; slot sz/2 is the median
-                const uint32_t ni = mnorm[base + i], pi = members[base + i];
-                int cnt = 0, eq = 0;
-                for (int j = 0; j < sz; ++j) {
-                    const uint32_t nj = mnorm[base + j], pj = members[base + j];
-                    cnt += (nj < ni) || (nj == ni && pj < pi);
-                    eq += nj == ni;
+            if (key32) {
+                // (norm^2, pid) packed into one word: one shared load and one compare per pair
+                for (int i = lane; i < sz; i += 32) mnorm[base + i] = (mnorm[base + i] << pbits) | members[base + i];
+                __syncwarp();
+                uint32_t mkey = 0;
+                for (int i = lane; i < sz; i += 32) {  // rank among the members; slot sz/2 is the median
+                    const uint32_t ki = mnorm[base + i];
+                    int cnt = 0;
+                    for (int j = 0; j < sz; ++j) cnt += mnorm[base + j] < ki;
+                    if (cnt == sz / 2) mkey = ki;
                 }
-                if (cnt == sz / 2) {
-                    med = (int) pi;
-                    tie = eq > 1;  // std::nth_element's pick among equal norms depends on the member order
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mkey = max(mkey, __shfl_xor_sync(0xffffffffu, mkey, o));
+                med = (int) (mkey & ((1u << pbits) - 1u));
+                int eq = 0;  // std::nth_element's pick among equal norms depends on the member order
+                for (int i = lane; i < sz; i += 32) eq += (mnorm[base + i] >> pbits) == (mkey >> pbits);
+                tie = __reduce_add_sync(0xffffffffu, eq) > 1;
+                if (lane != 0) med = -1;
+            } else {
+                for (int i = lane; i < sz; i += 32) {  // rank of (norm^2, pid) among the members; slot sz/2 is the median
+                    const uint32_t ni = mnorm[base + i], pi = members[base + i];
+                    int cnt = 0, eq = 0;
+                    for (int j = 0; j < sz; ++j) {
+                        const uint32_t nj = mnorm[base + j], pj = members[base + j];
+                        cnt += (nj < ni) || (nj == ni && pj < pi);
+                        eq += nj == ni;
+                    }
+                    if (cnt == sz / 2) {
+                        med = (int) pi;
+                        tie = eq > 1;
+                    }
                 }
             }
             if (a.exact_order && __any_sync(0xffffffffu, tie) && lane == 0) {

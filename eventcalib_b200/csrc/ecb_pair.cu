@@ -90,11 +90,38 @@ __device__ __noinline__ double warp_abs_dev(const uint32_t *pts, const uint32_t 
 
 // k nearest medians (ascending squared distance, ties by index), warp cooperative
 __device__ __noinline__ void warp_knn(const int *mx, const int *my, int n, int qx, int qy, int k, int *idx, unsigned long long *d2) {
+    // key = (squared distance, index); the k smallest keys in ascending order.  n <= 64 (the usual case: ~40 kept clusters):
+    // every lane computes its two keys once, each round is one warp min over registers
+    const int lane = threadIdx.x & 31;
     unsigned long long last = 0;
     bool first = true;
+    if (n <= 64) {
+        unsigned long long key0 = ~0ull, key1 = ~0ull;
+        if (lane < n) {
+            const long long dx = qx - mx[lane], dy = qy - my[lane];
+            key0 = ((unsigned long long) (dx * dx + dy * dy) << 32) | (unsigned) lane;
+        }
+        if (lane + 32 < n) {
+            const long long dx = qx - mx[lane + 32], dy = qy - my[lane + 32];
+            key1 = ((unsigned long long) (dx * dx + dy * dy) << 32) | (unsigned) (lane + 32);
+        }
+        for (int j = 0; j < k; ++j) {
+            unsigned long long best = key0 < key1 ? key0 : key1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+                best = t < best ? t : best;
+            }
+            idx[j] = best == ~0ull ? -1 : (int) (best & 0xFFFFFFFFu);
+            d2[j] = best >> 32;
+            if (key0 == best) key0 = ~0ull;  // keys are unique (they carry the index)
+            if (key1 == best) key1 = ~0ull;
+        }
+        return;
+    }
     for (int j = 0; j < k; ++j) {
         unsigned long long best = ~0ull;
-        for (int i = threadIdx.x & 31; i < n; i += 32) {
+        for (int i = lane; i < n; i += 32) {
             const long long dx = qx - mx[i], dy = qy - my[i];
             const unsigned long long key = ((unsigned long long) (dx * dx + dy * dy) << 32) | (unsigned) i;
             if ((first || key > last) && key < best) best = key;
