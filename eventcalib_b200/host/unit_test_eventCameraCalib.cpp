@@ -5,11 +5,12 @@
 // "N frames in Map." / "Frame t contain n events." lines — with the window loop running as ONE batched GPU launch per
 // lattice instead of hardware_concurrency()-2 CPU threads.  Headless (the reference opens a Pangolin viewer, :129).
 //
-// Round-1 limits (SURVEY §8 rows f-1, f-2, f-4 are "next"): windows are the reference's first lattice level
-// (length 3*MotionTimeStep, advanced by length + 5*MotionTimeStep as after a successful detection, :60-62) without the
-// grow/slide retries; a frame is kept when at least rows*cols candidate circles were found (the reference additionally
-// orders them with findCirclesGrid); the OpenCV initialisation and therefore the spline optimisation are not run here —
-// the candidates are written to SavePath/candidates.txt for the next stage.
+// The window loop is the reference's adaptive one (accept -> jump by length + 5 steps, else grow by one step until the
+// window holds FrameEventNumThreshold events or exceeds 3 lengths, then slide; :49-81) over the reference's time pieces.
+// Round-1 limits (SURVEY §8 rows f-1, f-2, f-4 are "next"): a window counts as a frame when at least rows*cols candidate
+// circles were found (the reference additionally orders them with findCirclesGrid and applies the tracking gate); the OpenCV
+// initialisation and therefore the spline optimisation are not run here — the candidates are written to
+// SavePath/candidates.txt for the next stage.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
 #include <vector>
 
 #include "../../include/ecb/event_calib.hpp"
@@ -116,36 +118,86 @@ int main(int argc, char **argv) {
     params.clusterMinSample = (int) fs.num("clusterMinSample", 5);
     params.knn_num = (int) fs.num("knn_num", 3);
     params.fitCircle = fs.num("fitCircle", 0) != 0;
+    // The reference's adaptive window loop (MultiProcess::process, eventCameraCalib.cpp:34-97) over its time pieces (:172-180),
+    // run as a wavefront: every round evaluates the CURRENT window of every unfinished piece in one batched GPU call, then
+    // each piece applies the reference's accept / grow / slide rule to its own result.  The pieces are independent, so the
+    // frames found are those of the reference run with one worker per piece.  pieceNum = 5 * (hardware_concurrency() - 2)
+    // like the reference (:172-174), or ECB_PIECES.
     const double len = 3 * motionTimeStep, frameGap = 5 * motionTimeStep;
-    std::vector<std::pair<double, double>> windows;
-    for (double t = startTime; t + len < endTime; t += len + frameGap) windows.emplace_back(t, t + len);
-
+    const int frameEventNumThreshold = (int) fs.num("FrameEventNumThreshold", 4000);
+    int pieceNum = 5 * std::max(1, (int) std::thread::hardware_concurrency() - 2);
+    if (getenv("ECB_PIECES")) pieceNum = std::max(1, atoi(getenv("ECB_PIECES")));
+    const double pstep = (endTime - startTime) / pieceNum;
+    struct Piece {
+        double lo, hi, first, second;
+        bool done;
+    };
+    std::vector<Piece> pieces;
+    for (int k = 0; k < pieceNum; ++k) {
+        Piece pc{endTime - pstep * (k + 1), endTime - pstep * k, 0, 0, false};
+        pc.first = pc.lo;
+        pc.second = pc.lo + len;
+        pc.done = !(pc.second < pc.hi);
+        pieces.push_back(pc);
+    }
+    struct Frame {
+        double ts;
+        int events;
+        std::vector<CalibCircleLite> circles;
+    };
+    std::map<double, Frame> frames;  // MapBase keeps key frames ordered by time stamp
+    const int need = pattern->rows * pattern->cols;
     FrontEnd fe(container, pattern, params);
-    try {
-        fe.run(windows);
-    } catch (const std::exception &ex) {
-        std::cerr << "ecb: " << ex.what() << std::endl;
-        return 1;
+    size_t rounds = 0, evaluated = 0;
+    for (;;) {
+        std::vector<std::pair<double, double>> windows;
+        std::vector<int> owner;
+        for (int k = 0; k < pieceNum; ++k)
+            if (!pieces[(size_t) k].done) {
+                windows.emplace_back(pieces[(size_t) k].first, pieces[(size_t) k].second);
+                owner.push_back(k);
+            }
+        if (windows.empty()) break;
+        try {
+            fe.run(windows);
+        } catch (const std::exception &ex) {
+            std::cerr << "ecb: " << ex.what() << std::endl;
+            return 1;
+        }
+        ++rounds;
+        evaluated += windows.size();
+        for (size_t w = 0; w < windows.size(); ++w) {
+            Piece &pc = pieces[(size_t) owner[w]];
+            const int events_num = fe.eventsNum(w);
+            const auto c = fe.candidates(w);
+            // extractFeatures() (:56): here "enough candidate circles"; the reference additionally needs findCirclesGrid to
+            // order them and the tracking gate to accept the frame (not part of this build)
+            if ((int) c.size() >= need) {
+                const double ts = (pc.first + pc.second) / 2;  // Bodyframe time stamp (:57)
+                frames[ts] = Frame{ts, events_num, c};
+                pc.first = pc.second + frameGap;  // :60-62
+                pc.second = pc.first + len;
+            } else if (events_num > frameEventNumThreshold || (pc.second - pc.first) > 3 * len) {  // :66-68,75-77
+                pc.first += motionTimeStep;
+                pc.second = pc.first + len;
+            } else {
+                pc.second += motionTimeStep;  // :70,79
+            }
+            pc.done = !(pc.second < pc.hi);  // :50
+        }
     }
     mkdir(argv[3], 0755);
     std::ofstream out(std::string(argv[3]) + "/candidates.txt");
     out.precision(17);
-    size_t frames = 0;
-    const int need = pattern->rows * pattern->cols;
-    std::ostringstream lines;
-    lines.precision(8);
-    for (size_t w = 0; w < windows.size(); ++w) {
-        const auto c = fe.candidates(w);
-        if ((int) c.size() < need) continue;
-        ++frames;
-        const double ts = (windows[w].first + windows[w].second) / 2;  // Bodyframe time stamp (:57)
-        lines << "Frame " << ts << " contain " << fe.eventsNum(w) << " events." << std::endl;
-        for (size_t k = 0; k < c.size(); ++k)
-            out << ts << " " << k << " " << c[k].center[0] << " " << c[k].center[1] << " " << c[k].radius << "\n";
+    std::cout << frames.size() << " frames in Map." << std::endl;
+    for (const auto &kv : frames) {
+        const Frame &f = kv.second;
+        std::cout << "Frame " << f.ts << " contain " << f.events << " events." << std::endl;
+        for (size_t k = 0; k < f.circles.size(); ++k)
+            out << f.ts << " " << k << " " << f.circles[k].center[0] << " " << f.circles[k].center[1] << " " << f.circles[k].radius << "\n";
     }
-    std::cout << frames << " frames in Map." << std::endl << lines.str();
-    std::cout << windows.size() << " windows evaluated on the GPU in one batch; candidate circles written to " << argv[3]
-              << "/candidates.txt" << std::endl;
+    std::cout << evaluated << " windows evaluated on the GPU in " << rounds << " batched rounds over " << pieceNum
+              << " time pieces; candidate circles written to " << argv[3] << "/candidates.txt" << std::endl;
     std::cout << "NOTE: OpenCV initialisation / grid ordering / spline optimisation stage not part of this build "
                  "(SURVEY.md §8 rows f-2, f-4)." << std::endl;
     std::cout << "press Enter to exit..." << std::endl;

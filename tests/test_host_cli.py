@@ -67,12 +67,42 @@ def test_cli_on_synthetic_stream(built, tmp_path):
     synth.write_bin(str(tmp_path / "ev.bin"), full)
     (tmp_path / "cfg.yaml").write_text(YAML)
     save = tmp_path / "out"
+    env = dict(os.environ, ECB_PIECES="3")
     r = subprocess.run([built, str(tmp_path / "cfg.yaml"), str(tmp_path / "ev.bin"), str(save)], capture_output=True, text=True,
-                       stdin=subprocess.DEVNULL, timeout=300)
+                       stdin=subprocess.DEVNULL, timeout=300, env=env)
     assert r.returncode == 0, r.stderr
     assert "Events from 5 second to" in r.stdout and "frames in Map." in r.stdout and "press Enter to exit..." in r.stdout
     frames = int([l for l in r.stdout.splitlines() if l.endswith("frames in Map.")][0].split()[0])
-    assert frames >= 20
+    assert frames >= 15
     cand = np.loadtxt(str(save / "candidates.txt"))
     assert cand.shape[1] == 5 and len(np.unique(cand[:, 0])) == frames
     assert np.all((cand[:, 4] > 1) & (cand[:, 4] < 16))      # circle radii in pixels (< circleRadiusThreshold)
+    # the adaptive window loop (eventCameraCalib.cpp:49-81) replayed window by window through the Python binding
+    import eventcalib_b200 as ecb
+    ctx = ecb.Context(0)
+    ctx.set_sensor(346, 260)
+    ctx.load_events(synth.to_records(ev))
+    rthr = ecb.radius_threshold(346, 260, 9, 4, True, 5.5, 1.75)
+    prm = ecb.default_params(fit_circle=0, radius_threshold=rthr, order_mode=1, median_mode=1)
+    step, t_end = 5e-4, float(ev["t"][-1])
+    ln, gap, pstep = 3 * step, 5 * step, (t_end - 5.0) / 3
+    stamps = []
+    for k in range(3):
+        lo, hi = t_end - pstep * (k + 1), t_end - pstep * k
+        a, b = lo, lo + ln
+        while b < hi:
+            ctx.frontend_run(np.array([[a, b]]), prm)
+            s = ctx.summary()[0]
+            n_ev = int(s["n_points"].sum())
+            if s["n_candidates"] >= 36:
+                stamps.append((a + b) / 2)
+                a = b + gap
+                b = a + ln
+            elif n_ev > 4000 or (b - a) > 3 * ln:
+                a += step
+                b = a + ln
+            else:
+                b += step
+    ctx.close()
+    assert len(stamps) == frames
+    np.testing.assert_allclose(np.sort(stamps), np.unique(cand[:, 0]), rtol=0, atol=1e-12)
