@@ -1,7 +1,7 @@
 // Ingest + window kernels.
 //
 //   k_ingest   25-byte packed reference records (Event.hpp:41-47) -> SoA  t f64[n], xyp u32[n]
-//              (HBM streaming: 16-byte vector loads of the byte stream into shared memory, funnel-shift
+//              (HBM streaming: TMA bulk copies of the byte stream into a 4-stage shared-memory ring, funnel-shift
 //              unpack, coalesced 8-byte / 4-byte stores).  Algorithmic traffic 25 B read + 12 B written.
 //   k_bounds   window [t0,t1] CLOSED -> event index range [lower_bound(t0), upper_bound(t1))
 //              (EventFrame.cpp:14-15 on the time-ordered multimap)
@@ -24,30 +24,81 @@ __device__ __forceinline__ uint32_t ld_unaligned32(const uint32_t *w, int byte_o
     return __funnelshift_r(w[wi], w[wi + 1], sh);
 }
 
+// TMA (1-D bulk async copy) staging: one elected thread streams 6400-byte tiles of the packed record stream into a ring of
+// shared-memory buffers (cp.async.bulk ... mbarrier::complete_tx), ING_STAGES tiles ahead of the threads that unpack
+// them, so every SM keeps ~200 KB of HBM reads in flight instead of one synchronous tile per CTA.
+constexpr int ING_STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(ING_THREADS) k_ingest(const uint8_t *__restrict__ raw, int64_t n, int W, int H,
                                                          double *__restrict__ out_t, uint32_t *__restrict__ out_xyp,
                                                          uint32_t *__restrict__ flags) {
-    __shared__ __align__(16) uint32_t sm[ING_BYTES / 4 + 4];
+    __shared__ __align__(128) uint32_t sm[ING_STAGES][ING_BYTES / 4 + 4];
+    __shared__ __align__(8) uint64_t full[ING_STAGES];
     const int64_t n_tiles = (n + ING_REC - 1) / ING_REC;
+    const int64_t total_bytes = n * 25;
+    const int tid = threadIdx.x;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](int64_t it) {  // thread 0: arm the stage's barrier and start the bulk copy of local tile `it`
+        const int st = (int) (it % ING_STAGES);
+        const int64_t byte0 = (blockIdx.x + it * gridDim.x) * (int64_t) ING_BYTES;
+        const uint32_t bytes = (uint32_t) (min((int64_t) ING_BYTES, total_bytes - byte0) & ~(int64_t) 15);
+        mbar_expect_tx(&full[st], bytes);
+        if (bytes) bulk_g2s(sm[st], raw + byte0, bytes, &full[st]);
+    };
+    if (tid == 0) {
+        for (int st = 0; st < ING_STAGES; ++st) mbar_init(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int64_t it = 0; it < my_tiles && it < ING_STAGES; ++it) issue(it);
     uint32_t bad = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int st = (int) (it % ING_STAGES);
+        const int64_t tile = blockIdx.x + it * gridDim.x;
         const int64_t rec0 = tile * ING_REC;
         const int64_t byte0 = rec0 * 25;
-        const int64_t bytes = min((int64_t) ING_BYTES, n * 25 - byte0);
-        const uint4 *src = reinterpret_cast<const uint4 *>(raw + byte0);
-        const int nvec = (int) (bytes >> 4);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nvec; i += ING_THREADS) reinterpret_cast<uint4 *>(sm)[i] = __ldg(src + i);
-        for (int i = (nvec << 4) + threadIdx.x; i < bytes; i += ING_THREADS)  // tail of the last tile
-            reinterpret_cast<uint8_t *>(sm)[i] = raw[byte0 + i];
-        __syncthreads();
-        const int r = threadIdx.x;
+        const int64_t bytes = min((int64_t) ING_BYTES, total_bytes - byte0);
+        uint32_t *buf = sm[st];
+        // the < 16 trailing bytes of the stream are not a whole bulk-copy unit
+        if ((bytes & 15) && tid < (int) (bytes & 15)) {
+            const int o = (int) (bytes & ~(int64_t) 15) + tid;
+            reinterpret_cast<uint8_t *>(buf)[o] = raw[byte0 + o];
+        }
+        mbar_wait(&full[st], (uint32_t) ((it / ING_STAGES) & 1));
+        if (bytes & 15) __syncthreads();
+        const int r = tid;
         if (rec0 + r < n) {
             const int o = r * 25;
-            const uint32_t t_lo = ld_unaligned32(sm, o), t_hi = ld_unaligned32(sm, o + 4);
-            const uint32_t x_lo = ld_unaligned32(sm, o + 8), x_hi = ld_unaligned32(sm, o + 12);
-            const uint32_t y_lo = ld_unaligned32(sm, o + 16), y_hi = ld_unaligned32(sm, o + 20);
-            const uint32_t pol = reinterpret_cast<const uint8_t *>(sm)[o + 24];
+            const uint32_t t_lo = ld_unaligned32(buf, o), t_hi = ld_unaligned32(buf, o + 4);
+            const uint32_t x_lo = ld_unaligned32(buf, o + 8), x_hi = ld_unaligned32(buf, o + 12);
+            const uint32_t y_lo = ld_unaligned32(buf, o + 16), y_hi = ld_unaligned32(buf, o + 20);
+            const uint32_t pol = reinterpret_cast<const uint8_t *>(buf)[o + 24];
             const double t = __hiloint2double((int) t_hi, (int) t_lo);
             const double x = __hiloint2double((int) x_hi, (int) x_lo);
             const double y = __hiloint2double((int) y_hi, (int) y_lo);
@@ -62,7 +113,7 @@ __global__ void __launch_bounds__(ING_THREADS) k_ingest(const uint8_t *__restric
             // time order: compare with the previous record (same tile: shared memory; else global)
             double tp = t;
             if (r > 0) {
-                tp = __hiloint2double((int) ld_unaligned32(sm, o - 25 + 4), (int) ld_unaligned32(sm, o - 25));
+                tp = __hiloint2double((int) ld_unaligned32(buf, o - 25 + 4), (int) ld_unaligned32(buf, o - 25));
             } else if (rec0 > 0) {
                 const uint8_t *q = raw + byte0 - 25;
                 unsigned long long v = 0;
@@ -72,6 +123,11 @@ __global__ void __launch_bounds__(ING_THREADS) k_ingest(const uint8_t *__restric
             if (!(tp <= t)) bad |= 2u;
             out_t[rec0 + r] = t;
             out_xyp[rec0 + r] = w;
+        }
+        __syncthreads();  // every thread is done with this stage's buffer
+        if (tid == 0 && it + ING_STAGES < my_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads above before the async write below
+            issue(it + ING_STAGES);
         }
     }
     if (bad) atomicOr(flags, bad);
@@ -222,7 +278,7 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window(const WindowArgs a) {
 int ecb_launch_ingest(ecb_ctx *ctx, const void *d_raw, int64_t n) {
     if (n <= 0) return ECB_OK;
     int64_t tiles = (n + ING_REC - 1) / ING_REC;
-    int grid = (int) (tiles < (int64_t) ctx->sm_count * 16 ? tiles : (int64_t) ctx->sm_count * 16);
+    int grid = (int) (tiles < (int64_t) ctx->sm_count * 8 ? tiles : (int64_t) ctx->sm_count * 8);  // 8 CTAs x 4 stages x 6.4 KB per SM
     ECB_PROF_BEGIN(ctx, ECB_STAGE_INGEST);
     k_ingest<<<grid, ING_THREADS, 0, ctx->stream>>>((const uint8_t *) d_raw, n, ctx->width, ctx->height,
                                                      (double *) ctx->ev_t.p, (uint32_t *) ctx->ev_xyp.p,
