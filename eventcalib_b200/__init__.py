@@ -60,7 +60,9 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_frontend_clusters", "ecb_frontend_rectify", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
            "ecb_dbscan_run_ordered", "ecb_dbscan_run_batch_ordered",
            "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_set_rotation_model", "ecb_cost_layout",
-           "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq", "ecb_lm_default_options", "ecb_lm_create",
+           "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq",
+           "ecb_exchange_buffer_bytes", "ecb_cost_normal_eq_exchange", "ecb_device_alloc", "ecb_device_free", "ecb_ipc_export",
+           "ecb_ipc_open", "ecb_ipc_close", "ecb_lm_default_options", "ecb_lm_create",
            "ecb_lm_destroy", "ecb_lm_dimension", "ecb_lm_begin", "ecb_lm_propose", "ecb_lm_feedback", "ecb_lm_update",
            "ecb_lm_state", "ecb_lm_trace", "ecb_calibrate"]
 
@@ -100,6 +102,14 @@ def load_library():
     lib.ecb_frontend_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
     lib.ecb_frontend_rectify.argtypes = [vp, vp, i32, i32, vp, dbl, i32, i32, i32, vp, vp]
     lib.ecb_cost_set_rotation_model.argtypes = [vp, i32]
+    lib.ecb_exchange_buffer_bytes.argtypes = [vp, i32]
+    lib.ecb_exchange_buffer_bytes.restype = C.c_size_t
+    lib.ecb_cost_normal_eq_exchange.argtypes = [vp, vp, vp, vp, i32, i32, vp, C.c_uint64, i32, vp, vp]
+    lib.ecb_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.ecb_device_free.argtypes = [vp, vp]
+    lib.ecb_ipc_export.argtypes = [vp, vp, vp]
+    lib.ecb_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.ecb_ipc_close.argtypes = [vp, vp]
     lib.ecb_dbscan_run.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32)]
     lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
     lib.ecb_dbscan_run_ordered.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32), vp, vp]
@@ -343,6 +353,42 @@ class Context:
     def cost_set_rotation_model(self, use_so3):
         """0: normalised quaternion spline (useSO3: 0); 1: cumulative SO(3) spline + LocalParameterizationSO3 (useSO3: 1)"""
         self._chk(self.lib.ecb_cost_set_rotation_model(self.h, int(use_so3)))
+
+    # ---- fused reduce + inter-GPU exchange of the normal equations ----
+    def exchange_buffer_bytes(self, n_ranks):
+        return int(self.lib.ecb_exchange_buffer_bytes(self.h, n_ranks))
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._chk(self.lib.ecb_device_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        self._chk(self.lib.ecb_device_free(self.h, C.c_void_p(ptr)))
+
+    def ipc_export(self, ptr):
+        h = np.zeros(64, np.uint8)
+        self._chk(self.lib.ecb_ipc_export(self.h, C.c_void_p(ptr), _ptr(h)))
+        return h
+
+    def ipc_open(self, handle):
+        h = np.ascontiguousarray(handle, np.uint8)
+        p = C.c_void_p()
+        self._chk(self.lib.ecb_ipc_open(self.h, _ptr(h), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._chk(self.lib.ecb_ipc_close(self.h, C.c_void_p(ptr)))
+
+    def cost_normal_eq_exchange(self, intr, rot, trans, rank, recv_ptrs, epoch, d_out, want_cost=True, phases=3):
+        """normal equations with the inter-GPU sum fused in; recv_ptrs: device pointers of every rank's receive buffer"""
+        a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans)]
+        ptrs = (C.c_void_p * len(recv_ptrs))(*[C.c_void_p(p) for p in recv_ptrs])
+        cost = C.c_double(0)
+        self._chk(self.lib.ecb_cost_normal_eq_exchange(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), rank, len(recv_ptrs), ptrs,
+                                                       C.c_uint64(epoch), int(phases), C.c_void_p(d_out),
+                                                       C.cast(C.byref(cost), C.c_void_p) if want_cost else None))
+        return cost.value if want_cost else None
 
     def cost_layout(self):
         cp, sp = C.c_int32(), C.c_int32()

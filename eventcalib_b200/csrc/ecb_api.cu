@@ -746,4 +746,43 @@ int ecb_fit_circles(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int 
     return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "fit copy");
 }
 
+// ---- receive buffers of the multi-GPU exchange ----
+int ecb_device_alloc(ecb_ctx *ctx, size_t bytes, void **d_ptr) {
+    if (!ctx || !d_ptr || bytes == 0) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    ECB_CUDA(ctx, cudaMalloc(d_ptr, bytes));
+    ECB_CUDA(ctx, cudaMemset(*d_ptr, 0, bytes));
+    return ECB_OK;
+}
+
+int ecb_device_free(ecb_ctx *ctx, void *d_ptr) {
+    if (!ctx) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return ecb_check(ctx, cudaFree(d_ptr), "cudaFree");
+}
+
+int ecb_ipc_export(ecb_ctx *ctx, void *d_ptr, void *handle64) {
+    if (!ctx || !d_ptr || !handle64) return ECB_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    ECB_CUDA(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64, &h, 64);
+    return ECB_OK;
+}
+
+int ecb_ipc_open(ecb_ctx *ctx, const void *handle64, void **d_ptr) {
+    if (!ctx || !d_ptr || !handle64) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    return ecb_check(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int ecb_ipc_close(ecb_ctx *ctx, void *d_ptr) {
+    if (!ctx) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return ecb_check(ctx, cudaIpcCloseMemHandle(d_ptr), "cudaIpcCloseMemHandle");
+}
+
 }  // extern "C"

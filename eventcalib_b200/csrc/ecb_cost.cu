@@ -280,6 +280,120 @@ __global__ void k_reduce_spans(const double *__restrict__ part, const int *__res
     }
 }
 
+// ---------------------------------------------------------------- fused reduce + inter-GPU exchange ----
+// Multi-GPU normal equations without a separate collective: the span reduction of every rank stores its result straight
+// into a slot of EVERY peer's receive buffer over NVLink (peer-mapped memory), a one-warp kernel publishes
+// (epoch, span range, cost) to the peers, and each rank sums the slots in rank order once all have arrived — a one-shot
+// all-reduce whose send side is the epilogue of k_reduce_spans.  Deterministic (fixed rank order), identical on every
+// rank, double-buffered by epoch parity (a rank can be at most one exchange ahead of a peer).
+//
+// receive buffer of one rank:  [parity 0 | parity 1],  parity block = n_ranks slots,  slot = header (8 doubles:
+// epoch as u64, first span, last span, cost) + total_spans * OUT_STRIDE doubles (only [first, last] are written).
+constexpr int XH = 8;  // header doubles
+
+__host__ __device__ inline size_t xslot_doubles(int total_spans) { return (size_t) XH + (size_t) total_spans * OUT_STRIDE; }
+
+struct XPeers {
+    double *base[ECB_MAX_PEERS];
+    int n_ranks, rank;
+};
+
+// k_reduce_spans whose stores go to the slot of this rank in every peer's buffer
+__global__ void k_reduce_spans_push(const double *__restrict__ part, const int *__restrict__ item_start, int span_lo, int span_hi,
+                                    XPeers peers, size_t slot_off) {
+    const int s = span_lo + blockIdx.x;
+    if (s > span_hi) return;
+    const int i0 = item_start[s], i1 = item_start[s + 1];
+    for (int e = threadIdx.x; e < PART_SC + 2; e += blockDim.x) {
+        double v = 0.0;
+        for (int it = i0; it < i1; ++it) v += part[(size_t) it * PART_STRIDE + e];
+        int a0 = -1, a1 = -1;  // the (at most two, symmetric) destinations inside the span block
+        if (e < PART_E32) {
+            const int ti = e >> 6, r = (e >> 3) & 7, c = e & 7;
+            int I = 0, rem = ti;
+            while (rem >= 4 - I) {
+                rem -= 4 - I;
+                ++I;
+            }
+            const int Jt = I + rem;
+            const int i = 8 * I + r, j = 8 * Jt + c;
+            if (I != Jt || i <= j) {
+                a0 = i * 33 + j;
+                a1 = j * 33 + i;
+            }
+        } else if (e < PART_E33) {
+            const int j = e - PART_E32;
+            a0 = 32 * 33 + j;
+            a1 = j * 33 + 32;
+        } else if (e < PART_SC) {
+            a0 = 1089 + (e - PART_E33);
+        } else if (e == PART_SC) {
+            a0 = 32 * 33 + 32;
+        } else {
+            a0 = 1089 + 32;
+        }
+        if (a0 < 0) continue;
+        for (int p = 0; p < peers.n_ranks; ++p) {
+            double *o = peers.base[p] + slot_off + XH + (size_t) s * OUT_STRIDE;
+            o[a0] = v;
+            if (a1 >= 0) o[a1] = v;
+        }
+    }
+}
+
+// after the pushes (stream order): publish this rank's header to every peer
+__global__ void k_exchange_signal(XPeers peers, size_t slot_off, unsigned long long epoch, int span_lo, int span_hi,
+                                  const double *__restrict__ cost) {
+    const int p = threadIdx.x;
+    if (p >= peers.n_ranks) return;
+    double *h = peers.base[p] + slot_off;
+    h[1] = (double) span_lo;
+    h[2] = (double) span_hi;
+    h[3] = *cost;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(h) = epoch;
+}
+
+// one warp: wait until every rank's header of this parity carries `epoch` (bounded spin: ~2 s, then an error flag)
+__global__ void k_exchange_wait(const double *__restrict__ recv, size_t parity_off, size_t slot_stride, int n_ranks,
+                                unsigned long long epoch, unsigned *err) {
+    const int r = threadIdx.x;
+    if (r >= n_ranks) return;
+    const volatile unsigned long long *f = reinterpret_cast<const volatile unsigned long long *>(recv + parity_off + (size_t) r * slot_stride);
+    const long long t0 = clock64();
+    while (*f != epoch) {
+        if (clock64() - t0 > 4000000000LL) {
+            atomicOr(err, 1u << r);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// out[s] = sum over the ranks whose range holds s, in rank order; out[n_spans*OUT_STRIDE] = sum of the costs
+__global__ void k_exchange_sum(const double *__restrict__ recv, size_t parity_off, size_t slot_stride, int n_ranks, int n_spans,
+                               double *__restrict__ out) {
+    const int s = blockIdx.x;
+    if (s == n_spans) {
+        if (threadIdx.x == 0) {
+            double c = 0.0;
+            for (int r = 0; r < n_ranks; ++r) c += recv[parity_off + (size_t) r * slot_stride + 3];
+            out[(size_t) n_spans * OUT_STRIDE] = c;
+            out[(size_t) n_spans * OUT_STRIDE + 1] = 0.0;
+        }
+        return;
+    }
+    for (int e = threadIdx.x; e < OUT_STRIDE; e += blockDim.x) {
+        double v = 0.0;
+        for (int r = 0; r < n_ranks; ++r) {
+            const double *slot = recv + parity_off + (size_t) r * slot_stride;
+            if (s >= (int) slot[1] && s <= (int) slot[2]) v += slot[XH + (size_t) s * OUT_STRIDE + e];
+        }
+        out[(size_t) s * OUT_STRIDE + e] = v;
+    }
+}
+
 __global__ void k_reduce_cost(const double *__restrict__ part, int n, int stride, int offset, double *__restrict__ out) {
     // single block, fixed order: thread-strided partial sums, then a shared-memory tree
     __shared__ double sh[256];
@@ -332,6 +446,10 @@ struct AssocArgs {
     const double *kf_t, *kf_circ, *lm_tab;
     int K, n_circ;
     double gate2;  // (5 step)^2
+    // fused k_prepare (spline ranges sorted and disjoint): span / basis / first control point written with the record
+    const int *cp_off, *span_off;
+    double *basis;
+    int *cp0, *span;
 };
 
 // returns the spline index and the circle id (or -1) of one raw event
@@ -442,14 +560,24 @@ __global__ void __launch_bounds__(AS_THREADS) k_assoc_write(const AssocArgs a, c
         lm[3 * k] = a.lm_tab[3 * bi];
         lm[3 * k + 1] = a.lm_tab[3 * bi + 1];
         lm[3 * k + 2] = a.lm_tab[3 * bi + 2];
-        tt[k] = a.ev_t[i];
+        const double u = a.ev_t[i];
+        tt[k] = u;
         spl[k] = s;
         sel_event[k] = i;
         sel_circle[k] = bi;
+        if (a.basis) {  // what k_prepare would compute (findSpan / dersBasisFuns, EventCalibSpline.cpp:173-179)
+            const double *kn = a.knots + a.knot_off[s];
+            const int sp = find_span_dev(kn, a.ncp[s] + 4, u);
+            double N[4];
+            basis_dev(kn, sp, u, N);
+            reinterpret_cast<double4 *>(a.basis)[k] = make_double4(N[0], N[1], N[2], N[3]);
+            a.cp0[k] = a.cp_off[s] + sp - 3;
+            a.span[k] = a.span_off[s] + sp - 3;
+        }
     }
 }
 
-int prepare_records(ecb_ctx *ctx, CostState *st) {
+int prepare_records(ecb_ctx *ctx, CostState *st, bool have_basis = false) {
     int rc;
     const int64_t n = st->n_res;
     const size_t nn = (size_t) std::max<int64_t>(n, 1);
@@ -462,6 +590,7 @@ int prepare_records(ecb_ctx *ctx, CostState *st) {
     st->h_span_start.assign((size_t) st->total_spans + 1, 0);
     st->n_items = 0;
     if (n == 0) return ECB_OK;
+    if (!have_basis)
     k_prepare<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(
         (const double *) st->tt.p, (const int *) st->spl.p, n, (const double *) st->d_knots.p, (const int *) st->d_knot_off.p,
         (const int *) st->d_ncp.p, (const int *) st->d_cp_off.p, (const int *) st->d_span_off.p, (double *) st->basis.p,
@@ -657,6 +786,31 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if ((rc = ecb_reserve(ctx, st->spl, nn * 4))) return rc;
     if ((rc = ecb_reserve(ctx, st->sel_event, nn * 8))) return rc;
     if ((rc = ecb_reserve(ctx, st->sel_circle, nn * 4))) return rc;
+    // time-sorted events + spline ranges in ascending, disjoint order => records come out ordered by (spline, time): the
+    // basis pass (k_prepare) is folded into the record write; otherwise k_prepare runs and checks the order
+    bool fused = true;
+    {
+        size_t ko = 0;
+        double prev_end = -1e300;
+        for (int q = 0; q < st->n_splines; ++q) {
+            const double b = st->knots[ko], e = st->knots[ko + (size_t) st->n_cp[(size_t) q] + 3];
+            if (!(b > prev_end)) fused = false;
+            prev_end = e;
+            ko += (size_t) st->n_cp[(size_t) q] + 4;
+        }
+    }
+    a.cp_off = (const int *) st->d_cp_off.p;
+    a.span_off = (const int *) st->d_span_off.p;
+    a.basis = nullptr;
+    a.cp0 = a.span = nullptr;
+    if (fused) {
+        if ((rc = ecb_reserve(ctx, st->basis, nn * 32))) return rc;
+        if ((rc = ecb_reserve(ctx, st->cp0, nn * 4))) return rc;
+        if ((rc = ecb_reserve(ctx, st->span, nn * 4))) return rc;
+        a.basis = (double *) st->basis.p;
+        a.cp0 = (int *) st->cp0.p;
+        a.span = (int *) st->span.p;
+    }
     k_assoc_write<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (const uint16_t *) st->ev_tag.p, (const int64_t *) st->ev_flag.p, (double *) st->obs.p, (double *) st->lm.p,
                                                       (double *) st->tt.p, (int *) st->spl.p, (int64_t *) st->sel_event.p,
                                                       (int *) st->sel_circle.p);
@@ -665,7 +819,7 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if ((rc = ecb_check(ctx, cudaGetLastError(), "association kernels"))) return rc;
     st->n_res = total;
     if (n_residuals) *n_residuals = total;
-    return prepare_records(ctx, st);
+    return prepare_records(ctx, st, fused);
 }
 
 int ecb_cost_get_association(ecb_ctx *ctx, int64_t *event_index, int32_t *circle_id, int64_t cap) {
@@ -749,6 +903,94 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
         if (cost) *cost = h_out[(size_t) st->total_spans * OUT_STRIDE];
     } else if (cost) {
         return ecb_d2h(ctx, cost, out + (size_t) st->total_spans * OUT_STRIDE, 8);
+    }
+    return ECB_OK;
+}
+
+// ---- fused reduce + exchange (multi-GPU) ----
+size_t ecb_exchange_buffer_bytes(ecb_ctx *ctx, int n_ranks) {
+    if (!ctx || !ctx->cost || n_ranks < 1) return 0;
+    CostState *st = (CostState *) ctx->cost;
+    return 2 * (size_t) n_ranks * xslot_doubles(st->total_spans) * 8;
+}
+
+int ecb_cost_normal_eq_exchange(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, int rank,
+                                int n_ranks, void *const *recv_buffers, uint64_t epoch, int phases, void *d_out, double *cost) {
+    if (!ctx || !ctx->cost || !intrinsics || !rot_cp || !trans_cp || !recv_buffers || !d_out) return ECB_ERR_ARG;
+    if (!(phases & 3)) return ECB_ERR_ARG;
+    if (n_ranks < 1 || n_ranks > ECB_MAX_PEERS || rank < 0 || rank >= n_ranks || epoch == 0) return ECB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CostState *st = (CostState *) ctx->cost;
+    int rc;
+    if ((rc = upload_params(ctx, st, intrinsics, rot_cp, trans_cp))) return rc;
+    if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
+    XPeers peers;
+    memset(&peers, 0, sizeof peers);
+    peers.n_ranks = n_ranks;
+    peers.rank = rank;
+    for (int p = 0; p < n_ranks; ++p) {
+        if (!recv_buffers[p]) return ECB_ERR_ARG;
+        peers.base[p] = (double *) recv_buffers[p];
+    }
+    const size_t slot = xslot_doubles(st->total_spans);
+    const size_t parity_off = (size_t) (epoch & 1) * n_ranks * slot;
+    const size_t my_slot_off = parity_off + (size_t) rank * slot;
+    // span range this rank contributes to (host knows the work items)
+    int lo = 0, hi = -1;
+    for (int s = 0; s < st->total_spans; ++s)
+        if (st->h_span_start[(size_t) s + 1] > st->h_span_start[(size_t) s]) {
+            if (hi < 0) lo = s;
+            hi = s;
+        }
+    double *d_cost = (double *) st->cost_part.p + 4001;
+    if (phases & ECB_EXCHANGE_SEND) ECB_CUDA(ctx, cudaMemsetAsync(d_cost, 0, 8, ctx->stream));
+    unsigned *d_err = (unsigned *) ((double *) st->cost_part.p + 4002);
+    if (phases & ECB_EXCHANGE_SEND) {
+    if (st->n_items > 0 && hi >= lo) {
+        NeArgs a;
+        a.obs = (const double *) st->obs.p;
+        a.lm = (const double *) st->lm.p;
+        a.basis = (const double *) st->basis.p;
+        a.cp0 = (const int *) st->cp0.p;
+        a.items = (const Item *) st->items.p;
+        a.n_items = st->n_items;
+        a.params = (const double *) st->params.p;
+        a.total_cp = st->total_cp;
+        a.radius = st->radius;
+        a.huber = st->huber;
+        a.part = (double *) st->part.p;
+        const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
+        void (*kern)(const NeArgs) = st->so3 ? k_normal_eq<1, true> : k_normal_eq<2, false>;
+        ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        const int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * (st->so3 ? 1 : 2));
+        ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
+        kern<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
+        ECB_LAUNCHED(ctx);
+        const int *item_start = (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
+        k_reduce_spans_push<<<hi - lo + 1, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start, lo, hi, peers, my_slot_off);
+        ECB_LAUNCHED(ctx);
+        k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, PART_SC + 3, d_cost);
+        ECB_LAUNCHED(ctx);
+        ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);
+    }
+    ECB_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+    k_exchange_signal<<<1, 32, 0, ctx->stream>>>(peers, my_slot_off, (unsigned long long) epoch, lo, hi, d_cost);
+    ECB_LAUNCHED(ctx);
+    }
+    if (!(phases & ECB_EXCHANGE_RECV)) return ecb_check(ctx, cudaGetLastError(), "exchange kernels");
+    k_exchange_wait<<<1, 32, 0, ctx->stream>>>(peers.base[rank], parity_off, slot, n_ranks, (unsigned long long) epoch, d_err);
+    ECB_LAUNCHED(ctx);
+    k_exchange_sum<<<st->total_spans + 1, 192, 0, ctx->stream>>>(peers.base[rank], parity_off, slot, n_ranks, st->total_spans,
+                                                                 (double *) d_out);
+    ECB_LAUNCHED(ctx);
+    if ((rc = ecb_check(ctx, cudaGetLastError(), "exchange kernels"))) return rc;
+    if (cost) {
+        double hc[2];
+        if ((rc = ecb_d2h(ctx, hc, (double *) d_out + (size_t) st->total_spans * OUT_STRIDE, 8))) return rc;
+        unsigned herr = 0;
+        if ((rc = ecb_d2h(ctx, &herr, d_err, 4))) return rc;
+        if (herr) return ecb_fail(ctx, ECB_ERR_STATE, "normal-equation exchange timed out waiting for ranks (mask 0x%x)", herr);
+        *cost = hc[0];
     }
     return ECB_OK;
 }

@@ -201,6 +201,30 @@ int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, 
 int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, void *d_out,
                        double *h_out, double *cost);
 
+/* Multi-GPU (one process per GPU): the same evaluation with the inter-GPU sum fused in.  Every rank owns a receive
+ * buffer of ecb_exchange_buffer_bytes() bytes, ZERO-FILLED once, in device memory its peers can write (same process:
+ * any cudaMalloc pointer with peer access; other processes: ecb_device_alloc + ecb_ipc_export / ecb_ipc_open).
+ * recv_buffers[p] = rank p's buffer as seen from this process (own buffer at [rank]).  The span reduction writes this rank's
+ * result into its slot of every peer's buffer over NVLink, publishes (epoch, span range, cost), waits for all ranks'
+ * slots of this epoch and sums them in rank order into d_out (layout of ecb_cost_normal_eq; bit-identical on all ranks).
+ * epoch: 1, 2, 3, ... — the same sequence on every rank; `cost` (optional) synchronises the stream.
+ * phases: ECB_EXCHANGE_BOTH normally.  The receive side spins (one warp, bounded) until the peers' slots arrive, so
+ * "ranks" that share ONE device must not enqueue it before every rank's send side (CUDA does not promise that two streams
+ * of a device run concurrently): issue ECB_EXCHANGE_SEND on all of them first, then ECB_EXCHANGE_RECV. */
+#define ECB_MAX_PEERS 16
+#define ECB_EXCHANGE_SEND 1
+#define ECB_EXCHANGE_RECV 2
+#define ECB_EXCHANGE_BOTH 3
+size_t ecb_exchange_buffer_bytes(ecb_ctx *ctx, int n_ranks);
+int ecb_cost_normal_eq_exchange(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, int rank,
+                                int n_ranks, void *const *recv_buffers, uint64_t epoch, int phases, void *d_out, double *cost);
+/* plumbing for the receive buffers: device allocation (zero-filled) that can be exported to other processes of the node */
+int ecb_device_alloc(ecb_ctx *ctx, size_t bytes, void **d_ptr);
+int ecb_device_free(ecb_ctx *ctx, void *d_ptr);
+int ecb_ipc_export(ecb_ctx *ctx, void *d_ptr, void *handle64);          /* 64-byte cudaIpcMemHandle_t */
+int ecb_ipc_open(ecb_ctx *ctx, const void *handle64, void **d_ptr);     /* maps a peer's buffer (enables peer access) */
+int ecb_ipc_close(ecb_ctx *ctx, void *d_ptr);
+
 /* ---- a12: the LM step around the GPU normal equations (EventCalibSpline::optimize, src/EventCalibSpline.cpp:197-247) ---- */
 typedef struct {
     int32_t max_iterations;        /* 50 (Ceres default; BASELINE config C4) */

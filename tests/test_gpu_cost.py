@@ -129,3 +129,56 @@ def test_so3_variant_normal_equations(ctx, oracle_mod, problem):
         assert abs(c_q - c_ref) > 1e-6 * c_ref
     finally:
         ctx.cost_set_rotation_model(0)
+
+
+def test_fused_exchange_two_ranks_on_one_gpu(oracle_mod):
+    """The fused reduce + exchange (ecb_cost_normal_eq_exchange) with two contexts acting as two ranks on one GPU:
+    each holds one half of the events, both write their slots into both receive buffers; every rank's result equals
+    the sum of the two single-rank normal equations bit for bit, over several epochs (both parities)."""
+    import torch
+    import eventcalib_b200 as ecb
+    from eventcalib_b200 import synth, calib_problem
+    ev = synth.make_stream(200000, 346, 260, t0=5.0, duration=0.3, seed=1004, return_truth=True)
+    pb = calib_problem.build(ev, seed=3)
+    n = len(ev["t"])
+    cut = n // 2 + 777          # the halves overlap in one knot span
+    rec = synth.to_records(ev)
+    ranks = []
+    for r, (lo, hi) in enumerate(((0, cut), (cut, n))):
+        c = ecb.Context(0)
+        c.set_sensor(346, 260)
+        c.load_events(rec[lo:hi])
+        c.cost_setup([pb["n_cp"]], [pb["knots"]], pb["radius"], pb["huber"])
+        assert c.cost_associate(pb["kf_t"], pb["circles"], pb["landmarks"], pb["step"]) > 1000
+        ranks.append(c)
+    lay = ranks[0].cost_layout()
+    nbytes = ranks[0].exchange_buffer_bytes(2)
+    bufs = [c.device_alloc(nbytes) for c in ranks]
+    outs = [torch.zeros(lay["out_doubles"], dtype=torch.float64, device="cuda") for _ in ranks]
+    try:
+        rng = np.random.default_rng(0)
+        for epoch in (1, 2, 3):
+            x = (pb["intrinsics"] * (1 + 1e-3 * rng.normal(size=9)), pb["rot_cp"], pb["trans_cp"])
+            single = []
+            for c in ranks:
+                cst, H, g = c.cost_normal_eq(*x)
+                single.append((cst, H, g))
+            # two ranks on ONE device: all send sides first, then the (spinning) receive sides — see the header
+            for r in (0, 1):
+                ranks[r].cost_normal_eq_exchange(*x, r, bufs, epoch, outs[r].data_ptr(), want_cost=False, phases=1)
+            c0 = ranks[0].cost_normal_eq_exchange(*x, 0, bufs, epoch, outs[0].data_ptr(), want_cost=True, phases=2)
+            c1 = ranks[1].cost_normal_eq_exchange(*x, 1, bufs, epoch, outs[1].data_ptr(), want_cost=True, phases=2)
+            assert c0 == c1
+            a, b = outs[0].cpu().numpy(), outs[1].cpu().numpy()
+            assert np.array_equal(a, b)
+            ns = lay["total_spans"]
+            blk = a[:ns * 1122].reshape(ns, 1122)
+            H = blk[:, :1089].reshape(ns, 33, 33)
+            g = blk[:, 1089:]
+            assert np.array_equal(H, single[0][1] + single[1][1]) and np.array_equal(g, single[0][2] + single[1][2])
+            assert a[ns * 1122] == single[0][0] + single[1][0] == c1
+    finally:
+        for c, p in zip(ranks, bufs):
+            c.synchronize()
+            c.device_free(p)
+            c.close()
