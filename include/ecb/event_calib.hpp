@@ -9,14 +9,20 @@
 //
 // The batched entry point the reference lacks — many windows per launch — is ecb::FrontEnd below; the per-frame class
 // is kept so that the reference's MultiProcess loop (ECC/test/eventCameraCalib.cpp:34-97) compiles unchanged against it.
-// What is NOT here yet: the grid ordering of candidates (findCirclesGrid) and rectifyFeatures —
-// extractFeatures() therefore returns the candidate circles unordered and reports success when at least rows*cols
-// candidates were found.
+//   opengv2::EventStream::txt2bin  EV/src/EventStream.cpp:25-67 (text -> 25-byte records)
+//   EventCalibSpline::evaluate / time2splineIdx / saveKeyFrameTrajectoryTUM   ECC/.../EventCalibSpline.hpp:295-330,
+//                                  CORE/system/src/SystemBase.cpp:122-150 (TUM lines `t tx ty tz qx qy qz qw`, fixed, precision 10)
+// What is NOT here yet: the grid ordering of candidates (findCirclesGrid) — extractFeatures() therefore
+// returns the candidate circles unordered and reports success when at least rows*cols candidates were found.
 #ifndef ECB_EVENT_CALIB_HPP
 #define ECB_EVENT_CALIB_HPP
 
 #include <array>
 #include <cmath>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -26,6 +32,7 @@
 #include <vector>
 
 #include "../eventcalib_b200.h"
+#include "../../eventcalib_b200/csrc/ecb_so3.h"  // plain host/device header: the SO(3) spline of the useSO3 variant
 #include "dbscan.h"
 
 namespace opengv2 {
@@ -51,6 +58,70 @@ struct CirclePatternParameters {
     int rows = 9, cols = 4;
     double circleRadius = 1.75, squareSize = 5.5;
 };
+
+// EventStream::txt2bin (EV/src/EventStream.cpp:25-67): "timeStamp x y polarity" lines -> packed records next to the text
+// file (same name, .bin).  timeBase / endTime: LLONG_MIN = "first stamp" / "no limit" like the reference's defaults.
+struct EventStream {
+    static long long txt2bin(const std::string &txtFilePath, double timeMagnitude,
+                             long long timeBase_in = std::numeric_limits<long long>::min(),
+                             long long endTime_in = std::numeric_limits<long long>::min()) {
+        std::ifstream is(txtFilePath, std::ifstream::in);
+        if (!is.is_open()) throw std::invalid_argument("No such file: " + txtFilePath);
+        const auto lastIndex = txtFilePath.find_last_of('.');
+        std::ofstream os(txtFilePath.substr(0, lastIndex) + ".bin", std::ofstream::binary | std::ofstream::out | std::ofstream::trunc);
+        long long counter = 0, timeStamp = 0, timeBase = timeBase_in;
+        double x = 0, y = 0;
+        bool polarity = false;
+        while (is.good()) {
+            is >> timeStamp >> x >> y >> polarity;
+            if (counter == 0 && timeBase_in == std::numeric_limits<long long>::min()) timeBase = timeStamp;
+            if (endTime_in != std::numeric_limits<long long>::min() && timeStamp > endTime_in) break;
+            const double t = ((timeStamp - timeBase) * timeMagnitude);  // convert to second
+            if (t < 0) continue;
+            os.write((const char *) &t, sizeof t);
+            os.write((const char *) &x, sizeof x);
+            os.write((const char *) &y, sizeof y);
+            os.write((const char *) &polarity, sizeof polarity);
+            counter++;
+        }
+        std::cout << counter << " data processed." << std::endl;
+        std::cout.precision(30);
+        std::cout << "TimeBase :" << timeBase << std::endl;
+        std::cout.precision(15);
+        std::cout << "Last data is :" << timeStamp << " " << x << " " << y << " " << polarity << std::endl;
+        std::cout << "Duration :" << ((timeStamp - timeBase) * timeMagnitude) << std::endl;
+        return counter;
+    }
+};
+
+// cubic B-spline span / basis on the host (BsplineReal::findSpan :208-231, dersBasisFuns :107-145, derivative 0)
+inline int bspline_find_span(const std::vector<double> &kn, double u) {
+    const int degree = 3, n = (int) kn.size() - 2 - degree;
+    if (u == kn[(size_t) n + 1]) return n;
+    int low = degree, high = n + 1, mid = (low + high) / 2;
+    while (u < kn[(size_t) mid] || u >= kn[(size_t) mid + 1]) {
+        if (u < kn[(size_t) mid]) high = mid; else low = mid;
+        mid = (low + high) / 2;
+    }
+    return mid;
+}
+inline void bspline_basis(const std::vector<double> &kn, int span, double u, double N[4]) {
+    double ndu[4][4] = {{0}}, left[4] = {0}, right[4] = {0};
+    ndu[0][0] = 1.0;
+    for (int j = 1; j <= 3; ++j) {
+        left[j] = u - kn[(size_t) (span + 1 - j)];
+        right[j] = kn[(size_t) (span + j)] - u;
+        double saved = 0.0;
+        for (int r = 0; r < j; ++r) {
+            ndu[j][r] = right[r + 1] + left[j - r];
+            const double temp = ndu[r][j - 1] / ndu[j][r];
+            ndu[r][j] = saved + right[r + 1] * temp;
+            saved = left[j - r] * temp;
+        }
+        ndu[j][j] = saved;
+    }
+    for (int j = 0; j <= 3; ++j) N[j] = ndu[j][3];
+}
 
 // Time-ordered events resident on the device (replaces std::multimap<double, Event_loc_pol>, EventContainer.hpp:26)
 struct EventContainer {
@@ -284,6 +355,62 @@ public:
     }
     const std::array<double, 9> &intrinsics() const { return intr_; }
     const std::vector<Segment> &segments() const { return seg_; }
+    // EventCalibSpline.hpp:286-303: index of the segment whose knot range holds t, else -1
+    int time2splineIdx(double t) const { return time2splineIdx(seg_, t); }
+    static int time2splineIdx(const std::vector<Segment> &seg, double t) {
+        for (size_t i = 0; i < seg.size(); ++i)
+            if (t >= seg[i].knots.front() && t <= seg[i].knots.back()) return (int) i;
+        return -1;
+    }
+    // EventCalibSpline.hpp:305-330: pose of the spline at t — unitQwb as x,y,z,w and twb
+    bool evaluate(double t, double unitQwb[4], double twb[3]) const { return evaluate(seg_, useSO3_, t, unitQwb, twb); }
+    static bool evaluate(const std::vector<Segment> &seg, bool useSO3, double t, double unitQwb[4], double twb[3]) {
+        const int idx = time2splineIdx(seg, t);
+        if (idx < 0) return false;
+        const Segment &s = seg[(size_t) idx];
+        const int span = bspline_find_span(s.knots, t);
+        double N[4];
+        bspline_basis(s.knots, span, t, N);
+        for (int c = 0; c < 3; ++c) {
+            twb[c] = 0;
+            for (int j = 0; j < 4; ++j) twb[c] += N[j] * s.trans_cp[(size_t) (3 * (span - 3 + j) + c)];
+        }
+        const double *Q = &s.rot_cp[(size_t) (4 * (span - 3))];
+        if (useSO3) {  // BsplineSO3::evaluate: R0 * prod exp(beta_j log(R_{j-1}^-1 R_j))
+            double beta[3];
+            ecb_so3::cumulative_basis(N, beta);
+            ecb_so3::rotation_value(Q, beta, unitQwb);
+        } else {  // BsplineReal<4>::evaluate + normalize() (EventCalibSpline.cpp:283-286)
+            double n2 = 0;
+            for (int c = 0; c < 4; ++c) {
+                unitQwb[c] = 0;
+                for (int j = 0; j < 4; ++j) unitQwb[c] += N[j] * Q[4 * j + c];
+                n2 += unitQwb[c] * unitQwb[c];
+            }
+            const double n = std::sqrt(n2);
+            for (int c = 0; c < 4; ++c) unitQwb[c] /= n;
+        }
+        return true;
+    }
+    // SystemBase::saveKeyFrameTrajectoryTUM (SystemBase.cpp:122-150) for the key-frame stamps after updateMap() (:253-317);
+    // sensor = body (identity extrinsics, eventCameraCalib.cpp:133-134).  Returns the number of lines written.
+    int saveKeyFrameTrajectoryTUM(const std::string &filename, const std::vector<double> &keyframeStamps) const {
+        return saveKeyFrameTrajectoryTUM(seg_, useSO3_, filename, keyframeStamps);
+    }
+    static int saveKeyFrameTrajectoryTUM(const std::vector<Segment> &seg, bool useSO3, const std::string &filename,
+                                         const std::vector<double> &keyframeStamps) {
+        std::ofstream f(filename.c_str());
+        f << std::fixed;
+        int num = 0;
+        for (double ts : keyframeStamps) {
+            double q[4], t[3];
+            if (!evaluate(seg, useSO3, ts, q, t)) continue;
+            f << std::setprecision(10) << ts << " " << t[0] << " " << t[1] << " " << t[2] << " " << q[0] << " " << q[1] << " "
+              << q[2] << " " << q[3] << std::endl;
+            ++num;
+        }
+        return num;
+    }
 
 private:
     EventContainer::Ptr ev_;

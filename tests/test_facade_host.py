@@ -1,0 +1,90 @@
+"""Host-only parts of the C++ façade (include/ecb/event_calib.hpp), no GPU: EventStream::txt2bin (EventStream.cpp:25-67),
+EventCalibSpline::evaluate for both rotation models (EventCalibSpline.hpp:305-330) and the TUM trajectory writer
+(SystemBase.cpp:122-150)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    import eventcalib_b200.build as b
+    b.build()
+    so = os.path.join(ROOT, "tests", "_build", "libfacade_host.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "helpers", "facade_host.cpp"),
+                           "-L" + os.path.join(ROOT, "eventcalib_b200"), "-lecb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "eventcalib_b200")])
+    return C.CDLL(so)
+
+
+def test_txt2bin_round_trip(tmp_path):
+    from eventcalib_b200 import synth
+    lib = _lib()
+    lib.fh_txt2bin.restype = C.c_longlong
+    lib.fh_txt2bin.argtypes = [C.c_char_p, C.c_double]
+    rng = np.random.default_rng(0)
+    n = 1000
+    stamps = np.sort(rng.integers(1_000_000, 9_000_000, n)) + 1_600_000_000_000_000
+    x, y, p = rng.integers(0, 346, n), rng.integers(0, 260, n), rng.integers(0, 2, n)
+    txt = tmp_path / "ev.txt"
+    txt.write_text("\n".join("%d %d %d %d" % v for v in zip(stamps, x, y, p)) + "\n")
+    cnt = lib.fh_txt2bin(str(txt).encode(), 1e-6)
+    ev = synth.read_bin(str(tmp_path / "ev.bin"))
+    # the reference's reader loop re-emits the last line once when the stream ends with a newline (is.good() idiom)
+    assert cnt in (n, n + 1) and len(ev["t"]) == cnt
+    np.testing.assert_array_equal(ev["t"][:n], (stamps - stamps[0]) * 1e-6)
+    np.testing.assert_array_equal(ev["x"][:n], x)
+    np.testing.assert_array_equal(ev["y"][:n], y)
+    np.testing.assert_array_equal(ev["p"][:n], p)
+
+
+def test_spline_evaluate_and_tum(tmp_path):
+    from scipy.spatial.transform import Rotation as Rot
+    from eventcalib_b200 import synth, spline
+    lib = _lib()
+    board = synth.Board()
+    traj = synth.Trajectory(3, board, 78.0)
+    us = np.linspace(1.0, 1.5, 60)
+    n_cp = 9
+    kn = spline.knot_vector(us, n_cp)
+    q, tw = traj.quat_xyzw(us)
+    rot = np.ascontiguousarray(spline.fit_control_points(kn, us, q, n_cp))
+    rot /= np.linalg.norm(rot, axis=1, keepdims=True)
+    trans = np.ascontiguousarray(spline.fit_control_points(kn, us, tw, n_cp))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.fh_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    for t in (1.0, 1.1234, 1.3, 1.5):
+        sp = spline.find_span(kn, t)
+        N = spline.basis(kn, sp, t)
+        want_t = N @ trans[sp - 3: sp + 1]
+        qo, to = np.zeros(4), np.zeros(3)
+        assert lib.fh_eval(P(kn), n_cp, P(rot), P(trans), 0, t, P(qo), P(to)) == 1
+        wq = N @ rot[sp - 3: sp + 1]
+        np.testing.assert_allclose(qo, wq / np.linalg.norm(wq), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(to, want_t, rtol=0, atol=1e-13)
+        assert lib.fh_eval(P(kn), n_cp, P(rot), P(trans), 1, t, P(qo), P(to)) == 1
+        beta = [N[1] + N[2] + N[3], N[2] + N[3], N[3]]
+        R = [Rot.from_quat(v) for v in rot[sp - 3: sp + 1]]
+        Rw = R[0]
+        for j in range(1, 4):
+            Rw = Rw * Rot.from_rotvec(beta[j - 1] * (R[j - 1].inv() * R[j]).as_rotvec())
+        wq = Rw.as_quat()
+        assert min(np.abs(qo - wq).max(), np.abs(qo + wq).max()) < 1e-13
+    assert lib.fh_eval(P(kn), n_cp, P(rot), P(trans), 0, 2.0, P(qo), P(to)) == 0   # outside every segment
+    ts = np.array([0.5, 1.05, 1.25, 1.45, 3.0])
+    out = tmp_path / "TrajectoryByEvent.txt"
+    lib.fh_tum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int]
+    assert lib.fh_tum(P(kn), n_cp, P(rot), P(trans), 0, str(out).encode(), P(ts), len(ts)) == 3
+    lines = out.read_text().splitlines()
+    assert len(lines) == 3
+    for line, t in zip(lines, ts[1:4]):
+        f = line.split()
+        assert len(f) == 8 and all(len(v.split(".")[1]) == 10 for v in f)     # fixed, precision 10
+        assert abs(float(f[0]) - t) < 1e-9
+        v = np.array(list(map(float, f[1:])))
+        assert abs(np.linalg.norm(v[3:]) - 1) < 1e-8
