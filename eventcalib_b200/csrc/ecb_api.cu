@@ -363,15 +363,11 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     int bfs_cap = 0;
     if (exact) {  // reference-exact medians: export the kd-tree, queue the clusters whose median norm is tied
         bfs_cap = (int) std::min<size_t>((size_t) 2 * n_win * max_k, 2 * slots / std::max<uint32_t>(params->cluster_min, 1u) + 16);
-        if ((rc = ecb_reserve(ctx, ctx->kd_tree, 6 * slots * 4))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->kd_tree, 8 * slots * 4))) return rc;
         if ((rc = ecb_reserve(ctx, ctx->bfs_key, 2 * slots * 8))) return rc;
         if ((rc = ecb_reserve(ctx, ctx->bfs_items, (size_t) bfs_cap * sizeof(BfsItem) + 16))) return rc;
         ca.exact_order = 1;
-        for (int p = 0; p < 2; ++p) {
-            ca.kd_left[p] = (uint32_t *) ctx->kd_tree.p + (size_t) (3 * p) * slots;
-            ca.kd_right[p] = (uint32_t *) ctx->kd_tree.p + (size_t) (3 * p + 1) * slots;
-            ca.kd_parent[p] = (uint32_t *) ctx->kd_tree.p + (size_t) (3 * p + 2) * slots;
-        }
+        for (int p = 0; p < 2; ++p) ca.kd_nodes[p] = (uint32_t *) ctx->kd_tree.p + (size_t) (4 * p) * slots;
         ca.bfs_items = (BfsItem *) ((char *) ctx->bfs_items.p + 16);
         ca.bfs_count = (unsigned *) ctx->bfs_items.p;
         ca.bfs_cap = bfs_cap;
@@ -388,9 +384,7 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
         for (int p = 0; p < 2; ++p) {
             ba.pix[p] = ca.pix[p];
             ba.labels[p] = ca.labels[p];
-            ba.kd_left[p] = ca.kd_left[p];
-            ba.kd_right[p] = ca.kd_right[p];
-            ba.kd_parent[p] = ca.kd_parent[p];
+            ba.kd_nodes[p] = (const uint4 *) ca.kd_nodes[p];
             ba.members[p] = ca.kmem[p];
             ba.scratch[p] = wa.arrive[p];  // the arrival lists are dead by now
             ba.key[p] = (unsigned long long *) ctx->bfs_key.p + (size_t) p * slots;
@@ -641,11 +635,9 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
     ca.min_pts = min_pts;
     ca.cluster_min = 0x7FFFFFFF;  // no kept-cluster tables on this path
     if (ordered) {
-        if ((rc = ecb_reserve(ctx, ctx->kd_tree, 3 * slots * 4))) return rc;
+        if ((rc = ecb_reserve(ctx, ctx->kd_tree, 4 * slots * 4))) return rc;
         ca.exact_order = 1;
-        ca.kd_left[0] = ca.kd_left[1] = (uint32_t *) ctx->kd_tree.p;
-        ca.kd_right[0] = ca.kd_right[1] = (uint32_t *) ctx->kd_tree.p + slots;
-        ca.kd_parent[0] = ca.kd_parent[1] = (uint32_t *) ctx->kd_tree.p + 2 * slots;
+        ca.kd_nodes[0] = ca.kd_nodes[1] = (uint32_t *) ctx->kd_tree.p;
         ca.bfs_count = (unsigned *) ctx->db_counter.p + 4;  // unused by k_cluster here (no kept clusters), must be valid
         ca.bfs_cap = 0;
     }
@@ -672,9 +664,7 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
         for (int p = 0; p < 2; ++p) {
             ba.pix[p] = ca.pix[0];
             ba.labels[p] = ca.labels[0];
-            ba.kd_left[p] = ca.kd_left[0];
-            ba.kd_right[p] = ca.kd_right[0];
-            ba.kd_parent[p] = ca.kd_parent[0];
+            ba.kd_nodes[p] = (const uint4 *) ca.kd_nodes[0];
             ba.members[p] = (uint32_t *) ctx->db_scratch.p;
             ba.scratch[p] = (uint32_t *) ctx->bfs_front.p;
             ba.key[p] = (unsigned long long *) ctx->bfs_key.p;

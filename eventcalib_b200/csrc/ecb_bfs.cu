@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs_order(const BfsArgs a) {
         const ProbDesc d = a.prob[it.pb];
         const uint32_t *pix = a.pix[d.pol] + d.off;
         const int32_t *lab = a.labels[d.pol] + d.off;
-        const uint32_t *kl = a.kd_left[d.pol] + d.off, *kr = a.kd_right[d.pol] + d.off, *kp = a.kd_parent[d.pol] + d.off;
+        const uint4 *nodes = a.kd_nodes[d.pol] + d.off;  // one 16-byte load per node visit
         uint32_t *O = a.members[d.pol] + d.off + it.mem_off;
         uint32_t *F = a.scratch[d.pol] + d.off + it.mem_off;
         unsigned long long *key = a.key[d.pol] + d.off;
@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs_order(const BfsArgs a) {
                     uint32_t node = 0;
                     int dir = 0, from = 0;  // 0: from the parent, 1: back from the near child, 2: back from the far child
                     uint32_t t = 0;
+                    uint4 nd = __ldg(nodes + node);
                     for (;;) {
-                        const uint32_t pn = pix[node];
+                        const uint32_t pn = nd.x;
                         const double dx = (dir ? qy : qx) - pix_coord(pn, dir);
                         if (from == 0) {
                             const double ex = (double) ECB_PIX_X(pn) - qx, ey = (double) ECB_PIX_Y(pn) - qy;
@@ -76,18 +77,20 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs_order(const BfsArgs a) {
                                 if (old == UNSEEN) F[le + atomicAdd(&s_cnt[wib], 1u)] = node;
                             }
                             ++t;
-                            const uint32_t nearc = dx <= 0.0 ? kl[node] : kr[node];
+                            const uint32_t nearc = dx <= 0.0 ? nd.y : nd.z;
                             if (nearc != ECB_NONE) {
                                 node = nearc;
+                                nd = __ldg(nodes + node);
                                 dir ^= 1;
                                 continue;
                             }
                             from = 1;
                         }
                         if (from == 1) {
-                            const uint32_t farc = dx <= 0.0 ? kr[node] : kl[node];
+                            const uint32_t farc = dx <= 0.0 ? nd.z : nd.y;
                             if (fabs(dx) < eps && farc != ECB_NONE) {
                                 node = farc;
+                                nd = __ldg(nodes + node);
                                 dir ^= 1;
                                 from = 0;
                                 continue;
@@ -96,10 +99,11 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs_order(const BfsArgs a) {
                         // this subtree is done: climb, and find out which child we are coming back from
                         if (node == 0) break;
                         const uint32_t child = node;
-                        node = kp[node];
+                        node = nd.w;
+                        nd = __ldg(nodes + node);
                         dir ^= 1;
-                        const double dxp = (dir ? qy : qx) - pix_coord(pix[node], dir);
-                        from = child == (dxp <= 0.0 ? kl[node] : kr[node]) ? 1 : 2;
+                        const double dxp = (dir ? qy : qx) - pix_coord(nd.x, dir);
+                        from = child == (dxp <= 0.0 ? nd.y : nd.z) ? 1 : 2;
                     }
                 }
                 __syncwarp();

@@ -220,17 +220,17 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             }
         }
         __syncthreads();
-        if (a.exact_order) {  // the emulated tree itself, for the member-order pass
-            uint32_t *gl = a.kd_left[d.pol] + d.off, *gr = a.kd_right[d.pol] + d.off;
-            uint32_t *gp = a.kd_parent[d.pol] + d.off;
+        if (a.exact_order) {  // the emulated tree itself, for the member-order pass: one 16-byte node per point
+            uint32_t *nodes = a.kd_nodes[d.pol] + 4 * d.off;  // {pixel, left, right, parent}
             for (int pid = tid; pid < n; pid += nthr) {
                 const uint32_t l = child[2 * pid], r = child[2 * pid + 1];
-                gl[pid] = l;
-                gr[pid] = r;
-                if (l != ECB_NONE) gp[l] = (uint32_t) pid;
-                if (r != ECB_NONE) gp[r] = (uint32_t) pid;
+                nodes[4 * pid] = gpix[pid];
+                nodes[4 * pid + 1] = l;
+                nodes[4 * pid + 2] = r;
+                if (l != ECB_NONE) nodes[4 * l + 3] = (uint32_t) pid;
+                if (r != ECB_NONE) nodes[4 * r + 3] = (uint32_t) pid;
             }
-            if (tid == 0 && n > 0) gp[0] = ECB_NONE;
+            if (tid == 0 && n > 0) nodes[3] = ECB_NONE;
         }
         // tie flag of the (occupied) pixel (x,y): bit0 = FX, bit1 = FY
         auto flag_of = [&](int x, int y) -> uint32_t { return s.r_flag[rank_of(x, y)]; };

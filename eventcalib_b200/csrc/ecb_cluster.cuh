@@ -59,10 +59,10 @@ struct ClusterArgs {
     int eps_int;                // eps if it is an integer (the kd tie rule can fire), else -1
     uint32_t min_pts, cluster_min;
     int8_t halfw[ECB_MAX_EPS + 1];  // half width of the eps-disc at |dy|
-    // exact-order mode: the emulated kd-tree is exported (left / right / parent pid per point slot, same indexing as
-    // pix[pol]) and every kept cluster whose median norm is tied is queued for k_bfs_order
+    // exact-order mode: the emulated kd-tree is exported (one 16-byte node {pixel, left, right, parent} per point slot, same
+    // indexing as pix[pol]) and every kept cluster whose median norm is tied is queued for k_bfs_order
     int exact_order;
-    uint32_t *kd_left[2], *kd_right[2], *kd_parent[2];
+    uint32_t *kd_nodes[2];
     BfsItem *bfs_items;
     unsigned *bfs_count;
     int bfs_cap;
@@ -75,7 +75,7 @@ struct BfsArgs {
     const ProbDesc *prob;
     const uint32_t *pix[2];
     const int32_t *labels[2];
-    const uint32_t *kd_left[2], *kd_right[2], *kd_parent[2];
+    const uint4 *kd_nodes[2];   // {pixel, left, right, parent}
     uint32_t *members[2];       // in: nothing required / out: member pids in BFS pop order at [off + mem_off, +size)
     uint32_t *scratch[2];       // same layout as members: unsorted frontier
     unsigned long long *key[2]; // per point slot
