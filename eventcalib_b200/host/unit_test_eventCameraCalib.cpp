@@ -7,10 +7,10 @@
 //
 // The window loop is the reference's adaptive one (accept -> jump by length + 5 steps, else grow by one step until the
 // window holds FrameEventNumThreshold events or exceeds 3 lengths, then slide; :49-81) over the reference's time pieces.
-// Round-1 limits (SURVEY §8 rows f-1, f-2, f-4 are "next"): a window counts as a frame when at least rows*cols candidate
-// circles were found (the reference additionally orders them with findCirclesGrid and applies the tracking gate); the OpenCV
-// initialisation and therefore the spline optimisation are not run here — the candidates are written to
-// SavePath/candidates.txt for the next stage.
+// Round-1 limits (SURVEY §8 rows f-1, f-4 are "next"): a window counts as a frame when the candidate circles are found and
+// ordered as the rows x cols grid (the reference additionally applies the tracking gate, EventCalibIni::track); the OpenCV
+// initialisation and therefore the spline optimisation are not run here — the ordered circles (board order, 36 per frame)
+// are written to SavePath/candidates.txt for the next stage.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -146,7 +146,6 @@ int main(int argc, char **argv) {
         std::vector<CalibCircleLite> circles;
     };
     std::map<double, Frame> frames;  // MapBase keeps key frames ordered by time stamp
-    const int need = pattern->rows * pattern->cols;
     FrontEnd fe(container, pattern, params);
     size_t rounds = 0, evaluated = 0;
     for (;;) {
@@ -169,10 +168,11 @@ int main(int argc, char **argv) {
         for (size_t w = 0; w < windows.size(); ++w) {
             Piece &pc = pieces[(size_t) owner[w]];
             const int events_num = fe.eventsNum(w);
-            const auto c = fe.candidates(w);
-            // extractFeatures() (:56): here "enough candidate circles"; the reference additionally needs findCirclesGrid to
-            // order them and the tracking gate to accept the frame (not part of this build)
-            if ((int) c.size() >= need) {
+            // extractFeatures() (:56): candidate circles found AND ordered by the grid finder (findCirclesGrid, :332-356); the
+            // reference additionally applies the tracking gate to accept the frame (needs the OpenCV
+            // initialisation side, not part of this build)
+            std::vector<CalibCircleLite> c;
+            if (CirclesEventFrame::orderFeatures(fe.candidates(w), *pattern, c)) {
                 const double ts = (pc.first + pc.second) / 2;  // Bodyframe time stamp (:57)
                 frames[ts] = Frame{ts, events_num, c};
                 pc.first = pc.second + frameGap;  // :60-62

@@ -12,8 +12,8 @@
 //   opengv2::EventStream::txt2bin  EV/src/EventStream.cpp:25-67 (text -> 25-byte records)
 //   EventCalibSpline::evaluate / time2splineIdx / saveKeyFrameTrajectoryTUM   ECC/.../EventCalibSpline.hpp:295-330,
 //                                  CORE/system/src/SystemBase.cpp:122-150 (TUM lines `t tx ty tz qx qy qz qw`, fixed, precision 10)
-// What is NOT here yet: the grid ordering of candidates (findCirclesGrid) — extractFeatures() therefore
-// returns the candidate circles unordered and reports success when at least rows*cols candidates were found.
+// extractFeatures() orders the candidates with include/ecb/circles_grid.hpp (the canonical result of the reference's
+// findCirclesGrid call, CirclesEventFrame.cpp:332-356) and reports success when the grid is found.
 #ifndef ECB_EVENT_CALIB_HPP
 #define ECB_EVENT_CALIB_HPP
 
@@ -33,6 +33,7 @@
 
 #include "../eventcalib_b200.h"
 #include "../../eventcalib_b200/csrc/ecb_so3.h"  // plain host/device header: the SO(3) spline of the useSO3 variant
+#include "circles_grid.hpp"
 #include "dbscan.h"
 
 namespace opengv2 {
@@ -232,11 +233,23 @@ public:
         : fe_(container, pattern, params), duration_(duration), pattern_(pattern) {
         fe_.run({duration_});  // the EventFrame ctor does the window / dedupe / cancel work (EventFrame.cpp:10-36)
     }
-    bool extractFeatures() {  // CirclesEventFrame.cpp:61-359 up to the grid ordering
+    bool extractFeatures() {  // CirclesEventFrame.cpp:61-359
         const ecb_window_summary &s = fe_.summary(0);
         if (s.n_points[0] == 0 || s.n_points[1] == 0) return false;  // :62-64
-        features_ = fe_.candidates(0);
-        return (int) features_.size() >= pattern_->rows * pattern_->cols;
+        return orderFeatures(fe_.candidates(0), *pattern_, features_);
+    }
+    // :320-356: the candidates in pattern order (findCirclesGrid, CALIB_CB_ASYMMETRIC_GRID) -> features_; false when the grid
+    // is not found.  Grid ordering: include/ecb/circles_grid.hpp (the canonical RESULT of OpenCV's finder).
+    static bool orderFeatures(const std::vector<CalibCircleLite> &cand, const CirclePatternParameters &pattern,
+                              std::vector<CalibCircleLite> &features) {
+        features.clear();
+        if ((int) cand.size() < pattern.rows * pattern.cols || !pattern.isAsymmetric) return false;
+        std::vector<ecb::Pt2> pts;
+        for (const auto &c : cand) pts.push_back(ecb::Pt2{(double) (float) c.center[0], (double) (float) c.center[1]});  // cv::Point2f (:322-324)
+        std::vector<int> order;
+        if (!ecb::find_asymmetric_circles_grid(pts, pattern.rows, pattern.cols, order)) return false;
+        for (int idx : order) features.push_back(cand[(size_t) idx]);
+        return true;
     }
     // rectifyFeatures (CirclesEventFrame.cpp:417-609).  The reference projects every feature's landmark and four quadrant
     // points with cv::projectPoints (:431-456) from (outlierIdxs, Rcw, tcw); that projection needs the OpenCV initialisation

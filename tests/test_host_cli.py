@@ -77,8 +77,12 @@ def test_cli_on_synthetic_stream(built, tmp_path):
     cand = np.loadtxt(str(save / "candidates.txt"))
     assert cand.shape[1] == 5 and len(np.unique(cand[:, 0])) == frames
     assert np.all((cand[:, 4] > 1) & (cand[:, 4] < 16))      # circle radii in pixels (< circleRadiusThreshold)
+    # every frame holds the 36 circles in board order
+    assert np.all(np.bincount(np.unique(cand[:, 0], return_inverse=True)[1]) == 36)
     # the adaptive window loop (eventCameraCalib.cpp:49-81) replayed window by window through the Python binding
     import eventcalib_b200 as ecb
+    from test_circles_grid import _lib as grid_lib, _order as grid_order
+    glib = grid_lib()
     ctx = ecb.Context(0)
     ctx.set_sensor(346, 260)
     ctx.load_events(synth.to_records(ev))
@@ -94,7 +98,11 @@ def test_cli_on_synthetic_stream(built, tmp_path):
             ctx.frontend_run(np.array([[a, b]]), prm)
             s = ctx.summary()[0]
             n_ev = int(s["n_points"].sum())
-            if s["n_candidates"] >= 36:
+            ok = False
+            if s["n_candidates"] >= 36:   # extractFeatures(): candidates found and ordered as the 9 x 4 grid
+                cpts = ctx.candidates(128)[0, :int(s["n_candidates"]), 2:4].astype(np.float32).astype(np.float64)
+                ok, _ = grid_order(glib, cpts)
+            if ok:
                 stamps.append((a + b) / 2)
                 a = b + gap
                 b = a + ln
