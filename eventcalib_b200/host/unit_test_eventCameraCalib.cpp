@@ -7,8 +7,9 @@
 //
 // The window loop is the reference's adaptive one (accept -> jump by length + 5 steps, else grow by one step until the
 // window holds FrameEventNumThreshold events or exceeds 3 lengths, then slide; :49-81) over the reference's time pieces.
-// Round-1 limits (SURVEY §8 rows f-1, f-4 are "next"): a window counts as a frame when the candidate circles are found and
-// ordered as the rows x cols grid (the reference additionally applies the tracking gate, EventCalibIni::track); the OpenCV
+// A window becomes a key frame when the candidate circles are found, ordered as the rows x cols grid, and pass the tracking
+// gate (EventCalibIni::track: row directions vs the neighbouring key frame; the reference's worker threads race on the
+// shared map, here the pieces of one round are gated in piece order).  Round-1 limit: the OpenCV
 // initialisation and therefore the spline optimisation are not run here — the ordered circles (board order, 36 per frame)
 // are written to SavePath/candidates.txt for the next stage.
 #include <algorithm>
@@ -147,6 +148,7 @@ int main(int argc, char **argv) {
     };
     std::map<double, Frame> frames;  // MapBase keeps key frames ordered by time stamp
     FrontEnd fe(container, pattern, params);
+    TrackingGate gate(pattern->rows, pattern->cols, motionTimeStep);  // EventCalibIni::track; pieces of one round in piece order
     size_t rounds = 0, evaluated = 0;
     for (;;) {
         std::vector<std::pair<double, double>> windows;
@@ -168,11 +170,11 @@ int main(int argc, char **argv) {
         for (size_t w = 0; w < windows.size(); ++w) {
             Piece &pc = pieces[(size_t) owner[w]];
             const int events_num = fe.eventsNum(w);
-            // extractFeatures() (:56): candidate circles found AND ordered by the grid finder (findCirclesGrid, :332-356); the
-            // reference additionally applies the tracking gate to accept the frame (needs the OpenCV
-            // initialisation side, not part of this build)
+            // extractFeatures() (:56): candidate circles found AND ordered by the grid finder (findCirclesGrid, :332-356), then
+            // the tracking gate (tracking->process, :60 -> EventCalibIni::track)
             std::vector<CalibCircleLite> c;
-            if (CirclesEventFrame::orderFeatures(fe.candidates(w), *pattern, c)) {
+            const double ts0 = (pc.first + pc.second) / 2;
+            if (CirclesEventFrame::orderFeatures(fe.candidates(w), *pattern, c) && gate.process(ts0, c)) {  // :56-60
                 const double ts = (pc.first + pc.second) / 2;  // Bodyframe time stamp (:57)
                 frames[ts] = Frame{ts, events_num, c};
                 pc.first = pc.second + frameGap;  // :60-62

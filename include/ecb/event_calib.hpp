@@ -23,6 +23,7 @@
 #include <iomanip>
 #include <iostream>
 #include <limits>
+#include <map>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -297,6 +298,91 @@ private:
     std::pair<double, double> duration_;
     CirclePatternParameters::Ptr pattern_;
     std::vector<CalibCircleLite> features_;
+};
+
+// ---- the tracking gate: TrackingBase::process (core/tracking/src/TrackingBase.cpp:16-46) + EventCalibIni::track
+// (event_camera_calib/src/EventCalibIni.cpp:23-97).  The first frame initialises the map; a later frame is accepted when the
+// median angle between the directions of its grid rows and those of the neighbouring key frame (lower_bound of its time
+// stamp, else the last one), divided by the time between them, stays below 5e-4*pi / MotionTimeStep rad/s.
+// Row direction: total-least-squares line through the row's centres (the reference takes the last right singular vector of
+// [x y 1]; here the eigenvector of the 3x3 normal matrix, same line).  Host only.
+class TrackingGate {
+public:
+    TrackingGate(int rows, int cols, double motionTimeStep) : rows_(rows), cols_(cols), step_(motionTimeStep) {}
+    bool process(double timeStamp, const std::vector<CalibCircleLite> &features) {
+        if (keyframes_.empty()) {  // initialization(): addFrame, state = OK
+            keyframes_[timeStamp] = features;
+            return true;
+        }
+        auto itr = keyframes_.lower_bound(timeStamp);
+        const auto &ref = itr != keyframes_.end() ? *itr : *keyframes_.rbegin();
+        const double duration = std::abs(timeStamp - ref.first);
+        std::vector<double> theta;
+        for (int i = 0; i < rows_; ++i) {
+            double r[2], c[2];
+            rowDirection(ref.second, i, r);
+            rowDirection(features, i, c);
+            theta.push_back(std::acos((r[0] * c[0] + r[1] * c[1]) / (std::sqrt(r[0] * r[0] + r[1] * r[1]) * std::sqrt(c[0] * c[0] + c[1] * c[1]))));
+        }
+        std::nth_element(theta.begin(), theta.begin() + theta.size() / 2, theta.end());
+        if (theta[theta.size() / 2] / duration < (5e-4 * M_PI) / step_) {
+            keyframes_.emplace(timeStamp, features);  // MapBase::addFrame
+            return true;
+        }
+        return false;
+    }
+    const std::map<double, std::vector<CalibCircleLite>> &keyframes() const { return keyframes_; }
+
+private:
+    // direction (B, -A) of the line A x + B y + C = 0 through row i, pointing from its first to its last centre
+    void rowDirection(const std::vector<CalibCircleLite> &f, int i, double d[2]) const {
+        double M[3][3] = {{0}};
+        for (int j = 0; j < cols_; ++j) {
+            const double v[3] = {f[(size_t) (i * cols_ + j)].center[0], f[(size_t) (i * cols_ + j)].center[1], 1.0};
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) M[a][b] += v[a] * v[b];
+        }
+        double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int sweep = 0; sweep < 60; ++sweep) {  // cyclic Jacobi on the symmetric 3x3
+            double off = 0;
+            for (int p = 0; p < 3; ++p)
+                for (int q = p + 1; q < 3; ++q) off += M[p][q] * M[p][q];
+            if (off < 1e-300) break;
+            for (int p = 0; p < 3; ++p)
+                for (int q = p + 1; q < 3; ++q) {
+                    if (M[p][q] == 0) continue;
+                    const double th = (M[q][q] - M[p][p]) / (2 * M[p][q]);
+                    const double t = (th >= 0 ? 1.0 : -1.0) / (std::abs(th) + std::sqrt(th * th + 1));
+                    const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                    for (int k = 0; k < 3; ++k) {
+                        const double mkp = M[k][p], mkq = M[k][q];
+                        M[k][p] = c * mkp - s * mkq;
+                        M[k][q] = s * mkp + c * mkq;
+                    }
+                    for (int k = 0; k < 3; ++k) {
+                        const double mpk = M[p][k], mqk = M[q][k];
+                        M[p][k] = c * mpk - s * mqk;
+                        M[q][k] = s * mpk + c * mqk;
+                    }
+                    for (int k = 0; k < 3; ++k) {
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = c * vkp - s * vkq;
+                        V[k][q] = s * vkp + c * vkq;
+                    }
+                }
+        }
+        int m = 0;
+        for (int k = 1; k < 3; ++k)
+            if (M[k][k] < M[m][m]) m = k;
+        d[0] = V[1][m];
+        d[1] = -V[0][m];
+        const double ex = f[(size_t) (i * cols_ + cols_ - 1)].center[0] - f[(size_t) (i * cols_)].center[0];
+        const double ey = f[(size_t) (i * cols_ + cols_ - 1)].center[1] - f[(size_t) (i * cols_)].center[1];
+        if (d[0] * ex + d[1] * ey < 0) d[0] = -d[0], d[1] = -d[1];
+    }
+    int rows_, cols_;
+    double step_;
+    std::map<double, std::vector<CalibCircleLite>> keyframes_;
 };
 
 // ---- spline calibration: EventCalibSpline::optimize on the GPU ----

@@ -19,3 +19,13 @@ int fh_tum(const double *knots, int n_cp, const double *rot, const double *trans
     return EventCalibSpline::saveKeyFrameTrajectoryTUM(seg, so3 != 0, file, std::vector<double>(ts, ts + n));
 }
 }
+// tracking gate (TrackingGate): feed frames one by one; features = n x 2 centres in board order
+extern "C" {
+void *fh_gate_new(int rows, int cols, double step) { return new TrackingGate(rows, cols, step); }
+void fh_gate_free(void *g) { delete (TrackingGate *) g; }
+int fh_gate_process(void *g, double ts, const double *xy, int n) {
+    std::vector<CalibCircleLite> f((size_t) n);
+    for (int i = 0; i < n; ++i) f[(size_t) i] = CalibCircleLite{{{xy[2 * i], xy[2 * i + 1]}}, 1.0, -1, -1};
+    return ((TrackingGate *) g)->process(ts, f) ? 1 : 0;
+}
+}

@@ -88,3 +88,40 @@ def test_spline_evaluate_and_tum(tmp_path):
         assert abs(float(f[0]) - t) < 1e-9
         v = np.array(list(map(float, f[1:])))
         assert abs(np.linalg.norm(v[3:]) - 1) < 1e-8
+
+
+def test_tracking_gate_matches_numpy_restatement():
+    """TrackingGate (EventCalibIni::track) against tests/gate_py.py on a sequence with slow and fast rotations"""
+    import gate_py
+    from eventcalib_b200 import synth
+    lib = _lib()
+    lib.fh_gate_new.restype = C.c_void_p
+    lib.fh_gate_new.argtypes = [C.c_int, C.c_int, C.c_double]
+    lib.fh_gate_process.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int]
+    lib.fh_gate_free.argtypes = [C.c_void_p]
+    board, cam = synth.Board(), synth.Camera()
+    c = board.centres()
+    ctr = c.mean(0)
+    rng = np.random.default_rng(1)
+    g = C.c_void_p(lib.fh_gate_new(9, 4, 5e-4))
+    ref = gate_py.Gate(9, 4, 5e-4)
+    th, t = 0.3, 5.0
+    verdicts = []
+    order = []
+    for k in range(60):
+        t += 4e-3
+        th += (0.002 if k % 5 else 0.06) * rng.uniform(0.5, 1.5)      # every fifth frame jumps: > pi rad/s
+        order.append((t, th))
+    order[10], order[11] = order[11], order[10]                       # out-of-order arrival: lower_bound finds a LATER key frame
+    for t_, th_ in order:
+        cz, sz = np.cos(th_), np.sin(th_)
+        R = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[1, 0, 0], [0, np.cos(0.2), -np.sin(0.2)], [0, np.sin(0.2), np.cos(0.2)]])
+        tw = ctr + R @ np.array([0, 0, -95.0])
+        u, v = synth.project(cam, np.repeat(R[None], 36, 0), np.repeat(tw[None], 36, 0), c)
+        f = np.ascontiguousarray(np.stack([u, v], 1) + rng.normal(0, 0.1, (36, 2)))
+        a = lib.fh_gate_process(g, t_, f.ctypes.data_as(C.c_void_p), 36)
+        b = ref.process(t_, f)
+        verdicts.append((a, int(b)))
+    lib.fh_gate_free(g)
+    assert all(a == b for a, b in verdicts)
+    assert 0 < sum(a for a, _ in verdicts) < len(verdicts)            # both accepted and rejected frames occurred

@@ -90,18 +90,27 @@ def test_cli_on_synthetic_stream(built, tmp_path):
     prm = ecb.default_params(fit_circle=0, radius_threshold=rthr, order_mode=1, median_mode=1)
     step, t_end = 5e-4, float(ev["t"][-1])
     ln, gap, pstep = 3 * step, 5 * step, (t_end - 5.0) / 3
+    import gate_py
+    gate = gate_py.Gate(9, 4, step)
     stamps = []
+    pieces = []
     for k in range(3):
         lo, hi = t_end - pstep * (k + 1), t_end - pstep * k
-        a, b = lo, lo + ln
-        while b < hi:
+        pieces.append([lo, lo + ln, hi])
+    while any(b < hi for a, b, hi in pieces):          # the CLI's wavefront: one window per unfinished piece per round
+        for pc in pieces:
+            a, b, hi = pc
+            if not b < hi:
+                continue
             ctx.frontend_run(np.array([[a, b]]), prm)
             s = ctx.summary()[0]
             n_ev = int(s["n_points"].sum())
             ok = False
             if s["n_candidates"] >= 36:   # extractFeatures(): candidates found and ordered as the 9 x 4 grid
-                cpts = ctx.candidates(128)[0, :int(s["n_candidates"]), 2:4].astype(np.float32).astype(np.float64)
-                ok, _ = grid_order(glib, cpts)
+                cpts = ctx.candidates(128)[0, :int(s["n_candidates"]), 2:4]
+                ok, order36 = grid_order(glib, cpts.astype(np.float32).astype(np.float64))
+            if ok:   # tracking->process (eventCameraCalib.cpp:60): EventCalibIni::track on the ordered centres
+                ok = gate.process((a + b) / 2, cpts[order36])
             if ok:
                 stamps.append((a + b) / 2)
                 a = b + gap
@@ -111,6 +120,7 @@ def test_cli_on_synthetic_stream(built, tmp_path):
                 b = a + ln
             else:
                 b += step
+            pc[0], pc[1] = a, b
     ctx.close()
     assert len(stamps) == frames
     np.testing.assert_allclose(np.sort(stamps), np.unique(cand[:, 0]), rtol=0, atol=1e-12)
