@@ -707,6 +707,7 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     int by_smem = 1;
     ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&by_smem, kern, 32, smem));
     int threads = std::max(128, std::min(ECB_CL_THREADS, (1024 / std::max(by_smem, 1)) & ~31));
+    if (!a.arrays_in_smem) threads = ECB_CL_THREADS;  // large problems in L2 scratch: few CTAs, each wants all the threads it can get
     if (const char *e = getenv("ECB_CL_THREADS")) threads = std::max(64, std::min(ECB_CL_THREADS, atoi(e) & ~31));
     ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;

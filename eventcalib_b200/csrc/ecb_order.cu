@@ -21,7 +21,8 @@
 
 namespace {
 
-constexpr int ORD_THREADS = 256;
+constexpr int ORD_THREADS = 256;       // problems that fit shared memory: several CTAs per SM
+constexpr int ORD_THREADS_BIG = 1024;  // large problems in L2 scratch: few CTAs, as many threads each as possible
 constexpr int ORD_NSTAGE = 17;
 __constant__ uint32_t c_prime[ORD_NSTAGE] = {13,    29,     59,     127,    257,    541,     1109,   2357,   5087,
                                              10273, 20753,  42043,  85229,  172933, 351061,  712697, 1447153};
@@ -77,11 +78,11 @@ __device__ __forceinline__ uint32_t bucket_of(uint64_t h, int stage) {
 
 // SM: arrays in shared memory (pointers derived from the shared array only -> LDS/STS/ATOMS), else per-CTA L2 scratch
 template <bool SM>
-__global__ void __launch_bounds__(ORD_THREADS) k_uset_order(const OrderArgs a) {
+__global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_order(const OrderArgs a) {
     extern __shared__ __align__(16) uint32_t smo[];
     __shared__ uint32_t ws[33];
     __shared__ uint32_t s_pb;
-    const int tid = threadIdx.x, nthr = ORD_THREADS, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
+    const int tid = threadIdx.x, nthr = SM ? ORD_THREADS : ORD_THREADS_BIG, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     uint32_t *base;
     if constexpr (SM) base = smo;
     else base = a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
@@ -213,7 +214,8 @@ int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
     void (*kern)(const OrderArgs) = a.arrays_in_smem ? k_uset_order<true> : k_uset_order<false>;
     ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
     int per_sm = 1;
-    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ORD_THREADS, smem));
+    const int threads = a.arrays_in_smem ? ORD_THREADS : ORD_THREADS_BIG;
+    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_prob) grid = a.n_prob;
@@ -225,7 +227,7 @@ int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
     }
     ECB_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, 4, ctx->stream));
     ECB_PROF_BEGIN(ctx, ECB_STAGE_ORDER);
-    kern<<<grid, ORD_THREADS, smem, ctx->stream>>>(a);
+    kern<<<grid, threads, smem, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_ORDER);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_uset_order launch");
