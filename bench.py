@@ -205,9 +205,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--events", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--slices", type=int, default=4, help="time slices (contexts/streams/host threads) of the e2e pipeline")
+    ap.add_argument("--slices", type=int, default=8, help="time slices (contexts/streams/host threads) of the e2e pipeline")
     ap.add_argument("--order-mode", type=int, default=1, help="pid order: 0 first arrival, 1 libstdc++ unordered_set order (the reference's)")
     ap.add_argument("--median-mode", type=int, default=1, help="cluster centre: 0 canonical, 1 std::nth_element over BFS order (the reference's)")
+    ap.add_argument("--slice-plan", default="", help="relative sizes of the e2e time slices, e.g. 1,2,3,3,2,1 (overrides --slices)")
     ap.add_argument("--lm-iters", type=int, default=50, help="LM iterations of the C4 side measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -317,10 +318,14 @@ def main():
     # of slice k+1 overlaps the kernels of slice k (the C ABI is re-entrant per context; ctypes releases the GIL).
     from concurrent.futures import ThreadPoolExecutor
     from eventcalib_b200 import sharding
-    S = max(1, args.slices)
+    # slice sizes: the pipeline is balanced (H2D time ~ kernel time), so its length is  first upload + all kernels  or
+    # all uploads + last slice's kernels — short first and last slices, long ones in between (--slice-plan fractions)
+    plan = [float(v) for v in args.slice_plan.split(",")] if args.slice_plan else [1.0] * max(1, args.slices)
+    S = len(plan)
+    cuts = np.round(np.cumsum([0.0] + plan) / sum(plan) * len(win)).astype(int)
     slices = []
     for j in range(S):
-        w0, w1 = sharding.window_shard(len(win), j, S)
+        w0, w1 = int(cuts[j]), int(cuts[j + 1])
         lo = int(np.searchsorted(ev["t"], win[w0, 0], side="left")) if j > 0 else 0
         slices.append(dict(w0=w0, w1=w1, lo=lo))
     for j in range(S):
@@ -523,8 +528,8 @@ def main():
                            "found_circles_per_window": float(s["n_candidates"].mean())},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "pipeline": "%d time slices, one context/stream/host thread each "
-                        "(H2D of slice k+1 overlaps the kernels of slice k)" % S}}
+                        "d2h_bytes_per_step": int(d2h), "pipeline": "%d time slices (relative sizes %s), one context/stream/host thread each "
+                        "(H2D of slice k+1 overlaps the kernels of slice k)" % (S, ":".join("%g" % v for v in plan))}}
         if lm_info:
             line["lm"] = lm_info
         if not args.no_cpu and world == 1:

@@ -38,13 +38,20 @@ int ecb_reserve(ecb_ctx *ctx, DevBuf &b, size_t bytes) {
     return ECB_OK;
 }
 
+__global__ void k_pull(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t words, size_t bytes) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t) gridDim.x * blockDim.x)
+        dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x < (bytes & 3))
+        ((uint8_t *) dst)[words * 4 + threadIdx.x] = ((const uint8_t *) src)[words * 4 + threadIdx.x];
+}
+
 static int reserve_pinned(ecb_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->pinned_cap) return ECB_OK;
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     ctx->pinned = nullptr;
     ctx->pinned_cap = 0;
     bytes += bytes / 4 + 4096;
-    ECB_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ECB_CUDA(ctx, cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocMapped));
     ctx->pinned_cap = bytes;
     return ECB_OK;
 }
@@ -59,18 +66,23 @@ int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     }
     int rc = reserve_pinned(ctx, bytes);
     if (rc) return rc;
-    ECB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes <= ((size_t) 1 << 20) && !((uintptr_t) src & 3u)) {
+        // small results never touch the copy engines either: a kernel stores them into the (device-mapped) pinned buffer,
+        // so a window table or a scalar cannot queue behind another context's bulk record DMA
+        void *dpin = nullptr;
+        ECB_CUDA(ctx, cudaHostGetDevicePointer(&dpin, ctx->pinned, 0));
+        const size_t words = bytes >> 2;
+        const int grid = (int) std::min<size_t>((words + 255) / 256 + 1, 128);
+        k_pull<<<grid, 256, 0, ctx->stream>>>((uint32_t *) dpin, (const uint32_t *) src, words, bytes);
+        ECB_LAUNCHED(ctx);
+        ECB_CUDA(ctx, cudaGetLastError());
+    } else {
+        ECB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->up_off = 0;  // every staged upload has been pulled
     memcpy(dst, ctx->pinned, bytes);
     return ECB_OK;
-}
-
-__global__ void k_pull(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t words, size_t bytes) {
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t) gridDim.x * blockDim.x)
-        dst[i] = src[i];
-    if (blockIdx.x == 0 && threadIdx.x < (bytes & 3))
-        ((uint8_t *) dst)[words * 4 + threadIdx.x] = ((const uint8_t *) src)[words * 4 + threadIdx.x];
 }
 
 int ecb_h2d(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
