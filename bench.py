@@ -500,6 +500,7 @@ def main():
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             k = tr["kernels"].get("k_" + dom)
             if k:
+                roofline["ncu"] = {m: k[m] for m in ("issue_active_pct", "warps_active_pct", "dram_throughput_pct", "fp64_pipe_active_pct") if m in k}
                 roofline["traffic"] = (k["dram_bytes_read"] + k["dram_bytes_write"]) * (n / float(tr["events"]))
                 roofline["traffic_source"] = tr["source"] + ("" if n == tr["events"] else " (scaled from %d events)" % tr["events"])
         except Exception:

@@ -237,3 +237,22 @@ def test_rectify_features(ctx, oracle_mod, fit_circle):
         np.testing.assert_allclose(out[w][alive], ref[alive], rtol=RTOL, atol=0)
         assert ok[w] == ref_ok
     assert n_alive > 10 * len(win) and (ok == 1).any() and (ok == 0).any()
+
+
+def test_closed_window_bounds_and_equal_stamps(ctx, oracle_mod):
+    """EventFrame.cpp:14-15: lower_bound(first) .. upper_bound(second) — both ends closed; events with EQUAL time stamps
+    (multimap keeps file order) straddling a window bound are all inside"""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(20000, 346, 260, t0=5.0, duration=0.01, seed=77)
+    t = ev["t"].copy()
+    for k in (3000, 3001, 3002, 9000, 9001, 15000):      # runs of identical stamps
+        t[k] = t[k - 1]
+    ev = dict(ev, t=t)
+    win = np.array([[t[2999], t[9001]],        # starts and ends exactly on repeated stamps
+                    [t[9001], t[15000]],       # shares its first stamp with the previous window's last
+                    [t[100], t[100]],          # a single instant
+                    [np.nextafter(t[3002], 10), np.nextafter(t[9000], 0)],   # just inside the repeated stamps
+                    [t[0], t[-1]]])
+    _check_stream(ctx, oracle_mod, ev, win, 346, 260, 1, order_mode=1, median_mode=1)
+    s = ctx.summary()
+    assert s["ev_lo"][0] == 2999 and s["ev_hi"][0] == 9002 and s["ev_lo"][1] == 8999 and s["ev_hi"][2] - s["ev_lo"][2] == 1
