@@ -38,6 +38,7 @@ struct CostState {
     std::vector<int> n_cp, cp_off, span_off, knot_off;
     std::vector<double> knots;
     double radius = 1.75, huber = 0.35;
+    bool use_circ = false;  // residuals carry a landmark index (association path) instead of explicit landmark coordinates
     int so3 = 0;  // rotation model: 0 normalised quaternion spline (useSO3: 0), 1 cumulative SO(3) spline (useSO3: 1)
     int64_t n_res = 0;
     int n_items = 0;
@@ -135,6 +136,8 @@ struct Item {
 
 struct NeArgs {
     const double *obs, *lm, *basis;
+    const int *circ;        // landmark index per residual into lm_tab (association path), or null: explicit `lm` per residual
+    const double *lm_tab;
     const int *cp0;
     const Item *items;
     int n_items;
@@ -176,13 +179,15 @@ __global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) 
                 const double4 b4 = reinterpret_cast<const double4 *>(a.basis)[k];
                 const double b[4] = {b4.x, b4.y, b4.z, b4.w};
                 const double2 o = reinterpret_cast<const double2 *>(a.obs)[k];
+                const double *L = a.circ ? a.lm_tab + 3 * a.circ[k] : a.lm + 3 * k;
+                const double Lx = L[0], Ly = L[1], Lz = L[2];
                 // the Jacobian is scattered straight into column `lane` of the shared tile (no register array)
                 const EcbResidualOut r =
                     SO3 ? ecb_residual_so3<true, TILE_LD>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y,
-                                                          a.lm[3 * k], a.lm[3 * k + 1], a.lm[3 * k + 2], a.radius, a.huber,
+                                                          Lx, Ly, Lz, a.radius, a.huber,
                                                           tile + lane)
                         : ecb_residual<true, TILE_LD>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y,
-                                                      a.lm[3 * k], a.lm[3 * k + 1], a.lm[3 * k + 2], a.radius, a.huber,
+                                                      Lx, Ly, Lz, a.radius, a.huber,
                                                       tile + lane);
                 res = r.res;
                 cost += r.cost;
@@ -410,6 +415,7 @@ __global__ void k_reduce_cost(const double *__restrict__ part, int n, int stride
 
 template <bool SO3>
 __global__ void __launch_bounds__(256) k_cost(const double *__restrict__ obs, const double *__restrict__ lm,
+                                             const int *__restrict__ circ, const double *__restrict__ lm_tab,
                                              const double *__restrict__ basis, const int *__restrict__ cp0, int64_t n,
                                              const double *__restrict__ params, int total_cp, double radius, double huber,
                                              double *__restrict__ block_part) {
@@ -421,10 +427,12 @@ __global__ void __launch_bounds__(256) k_cost(const double *__restrict__ obs, co
         const double4 b4 = reinterpret_cast<const double4 *>(basis)[k];
         const double b[4] = {b4.x, b4.y, b4.z, b4.w};
         const double2 o = reinterpret_cast<const double2 *>(obs)[k];
-        c += SO3 ? ecb_residual_so3<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, lm[3 * k],
-                                           lm[3 * k + 1], lm[3 * k + 2], radius, huber, nullptr).cost
-                 : ecb_residual<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, lm[3 * k],
-                                       lm[3 * k + 1], lm[3 * k + 2], radius, huber, nullptr).cost;
+        const double *L = circ ? lm_tab + 3 * circ[k] : lm + 3 * k;
+        const double Lx = L[0], Ly = L[1], Lz = L[2];
+        c += SO3 ? ecb_residual_so3<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, Lx, Ly, Lz, radius,
+                                           huber, nullptr).cost
+                 : ecb_residual<false>(intr, rot + 4 * (size_t) c0, trans + 3 * (size_t) c0, b, o.x, o.y, Lx, Ly, Lz, radius, huber,
+                                       nullptr).cost;
     }
     sh[threadIdx.x] = c;
     __syncthreads();
@@ -557,14 +565,16 @@ __global__ void __launch_bounds__(AS_THREADS) k_assoc_write(const AssocArgs a, c
         const int64_t k = block_off[blockIdx.x] + ex;
         const uint32_t e = a.ev_xyp[i];
         reinterpret_cast<double2 *>(obs)[k] = make_double2((double) ECB_PIX_X(e), (double) ECB_PIX_Y(e));
-        lm[3 * k] = a.lm_tab[3 * bi];
-        lm[3 * k + 1] = a.lm_tab[3 * bi + 1];
-        lm[3 * k + 2] = a.lm_tab[3 * bi + 2];
         const double u = a.ev_t[i];
-        tt[k] = u;
-        spl[k] = s;
         sel_event[k] = i;
-        sel_circle[k] = bi;
+        sel_circle[k] = bi;  // the evaluation kernels read the landmark from lm_tab[circle]
+        if (!a.basis) {      // unfused path: k_prepare needs time and spline, the kernels the explicit landmark
+            lm[3 * k] = a.lm_tab[3 * bi];
+            lm[3 * k + 1] = a.lm_tab[3 * bi + 1];
+            lm[3 * k + 2] = a.lm_tab[3 * bi + 2];
+            tt[k] = u;
+            spl[k] = s;
+        }
         if (a.basis) {  // what k_prepare would compute (findSpan / dersBasisFuns, EventCalibSpline.cpp:173-179)
             const double *kn = a.knots + a.knot_off[s];
             const int sp = find_span_dev(kn, a.ncp[s] + 4, u);
@@ -734,6 +744,7 @@ int ecb_cost_set_residuals(ecb_ctx *ctx, const double *obs_xy, const double *lm_
         ECB_CUDA(ctx, cudaMemcpyAsync(st->spl.p, spline, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     st->n_res = n;
+    st->use_circ = false;
     return prepare_records(ctx, st);
 }
 
@@ -818,6 +829,7 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     ECB_PROF_END(ctx, ECB_STAGE_ASSOC);
     if ((rc = ecb_check(ctx, cudaGetLastError(), "association kernels"))) return rc;
     st->n_res = total;
+    st->use_circ = fused;
     if (n_residuals) *n_residuals = total;
     return prepare_records(ctx, st, fused);
 }
@@ -845,7 +857,9 @@ int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, 
     if (st->n_res == 0) return ECB_OK;
     int grid = (int) std::min<int64_t>((st->n_res + 255) / 256, (int64_t) ctx->sm_count * 8);
     ECB_PROF_BEGIN(ctx, ECB_STAGE_COST);
-    (st->so3 ? k_cost<true> : k_cost<false>)<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p, (const double *) st->basis.p,
+    (st->so3 ? k_cost<true> : k_cost<false>)<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p,
+                                          st->use_circ ? (const int *) st->sel_circle.p : nullptr, (const double *) st->lm_tab.p,
+                                          (const double *) st->basis.p,
                                           (const int *) st->cp0.p, st->n_res, (const double *) st->params.p, st->total_cp,
                                           st->radius, st->huber, (double *) st->cost_part.p);
     ECB_LAUNCHED(ctx);
@@ -872,6 +886,8 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
         NeArgs a;
         a.obs = (const double *) st->obs.p;
         a.lm = (const double *) st->lm.p;
+        a.circ = st->use_circ ? (const int *) st->sel_circle.p : nullptr;
+        a.lm_tab = (const double *) st->lm_tab.p;
         a.basis = (const double *) st->basis.p;
         a.cp0 = (const int *) st->cp0.p;
         a.items = (const Item *) st->items.p;
@@ -950,6 +966,8 @@ int ecb_cost_normal_eq_exchange(ecb_ctx *ctx, const double *intrinsics, const do
         NeArgs a;
         a.obs = (const double *) st->obs.p;
         a.lm = (const double *) st->lm.p;
+        a.circ = st->use_circ ? (const int *) st->sel_circle.p : nullptr;
+        a.lm_tab = (const double *) st->lm_tab.p;
         a.basis = (const double *) st->basis.p;
         a.cp0 = (const int *) st->cp0.p;
         a.items = (const Item *) st->items.p;
