@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                 if (r != ECB_NONE) nodes[4 * r + 3] = (uint32_t) pid;
             }
             if (tid == 0 && n > 0) nodes[3] = ECB_NONE;
+            __syncthreads();  // `child` (r_kd) is re-used as parent / glabel below
         }
         // tie flag of the (occupied) pixel (x,y): bit0 = FX, bit1 = FY
         auto flag_of = [&](int x, int y) -> uint32_t { return s.r_flag[rank_of(x, y)]; };
