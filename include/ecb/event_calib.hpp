@@ -385,6 +385,24 @@ private:
     std::map<double, std::vector<CalibCircleLite>> keyframes_;
 };
 
+// PinholeCamera::inverseRadialDistortion (core/sensor/src/PinholeCamera.cpp:70-95): the 5-term inverse of the radial
+// polynomial 1 + k0 r^2 + k1 r^4 + k2 r^6 + k3 r^8 — the initial intrinsics_[4..8] of the spline problem
+// (EventCalibSpline.cpp:101-105: k = (distCoeffs(0), distCoeffs(1), distCoeffs(4), 0)).
+inline std::array<double, 5> inverseRadialDistortion(const std::array<double, 4> &k) {
+    const double k00 = k[0] * k[0], k000 = k[0] * k00, k0000 = k[0] * k000, k00000 = k[0] * k0000;
+    const double k01 = k[0] * k[1], k001 = k[0] * k01, k0001 = k[0] * k001;
+    const double k11 = k[1] * k[1], k011 = k[0] * k11;
+    const double k02 = k[0] * k[2], k002 = k[0] * k02;
+    const double k12 = k[1] * k[2], k03 = k[0] * k[3];
+    std::array<double, 5> b;
+    b[0] = -k[0];
+    b[1] = 3 * k00 - k[1];
+    b[2] = -12 * k000 + 8 * k01 - k[2];
+    b[3] = 55 * k0000 - 55 * k001 + 5 * k11 + 10 * k02 - k[3];
+    b[4] = -273 * k00000 + 364 * k0001 - 78 * k011 - 78 * k002 + 12 * k12 + 12 * k03;
+    return b;
+}
+
 // ---- spline calibration: EventCalibSpline::optimize on the GPU ----
 class EventCalibSpline {
 public:

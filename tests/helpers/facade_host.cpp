@@ -29,3 +29,7 @@ int fh_gate_process(void *g, double ts, const double *xy, int n) {
     return ((TrackingGate *) g)->process(ts, f) ? 1 : 0;
 }
 }
+extern "C" void fh_inverse_radial(const double *k4, double *b5) {
+    const auto b = inverseRadialDistortion({k4[0], k4[1], k4[2], k4[3]});
+    for (int i = 0; i < 5; ++i) b5[i] = b[(size_t) i];
+}

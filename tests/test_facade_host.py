@@ -125,3 +125,19 @@ def test_tracking_gate_matches_numpy_restatement():
     lib.fh_gate_free(g)
     assert all(a == b for a, b in verdicts)
     assert 0 < sum(a for a, _ in verdicts) < len(verdicts)            # both accepted and rejected frames occurred
+
+
+def test_inverse_radial_distortion_known_answer():
+    """PinholeCamera::inverseRadialDistortion on the values of the reference's unit_test_inverseDistortion.cpp:10-16
+    (known answer: SURVEY.md section 4) and against the oracle restatement, bit for bit"""
+    import oracle
+    oracle.build()
+    lib = _lib()
+    k = np.array([-0.34991902, -0.014698517, 0.59684463, 0.0])
+    b = np.zeros(5)
+    lib.fh_inverse_radial(k.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    want = [0.34991902, 0.38202847867328127, -0.041555343865844696, -1.1638270394205459, -4.138165444396021]
+    np.testing.assert_allclose(b, want, rtol=1e-15)
+    ob = np.zeros(5)
+    oracle.port().orc_inverse_radial(k.ctypes.data_as(C.c_void_p), ob.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(b, ob)
