@@ -180,7 +180,7 @@ def run_reference(args, rank, world):
             "config": {"workload": "C2 per GPU: synthetic DAVIS346 circle-grid stream, 1.5 ms tiling windows, "
                                    "DBSCAN eps 4 minPts 2 + circle fit; CPU arm runs a bounded sample of it"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print_json(line)
 
 
 def build_cost_problem(ev_truth, world, n_events):
@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--events", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--slices", type=int, default=8, help="time slices (contexts/streams/host threads) of the e2e pipeline")
+    ap.add_argument("--slices", type=int, default=0, help="time slices (contexts/streams/host threads) of the e2e pipeline")
     ap.add_argument("--order-mode", type=int, default=1, help="pid order: 0 first arrival, 1 libstdc++ unordered_set order (the reference's)")
     ap.add_argument("--median-mode", type=int, default=1, help="cluster centre: 0 canonical, 1 std::nth_element over BFS order (the reference's)")
     ap.add_argument("--slice-plan", default="", help="relative sizes of the e2e time slices, e.g. 1,2,3,3,2,1 (overrides --slices)")
@@ -216,6 +216,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the result JSON: everything else that writes to file descriptor 1 (NCCL prints its
+    # version banner there) is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+    global print_json
+    def print_json(line):
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -320,6 +330,8 @@ def main():
     from eventcalib_b200 import sharding
     # slice sizes: the pipeline is balanced (H2D time ~ kernel time), so its length is  first upload + all kernels  or
     # all uploads + last slice's kernels — short first and last slices, long ones in between (--slice-plan fractions)
+    if args.slices <= 0:  # 8 slices on one GPU; with N ranks on one host keep about one host thread per core
+        args.slices = 8 if world == 1 else max(2, min(8, (os.cpu_count() or 16) // world))
     plan = [float(v) for v in args.slice_plan.split(",")] if args.slice_plan else [1.0] * max(1, args.slices)
     S = len(plan)
     cuts = np.round(np.cumsum([0.0] + plan) / sum(plan) * len(win)).astype(int)
@@ -537,7 +549,7 @@ def main():
             cb, _ = cpu_reference_rate(ev, win, rthr)
             cb.pop("seconds", None)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        print_json(line)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
