@@ -434,6 +434,121 @@ public:
             throw std::logic_error(ecb_last_error(ev_->ctx));  // HuberLoss(0.2 r), EventCalibSpline.cpp:197
         ecb_cost_set_rotation_model(ev_->ctx, useSO3_ ? 1 : 0);
     }
+    // ---- the reference constructor's own set-up (EventCalibSpline.cpp:14-113) from the key frames of the map ----
+    struct KeyPose {
+        double timeStamp;
+        double unitQwb[4];  // x y z w
+        double twb[3];
+    };
+    // reduceMap() :319-348: segments at gaps > 50 * MotionTimeStep, segments with fewer than degree + 1 frames dropped
+    static std::vector<std::vector<KeyPose>> segmentKeyframes(const std::vector<KeyPose> &kf, double motionTimeStep) {
+        std::vector<std::vector<KeyPose>> sets(1);
+        if (kf.empty()) return {};
+        double last = kf.front().timeStamp;
+        for (const auto &k : kf) {
+            if (k.timeStamp - last > 50 * motionTimeStep) sets.emplace_back();
+            sets.back().push_back(k);
+            last = k.timeStamp;
+        }
+        std::vector<std::vector<KeyPose>> out;
+        for (auto &s : sets)
+            if (s.size() >= 4) out.push_back(s);
+        return out;
+    }
+    // BsplineReal(dim, samples, cpNum, timestamps) (BsplineReal.hpp:31-100,329-449 without derivative samples): clamped
+    // knots by NURBS-book eq. 9.68, first / last control point = first / last sample, interior ones by least squares
+    static void fitSpline(const std::vector<double> &us, const std::vector<double> &data, int dim, int cpNum,
+                          std::vector<double> &knots, std::vector<double> &cp) {
+        const int degree = 3, n = (int) us.size();
+        knots.assign((size_t) cpNum + degree + 1, 0.0);
+        for (int i = 0; i <= degree; ++i) knots[(size_t) i] = us.front(), knots[knots.size() - 1 - (size_t) i] = us.back();
+        const double d = n / double(cpNum - degree);
+        for (int j = 1; j <= cpNum - 1 - degree; ++j) {
+            const int i = (int) std::floor(j * d);
+            const double alpha = j * d - i;
+            knots[(size_t) (degree + j)] = (1 - alpha) * us[(size_t) i - 1] + alpha * us[(size_t) i];
+        }
+        cp.assign((size_t) cpNum * dim, 0.0);
+        for (int c = 0; c < dim; ++c) cp[(size_t) c] = data[(size_t) c], cp[(size_t) (cpNum - 1) * dim + c] = data[(size_t) (n - 1) * dim + c];
+        const int m = cpNum - 2;
+        if (m <= 0) return;
+        std::vector<double> A((size_t) m * m, 0.0), B((size_t) m * dim, 0.0);
+        for (int k = 1; k < n - 1; ++k) {  // interior samples (rows 1 .. n-2 of N)
+            const int span = bspline_find_span(knots, us[(size_t) k]);
+            double N[4];
+            bspline_basis(knots, span, us[(size_t) k], N);
+            double n0 = 0, nl = 0;  // N_{0,p}(u_k), N_{cpNum-1,p}(u_k)
+            for (int j = 0; j <= degree; ++j) {
+                if (span - degree + j == 0) n0 = N[j];
+                if (span - degree + j == cpNum - 1) nl = N[j];
+            }
+            for (int a = 0; a <= degree; ++a) {
+                const int ia = span - degree + a - 1;  // interior control point index 0 .. m-1
+                if (ia < 0 || ia >= m || N[a] == 0) continue;
+                for (int b = 0; b <= degree; ++b) {
+                    const int ib = span - degree + b - 1;
+                    if (ib < 0 || ib >= m) continue;
+                    A[(size_t) ia * m + ib] += N[a] * N[b];
+                }
+                for (int c = 0; c < dim; ++c)
+                    B[(size_t) ia * dim + c] += N[a] * (data[(size_t) k * dim + c] - n0 * data[(size_t) c] - nl * data[(size_t) (n - 1) * dim + c]);
+            }
+        }
+        // A = L L^T (dense Cholesky; cpNum is a few hundred at most), then the dim right-hand sides
+        for (int j = 0; j < m; ++j) {
+            for (int k = 0; k < j; ++k)
+                for (int i = j; i < m; ++i) A[(size_t) i * m + j] -= A[(size_t) i * m + k] * A[(size_t) j * m + k];
+            const double dgl = std::sqrt(A[(size_t) j * m + j]);
+            if (!(dgl > 0)) throw std::logic_error("Function optimization: decomposition failed!");
+            for (int i = j; i < m; ++i) A[(size_t) i * m + j] /= dgl;
+        }
+        for (int c = 0; c < dim; ++c) {
+            std::vector<double> y((size_t) m);
+            for (int i = 0; i < m; ++i) {
+                double v = B[(size_t) i * dim + c];
+                for (int k = 0; k < i; ++k) v -= A[(size_t) i * m + k] * y[(size_t) k];
+                y[(size_t) i] = v / A[(size_t) i * m + i];
+            }
+            for (int i = m - 1; i >= 0; --i) {
+                double v = y[(size_t) i];
+                for (int k = i + 1; k < m; ++k) v -= A[(size_t) k * m + i] * cp[(size_t) (k + 1) * dim + c];
+                cp[(size_t) (i + 1) * dim + c] = v / A[(size_t) i * m + i];
+            }
+        }
+    }
+    // Spline segments from the map's key frames like the reference constructor (:25-91): frame count check, segmentation,
+    // time bounds extended by 3 steps, cpNum = floor(T / (50 step)) clamped, spline fits.  useSO3: the reference fits the
+    // SO(3) control points with Ceres (BsplineSO3::optimizeCP); here they start from the normalised quaternion-spline fit.
+    static std::vector<Segment> segmentsFromKeyframes(const std::vector<KeyPose> &kf, double motionTimeStep, bool useSO3 = false) {
+        if (kf.size() <= 10) throw std::logic_error("too few frames in the map.");
+        std::vector<Segment> out;
+        for (auto &set : segmentKeyframes(kf, motionTimeStep)) {
+            std::vector<double> us, tw, qw;
+            for (auto &k : set) {
+                us.push_back(k.timeStamp);
+                tw.insert(tw.end(), k.twb, k.twb + 3);
+                qw.insert(qw.end(), k.unitQwb, k.unitQwb + 4);
+            }
+            us.front() -= 3 * motionTimeStep;
+            us.back() += 3 * motionTimeStep;
+            int cpNum = (int) std::floor((us.back() - us.front()) / (50 * motionTimeStep));
+            if (cpNum > (int) us.size()) cpNum = (int) us.size() - 1;
+            if (cpNum < 4) cpNum = 4;  // become a bezier curve
+            Segment sg;
+            std::vector<double> kn2;
+            fitSpline(us, tw, 3, cpNum, sg.knots, sg.trans_cp);
+            fitSpline(us, qw, 4, cpNum, kn2, sg.rot_cp);
+            if (useSO3)
+                for (size_t c = 0; c + 3 < sg.rot_cp.size(); c += 4) {
+                    const double nq = std::sqrt(sg.rot_cp[c] * sg.rot_cp[c] + sg.rot_cp[c + 1] * sg.rot_cp[c + 1] +
+                                                sg.rot_cp[c + 2] * sg.rot_cp[c + 2] + sg.rot_cp[c + 3] * sg.rot_cp[c + 3]);
+                    for (int a = 0; a < 4; ++a) sg.rot_cp[c + (size_t) a] /= nq;
+                }
+            out.push_back(std::move(sg));
+        }
+        if (out.empty()) throw std::logic_error("sampleSets not filtered");
+        return out;
+    }
     // association loop, EventCalibSpline.cpp:157-192; landmarks: board points (EventCalibIni.cpp:99-113)
     int64_t associate(const std::vector<KeyFrame> &kf, const std::vector<std::array<double, 3>> &landmarks) {
         const int nc = (int) landmarks.size();

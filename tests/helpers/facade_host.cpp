@@ -33,3 +33,27 @@ extern "C" void fh_inverse_radial(const double *k4, double *b5) {
     const auto b = inverseRadialDistortion({k4[0], k4[1], k4[2], k4[3]});
     for (int i = 0; i < 5; ++i) b5[i] = b[(size_t) i];
 }
+// spline set-up from key frames (EventCalibSpline::segmentsFromKeyframes): returns the number of segments; segment `which`
+// is copied out (knots n_cp+4, rot 4 n_cp, trans 3 n_cp); n_cp_out = its control point count
+extern "C" int fh_segments(const double *ts, const double *q, const double *t, int n, double step, int which, int *n_cp_out,
+                           double *knots, double *rot, double *trans) {
+    std::vector<EventCalibSpline::KeyPose> kf((size_t) n);
+    for (int i = 0; i < n; ++i) {
+        kf[(size_t) i].timeStamp = ts[i];
+        for (int a = 0; a < 4; ++a) kf[(size_t) i].unitQwb[a] = q[4 * i + a];
+        for (int a = 0; a < 3; ++a) kf[(size_t) i].twb[a] = t[3 * i + a];
+    }
+    try {
+        auto seg = EventCalibSpline::segmentsFromKeyframes(kf, step, false);
+        if (which >= 0 && which < (int) seg.size()) {
+            const auto &s = seg[(size_t) which];
+            *n_cp_out = (int) s.rot_cp.size() / 4;
+            std::copy(s.knots.begin(), s.knots.end(), knots);
+            std::copy(s.rot_cp.begin(), s.rot_cp.end(), rot);
+            std::copy(s.trans_cp.begin(), s.trans_cp.end(), trans);
+        }
+        return (int) seg.size();
+    } catch (const std::logic_error &) {
+        return -1;
+    }
+}

@@ -141,3 +141,51 @@ def test_inverse_radial_distortion_known_answer():
     ob = np.zeros(5)
     oracle.port().orc_inverse_radial(k.ctypes.data_as(C.c_void_p), ob.ctypes.data_as(C.c_void_p))
     assert np.array_equal(b, ob)
+
+
+def _fit_fixed_ends(us, data, n_cp):
+    """numpy restatement of BsplineReal::approximation + optimization (BsplineReal.hpp:87-100,329-449, no derivative
+    samples): eq. 9.68 knots, end control points = end samples, interior ones by least squares over the interior samples"""
+    from eventcalib_b200 import spline
+    kn = spline.knot_vector(us, n_cp)
+    N = np.zeros((len(us), n_cp))
+    for k, u in enumerate(us):
+        sp = spline.find_span(kn, u)
+        N[k, sp - 3: sp + 1] = spline.basis(kn, sp, u)
+    cp = np.zeros((n_cp, data.shape[1]))
+    cp[0], cp[-1] = data[0], data[-1]
+    R = data[1:-1] - np.outer(N[1:-1, 0], data[0]) - np.outer(N[1:-1, -1], data[-1])
+    Nc = N[1:-1, 1:-1]
+    cp[1:-1] = np.linalg.solve(Nc.T @ Nc, Nc.T @ R)
+    return kn, cp
+
+
+def test_spline_setup_from_keyframes():
+    """EventCalibSpline constructor set-up (EventCalibSpline.cpp:25-91): frame count check, gap segmentation (reduceMap
+    :319-348), extended bounds, cpNum rule and the BsplineReal fits"""
+    from eventcalib_b200 import synth
+    lib = _lib()
+    board = synth.Board()
+    traj = synth.Trajectory(5, board, 78.0)
+    step = 5e-4
+    ts = np.concatenate([np.arange(1.0, 1.4, 4e-3), np.arange(1.5, 1.506, 4e-3), np.arange(1.6, 2.3, 4e-3)])  # middle: 2 frames only
+    q, tw = traj.quat_xyzw(ts)
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    lib.fh_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p] + [C.c_void_p] * 3
+    ncp = C.c_int(0)
+    kn, rot, tr = np.zeros(2000), np.zeros(8000), np.zeros(6000)
+    assert lib.fh_segments(P(ts[:10]), P(q[:10]), P(tw[:10]), 10, step, 0, C.byref(ncp), P(kn), P(rot), P(tr)) == -1   # <= 10 frames
+    segs = [np.arange(0, 100), np.arange(102, len(ts))]
+    for which, idx in enumerate(segs):
+        assert lib.fh_segments(P(ts), P(q), P(tw), len(ts), step, which, C.byref(ncp), P(kn), P(rot), P(tr)) == 2
+        us = ts[idx].copy()
+        us[0] -= 3 * step
+        us[-1] += 3 * step
+        want_cp = int(np.floor((us[-1] - us[0]) / (50 * step)))
+        want_cp = max(4, len(us) - 1 if want_cp > len(us) else want_cp)
+        assert ncp.value == want_cp
+        k_ref, t_ref = _fit_fixed_ends(us, tw[idx], want_cp)
+        _, q_ref = _fit_fixed_ends(us, q[idx], want_cp)
+        np.testing.assert_array_equal(kn[:want_cp + 4], k_ref)
+        np.testing.assert_allclose(tr[:3 * want_cp].reshape(-1, 3), t_ref, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(rot[:4 * want_cp].reshape(-1, 4), q_ref, rtol=1e-9, atol=1e-9)
