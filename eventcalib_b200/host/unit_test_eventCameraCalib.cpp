@@ -1,17 +1,20 @@
 // unit_test_eventCameraCalib settingFilePath binFilePath SavePath
 //
-// Drop-in for the reference CLI's front half (ECC/test/eventCameraCalib.cpp:104-197): same 3 positional arguments, same
-// usage / exit codes, same `parameter/event_calibration/example.yaml` keys, same "Events from ... loaded." /
-// "N frames in Map." / "Frame t contain n events." lines — with the window loop running as ONE batched GPU launch per
-// lattice instead of hardware_concurrency()-2 CPU threads.  Headless (the reference opens a Pangolin viewer, :129).
+// Drop-in for the reference CLI (ECC/test/eventCameraCalib.cpp:104-233): same 3 positional arguments, same usage / exit
+// codes, same `parameter/event_calibration/example.yaml` keys, same stdout lines ("Events from ... loaded.", "N frames in
+// Map.", "Frame t contain n events.", the calibrateCamera report, "N frames in Map after Initialization.", the intrinsics
+// before / after the optimisation) and the same SavePath/TrajectoryByEvent.txt — with the window loop running as ONE batched
+// GPU launch per lattice instead of hardware_concurrency()-2 CPU threads, rectifyFeatures batched over all key frames, and the
+// spline optimisation's residuals / Jacobians / normal equations on the GPU.  Headless (the reference opens a Pangolin
+// viewer, :129; the per-frame debug PNGs of :214-227 are not written).
 //
 // The window loop is the reference's adaptive one (accept -> jump by length + 5 steps, else grow by one step until the
 // window holds FrameEventNumThreshold events or exceeds 3 lengths, then slide; :49-81) over the reference's time pieces.
 // A window becomes a key frame when the candidate circles are found, ordered as the rows x cols grid, and pass the tracking
 // gate (EventCalibIni::track: row directions vs the neighbouring key frame; the reference's worker threads race on the
-// shared map, here the pieces of one round are gated in piece order).  Round-1 limit: the OpenCV
-// initialisation and therefore the spline optimisation are not run here — the ordered circles (board order, 36 per frame)
-// are written to SavePath/candidates.txt for the next stage.
+// shared map, here the pieces of one round are gated in piece order).  The initialisation (EventCalibIni::cvCalibration)
+// runs without OpenCV (include/ecb/calib_init.hpp); the ordered circles of the key frames are also written to
+// SavePath/candidates.txt.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -73,6 +76,18 @@ int main(int argc, char **argv) {
     pattern->squareSize = fs.num("Square_Size", 5.5);
     pattern->isAsymmetric = fs.num("Is_Pattern_Asymmetric", 1) != 0;
     pattern->circleRadius = fs.num("Circles_Radius", 1.75);
+    CalibrationSetting setting;  // parameters.hpp:32-46
+    setting.circlePatternParameters = pattern;
+    setting.aspectRatio = (float) fs.num("Calibrate_FixAspectRatio", 1);
+    setting.calibZeroTangentDist = fs.num("Calibrate_AssumeZeroTangentialDistortion", 1) != 0;
+    setting.calibFixPrincipalPoint = fs.num("Calibrate_FixPrincipalPointAtTheCenter", 1) != 0;
+    setting.useFisheye = fs.num("Calibrate_UseFisheyeModel", 0) != 0;
+    setting.fixK1 = fs.num("Fix_K1", 0) != 0;
+    setting.fixK2 = fs.num("Fix_K2", 0) != 0;
+    setting.fixK3 = fs.num("Fix_K3", 0) != 0;
+    setting.fixK4 = fs.num("Fix_K4", 1) != 0;
+    setting.fixK5 = fs.num("Fix_K5", 1) != 0;
+    setting.NumOfFrameToUse = (int) fs.num("Calibrate_NrOfFrameToUse", 200);
     const double motionTimeStep = fs.num("MotionTimeStep");
     const int width = (int) fs.num("Camera.width"), height = (int) fs.num("Camera.height");
     if (!(motionTimeStep > 0) || width <= 0 || height <= 0) {
@@ -141,11 +156,7 @@ int main(int argc, char **argv) {
         pc.done = !(pc.second < pc.hi);
         pieces.push_back(pc);
     }
-    struct Frame {
-        double ts;
-        int events;
-        std::vector<CalibCircleLite> circles;
-    };
+    typedef EventCalibIni::KeyFrame Frame;
     std::map<double, Frame> frames;  // MapBase keeps key frames ordered by time stamp
     FrontEnd fe(container, pattern, params);
     TrackingGate gate(pattern->rows, pattern->cols, motionTimeStep);  // EventCalibIni::track; pieces of one round in piece order
@@ -176,7 +187,12 @@ int main(int argc, char **argv) {
             const double ts0 = (pc.first + pc.second) / 2;
             if (CirclesEventFrame::orderFeatures(fe.candidates(w), *pattern, c) && gate.process(ts0, c)) {  // :56-60
                 const double ts = (pc.first + pc.second) / 2;  // Bodyframe time stamp (:57)
-                frames[ts] = Frame{ts, events_num, c};
+                Frame f;
+                f.timeStamp = ts;
+                f.duration = {pc.first, pc.second};
+                f.eventsNum = events_num;
+                f.features = c;
+                frames[ts] = f;
                 pc.first = pc.second + frameGap;  // :60-62
                 pc.second = pc.first + len;
             } else if (events_num > frameEventNumThreshold || (pc.second - pc.first) > 3 * len) {  // :66-68,75-77
@@ -194,14 +210,88 @@ int main(int argc, char **argv) {
     std::cout << frames.size() << " frames in Map." << std::endl;
     for (const auto &kv : frames) {
         const Frame &f = kv.second;
-        std::cout << "Frame " << f.ts << " contain " << f.events << " events." << std::endl;
-        for (size_t k = 0; k < f.circles.size(); ++k)
-            out << f.ts << " " << k << " " << f.circles[k].center[0] << " " << f.circles[k].center[1] << " " << f.circles[k].radius << "\n";
+        std::cout << "Frame " << f.timeStamp << " contain " << f.eventsNum << " events." << std::endl;
+        for (size_t k = 0; k < f.features.size(); ++k)
+            out << f.timeStamp << " " << k << " " << f.features[k].center[0] << " " << f.features[k].center[1] << " "
+                << f.features[k].radius << "\n";
     }
-    std::cout << evaluated << " windows evaluated on the GPU in " << rounds << " batched rounds over " << pieceNum
-              << " time pieces; candidate circles written to " << argv[3] << "/candidates.txt" << std::endl;
-    std::cout << "NOTE: OpenCV initialisation / grid ordering / spline optimisation stage not part of this build "
-                 "(SURVEY.md §8 rows f-2, f-4)." << std::endl;
+    out.close();
+    std::cerr << evaluated << " windows evaluated on the GPU in " << rounds << " batched rounds over " << pieceNum
+              << " time pieces" << std::endl;
+
+    // EventCalibIni::cvCalibration (eventCameraCalib.cpp:199): intrinsics, frame poses, checkPose, rectifyFeatures
+    EventCalibIni ini(setting, motionTimeStep, width, height);
+    bool ok = false;
+    try {
+        ok = ini.cvCalibration(fe, frames, std::cout);
+    } catch (const std::exception &ex) {
+        std::cerr << "ecb: " << ex.what() << std::endl;
+        return 1;
+    }
+    std::cout << frames.size() << " frames in Map after Initialization." << std::endl;
+
+    // EventCalibSpline (eventCameraCalib.cpp:203-210): the constructor throws std::logic_error like the reference's
+    const bool useSO3 = fs.num("useSO3", 0) != 0;
+    if (!ok) {
+        std::cerr << "initialisation failed" << std::endl;
+        return 1;
+    }
+    std::vector<EventCalibSpline::KeyPose> poses;
+    std::vector<EventCalibSpline::KeyFrame> kfs;
+    std::vector<double> stamps;
+    for (const auto &kv : frames) {
+        EventCalibSpline::KeyPose kp;
+        kp.timeStamp = kv.second.timeStamp;
+        std::copy(kv.second.unitQwb, kv.second.unitQwb + 4, kp.unitQwb);
+        std::copy(kv.second.twb, kv.second.twb + 3, kp.twb);
+        poses.push_back(kp);
+        kfs.push_back(EventCalibSpline::KeyFrame{kv.second.timeStamp, kv.second.circles});
+        stamps.push_back(kv.second.timeStamp);
+    }
+    for (size_t i = 1; i < poses.size(); ++i) {  // one sign per quaternion so the real-valued spline fit sees a continuous curve
+        double d = 0;
+        for (int a = 0; a < 4; ++a) d += poses[i].unitQwb[a] * poses[i - 1].unitQwb[a];
+        if (d < 0)
+            for (int a = 0; a < 4; ++a) poses[i].unitQwb[a] = -poses[i].unitQwb[a];
+    }
+    try {
+        std::vector<EventCalibSpline::Segment> segments = EventCalibSpline::segmentsFromKeyframes(poses, motionTimeStep, useSO3);
+        // EventCalibSpline.cpp:94-108: radial part of the OpenCV model -> 5-term inverse polynomial
+        const ecb::CameraModel &cam = ini.camera;
+        const std::array<double, 4> radial = {cam.dist[0], cam.dist[1], cam.dist[4], 0.0};
+        const std::array<double, 5> inv = inverseRadialDistortion(radial);
+        const std::array<double, 9> intrinsics = {cam.fx, cam.fy, cam.cx, cam.cy, inv[0], inv[1], inv[2], inv[3], inv[4]};
+        std::cout << "OpenCV Distortion before optimization:";
+        printEigenLike(std::cout, radial.data(), 1, 4);
+        std::cout << std::endl << "Intrinsics before optimization:";
+        printEigenLike(std::cout, intrinsics.data(), 1, 9);
+        std::cout << std::endl;
+        EventCalibSpline spline(container, segments, intrinsics, motionTimeStep, pattern->circleRadius, useSO3);
+        std::vector<std::array<double, 3>> landmarks;
+        const std::vector<double> board = ini.boardPoints();
+        for (size_t k = 0; k + 2 < board.size(); k += 3) landmarks.push_back({board[k], board[k + 1], board[k + 2]});
+        const int64_t n_res = spline.associate(kfs, landmarks);
+        ecb_lm_summary sum;
+        if (!spline.optimize(&sum)) {
+            std::cerr << "ecb: " << ecb_last_error(container->ctx) << std::endl;
+            return 1;
+        }
+        // in place of ceres::Solver::Summary::FullReport() (EventCalibSpline.cpp:248)
+        std::cout << "Solver Summary: residuals " << n_res << ", splines " << segments.size() << ", iterations " << sum.iterations
+                  << " (successful " << sum.successful_steps << "), cost " << sum.initial_cost << " -> " << sum.final_cost
+                  << ", termination " << sum.termination << std::endl;
+        std::cout.precision(12);  // updateMap(), EventCalibSpline.cpp:263-264
+        std::cout << "Intrinsics after optimization:";
+        printEigenLike(std::cout, spline.intrinsics().data(), 1, 9);
+        std::cout << std::endl;
+        spline.saveKeyFrameTrajectoryTUM(std::string(argv[3]) + "/TrajectoryByEvent.txt", stamps);  // eventCameraCalib.cpp:212
+    } catch (const std::logic_error &ex) {
+        std::cerr << "terminate called after throwing an instance of 'std::logic_error'\n  what():  " << ex.what() << std::endl;
+        return 134;  // the reference aborts on the uncaught exception
+    } catch (const std::exception &ex) {
+        std::cerr << "ecb: " << ex.what() << std::endl;
+        return 1;
+    }
     std::cout << "press Enter to exit..." << std::endl;
     std::cin.ignore();
     return 0;

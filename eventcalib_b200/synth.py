@@ -85,11 +85,12 @@ class Camera:
 class Trajectory:
     """Smooth camera pose (R_wb, t_wb) in the board frame: sum of sinusoids, board always in view."""
 
-    def __init__(self, seed, board: Board, dist=75.0, rot_amp=None):
+    def __init__(self, seed, board: Board, dist=75.0, rot_amp=None, orbit=False):
         r = np.random.default_rng(seed)
         c = board.centres()
         self.mid = np.array([c[:, 0].mean(), c[:, 1].mean(), 0.0])
         self.dist = dist
+        self.orbit = orbit  # True: the camera orbits the board centre and keeps looking at it (large tilts stay in view)
         self.w = r.uniform(1.5, 4.5, size=(6, 3))  # rad/s
         self.ph = r.uniform(0, 2 * np.pi, size=(6, 3))
         self.amp_t = np.array([3.0, 3.0, 6.0]) / 3.0  # cm per sinusoid
@@ -112,6 +113,9 @@ class Trajectory:
         Rx[:, 0, 0] = 1; Rx[:, 1, 1] = ca; Rx[:, 1, 2] = -sa; Rx[:, 2, 1] = sa; Rx[:, 2, 2] = ca
         Ry[:, 0, 0] = cb; Ry[:, 0, 2] = sb; Ry[:, 1, 1] = 1; Ry[:, 2, 0] = -sb; Ry[:, 2, 2] = cb
         R = Rz @ Rx @ Ry
+        if self.orbit:
+            tw = (self.mid[None, :] - R[:, :, 2] * (self.dist + self.amp_t[2] * self._sig(t, 2))[:, None]
+                  + R[:, :, 0] * (self.amp_t[0] * self._sig(t, 0))[:, None] + R[:, :, 1] * (self.amp_t[1] * self._sig(t, 1))[:, None])
         return R, tw
 
     def quat_xyzw(self, t):
@@ -149,9 +153,9 @@ def project(cam: Camera, R, tw, Xw):
 
 
 def _gen_chunk(args):
-    (s, e, n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter, board, dist, k, rot_amp, traj_seed) = args
+    (s, e, n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter, board, dist, k, rot_amp, traj_seed, orbit) = args
     cam = Camera(width, height)
-    traj = Trajectory(traj_seed, board, dist, rot_amp)
+    traj = Trajectory(traj_seed, board, dist, rot_amp, orbit)
     centres = board.centres()
     rng = np.random.default_rng([seed, k])
     dt = duration / n_events
@@ -184,7 +188,8 @@ def _gen_chunk(args):
 
 
 def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001, noise_frac=0.05, flip_frac=0.0,
-                jitter=0.7, board: Board = None, dist=None, chunk=1 << 19, return_truth=False, workers=1, rot_amp=None, traj_seed=None):
+                jitter=0.7, board: Board = None, dist=None, chunk=1 << 19, return_truth=False, workers=1, rot_amp=None, traj_seed=None,
+                orbit=False):
     """Returns dict(t, x, y, p) float64/uint8 arrays (time sorted, integer-valued pixel coordinates).
     Deterministic in (seed, n_events, chunk) — independent of `workers` (processes used to generate chunks)."""
     board = board or Board()
@@ -193,7 +198,7 @@ def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001
     if traj_seed is None:
         traj_seed = seed
     jobs = [(s, min(n_events, s + chunk), n_events, width, height, t0, duration, seed, noise_frac, flip_frac, jitter,
-             board, dist, k, rot_amp, traj_seed) for k, s in enumerate(range(0, n_events, chunk))]
+             board, dist, k, rot_amp, traj_seed, orbit) for k, s in enumerate(range(0, n_events, chunk))]
     if workers > 1 and len(jobs) > 1:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
@@ -206,7 +211,7 @@ def make_stream(n_events, width=346, height=260, t0=5.0, duration=0.5, seed=1001
     P = np.concatenate([p[3] for p in parts])
     out = dict(t=T, x=X, y=Y, p=P, width=width, height=height)
     if return_truth:
-        out.update(camera=Camera(width, height), trajectory=Trajectory(traj_seed, board, dist, rot_amp), board=board)
+        out.update(camera=Camera(width, height), trajectory=Trajectory(traj_seed, board, dist, rot_amp, orbit), board=board)
     return out
 
 

@@ -27,6 +27,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -34,6 +35,7 @@
 
 #include "../eventcalib_b200.h"
 #include "../../eventcalib_b200/csrc/ecb_so3.h"  // plain host/device header: the SO(3) spline of the useSO3 variant
+#include "calib_init.hpp"
 #include "circles_grid.hpp"
 #include "dbscan.h"
 
@@ -402,6 +404,183 @@ inline std::array<double, 5> inverseRadialDistortion(const std::array<double, 4>
     b[4] = -273 * k00000 + 364 * k0001 - 78 * k011 - 78 * k002 + 12 * k12 + 12 * k03;
     return b;
 }
+
+// ---- initialisation stage: EventCalibIni::cvCalibration (event_camera_calib/src/EventCalibIni.cpp:143-327) ----
+struct CalibrationSetting {  // include/opengv2/event_camera_calib/parameters.hpp:29-86 (same member names)
+    CirclePatternParameters::Ptr circlePatternParameters;
+    int NumOfFrameToUse = 200;
+    float aspectRatio = 1;
+    bool calibZeroTangentDist = true, calibFixPrincipalPoint = true, useFisheye = false;
+    bool fixK1 = false, fixK2 = false, fixK3 = false, fixK4 = true, fixK5 = true;
+    ecb::CalibFlags flags() const {  // validate(): the cv::CALIB_* bits; K4..K6 do not exist in the 5-coefficient model
+        ecb::CalibFlags f;
+        f.fixPrincipalPoint = calibFixPrincipalPoint;
+        f.zeroTangentDist = calibZeroTangentDist;
+        f.fixAspectRatio = aspectRatio != 0;
+        f.aspectRatio = aspectRatio != 0 ? aspectRatio : 1.0;  // cameraMatrix(0,0) = aspectRatio over (1,1) = 1 (:147-149)
+        f.fixK1 = fixK1, f.fixK2 = fixK2, f.fixK3 = fixK3;
+        return f;
+    }
+};
+
+// Eigen's default stream format for a dense matrix: every coefficient right-aligned to the widest one, rows on lines
+inline void printEigenLike(std::ostream &os, const double *m, int rows, int cols) {
+    std::vector<std::string> cell((size_t) rows * cols);
+    size_t width = 0;
+    for (int i = 0; i < rows * cols; ++i) {
+        std::ostringstream ss;
+        ss.precision(os.precision());
+        ss << m[i];
+        cell[(size_t) i] = ss.str();
+        width = std::max(width, cell[(size_t) i].size());
+    }
+    for (int r = 0; r < rows; ++r) {
+        for (int c = 0; c < cols; ++c) os << (c ? " " : "") << std::setw((int) width) << cell[(size_t) r * cols + c];
+        if (r + 1 < rows) os << "\n";
+    }
+}
+
+class EventCalibIni {
+public:
+    struct KeyFrame {
+        double timeStamp = 0;
+        std::pair<double, double> duration;        // the window of the frame (EventFrame ctor)
+        int eventsNum = 0;
+        std::vector<CalibCircleLite> features;     // board order, rows * cols
+        double unitQwb[4] = {0, 0, 0, 1}, twb[3] = {0, 0, 0};
+        std::vector<std::array<double, 3>> circles;  // after rectifyFeatures: (cx, cy, r) per board point, r < 0 = deleted
+    };
+    EventCalibIni(const CalibrationSetting &setting, double motionTimeStep, int width, int height)
+        : setting_(setting), step_(motionTimeStep), width_(width), height_(height) {}
+    // calcBoardCornerPositions (:99-113), as cv::Point3f
+    std::vector<double> boardPoints() const {
+        const CirclePatternParameters &p = *setting_.circlePatternParameters;
+        std::vector<double> c;
+        for (int i = 0; i < p.rows; ++i)
+            for (int j = 0; j < p.cols; ++j) {
+                c.push_back((double) (float) ((p.isAsymmetric ? (2 * j + i % 2) : j) * p.squareSize));
+                c.push_back((double) (float) (i * p.squareSize));
+                c.push_back(0.0);
+            }
+        return c;
+    }
+    // cvCalibration(): intrinsics from NumOfFrameToUse evenly spaced key frames, then for every key frame in time order the
+    // planar PnP pose, checkPose against the last frame kept, rectifyFeatures (one batched GPU call over all frames — its
+    // verdict does not depend on the other frames) -> `frames` is replaced by the frames that stay in the map.
+    bool cvCalibration(FrontEnd &fe, std::map<double, KeyFrame> &frames, std::ostream &os) {
+        if (setting_.useFisheye) {
+            os << "Calibration failed: the fisheye model (cv::fisheye::calibrate) is not part of this build" << std::endl;
+            return false;
+        }
+        if (frames.empty()) return false;
+        const CirclePatternParameters &pat = *setting_.circlePatternParameters;
+        const int nc = pat.rows * pat.cols, frameNum = (int) frames.size();
+        int use = setting_.NumOfFrameToUse, step = use > 0 ? frameNum / use : 0;
+        if (step == 0) {
+            use = frameNum;
+            step = 1;
+        }
+        std::vector<std::vector<double>> imagePoints;
+        auto itr = frames.cbegin();
+        for (int counter = 0; counter < use; ++counter) {
+            std::vector<double> ip;
+            for (const auto &f : itr->second.features) {  // cv::Point2f
+                ip.push_back((double) (float) f.center[0]);
+                ip.push_back((double) (float) f.center[1]);
+            }
+            imagePoints.push_back(std::move(ip));
+            for (int k = 0; k < step && itr != frames.cend(); ++k) ++itr;
+        }
+        const std::vector<double> obj = boardPoints();
+        std::vector<std::array<double, 3>> rvecs, tvecs;
+        const double rms = ecb::calibrateCamera(obj, imagePoints, width_, height_, setting_.flags(), camera, rvecs, tvecs);
+        os << "Re-projection error reported by calibrateCamera: " << rms << std::endl;
+        bool ok = rms >= 0 && std::isfinite(camera.fx) && std::isfinite(camera.fy);
+        for (double d : camera.dist) ok = ok && std::isfinite(d);
+        std::vector<float> perView;
+        const double totalAvgErr = ok ? ecb::computeReprojectionErrors(obj, imagePoints, rvecs, tvecs, camera, perView) : 0.0;
+        os << (ok ? "Calibration succeeded" : "Calibration failed") << ". avg re projection error = " << totalAvgErr << std::endl;
+        int counter1 = 0, counter2 = 0;
+        if (ok) {
+            const double K[9] = {camera.fx, 0, camera.cx, 0, camera.fy, camera.cy, 0, 0, 1};
+            printEigenLike(os, K, 3, 3);
+            os << std::endl;
+            printEigenLike(os, camera.dist, 1, 5);
+            os << std::endl;
+            // poses of all frames (:246-275)
+            std::vector<KeyFrame *> all;
+            std::vector<std::pair<double, double>> windows;
+            std::vector<double> img;  // frames x circles x 5 x 2 projected points (CirclesEventFrame.cpp:431-456)
+            const double skewR = pat.circleRadius / std::sqrt(2.0);
+            for (auto &kv : frames) {
+                KeyFrame &kf = kv.second;
+                std::vector<double> ip;
+                for (const auto &f : kf.features) {
+                    ip.push_back((double) (float) f.center[0]);
+                    ip.push_back((double) (float) f.center[1]);
+                }
+                double rvec[3], tvec[3];
+                std::vector<int> inliers;
+                const bool solved = (int) kf.features.size() == nc && ecb::solvePnPPlanar(obj, ip, camera, 4.0, rvec, tvec, inliers);
+                if (!solved) {  // OpenCV leaves rvec / tvec empty and the reference would fail in cv::Rodrigues; drop the frame
+                    ++counter1;
+                    continue;
+                }
+                ecb::bodyPoseFromPnP(rvec, tvec, kf.unitQwb, kf.twb);
+                for (int k = 0; k < nc; ++k) {
+                    const double *c = &obj[(size_t) 3 * k];
+                    const double o5[15] = {c[0], c[1], c[2],
+                                           (double) (float) (c[0] + skewR), (double) (float) (c[1] + skewR), c[2],
+                                           (double) (float) (c[0] + skewR), (double) (float) (c[1] - skewR), c[2],
+                                           (double) (float) (c[0] - skewR), (double) (float) (c[1] - skewR), c[2],
+                                           (double) (float) (c[0] - skewR), (double) (float) (c[1] + skewR), c[2]};
+                    double p5[10];
+                    ecb::projectPoints(o5, 5, rvec, tvec, camera, p5);
+                    for (double v : p5) img.push_back((double) (float) v);  // vector<cv::Point2f>
+                }
+                all.push_back(&kf);
+                windows.push_back(kf.duration);
+            }
+            std::vector<double> out(all.size() * (size_t) nc * 3);
+            std::vector<int32_t> verdict(all.size(), 0), widx(all.size());
+            if (!all.empty()) {
+                fe.run(windows);
+                for (size_t i = 0; i < all.size(); ++i) widx[i] = (int32_t) i;
+                if (ecb_frontend_rectify(fe.context(), widx.data(), (int) all.size(), nc, img.data(), 3.0, pat.rows, pat.cols,
+                                         pat.isAsymmetric ? 1 : 0, out.data(), verdict.data()) != ECB_OK)
+                    throw std::runtime_error(ecb_last_error(fe.context()));
+            }
+            // replay of the sequential loop (:246-300): checkPose against the last frame kept, then the rectify verdict
+            std::map<double, KeyFrame> kept;
+            const KeyFrame *last = nullptr;
+            for (size_t i = 0; i < all.size(); ++i) {
+                KeyFrame &kf = *all[i];
+                if (last && !ecb::checkPose(last->timeStamp, last->unitQwb, last->twb, kf.timeStamp, kf.unitQwb, kf.twb, step_)) {
+                    ++counter1;
+                    continue;
+                }
+                if (!verdict[i]) {
+                    ++counter2;
+                    continue;
+                }
+                kf.circles.resize((size_t) nc);
+                for (int k = 0; k < nc; ++k)
+                    for (int a = 0; a < 3; ++a) kf.circles[(size_t) k][(size_t) a] = out[(i * nc + (size_t) k) * 3 + (size_t) a];
+                last = &kept.emplace(kf.timeStamp, kf).first->second;
+            }
+            frames.swap(kept);
+        }
+        os << counter1 << " frames discard by checkPose." << std::endl;
+        os << counter2 << " frames discard by rectifyFeature." << std::endl;
+        return ok;
+    }
+    ecb::CameraModel camera;  // K and distCoeffs (k1 k2 p1 p2 k3) after cvCalibration
+
+private:
+    CalibrationSetting setting_;
+    double step_;
+    int width_, height_;
+};
 
 // ---- spline calibration: EventCalibSpline::optimize on the GPU ----
 class EventCalibSpline {

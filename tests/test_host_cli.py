@@ -23,6 +23,16 @@ BoardSize_Rows: 9
 BoardSize_Cols: 4
 Square_Size: 5.5
 Circles_Radius: 1.75
+Calibrate_NrOfFrameToUse: 200
+Calibrate_UseFisheyeModel: 0
+Calibrate_FixAspectRatio: 1
+Calibrate_AssumeZeroTangentialDistortion: 1
+Calibrate_FixPrincipalPointAtTheCenter: 1
+Fix_K1: 0
+Fix_K2: 0
+Fix_K3: 0
+Fix_K4: 1
+Fix_K5: 1
 dbscan_eps: 4
 dbscan_startMinSample: 2
 clusterMinSample: 5
@@ -60,7 +70,7 @@ def test_facade_selftest(built):
 @pytest.mark.gpu
 def test_cli_on_synthetic_stream(built, tmp_path):
     from eventcalib_b200 import synth
-    ev = synth.make_stream(200000, 346, 260, t0=5.0, duration=0.1, seed=1001)
+    ev = synth.make_stream(500000, 346, 260, t0=5.0, duration=0.25, seed=1001)
     # a few events before StartTime must be skipped by the loader
     pre = synth.make_stream(1000, 346, 260, t0=4.0, duration=0.01, seed=1)
     full = {k: np.concatenate([pre[k], ev[k]]) for k in "txyp"}
@@ -69,14 +79,15 @@ def test_cli_on_synthetic_stream(built, tmp_path):
     save = tmp_path / "out"
     env = dict(os.environ, ECB_PIECES="3")
     r = subprocess.run([built, str(tmp_path / "cfg.yaml"), str(tmp_path / "ev.bin"), str(save)], capture_output=True, text=True,
-                       stdin=subprocess.DEVNULL, timeout=300, env=env)
-    assert r.returncode == 0, r.stderr
+                       stdin=subprocess.DEVNULL, timeout=600, env=env)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
     assert "Events from 5 second to" in r.stdout and "frames in Map." in r.stdout and "press Enter to exit..." in r.stdout
     frames = int([l for l in r.stdout.splitlines() if l.endswith("frames in Map.")][0].split()[0])
     assert frames >= 15
     cand = np.loadtxt(str(save / "candidates.txt"))
     assert cand.shape[1] == 5 and len(np.unique(cand[:, 0])) == frames
-    assert np.all((cand[:, 4] > 1) & (cand[:, 4] < 16))      # circle radii in pixels (< circleRadiusThreshold)
+    assert np.all((cand[:, 4] > 0) & (cand[:, 4] < 16))      # circle radii in pixels (< circleRadiusThreshold)
     # every frame holds the 36 circles in board order
     assert np.all(np.bincount(np.unique(cand[:, 0], return_inverse=True)[1]) == 36)
     # the adaptive window loop (eventCameraCalib.cpp:49-81) replayed window by window through the Python binding
@@ -124,3 +135,57 @@ def test_cli_on_synthetic_stream(built, tmp_path):
     ctx.close()
     assert len(stamps) == frames
     np.testing.assert_allclose(np.sort(stamps), np.unique(cand[:, 0]), rtol=0, atol=1e-12)
+
+    # the back half ran through (its results are checked on a well-posed stream in the next test)
+    assert "frames in Map after Initialization." in r.stdout and "Intrinsics after optimization:" in r.stdout
+    assert (save / "TrajectoryByEvent.txt").exists()
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_calibration(built, tmp_path):
+    """The whole CLI (eventCameraCalib.cpp:104-233) on a synthetic stream whose camera orbits the board with +-0.35 rad tilts
+    (the calibration is well posed), fitCircle 1: initialisation, spline optimisation on the GPU, trajectory file — checked
+    against the generator's ground-truth camera and trajectory."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(2000000, 346, 260, t0=5.0, duration=1.0, seed=1001, return_truth=True, workers=4,
+                           rot_amp=(0.35, 0.35, 0.3), orbit=True)
+    truth_cam, truth_traj = ev["camera"], ev["trajectory"]
+    synth.write_bin(str(tmp_path / "ev.bin"), ev)
+    (tmp_path / "cfg.yaml").write_text(YAML.replace("fitCircle: 0", "fitCircle: 1"))
+    save = tmp_path / "out"
+    env = dict(os.environ, ECB_PIECES="4")
+    r = subprocess.run([built, str(tmp_path / "cfg.yaml"), str(tmp_path / "ev.bin"), str(save)], capture_output=True, text=True,
+                       stdin=subprocess.DEVNULL, timeout=600, env=env)
+    print("\n".join(l for l in r.stdout.splitlines() if not l.startswith("Frame ")))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+    frames = int([l for l in r.stdout.splitlines() if l.endswith("frames in Map.")][0].split()[0])
+
+    # ---- the back half: initialisation (EventCalibIni::cvCalibration), spline optimisation, trajectory file ----
+    out = r.stdout
+    line = lambda key: [l for l in out.splitlines() if key in l][0]
+    assert "Calibration succeeded" in out
+    rms = float(line("Re-projection error reported by calibrateCamera:").split(":")[1])
+    assert 0 < rms < 1.0                                      # centres of fitted circles: sub-pixel
+    kept = int(line("frames in Map after Initialization.").split()[0])
+    assert 10 < kept <= frames
+    before = np.array(line("Intrinsics before optimization:").split(":")[1].split(), float)
+    after = np.array(line("Intrinsics after optimization:").split(":")[1].split(), float)
+    truth = truth_cam.intrinsics()
+    assert before.shape == (9,) and after.shape == (9,)
+    assert before[2] == 172.5 and before[3] == 129.5 and before[0] == before[1]   # CALIB_FIX_PRINCIPAL_POINT / FIX_ASPECT_RATIO
+    assert abs(before[0] / truth[0] - 1) < 2e-2                # the frame-based initialisation
+    # the event-based optimisation lands on the ground-truth camera of the generator: focal lengths within 1 %,
+    # principal point within 2 px, and it is closer than the frame-based initialisation was
+    assert abs(after[0] / truth[0] - 1) < 1e-2 and abs(after[1] / truth[1] - 1) < 1e-2, (before, after, truth)
+    assert abs(after[2] - truth[2]) < 2 and abs(after[3] - truth[3]) < 2
+    summ = line("Solver Summary:")
+    c0, c1 = (float(x) for x in summ.split("cost")[1].split(",")[0].split("->"))
+    assert c1 < c0
+    # TUM trajectory (SystemBase.cpp:122-150): one line per key frame, pose = ground truth within 1 cm / 0.5 degree
+    tum = np.loadtxt(str(save / "TrajectoryByEvent.txt"))
+    assert tum.shape == (kept, 8)
+    Rw, tw = truth_traj.pose(tum[:, 0])
+    assert np.abs(tum[:, 1:4] - tw).max() < 1.0, np.abs(tum[:, 1:4] - tw).max()
+    from scipy.spatial.transform import Rotation as Rot
+    ang = (Rot.from_quat(tum[:, 4:8]) * Rot.from_matrix(Rw).inv()).magnitude()
+    assert np.degrees(ang).max() < 0.5, np.degrees(ang).max()
