@@ -248,6 +248,16 @@ def main():
     pinned.numpy()[:] = rec.view(np.uint8).reshape(-1)
     d_raw = torch.empty(n * 25 + 16, dtype=torch.uint8, device="cuda")
     d_raw[: n * 25].copy_(pinned, non_blocking=False)
+    # the PCIe ceiling of the end-to-end number: plain pinned -> device copy of the same records (outside every timed region)
+    h2d_gbs = 0.0
+    for _ in range(3):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record()
+        d_raw[: n * 25].copy_(pinned, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = max(h2d_gbs, n * 25 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
 
     # one explicit (non-default) stream shared by torch (copies, NCCL, timing events) and the library's kernels
     stream = torch.cuda.Stream()
@@ -542,7 +552,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "pipeline": "%d time slices (relative sizes %s), one context/stream/host thread each "
-                        "(H2D of slice k+1 overlaps the kernels of slice k)" % (S, ":".join("%g" % v for v in plan))}}
+                        "(H2D of slice k+1 overlaps the kernels of slice k)" % (S, ":".join("%g" % v for v in plan)),
+                        "h2d_copy_gbs": h2d_gbs, "pcie_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3 if h2d_gbs > 0 else None}}
         if lm_info:
             line["lm"] = lm_info
         if not args.no_cpu and world == 1:

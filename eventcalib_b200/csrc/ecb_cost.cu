@@ -45,7 +45,7 @@ struct CostState {
     DevBuf d_knots, d_knot_off, d_ncp, d_cp_off, d_span_off;
     DevBuf obs, lm, tt, spl, basis, cp0, span;        // residual records (SoA)
     DevBuf span_start, items, part, out, params, cost_part, flags;
-    DevBuf ev_flag, ev_cnt, ev_tag, kf_t, kf_circ, lm_tab, sel_event, sel_circle;
+    DevBuf ev_flag, ev_cnt, ev_tag, kf_t, kf_circ, kf_c32, lm_tab, sel_event, sel_circle;
     std::vector<int64_t> h_span_start;
 };
 
@@ -452,7 +452,8 @@ struct AssocArgs {
     const int *knot_off, *ncp;
     int n_splines;
     const double *kf_t, *kf_circ, *lm_tab;
-    int K, n_circ;
+    const float2 *kf_c32;  // FP32 copy of the circle centres, row stride n_circ32 (even), absent / padding = far away
+    int K, n_circ, n_circ32;
     double gate2;  // (5 step)^2
     // fused k_prepare (spline ranges sorted and disjoint): span / basis / first control point written with the record
     const int *cp_off, *span_off;
@@ -488,13 +489,40 @@ __device__ __forceinline__ int assoc_one(const AssocArgs &a, int64_t i, int *spl
     const double *c = a.kf_circ + (size_t) best * a.n_circ * 3;
     int bi = -1;
     double bd = 0.0;
-    for (int q = 0; q < a.n_circ; ++q) {
-        if (c[3 * q + 2] < 0) continue;
-        const double dx = x - c[3 * q], dy = y - c[3 * q + 1];
-        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (bi < 0 || d2 < bd) {
-            bi = q;
-            bd = d2;
+    // Nearest centre: FP32 preselection over all circles with sortable keys (distance bits | circle index), keeping the two
+    // smallest.  When the runner-up is clearly farther than the winner the exact FP64 distance is evaluated for the winner
+    // alone; near-ties (and nothing else) take the exact FP64 loop, so the result is the exact arg-min either way.
+    {
+        const float xf = (float) ECB_PIX_X(e), yf = (float) ECB_PIX_Y(e);  // pixel coordinates are exact in FP32
+        const float4 *c4 = reinterpret_cast<const float4 *>(a.kf_c32 + (size_t) best * a.n_circ32);
+        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+#pragma unroll 6
+        for (int q = 0; q < a.n_circ32; q += 2) {
+            const float4 cc = c4[q >> 1];
+            const float dx0 = xf - cc.x, dy0 = yf - cc.y, dx1 = xf - cc.z, dy1 = yf - cc.w;
+            const uint32_t ka = (__float_as_uint(fmaf(dx0, dx0, dy0 * dy0)) & 0xFFFFFF00u) | (uint32_t) q;
+            const uint32_t kb = (__float_as_uint(fmaf(dx1, dx1, dy1 * dy1)) & 0xFFFFFF00u) | (uint32_t) (q + 1);
+            k2 = min(k2, max(ka, k1));
+            k1 = min(k1, ka);
+            k2 = min(k2, max(kb, k1));
+            k1 = min(k1, kb);
+        }
+        const float d1 = __uint_as_float(k1 & 0xFFFFFF00u), d2 = __uint_as_float(k2 | 0xFFu);
+        if (d2 > d1 * 1.0001f + 0.02f) {  // unambiguous (FP32 error <= 2e-7 d + 3e-4 |d|^(1/2), key quantisation 1.5e-5 d)
+            bi = (int) (k1 & 0xFFu);
+            if (bi >= a.n_circ || c[3 * bi + 2] < 0) return -1;  // only absent circles
+            const double dx = x - c[3 * bi], dy = y - c[3 * bi + 1];
+            bd = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        } else {
+            for (int q = 0; q < a.n_circ; ++q) {
+                if (c[3 * q + 2] < 0) continue;
+                const double dx = x - c[3 * q], dy = y - c[3 * q + 1];
+                const double dd = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (bi < 0 || dd < bd) {
+                    bi = q;
+                    bd = dd;
+                }
+            }
         }
     }
     if (bi < 0) return -1;
@@ -503,6 +531,20 @@ __device__ __forceinline__ int assoc_one(const AssocArgs &a, int64_t i, int *spl
 }
 
 constexpr int AS_THREADS = 256;
+
+// FP32 copy of the circle centres for the preselection in assoc_one: rows padded to an even count; absent circles (r < 0)
+// and padding sit at (3e18, 3e18) so they never win against a real circle
+__global__ void k_circ32(const double *__restrict__ c, int K, int n_circ, int n_circ32, float2 *__restrict__ o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * n_circ32) return;
+    const int k = i / n_circ32, q = i - k * n_circ32;
+    float2 v = make_float2(3e18f, 3e18f);
+    if (q < n_circ) {
+        const double *p = c + ((size_t) k * n_circ + q) * 3;
+        if (!(p[2] < 0)) v = make_float2((float) p[0], (float) p[1]);
+    }
+    o[i] = v;
+}
 
 // nearest key frame in time, ties -> the earlier frame (1-NN over the stamps, EventCalibSpline.cpp:166)
 __device__ __forceinline__ int nearest_kf(const double *kf_t, int K, double u) {
@@ -517,8 +559,8 @@ __device__ __forceinline__ int nearest_kf(const double *kf_t, int K, double u) {
 }
 
 // pass 1: decide every event once, remember the decision in a 16-bit tag (0 = no residual, else spline<<8 | circle+1)
-// (a shared-memory / FP32-preselect variant of this kernel measured slower on B200 — 1.45 vs 1.20 ms per 20 M events —
-//  the 36 FP64 distance evaluations per event are not the bottleneck)
+// (ncu, profiles/r1e: the 36 FP64 distance evaluations were 71 % of this kernel's instructions, issue-bound at 72 % — hence the
+//  FP32 preselection with sortable keys in assoc_one; an earlier shared-memory variant of the FP64 loop had measured slower)
 __global__ void __launch_bounds__(AS_THREADS) k_assoc_count(const AssocArgs a, uint16_t *__restrict__ tag,
                                                            uint32_t *__restrict__ block_cnt) {
     __shared__ uint32_t ws[33];
@@ -620,13 +662,29 @@ int prepare_records(ecb_ctx *ctx, CostState *st, bool have_basis = false) {
     }
     if (flag & 1u) return ecb_fail(ctx, ECB_ERR_ARG, "a residual's time stamp lies outside its spline's knot range");
     if (flag & 2u) return ecb_fail(ctx, ECB_ERR_ARG, "residual records must be ordered by (spline, time)");
-    // work items: chunks of <= CHUNK residuals inside one span (fixed => deterministic reduction order)
+    // work items: chunks of <= chunk residuals inside one span (a function of the record counts and the SM count only =>
+    // deterministic reduction order).  One item is one warp's latency-bound pass (0.45 ms per 2048 residuals on B200), so the
+    // chunk is sized to hand every resident warp of k_normal_eq the same number of items: small residual sets (a time slice
+    // of the end-to-end pipeline, one rank of eight) then use all warps with shorter items instead of half of them.
+    int chunk = CHUNK;
+    {
+        const int64_t warps = (int64_t) ctx->sm_count * (st->so3 ? 1 : 2) * NE_WARPS;
+        const int64_t rounds = std::max<int64_t>(1, (n + warps * CHUNK - 1) / (warps * CHUNK));
+        chunk = (int) (((n + warps * rounds - 1) / (warps * rounds) + 31) / 32 * 32);
+        chunk = std::min(std::max(chunk, 256), CHUNK);
+        for (; chunk < CHUNK; chunk += 32) {  // the partial chunks at span ends add items: grow until the count fits
+            int64_t cnt = 0;
+            for (int s = 0; s < st->total_spans; ++s)
+                cnt += (st->h_span_start[(size_t) s + 1] - st->h_span_start[(size_t) s] + chunk - 1) / chunk;
+            if (cnt <= warps * rounds) break;
+        }
+    }
     std::vector<Item> items;
     std::vector<int> item_start((size_t) st->total_spans + 1, 0);
     for (int s = 0; s < st->total_spans; ++s) {
         item_start[(size_t) s] = (int) items.size();
-        for (int64_t b = st->h_span_start[(size_t) s]; b < st->h_span_start[(size_t) s + 1]; b += CHUNK)
-            items.push_back(Item{b, std::min<int64_t>(b + CHUNK, st->h_span_start[(size_t) s + 1]), s, 0});
+        for (int64_t b = st->h_span_start[(size_t) s]; b < st->h_span_start[(size_t) s + 1]; b += chunk)
+            items.push_back(Item{b, std::min<int64_t>(b + chunk, st->h_span_start[(size_t) s + 1]), s, 0});
     }
     item_start[(size_t) st->total_spans] = (int) items.size();
     st->n_items = (int) items.size();
@@ -659,7 +717,7 @@ void ecb_cost_free(ecb_ctx *ctx) {
     CostState *st = (CostState *) ctx->cost;
     DevBuf *bufs[] = {&st->d_knots, &st->d_knot_off, &st->d_ncp, &st->d_cp_off, &st->d_span_off, &st->obs, &st->lm, &st->tt,
                       &st->spl, &st->basis, &st->cp0, &st->span, &st->span_start, &st->items, &st->part, &st->out, &st->params,
-                      &st->cost_part, &st->flags, &st->ev_flag, &st->ev_cnt, &st->ev_tag, &st->kf_t, &st->kf_circ, &st->lm_tab,
+                      &st->cost_part, &st->flags, &st->ev_flag, &st->ev_cnt, &st->ev_tag, &st->kf_t, &st->kf_circ, &st->kf_c32, &st->lm_tab,
                       &st->sel_event, &st->sel_circle};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -761,6 +819,8 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if ((rc = ecb_reserve(ctx, st->kf_t, (size_t) n_keyframes * 8))) return rc;
     if ((rc = ecb_reserve(ctx, st->kf_circ, (size_t) n_keyframes * n_circles * 24))) return rc;
     if ((rc = ecb_reserve(ctx, st->lm_tab, (size_t) n_circles * 24))) return rc;
+    const int n_circ32 = (n_circles + 1) & ~1;
+    if ((rc = ecb_reserve(ctx, st->kf_c32, (size_t) n_keyframes * n_circ32 * 8))) return rc;
     if (n_circles > 254 || st->n_splines > 255) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "more than 254 circles or 255 spline segments");
     if ((rc = ecb_reserve(ctx, st->ev_cnt, (size_t) nb * 4 + 16))) return rc;
     if ((rc = ecb_reserve(ctx, st->ev_tag, (size_t) n * 2 + 16))) return rc;
@@ -779,10 +839,15 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     a.kf_t = (const double *) st->kf_t.p;
     a.kf_circ = (const double *) st->kf_circ.p;
     a.lm_tab = (const double *) st->lm_tab.p;
+    a.kf_c32 = (const float2 *) st->kf_c32.p;
     a.K = n_keyframes;
     a.n_circ = n_circles;
+    a.n_circ32 = n_circ32;
     a.gate2 = 5 * motion_time_step * 5 * motion_time_step;  // EventCalibSpline.cpp:168
     ECB_PROF_BEGIN(ctx, ECB_STAGE_ASSOC);
+    k_circ32<<<(n_keyframes * n_circ32 + 255) / 256, 256, 0, ctx->stream>>>((const double *) st->kf_circ.p, n_keyframes, n_circles,
+                                                                           n_circ32, (float2 *) st->kf_c32.p);
+    ECB_LAUNCHED(ctx);
     k_assoc_count<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (uint16_t *) st->ev_tag.p, (uint32_t *) st->ev_cnt.p);
     ECB_LAUNCHED(ctx);
     int64_t *d_total = (int64_t *) st->ev_flag.p + nb;

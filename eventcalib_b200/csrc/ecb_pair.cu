@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
     __shared__ int acc_ni[ECB_MAXK_LIMIT];
     __shared__ double acc_c[ECB_MAXK_LIMIT][3];
     __shared__ uint32_t ws[33];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = PAIR_THREADS >> 5;
+    __shared__ int s_next;  // next unclaimed positive cluster of the window (the clusters' fit work varies: dynamic hand-out)
+    const int tid = threadIdx.x, lane = tid & 31;
 
     for (int w = blockIdx.x; w < a.n_win; w += gridDim.x) {
         const ProbDesc dn = a.prob[2 * w], dp = a.prob[2 * w + 1];
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
             my[1][i] = kp[i].med_y;
             acc_ni[i] = -1;
         }
+        if (tid == 0) s_next = 0;
         __syncthreads();
         const bool enough0 = dn.n > 0 && dp.n > 0 && (uint32_t) nkp >= a.rows_cols && (uint32_t) nkn >= a.rows_cols;
         const bool enough = enough0;
@@ -179,7 +181,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
         }
         const double gate = 4 * a.rthr * a.rthr;
         if (enough) {
-            for (int pi = wid; pi < nkp; pi += nwarp) {
+            for (;;) {
+                int pi = 0;
+                if (lane == 0) pi = atomicAdd(&s_next, 1);
+                pi = __shfl_sync(0xffffffffu, pi, 0);
+                if (pi >= nkp) break;
                 int nidx[KNN_MAX], pidx[KNN_MAX];
                 unsigned long long d2[KNN_MAX];
                 if (!FIT) {  // CirclesEventFrame.cpp:282-312
@@ -213,24 +219,59 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
                             break;
                         }
                     if (real == 0) continue;
-                    auto fit_pair = [&](int p, int n, double &cx, double &cy, double &r) -> double {
-                        double m[9];
+                    // Kasa fits of up to `cnt` candidate pairs at once: lane j solves pair j (moments + 3x3 LU, one pass for
+                    // all candidates instead of one warp-redundant solve per candidate), the results are broadcast and the
+                    // fit error of every pair is then summed warp-wide over its members
+                    double s_err = 0, s_cx = 0, s_cy = 0, s_r = 0;  // the fit of (pi, nsel), memoised like the reference's fit
+                    bool have_memo = false;                         // cache (CirclesEventFrame.cpp:199-225)
+                    auto fit_pairs = [&](const int *plist, const int *nlist, bool p_varies, int cnt) {
+                        int p = plist[0], n = nlist[0];
 #pragma unroll
-                        for (int q = 0; q < 9; ++q) m[q] = kp[p].m[q] + kn[n].m[q];
-                        fit_from_moments(m, (double) (kp[p].size + kn[n].size), cx, cy, r);
-                        const double ddx = (double) mx[1][p] - (double) mx[0][n], ddy = (double) my[1][p] - (double) my[0][n];
-                        const double approx = sqrt(ddx * ddx + ddy * ddy) / 2;
-                        if (r > a.rthr || r > 2 * approx) return DBL_MAX;
-                        double e = warp_abs_dev<DIRECT>(ptsP, memP + kp[p].mem_off, kp[p].size, cx, cy, r);
-                        e += warp_abs_dev<DIRECT>(ptsN, memN + kn[n].mem_off, kn[n].size, cx, cy, r);
-                        return e / ((double) (kp[p].size + kn[n].size) * r);
+                        for (int q = 1; q < KNN_MAX; ++q)
+                            if (lane == q) {
+                                if (p_varies) p = plist[q]; else n = nlist[q];
+                            }
+                        double lcx = 0, lcy = 0, lr = 0;
+                        bool lok = false;
+                        if (lane < cnt) {
+                            double m[9];
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) m[q] = kp[p].m[q] + kn[n].m[q];
+                            fit_from_moments(m, (double) (kp[p].size + kn[n].size), lcx, lcy, lr);
+                            const double ddx = (double) mx[1][p] - (double) mx[0][n], ddy = (double) my[1][p] - (double) my[0][n];
+                            const double approx = sqrt(ddx * ddx + ddy * ddy) / 2;
+                            lok = !(lr > a.rthr || lr > 2 * approx);
+                        }
+                        for (int j = 0; j < cnt; ++j) {
+                            const int pj = p_varies ? plist[j] : plist[0], nj = p_varies ? nlist[0] : nlist[j];
+                            fcx[j] = __shfl_sync(0xffffffffu, lcx, j);
+                            fcy[j] = __shfl_sync(0xffffffffu, lcy, j);
+                            fr[j] = __shfl_sync(0xffffffffu, lr, j);
+                            const int okj = __shfl_sync(0xffffffffu, (int) lok, j);
+                            if (have_memo && pj == pi) {  // same pair, same numbers
+                                ferr[j] = s_err;
+                                fcx[j] = s_cx;
+                                fcy[j] = s_cy;
+                                fr[j] = s_r;
+                                continue;
+                            }
+                            if (!okj) {
+                                ferr[j] = DBL_MAX;
+                                continue;
+                            }
+                            double e = warp_abs_dev<DIRECT>(ptsP, memP + kp[pj].mem_off, kp[pj].size, fcx[j], fcy[j], fr[j]);
+                            e += warp_abs_dev<DIRECT>(ptsN, memN + kn[nj].mem_off, kn[nj].size, fcx[j], fcy[j], fr[j]);
+                            ferr[j] = e / ((double) (kp[pj].size + kn[nj].size) * fr[j]);
+                        }
                     };
-                    for (int j = 0; j < real; ++j) ferr[j] = fit_pair(pi, nidx[j], fcx[j], fcy[j], fr[j]);
+                    fit_pairs(&pi, nidx, false, real);
                     int nmin = 0;
                     for (int j = 1; j < real; ++j)
                         if (ferr[j] < ferr[nmin]) nmin = j;
                     if (!(ferr[nmin] < 2 / fr[nmin])) continue;
                     const int nsel = nidx[nmin];
+                    s_err = ferr[nmin], s_cx = fcx[nmin], s_cy = fcy[nmin], s_r = fr[nmin];
+                    have_memo = true;
                     warp_knn(mx[1], my[1], nkp, mx[0][nsel], my[0][nsel], K, pidx, d2);
                     real = K;
                     for (int oi = 0; oi < K; ++oi)
@@ -239,7 +280,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
                             break;
                         }
                     if (real == 0) continue;
-                    for (int i = 0; i < real; ++i) ferr[i] = fit_pair(pidx[i], nsel, fcx[i], fcy[i], fr[i]);
+                    fit_pairs(pidx, &nsel, true, real);
                     int pmin = 0;
                     for (int i = 1; i < real; ++i)
                         if (ferr[i] < ferr[pmin]) pmin = i;
