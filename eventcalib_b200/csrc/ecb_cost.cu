@@ -67,6 +67,21 @@ __device__ __forceinline__ int find_span_dev(const double *knots, int nk, double
     return mid;
 }
 
+// same span (the one with knots[mid] <= u < knots[mid+1] is unique) from a proportional guess and a short walk: the
+// reference's interior knots are nearly uniform (NURBS-book eq. 9.68), so the dependent-load chain of the bisection goes away
+__device__ __forceinline__ int find_span_guess(const double *knots, int nk, double u) {
+    const int degree = 3;
+    const int n = nk - 2 - degree;
+    if (u == knots[n + 1]) return n;
+    const double k0 = knots[degree], k1 = knots[n + 1];
+    int mid = degree + (int) ((u - k0) / (k1 - k0) * (double) (n + 1 - degree));
+    mid = max(degree, min(n, mid));
+    for (int s = 0; s < 8 && mid > degree && u < knots[mid]; ++s) --mid;
+    for (int s = 0; s < 8 && mid < n && u >= knots[mid + 1]; ++s) ++mid;
+    if (u < knots[mid] || u >= knots[mid + 1]) return find_span_dev(knots, nk, u);
+    return mid;
+}
+
 __device__ __forceinline__ void basis_dev(const double *knots, int span, double u, double *N) {  // BsplineReal.hpp:107-145
     double ndu[4][4], left[4], right[4];
     ndu[0][0] = 1;
@@ -413,8 +428,8 @@ __global__ void k_reduce_cost(const double *__restrict__ part, int n, int stride
     if (threadIdx.x == 0) *out = sh[0];
 }
 
-template <bool SO3>
-__global__ void __launch_bounds__(256) k_cost(const double *__restrict__ obs, const double *__restrict__ lm,
+template <bool SO3, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_cost(const double *__restrict__ obs, const double *__restrict__ lm,
                                              const int *__restrict__ circ, const double *__restrict__ lm_tab,
                                              const double *__restrict__ basis, const int *__restrict__ cp0, int64_t n,
                                              const double *__restrict__ params, int total_cp, double radius, double huber,
@@ -573,22 +588,19 @@ __global__ void __launch_bounds__(AS_THREADS) k_assoc_count(const AssocArgs a, u
     if (threadIdx.x == 0) block_cnt[blockIdx.x] = tot;
 }
 
-__global__ void k_scan_blocks(uint32_t *cnt, int n, int64_t *off, int64_t *total) {  // single block, serial over chunks
+__global__ void k_scan_blocks(uint32_t *cnt, int n, int64_t *off, int64_t *total) {  // single block: one segment per thread
     __shared__ uint32_t ws[33];
-    __shared__ int64_t run;
-    if (threadIdx.x == 0) run = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < n; c0 += blockDim.x) {
-        const int i = c0 + threadIdx.x;
-        const uint32_t v = i < n ? cnt[i] : 0;
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan(v, ws, &tot);
-        if (i < n) off[i] = run + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) run += tot;
-        __syncthreads();
+    const int per = (n + (int) blockDim.x - 1) / (int) blockDim.x;
+    const int b = min(n, (int) threadIdx.x * per), e = min(n, b + per);
+    uint32_t sum = 0;
+    for (int i = b; i < e; ++i) sum += cnt[i];
+    uint32_t tot;
+    int64_t run = block_excl_scan(sum, ws, &tot);  // the per-launch total (tagged events) fits 32 bits: n_events < 2^32
+    for (int i = b; i < e; ++i) {
+        off[i] = run;
+        run += cnt[i];
     }
-    if (threadIdx.x == 0) *total = run;
+    if (threadIdx.x == 0) *total = tot;
 }
 
 // pass 2: ordered compaction of the tagged events into residual records (pure streaming)
@@ -619,7 +631,7 @@ __global__ void __launch_bounds__(AS_THREADS) k_assoc_write(const AssocArgs a, c
         }
         if (a.basis) {  // what k_prepare would compute (findSpan / dersBasisFuns, EventCalibSpline.cpp:173-179)
             const double *kn = a.knots + a.knot_off[s];
-            const int sp = find_span_dev(kn, a.ncp[s] + 4, u);
+            const int sp = find_span_guess(kn, a.ncp[s] + 4, u);
             double N[4];
             basis_dev(kn, sp, u, N);
             reinterpret_cast<double4 *>(a.basis)[k] = make_double4(N[0], N[1], N[2], N[3]);
@@ -811,6 +823,7 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if (!ctx || !ctx->cost) return ecb_fail(ctx, ECB_ERR_STATE, "ecb_cost_setup first");
     if (!kf_time || !kf_circles || !landmarks_xyz || n_keyframes < 1 || n_circles < 1) return ECB_ERR_ARG;
     if (ctx->n_events <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no events loaded");
+    if (ctx->n_events > 0xFFFFFFFFll) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "association over more than 2^32-1 events per context");
     cudaSetDevice(ctx->device);
     CostState *st = (CostState *) ctx->cost;
     int rc;
@@ -922,7 +935,8 @@ int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, 
     if (st->n_res == 0) return ECB_OK;
     int grid = (int) std::min<int64_t>((st->n_res + 255) / 256, (int64_t) ctx->sm_count * 8);
     ECB_PROF_BEGIN(ctx, ECB_STAGE_COST);
-    (st->so3 ? k_cost<true> : k_cost<false>)<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p,
+    static const int cost_minb = getenv("ECB_COST_MINB") ? atoi(getenv("ECB_COST_MINB")) : 4;  // 64 registers, 32 warps / SM: 0.35 -> 0.33 ms
+    (st->so3 ? k_cost<true, 2> : (cost_minb >= 4 ? k_cost<false, 4> : k_cost<false, 3>))<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p,
                                           st->use_circ ? (const int *) st->sel_circle.p : nullptr, (const double *) st->lm_tab.p,
                                           (const double *) st->basis.p,
                                           (const int *) st->cp0.p, st->n_res, (const double *) st->params.p, st->total_cp,
