@@ -57,7 +57,9 @@ def basis(kn, span, u):
 
 
 def fit_control_points(kn, us, data, n_cp):
-    """Least-squares control points (n_cp x dim) for samples data(us)."""
+    """Least-squares control points (n_cp x dim) for samples data(us) with free end points — a builder of synthetic problems
+    for tests / bench.  The reference's own fit (BsplineReal: first / last control point = first / last sample) is
+    EventCalibSpline::fitSpline in include/ecb/event_calib.hpp."""
     A = np.zeros((len(us), n_cp))
     for r, u in enumerate(us):
         s = find_span(kn, u)

@@ -7,6 +7,8 @@ Libraries (built by ``oracle/Makefile``; see the headers of the .cpp files for w
   * ``_build/libecb_oracle.so``  — the CPU restatement (always buildable)
   * ``_ref/libref_dbscan.so``    — the UNMODIFIED reference ``dbscan.h`` + ``kdtree.cpp`` compiled in place
   * ``_ref/libref_frontend.so``  — restated glue + verbatim reference DBSCAN (the "reference" CPU baseline)
+  * ``_ref/libref_functor.so``   — the UNMODIFIED reference residual functor (EventCalibSpline.hpp) and B-spline
+                                   (BsplineReal.hpp) compiled in place against the stand-in Eigen of ``shim_functor/``
 """
 import ctypes as C
 import os
@@ -18,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _PORT = os.path.join(_HERE, "_build", "libecb_oracle.so")
 _REF_DB = os.path.join(_HERE, "_ref", "libref_dbscan.so")
 _REF_FE = os.path.join(_HERE, "_ref", "libref_frontend.so")
+_REF_FN = os.path.join(_HERE, "_ref", "libref_functor.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -28,7 +31,7 @@ _lp = C.POINTER(C.c_int64)
 
 def build(force=False):
     """Compile the restatement and, when /root/reference is present, oracle/_ref."""
-    if force or not os.path.exists(_PORT) or (os.path.isdir("/root/reference") and not os.path.exists(_REF_DB)):
+    if force or not os.path.exists(_PORT) or (os.path.isdir("/root/reference") and not (os.path.exists(_REF_DB) and os.path.exists(_REF_FN))):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
     return _PORT
 
@@ -62,6 +65,55 @@ def port():
 
 def have_ref():
     return os.path.exists(_REF_DB)
+
+
+def have_ref_functor():
+    return os.path.exists(_REF_FN)
+
+
+def ref_functor_lib():
+    lib = _load(_REF_FN)
+    lib.ref_residual.restype = C.c_double
+    lib.ref_residual_jac.restype = C.c_double
+    return lib
+
+
+def ref_residual_jac(intr, rcp, tcp, obs, lm, radius, b):
+    """The reference's own CalibReprojectionError::operator() (EventCalibSpline.hpp:168-229) on Jet<37> and on double:
+    returns (value on Jet, 1x37 ambient Jacobian, value on double)."""
+    a = [np.ascontiguousarray(v, np.float64) for v in (intr, rcp, tcp, obs, lm, b)]
+    jac = np.zeros(37)
+    lib = ref_functor_lib()
+    r = lib.ref_residual_jac(_p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), _p(a[3], _dp), _p(a[4], _dp), C.c_double(radius),
+                             _p(a[5], _dp), _p(jac, _dp))
+    rd = lib.ref_residual(_p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), _p(a[3], _dp), _p(a[4], _dp), C.c_double(radius), _p(a[5], _dp))
+    return r, jac, rd
+
+
+def ref_undistort(intr, obs):
+    a = [np.ascontiguousarray(v, np.float64) for v in (intr, obs)]
+    out = np.zeros(3)
+    ref_functor_lib().ref_undistort(_p(a[0], _dp), _p(a[1], _dp), _p(out, _dp))
+    return out
+
+
+def ref_spline_fit(us, data, n_cp):
+    """The reference's BsplineReal<dim>(3, samples, cpNum, timestamps): (knot vector, control points)."""
+    us = np.ascontiguousarray(us, np.float64)
+    data = np.ascontiguousarray(data, np.float64)
+    dim = data.shape[1]
+    kn, cp = np.zeros(n_cp + 4), np.zeros((n_cp, dim))
+    n = ref_functor_lib().ref_spline_fit(C.c_int(dim), _p(us, _dp), _p(data, _dp), C.c_int(len(us)), C.c_int(n_cp), _p(kn, _dp), _p(cp, _dp))
+    return kn, cp, n
+
+
+def ref_basis(knots, u):
+    """The reference's BsplineReal::findSpan + dersBasisFuns(u, span, 0): (span, 4 basis values)."""
+    kn = np.ascontiguousarray(knots, np.float64)
+    span = C.c_int()
+    N = np.zeros(4)
+    ref_functor_lib().ref_basis(_p(kn, _dp), C.c_int(len(kn)), C.c_double(u), C.byref(span), _p(N, _dp))
+    return span.value, N
 
 
 def ref_dbscan_lib():

@@ -13,9 +13,12 @@
 //   HuberLoss + Corrector (rho'' <= 0 => residual and Jacobian scaled by sqrt(rho')), cost = 1/2 rho(r^2)
 //   EigenQuaternionParameterization::ComputeJacobian / Plus (storage x,y,z,w)
 //   Eigen: Vector4::normalize(), Quaternion * Vector3 (uv = 2 q.vec x v; v + w uv + q.vec x uv), norm(), dot()
-// Pinning: the only reference known-answer on this path is unit_test_inverseDistortion, checked in
-// tests/test_oracle_cost.py; the residual itself has no reference test => PARITY UNPINNED at that boundary; it is
-// cross-checked against an independent mpmath evaluation (tests/test_oracle_cost.py).
+// Pinning: (1) the reference's only known-answer on this path, unit_test_inverseDistortion, checked in
+// tests/test_oracle_cost.py; (2) the reference's OWN functor and B-spline compiled where they lie against stand-in Eigen
+// headers (oracle/ref_functor_capi.cpp -> oracle/_ref/libref_functor.so): the restated residual() below equals it bit for bit
+// on Jet<37> (value + 37 partials), knots / findSpan / dersBasisFuns are bit-identical (tests/test_oracle_reference_source.py);
+// (3) an independent 40-digit mpmath evaluation (tests/test_oracle_cost.py).  Still PARITY UNPINNED: what Ceres and Sophus do
+// (corrector, parameterisations, SO(3) exp / log) — external, restated from their published behaviour.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -1,0 +1,166 @@
+// TEST INFRASTRUCTURE — C wrapper around the reference's OWN residual functor and B-spline, compiled where they lie under
+// /root/reference (never copied) into oracle/_ref/libref_functor.so by oracle/Makefile:
+//
+//   opengv2::EventCalibSpline::CalibReprojectionError::operator()<T>   event_camera_calib/include/opengv2/event_camera_calib/
+//   opengv2::EventCalibSpline::unDistort<T>                            EventCalibSpline.hpp:36-63,158-250
+//   opengv2::BsplineReal<dim> (ctor fit, findSpan, dersBasisFuns, evaluate)   core/spline/include/opengv2/spline/BsplineReal.hpp
+//
+// against the stand-in headers of oracle/shim_functor/ (Eigen / Ceres / Sophus are external and absent: what the two reference
+// headers need from Eigen is restated there; nothing of the functor's or the spline's own arithmetic is).  T = double gives the
+// residual, T = Jet<37> (ceres/jet.h semantics: value + 37 partials, restated below like in ecb_oracle_cost.cpp) gives the
+// 1 x 37 ambient Jacobian Ceres' AutoDiffCostFunction would produce (EventCalibSpline.hpp:233-239).
+// Only tests/ use this library: it pins the oracle's restatement (ecb_oracle_cost.cpp) to the reference's source text.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+namespace jet {
+template <int NP>
+struct Jet {
+    double a;
+    double v[NP];
+    Jet() : a(0) { std::memset(v, 0, sizeof v); }
+    Jet(double s) : a(s) { std::memset(v, 0, sizeof v); }  // NOLINT
+};
+#define JET_BIN(op, expr_a, expr_v)                                              \
+    template <int NP> Jet<NP> operator op(const Jet<NP> &f, const Jet<NP> &g) { \
+        Jet<NP> h;                                                               \
+        h.a = expr_a;                                                            \
+        for (int i = 0; i < NP; ++i) h.v[i] = expr_v;                            \
+        return h;                                                                \
+    }
+JET_BIN(+, f.a + g.a, f.v[i] + g.v[i])
+JET_BIN(-, f.a - g.a, f.v[i] - g.v[i])
+JET_BIN(*, f.a *g.a, f.a *g.v[i] + f.v[i] * g.a)
+template <int NP> Jet<NP> operator/(const Jet<NP> &f, const Jet<NP> &g) {  // ceres/jet.h: g_a_inverse, f_a_by_g_a
+    Jet<NP> h;
+    const double gi = 1.0 / g.a, fg = f.a * gi;
+    h.a = fg;
+    for (int i = 0; i < NP; ++i) h.v[i] = (f.v[i] - fg * g.v[i]) * gi;
+    return h;
+}
+template <int NP> Jet<NP> operator*(double s, const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = s * f.a;
+    for (int i = 0; i < NP; ++i) h.v[i] = s * f.v[i];
+    return h;
+}
+template <int NP> Jet<NP> operator*(const Jet<NP> &f, double s) { return s * f; }
+template <int NP> Jet<NP> operator-(const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = -f.a;
+    for (int i = 0; i < NP; ++i) h.v[i] = -f.v[i];
+    return h;
+}
+template <int NP> Jet<NP> operator-(double s, const Jet<NP> &f) { return Jet<NP>(s) - f; }
+template <int NP> Jet<NP> operator-(const Jet<NP> &f, double s) { return f - Jet<NP>(s); }
+template <int NP> Jet<NP> operator+(double s, const Jet<NP> &f) { return Jet<NP>(s) + f; }
+template <int NP> Jet<NP> operator+(const Jet<NP> &f, double s) { return Jet<NP>(s) + f; }
+template <int NP> Jet<NP> &operator*=(Jet<NP> &f, const Jet<NP> &g) { return f = f * g; }
+template <int NP> Jet<NP> &operator+=(Jet<NP> &f, const Jet<NP> &g) { return f = f + g; }
+template <int NP> bool operator>(const Jet<NP> &f, const Jet<NP> &g) { return f.a > g.a; }
+template <int NP> bool operator!=(const Jet<NP> &f, const Jet<NP> &g) { return f.a != g.a; }
+template <int NP> Jet<NP> sqrt(const Jet<NP> &f) {  // ceres/jet.h
+    Jet<NP> h;
+    h.a = std::sqrt(f.a);
+    const double t = 1.0 / (2.0 * h.a);
+    for (int i = 0; i < NP; ++i) h.v[i] = f.v[i] * t;
+    return h;
+}
+}  // namespace jet
+
+#include <opengv2/event_camera_calib/EventCalibSpline.hpp>  // the reference's header, resolved through -I by the Makefile
+
+using opengv2::EventCalibSpline;
+typedef EventCalibSpline::CalibReprojectionError Functor;
+
+namespace {
+template <class T>
+T run_functor(const T *intr, const T *rcp16, const T *tcp12, const double *obs, const double *lm, double radius, const double *basis) {
+    const Eigen::Vector2d o(obs[0], obs[1]);
+    const Eigen::Vector3d l(lm[0], lm[1], lm[2]);
+    const Eigen::Quaterniond Qbs(1, 0, 0, 0);
+    const Eigen::Vector3d tbs(0, 0, 0);
+    auto rB = std::make_shared<std::vector<std::vector<double>>>(1, std::vector<double>(basis, basis + 4));
+    auto tB = std::make_shared<std::vector<std::vector<double>>>(1, std::vector<double>(basis, basis + 4));
+    Functor f(&o, &l, &radius, &Qbs, &tbs, rB, tB);
+    T res;
+    f(intr, rcp16, rcp16 + 4, rcp16 + 8, rcp16 + 12, tcp12, tcp12 + 3, tcp12 + 6, tcp12 + 9, &res);
+    return res;
+}
+}  // namespace
+
+extern "C" {
+
+// value of the reference functor with T = double
+double ref_residual(const double *intr, const double *rcp16, const double *tcp12, const double *obs, const double *lm, double radius,
+                    const double *basis) {
+    return run_functor<double>(intr, rcp16, tcp12, obs, lm, radius, basis);
+}
+
+// value and 1 x 37 ambient Jacobian (9 intrinsics | 4 x 4 rotation control points x y z w | 4 x 3 translation control points)
+double ref_residual_jac(const double *intr, const double *rcp16, const double *tcp12, const double *obs, const double *lm,
+                        double radius, const double *basis, double *jac37) {
+    typedef jet::Jet<37> J;
+    J p[37];
+    for (int k = 0; k < 9; ++k) p[k] = J(intr[k]);
+    for (int k = 0; k < 16; ++k) p[9 + k] = J(rcp16[k]);
+    for (int k = 0; k < 12; ++k) p[25 + k] = J(tcp12[k]);
+    for (int k = 0; k < 37; ++k) p[k].v[k] = 1.0;
+    const J r = run_functor<J>(p, p + 9, p + 25, obs, lm, radius, basis);
+    for (int k = 0; k < 37; ++k) jac37[k] = r.v[k];
+    return r.a;
+}
+
+// EventCalibSpline::unDistort<double>
+void ref_undistort(const double *intr, const double *obs, double *Xc3) {
+    Sophus::Vector3<double> Xc;
+    EventCalibSpline::unDistort<double>(intr[0], intr[1], intr[2], intr[3], intr[4], intr[5], intr[6], intr[7], intr[8],
+                                        Eigen::Vector2d(obs[0], obs[1]), Xc);
+    for (int k = 0; k < 3; ++k) Xc3[k] = Xc[k];
+}
+}
+
+// ---- BsplineReal ----
+namespace {
+template <int dim>
+struct Probe : opengv2::BsplineReal<dim> {
+    typedef Eigen::Matrix<double, dim, 1> V;
+    typedef std::vector<V, Eigen::aligned_allocator<V>> VV;
+    Probe() : opengv2::BsplineReal<dim>(3) {}
+    Probe(const VV &Q, int cpNum, const std::vector<double> &u) : opengv2::BsplineReal<dim>(3, Q, cpNum, u) {}
+    void setKnots(const double *k, int nk) { this->knotVector.assign(k, k + nk); }
+};
+template <int dim>
+int fit(const double *us, const double *data, int n, int cp_num, double *knots, double *cp) {
+    typename Probe<dim>::VV Q((size_t) n);
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < dim; ++c) Q[(size_t) i][c] = data[(size_t) i * dim + c];
+    Probe<dim> sp(Q, cp_num, std::vector<double>(us, us + n));
+    const std::vector<double> &kv = sp.getKnotVector();
+    for (size_t i = 0; i < kv.size(); ++i) knots[i] = kv[i];
+    auto &C = sp.getCP();
+    for (size_t i = 0; i < C.size(); ++i)
+        for (int c = 0; c < dim; ++c) cp[i * dim + (size_t) c] = C[i][c];
+    return (int) C.size();
+}
+}  // namespace
+
+extern "C" {
+// BsplineReal<dim>(degree 3, samples, cpNum, timestamps): knot vector (cpNum + 4) and control points (cpNum x dim); returns the
+// number of control points the reference produced (0 when its fit failed)
+int ref_spline_fit(int dim, const double *us, const double *data, int n, int cp_num, double *knots, double *cp) {
+    return dim == 3 ? fit<3>(us, data, n, cp_num, knots, cp) : dim == 4 ? fit<4>(us, data, n, cp_num, knots, cp) : -1;
+}
+// findSpan + dersBasisFuns(u, span, 0) on a given knot vector
+void ref_basis(const double *knots, int nk, double u, int *span, double *N4) {
+    Probe<3> sp;
+    sp.setKnots(knots, nk);
+    const size_t s = sp.findSpan(u);
+    std::vector<std::vector<double>> ders;
+    sp.dersBasisFuns(u, s, 0, ders);
+    *span = (int) s;
+    for (int j = 0; j < 4; ++j) N4[j] = ders[0][(size_t) j];
+}
+}

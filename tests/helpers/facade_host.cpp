@@ -57,3 +57,10 @@ extern "C" int fh_segments(const double *ts, const double *q, const double *t, i
         return -1;
     }
 }
+// EventCalibSpline::fitSpline (BsplineReal constructor fit): knots (cpNum + 4) and control points (cpNum x dim)
+extern "C" void fh_fit_spline(const double *us, const double *data, int n, int dim, int cpNum, double *knots, double *cp) {
+    std::vector<double> u(us, us + n), d(data, data + (size_t) n * dim), k, c;
+    EventCalibSpline::fitSpline(u, d, dim, cpNum, k, c);
+    std::copy(k.begin(), k.end(), knots);
+    std::copy(c.begin(), c.end(), cp);
+}

@@ -1,0 +1,144 @@
+"""Pins the cost-evaluation oracle to the reference's OWN source text: oracle/_ref/libref_functor.so is the UNMODIFIED
+`CalibReprojectionError::operator()` / `unDistort` (event_camera_calib/include/opengv2/event_camera_calib/EventCalibSpline.hpp:
+36-63,158-250) and `BsplineReal` (core/spline/include/opengv2/spline/BsplineReal.hpp) compiled where they lie against the
+stand-in Eigen / Ceres / Sophus headers of oracle/shim_functor/ (oracle/Makefile, oracle/ref_functor_capi.cpp).
+
+  * restated functor (oracle/ecb_oracle_cost.cpp) == reference functor on Jet<37>: value and all 37 partials BIT-EXACT
+  * reference functor on double vs on Jet: 1e-12 relative (ceres' Jet divides by multiplying with the reciprocal)
+  * the product's closed-form residual / Jacobian (csrc/ecb_residual.h, host build) vs the reference functor: 1e-9 relative
+  * knot vector (NURBS-book eq. 9.68), findSpan, dersBasisFuns: bit-exact for the oracle, the Python builder and the façade
+  * control points of the reference's constructor fit vs the façade's EventCalibSpline::fitSpline: 1e-12 relative (the
+    stand-in LDLT factorises in another order than Eigen's SimplicialLDLT; same normal equations)
+
+The library is built in the build container (where /root/reference exists) and travels as a prebuilt file; without it the
+tests skip."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def ref(oracle_mod):
+    oracle_mod.build()
+    if not oracle_mod.have_ref_functor():
+        pytest.skip("oracle/_ref/libref_functor.so not built (no /root/reference here)")
+    return oracle_mod
+
+
+def _random_case(rng, cam):
+    intr = cam.intrinsics() * (1 + rng.normal(0, 0.01, 9))
+    q = rng.normal(0, 1, 4)
+    q /= np.linalg.norm(q)
+    rcp = np.ascontiguousarray(q[None, :] + rng.normal(0, 0.05, (4, 4)))
+    tcp = np.ascontiguousarray(np.array([20, 20, -75.0])[None, :] + rng.normal(0, 2, (4, 3)))
+    obs = np.array([rng.integers(0, 346), rng.integers(0, 260)], float)
+    lm = np.array([rng.uniform(0, 40), rng.uniform(0, 44), 0.0])
+    b = rng.uniform(0, 1, 4)
+    b /= b.sum()
+    return intr, rcp, tcp, obs, lm, b
+
+
+def test_restated_functor_is_bit_identical_to_the_reference_source(ref):
+    from eventcalib_b200 import synth
+    rng = np.random.default_rng(2024)
+    cam = synth.Camera()
+    for _ in range(1000):
+        intr, rcp, tcp, obs, lm, b = _random_case(rng, cam)
+        r0, j0 = ref.residual_jac(intr, rcp, tcp, obs, lm, 1.75, b)
+        r1, j1, rd = ref.ref_residual_jac(intr, rcp, tcp, obs, lm, 1.75, b)
+        assert r0 == r1
+        np.testing.assert_array_equal(j0, j1)
+        assert abs(rd - r1) <= 1e-12 * max(1.0, abs(r1))
+
+
+def test_undistort_reference_source(ref):
+    from eventcalib_b200 import synth
+    rng = np.random.default_rng(5)
+    cam = synth.Camera()
+    intr = cam.intrinsics()
+    for _ in range(200):
+        obs = np.array([rng.integers(0, 346), rng.integers(0, 260)], float)
+        X = ref.ref_undistort(intr, obs)
+        x, y = (obs[0] - intr[2]) / intr[0], (obs[1] - intr[3]) / intr[1]
+        r2 = x * x + y * y
+        s = 1.0 + intr[4] * r2 + intr[5] * r2**2 + intr[6] * r2**3 + intr[7] * r2**4 + intr[8] * r2**5
+        np.testing.assert_allclose(X, [x * s, y * s, 1.0], rtol=1e-14)
+
+
+def test_product_residual_header_vs_reference_source(ref):
+    """csrc/ecb_residual.h (the closed-form residual + Jacobian the kernels use), built for the host like in
+    test_oracle_cost.py, against the reference functor: 1e-9 relative (north star), measured ~1e-12.  The 1x37 ambient
+    Jacobian of the functor goes to the 1x33 tangent one through EigenQuaternionParameterization's Plus Jacobian, like in
+    Ceres; the Huber corrector is switched off (huge threshold) so that the raw functor is what is compared."""
+    so = os.path.join(ROOT, "tests", "_build", "libresid_host.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so,
+                           os.path.join(ROOT, "tests", "helpers", "residual_host.cpp")])
+    h = C.CDLL(so)
+    h.host_residual.restype = C.c_double
+    from eventcalib_b200 import synth
+    rng = np.random.default_rng(77)
+    cam = synth.Camera()
+    worst = 0.0
+    for _ in range(300):
+        intr, Q, T, obs, lm, b = _random_case(rng, cam)
+        r1, jac, _ = ref.ref_residual_jac(intr, Q, T, obs, lm, 1.75, b)
+        J = np.zeros(33)
+        cost, raw = C.c_double(), C.c_double()
+        res = h.host_residual(P(intr), P(Q), P(T), P(b), P(obs), P(lm), C.c_double(1.75), C.c_double(1e30), P(J),
+                              C.byref(cost), C.byref(raw))
+        Jr = np.zeros(33)
+        Jr[:9] = jac[:9]
+        for k in range(4):
+            x, y, z, w = Q[k]
+            Jr[9 + 3 * k: 12 + 3 * k] = jac[9 + 4 * k: 13 + 4 * k] @ np.array([[w, z, -y], [-z, w, x], [y, -x, w], [-x, -y, -z]])
+        Jr[21:] = jac[25:]
+        assert abs(res - r1) <= 1e-9 * max(1.0, abs(r1)) and abs(raw.value - r1) <= 1e-9 * max(1.0, abs(r1))
+        worst = max(worst, np.abs(J - Jr).max() / np.abs(Jr).max())
+    assert worst < 1e-9, worst
+
+
+def test_spline_knots_basis_and_fit_vs_reference_source(ref):
+    from eventcalib_b200 import synth, spline
+    lib = None
+    so = os.path.join(ROOT, "tests", "_build", "libfacade_host.so")
+    import eventcalib_b200.build as b
+    b.build()
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "helpers", "facade_host.cpp"),
+                           "-L" + os.path.join(ROOT, "eventcalib_b200"), "-lecb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "eventcalib_b200")])
+    lib = C.CDLL(so)
+    board = synth.Board()
+    traj = synth.Trajectory(3, board, 78.0)
+    rng = np.random.default_rng(0)
+    us = np.sort(rng.uniform(1.0, 1.5, 80))
+    us[0], us[-1] = 1.0, 1.5
+    q, tw = traj.quat_xyzw(us)
+    for data in (tw, q):
+        data = np.ascontiguousarray(data)
+        dim = data.shape[1]
+        for n_cp in (4, 5, 9, 20, 40):
+            kn, cp, n = ref.ref_spline_fit(us, data, n_cp)
+            assert n == n_cp
+            np.testing.assert_array_equal(kn, ref.knots(us, n_cp))            # oracle restatement
+            np.testing.assert_array_equal(kn, spline.knot_vector(us, n_cp))   # Python builder
+            kn2, cp2 = np.zeros(n_cp + 4), np.zeros((n_cp, dim))
+            lib.fh_fit_spline(P(us), P(data), len(us), dim, n_cp, P(kn2), P(cp2))   # façade: EventCalibSpline::fitSpline
+            np.testing.assert_array_equal(kn, kn2)
+            assert np.abs(cp - cp2).max() <= 1e-12 * np.abs(cp).max()
+            np.testing.assert_array_equal(cp[0], data[0])
+            np.testing.assert_array_equal(cp[-1], data[-1])
+    kn = ref.knots(us, 20)
+    for u in np.r_[rng.uniform(1.0, 1.5, 3000), us, kn]:
+        s1, N1 = ref.ref_basis(kn, float(u))
+        s2, N2 = ref.basis(kn, float(u))
+        assert s1 == s2 == spline.find_span(kn, float(u))
+        np.testing.assert_array_equal(N1, N2)
