@@ -7,8 +7,9 @@ Libraries (built by ``oracle/Makefile``; see the headers of the .cpp files for w
   * ``_build/libecb_oracle.so``  — the CPU restatement (always buildable)
   * ``_ref/libref_dbscan.so``    — the UNMODIFIED reference ``dbscan.h`` + ``kdtree.cpp`` compiled in place
   * ``_ref/libref_frontend.so``  — restated glue + verbatim reference DBSCAN (the "reference" CPU baseline)
-  * ``_ref/libref_functor.so``   — the UNMODIFIED reference residual functor (EventCalibSpline.hpp) and B-spline
-                                   (BsplineReal.hpp) compiled in place against the stand-in Eigen of ``shim_functor/``
+  * ``_ref/libref_functor.so``   — the UNMODIFIED reference residual functor (EventCalibSpline.hpp), B-spline
+                                   (BsplineReal.hpp), event window (EventFrame.cpp + utility.hpp hash) and record reader
+                                   (Event.hpp) compiled in place against the stand-in headers of ``shim_functor/``
 """
 import ctypes as C
 import os
@@ -114,6 +115,28 @@ def ref_basis(knots, u):
     N = np.zeros(4)
     ref_functor_lib().ref_basis(_p(kn, _dp), C.c_int(len(kn)), C.c_double(u), C.byref(span), _p(N, _dp))
     return span.value, N
+
+
+def ref_event_frame(t, x, y, pol, t0, t1):
+    """The reference's own EventFrame constructor (event/src/EventFrame.cpp:10-36): (positive xy, negative xy) in the
+    iteration order of its hash sets."""
+    t, x, y = (np.ascontiguousarray(v, np.float64) for v in (t, x, y))
+    pol = np.ascontiguousarray(pol, np.uint8)
+    n = len(t)
+    pos, neg = np.zeros((max(n, 1), 2)), np.zeros((max(n, 1), 2))
+    n_pos, n_neg = C.c_longlong(), C.c_longlong()
+    ref_functor_lib().ref_event_frame(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(n), C.c_double(t0),
+                                      C.c_double(t1), _p(pos, _dp), _p(neg, _dp), C.byref(n_pos), C.byref(n_neg))
+    return pos[:n_pos.value].copy(), neg[:n_neg.value].copy()
+
+
+def ref_read_bin(path, cap):
+    """The reference's own record reader (Event.hpp:41-47 operator>>) over a .bin file."""
+    t, x, y, pol = np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros(cap, np.uint8)
+    lib = ref_functor_lib()
+    lib.ref_read_bin.restype = C.c_longlong
+    n = lib.ref_read_bin(path.encode(), C.c_longlong(cap), _p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp))
+    return t[:n], x[:n], y[:n], pol[:n]
 
 
 def ref_dbscan_lib():

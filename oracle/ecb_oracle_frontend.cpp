@@ -10,7 +10,10 @@
 // ref_dbscan_capi.cpp) as ordered lists in tests/test_oracle_dbscan.py, and the
 // toy known-answer of SURVEY.md Appendix E.  The window/dedupe order uses the
 // real libstdc++ std::unordered_set with the reference's hash, so it is the
-// reference's order by construction (known answers: SURVEY.md Appendix E).
+// reference's order by construction (known answers: SURVEY.md Appendix E), and
+// it is checked element for element against the reference's own EventFrame.cpp
+// compiled in place (oracle/_ref/libref_functor.so, ref_functor_capi.cpp) in
+// tests/test_oracle_reference_source.py.
 // extractFeatures / fitCircle have no reference test or golden vector and the
 // reference cannot be built here (OpenCV/Eigen/nanoflann absent): PARITY
 // UNPINNED for those; they are cross-checked only by independent numpy code.

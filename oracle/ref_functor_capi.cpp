@@ -4,6 +4,10 @@
 //   opengv2::EventCalibSpline::CalibReprojectionError::operator()<T>   event_camera_calib/include/opengv2/event_camera_calib/
 //   opengv2::EventCalibSpline::unDistort<T>                            EventCalibSpline.hpp:36-63,158-250
 //   opengv2::BsplineReal<dim> (ctor fit, findSpan, dersBasisFuns, evaluate)   core/spline/include/opengv2/spline/BsplineReal.hpp
+//   opengv2::EventFrame::EventFrame (window, per-polarity pixel sets, +/- cancellation, hash-set order)
+//                                                                      camera_calibration/event/src/EventFrame.cpp:10-36 with
+//                                                                      EigenMatrixHash (core/utility/.../utility.hpp:38-51)
+//   opengv2::Event operator>> (the 25-byte record reader)              camera_calibration/event/include/opengv2/event/Event.hpp:41-47
 //
 // against the stand-in headers of oracle/shim_functor/ (Eigen / Ceres / Sophus are external and absent: what the two reference
 // headers need from Eigen is restated there; nothing of the functor's or the spline's own arithmetic is).  T = double gives the
@@ -162,5 +166,56 @@ void ref_basis(const double *knots, int nk, double u, int *span, double *N4) {
     sp.dersBasisFuns(u, s, 0, ders);
     *span = (int) s;
     for (int j = 0; j < 4; ++j) N4[j] = ders[0][(size_t) j];
+}
+}
+
+// ---- EventFrame (a2) and the record reader (a1) ----
+#include <fstream>
+#include <unordered_set>
+
+#include <opengv2/event/Event.hpp>
+#include <opengv2/event/EventFrame.hpp>
+
+namespace {
+struct FrameProbe : opengv2::EventFrame {
+    FrameProbe(opengv2::EventContainer::Ptr c, const std::pair<double, double> &d) : opengv2::EventFrame(c, d) {}
+    bool rectifyFeatures(const std::unordered_set<int> &, const Eigen::Ref<const Eigen::Matrix3d> &,
+                         const Eigen::Ref<const Eigen::Vector3d> &) override {
+        return true;
+    }
+    const opengv2::vectorofEigenMatrix<Eigen::Vector2d> &pos() const { return positiveEvents_; }
+    const opengv2::vectorofEigenMatrix<Eigen::Vector2d> &neg() const { return negativeEvents_; }
+};
+}  // namespace
+
+extern "C" {
+// The reference's EventFrame constructor over events (t, x, y, polarity) inserted like its load loop does
+// (event_camera_calib/test/eventCameraCalib.cpp:158-160): closed window [t0, t1]; pixel lists in the hash sets' iteration order
+void ref_event_frame(const double *t, const double *x, const double *y, const unsigned char *pol, long long n, double t0, double t1,
+                     double *pos_xy, double *neg_xy, long long *n_pos, long long *n_neg) {
+    auto container = std::make_shared<opengv2::EventContainer>();
+    container->camera = std::make_shared<opengv2::CameraBase>(Eigen::Vector2d(346, 260));
+    for (long long i = 0; i < n; ++i)
+        container->container.emplace(t[i], opengv2::Event_loc_pol(Eigen::Vector2d(x[i], y[i]), pol[i] != 0));
+    FrameProbe f(container, std::make_pair(t0, t1));
+    *n_pos = (long long) f.pos().size();
+    *n_neg = (long long) f.neg().size();
+    for (size_t i = 0; i < f.pos().size(); ++i) pos_xy[2 * i] = f.pos()[i][0], pos_xy[2 * i + 1] = f.pos()[i][1];
+    for (size_t i = 0; i < f.neg().size(); ++i) neg_xy[2 * i] = f.neg()[i][0], neg_xy[2 * i + 1] = f.neg()[i][1];
+}
+
+// the reference's record reader: Event's operator>> until the stream fails; returns the number of records read
+long long ref_read_bin(const char *path, long long cap, double *t, double *x, double *y, unsigned char *pol) {
+    std::ifstream is(path, std::ifstream::binary | std::ifstream::in);
+    long long n = 0;
+    opengv2::Event e;
+    while (n < cap && (is >> e) && is.good()) {
+        t[n] = e.timeStamp();
+        x[n] = e.location()[0];
+        y[n] = e.location()[1];
+        pol[n] = e.polarity() ? 1 : 0;
+        ++n;
+    }
+    return n;
 }
 }

@@ -1,0 +1,4 @@
+// TEST INFRASTRUCTURE.  Empty stand-in (the object model is not on the hot path).
+#ifndef ECB_ORACLE_BODYFRAME_SHIM
+#define ECB_ORACLE_BODYFRAME_SHIM
+#endif

@@ -10,6 +10,10 @@ stand-in Eigen / Ceres / Sophus headers of oracle/shim_functor/ (oracle/Makefile
   * control points of the reference's constructor fit vs the façade's EventCalibSpline::fitSpline: 1e-12 relative (the
     stand-in LDLT factorises in another order than Eigen's SimplicialLDLT; same normal equations)
 
+  * event window (a2): pixel lists of both polarities after dedupe / cancellation, in hash-set iteration order, element for
+    element equal between the restatement (oracle/ecb_oracle_frontend.cpp) and the reference's EventFrame.cpp compiled in
+    place with its own EigenMatrixHash (utility.hpp:38-51); record reader (a1): Event.hpp's operator>> reads our .bin files
+
 The library is built in the build container (where /root/reference exists) and travels as a prebuilt file; without it the
 tests skip."""
 import ctypes as C
@@ -142,3 +146,36 @@ def test_spline_knots_basis_and_fit_vs_reference_source(ref):
         s2, N2 = ref.basis(kn, float(u))
         assert s1 == s2 == spline.find_span(kn, float(u))
         np.testing.assert_array_equal(N1, N2)
+
+
+def test_event_frame_and_record_reader_vs_reference_source(ref, tmp_path):
+    """a1 / a2: the reference's EventFrame constructor (event/src/EventFrame.cpp:10-36, closed window, per-polarity sets of
+    distinct pixels, +/- cancellation, std::unordered_set iteration order with the reference's own hash) and its record
+    reader (Event.hpp:41-47), compiled in place, against the restatement the GPU tests use."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(60000, 346, 260, t0=5.0, duration=0.03, seed=5)
+    t, x, y, p = ev["t"], ev["x"], ev["y"], ev["p"]
+    windows = [(5.0, 5.0015), (5.001, 5.004), (5.0101, 5.0116), (5.02, 5.03), (4.0, 4.5), (5.0, 5.03),
+               (float(t[100]), float(t[4000])),      # bounds exactly on time stamps: the window is closed on both ends
+               (float(t[7]), float(t[7]))]
+    for a, b in windows:
+        P0, N0, lo, hi = ref.event_frame(t, x, y, p, a, b)
+        P1, N1 = ref.ref_event_frame(t, x, y, p, a, b)
+        np.testing.assert_array_equal(P0, P1)
+        np.testing.assert_array_equal(N0, N1)
+    # every rehash boundary of the hash sets: growing prefixes of one window
+    sel = np.nonzero((t >= 5.0) & (t <= 5.02))[0]
+    for m in (1, 2, 12, 13, 14, 28, 29, 30, 58, 59, 60, 126, 127, 128, 256, 257, 258, 540, 541, 542, 1108, 1109, 1110, 2357, 5000):
+        s = sel[:m]
+        P0, N0, _, _ = ref.event_frame(t[s], x[s], y[s], p[s], 0.0, 10.0)
+        P1, N1 = ref.ref_event_frame(t[s], x[s], y[s], p[s], 0.0, 10.0)
+        np.testing.assert_array_equal(P0, P1)
+        np.testing.assert_array_equal(N0, N1)
+    path = str(tmp_path / "e.bin")
+    synth.write_bin(path, ev)
+    t1, x1, y1, p1 = ref.ref_read_bin(path, len(t) + 8)
+    assert len(t1) == len(t)
+    np.testing.assert_array_equal(t1, t)
+    np.testing.assert_array_equal(x1, x)
+    np.testing.assert_array_equal(y1, y)
+    np.testing.assert_array_equal(p1, p)
