@@ -8,8 +8,10 @@ Libraries (built by ``oracle/Makefile``; see the headers of the .cpp files for w
   * ``_ref/libref_dbscan.so``    — the UNMODIFIED reference ``dbscan.h`` + ``kdtree.cpp`` compiled in place
   * ``_ref/libref_frontend.so``  — restated glue + verbatim reference DBSCAN (the "reference" CPU baseline)
   * ``_ref/libref_functor.so``   — the UNMODIFIED reference residual functor (EventCalibSpline.hpp), B-spline
-                                   (BsplineReal.hpp), event window (EventFrame.cpp + utility.hpp hash) and record reader
-                                   (Event.hpp) compiled in place against the stand-in headers of ``shim_functor/``
+                                   (BsplineReal.hpp), event window (EventFrame.cpp + utility.hpp hash), record reader
+                                   (Event.hpp) and CirclesEventFrame.cpp (extractFeatures / fitCircle / rectifyFeatures /
+                                   findCenter, with dbscan.h + kdtree.cpp) compiled in place against the stand-in headers
+                                   of ``shim_functor/``
 """
 import ctypes as C
 import os
@@ -137,6 +139,50 @@ def ref_read_bin(path, cap):
     lib.ref_read_bin.restype = C.c_longlong
     n = lib.ref_read_bin(path.encode(), C.c_longlong(cap), _p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp))
     return t[:n], x[:n], y[:n], pol[:n]
+
+
+def ref_extract(t, x, y, pol, t0, t1, W, H, fitCircle, eps=4.0, minS=2, clusterMin=5, knn_num=3, rows=9, cols=4, asym=True,
+                square=5.5, radius=1.75):
+    """The reference's own CirclesEventFrame constructor + extractFeatures() (event_camera_calib/src/CirclesEventFrame.cpp:16-359,
+    with its DBSCAN) on raw events.  Returns dict(found, cand_f32 = the candidate centres handed to findCirclesGrid as
+    cv::Point2f (None when :127-129 returned before), features = rows*cols x (cx, cy, r) in board order when found, rthr)."""
+    t, x, y = (np.ascontiguousarray(v, np.float64) for v in (t, x, y))
+    pol = np.ascontiguousarray(pol, np.uint8)
+    prm = np.array([cols, rows, square, 1.0 if asym else 0.0, radius, eps, minS, clusterMin, knn_num, fitCircle], np.float64)
+    cap = 1024
+    cand = np.zeros((cap, 2), np.float32)
+    n_cand, rthr = C.c_int(), C.c_double()
+    feats = np.zeros((rows * cols, 3))
+    ok = ref_functor_lib().ref_extract(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)), C.c_double(t0),
+                                       C.c_double(t1), C.c_int(W), C.c_int(H), _p(prm, _dp), cand.ctypes.data_as(C.c_void_p),
+                                       C.c_int(cap), C.byref(n_cand), _p(feats, _dp), C.byref(rthr))
+    return dict(found=bool(ok), cand_f32=cand[:n_cand.value].copy() if n_cand.value >= 0 else None, features=feats, rthr=rthr.value)
+
+
+def ref_fit_circle(pxy, nxy):
+    """The reference's own CirclesEventFrame::fitCircle (CirclesEventFrame.cpp:361-415)."""
+    pxy = np.ascontiguousarray(pxy, np.float64).reshape(-1, 2)
+    nxy = np.ascontiguousarray(nxy, np.float64).reshape(-1, 2)
+    out = np.zeros(3)
+    ref_functor_lib().ref_fit_circle(_p(pxy, _dp), C.c_int(len(pxy)), _p(nxy, _dp), C.c_int(len(nxy)), _p(out, _dp))
+    return out
+
+
+def ref_rectify(t, x, y, pol, t0, t1, W, H, fitCircle, image_points, find_xy=None, rows=9, cols=4):
+    """The reference's own extractFeatures() + rectifyFeatures() (CirclesEventFrame.cpp:417-638) with the caller's projections
+    image_points[rows*cols][5][2]; then findCenter() (CirclesEventFrame.hpp:50-65) for the pixels find_xy.
+    Returns (verdict: -1 extractFeatures failed / 0 / 1, out[rows*cols][3] with r = -1 for deleted features, landmark ids)."""
+    t, x, y = (np.ascontiguousarray(v, np.float64) for v in (t, x, y))
+    pol = np.ascontiguousarray(pol, np.uint8)
+    img = np.ascontiguousarray(image_points, np.float64)
+    prm = np.array([cols, rows, 5.5, 1.0, 1.75, 4.0, 2, 5, 3, fitCircle], np.float64)
+    out = np.zeros((rows * cols, 3))
+    fxy = np.ascontiguousarray(find_xy if find_xy is not None else np.zeros((0, 2)), np.float64)
+    fid = np.full(max(len(fxy), 1), -2, np.int32)
+    rc = ref_functor_lib().ref_rectify(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)), C.c_double(t0),
+                                       C.c_double(t1), C.c_int(W), C.c_int(H), _p(prm, _dp), _p(img, _dp), _p(out, _dp), _p(fxy, _dp),
+                                       C.c_int(len(fxy)), _p(fid, _ip))
+    return rc, out, fid[:len(fxy)]
 
 
 def ref_dbscan_lib():

@@ -14,9 +14,14 @@
 // it is checked element for element against the reference's own EventFrame.cpp
 // compiled in place (oracle/_ref/libref_functor.so, ref_functor_capi.cpp) in
 // tests/test_oracle_reference_source.py.
-// extractFeatures / fitCircle have no reference test or golden vector and the
-// reference cannot be built here (OpenCV/Eigen/nanoflann absent): PARITY
-// UNPINNED for those; they are cross-checked only by independent numpy code.
+// extractFeatures / fitCircle / rectifyFeatures have no reference test or golden
+// vector, and the reference's own build needs OpenCV / Eigen / nanoflann; they
+// are pinned instead against the reference's CirclesEventFrame.cpp compiled in
+// place with stand-in headers and hooks (oracle/shim_functor/,
+// ref_functor_capi.cpp -> oracle/_ref/libref_functor.so): same candidate lists,
+// bit-identical features / rectified features / verdicts on raw events
+// (tests/test_oracle_reference_source.py).  Still unpinned: the external pieces
+// the stand-ins restate (Eigen PartialPivLU, nanoflann tie order, OpenCV).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -8,6 +8,12 @@
 //                                                                      camera_calibration/event/src/EventFrame.cpp:10-36 with
 //                                                                      EigenMatrixHash (core/utility/.../utility.hpp:38-51)
 //   opengv2::Event operator>> (the 25-byte record reader)              camera_calibration/event/include/opengv2/event/Event.hpp:41-47
+//   opengv2::CirclesEventFrame (ctor, extractFeatures, fitCircle, rectifyFeatures, findCenter) with the reference's DBSCAN
+//                                                                      camera_calibration/event_camera_calib/src/CirclesEventFrame.cpp,
+//                                                                      .../include/opengv2/event_camera_calib/CirclesEventFrame.hpp,
+//                                                                      camera_calibration/dbscan/{include/dbscan.h,src/kdtree.cpp}
+//     hooks (OpenCV is absent): findCirclesGrid = the product's grid finder (include/ecb/circles_grid.hpp) on the candidate
+//     centres the reference hands over; projectPoints = the 5 image points per board circle supplied by the caller
 //
 // against the stand-in headers of oracle/shim_functor/ (Eigen / Ceres / Sophus are external and absent: what the two reference
 // headers need from Eigen is restated there; nothing of the functor's or the spline's own arithmetic is).  T = double gives the
@@ -217,5 +223,144 @@ long long ref_read_bin(const char *path, long long cap, double *t, double *x, do
         ++n;
     }
     return n;
+}
+}
+
+// ---- CirclesEventFrame (a4 extractFeatures, a5 fitCircle, a6 rectifyFeatures, a7 findCenter) ----
+#include <cv_calib.hpp>
+#include <opengv2/event_camera_calib/CirclesEventFrame.hpp>
+#include <opengv2/sensor/PinholeCamera.hpp>
+
+#include "../include/ecb/circles_grid.hpp"  // the product's grid finder, used as the findCirclesGrid hook
+
+namespace hook {
+std::vector<cv::Point2f> grid_points;      // candidate centres of the last findCirclesGrid call (cv::Point2f like the reference's)
+int grid_calls = 0;
+const double *image_points = nullptr;      // [features][5][2] for projectPoints
+int project_calls = 0;
+}  // namespace hook
+
+namespace cv {
+bool findCirclesGrid(const std::vector<Point2f> &points_, Size patternSize, std::vector<Point2f> &centers, int flags) {
+    ++hook::grid_calls;
+    if (flags & CALIB_CB_CLUSTERING) return false;  // the reference's second attempt (CirclesEventFrame.cpp:335-336)
+    hook::grid_points = points_;
+    std::vector<ecb::Pt2> pts;
+    for (const auto &p : points_) pts.push_back(ecb::Pt2{(double) p.x, (double) p.y});
+    std::vector<int> order;
+    if (!ecb::find_asymmetric_circles_grid(pts, patternSize.height, patternSize.width, order)) return false;
+    centers.clear();
+    for (int idx : order) centers.push_back(points_[(size_t) idx]);
+    return true;
+}
+void projectPoints(const std::vector<Point3f> &objectPoints, const Mat &, const Mat &, const Mat &, const Mat &,
+                   std::vector<Point2f> &imagePoints) {
+    imagePoints.clear();
+    for (size_t i = 0; i < objectPoints.size(); ++i) {
+        const double *p = hook::image_points + ((size_t) hook::project_calls * objectPoints.size() + i) * 2;
+        imagePoints.emplace_back(p[0], p[1]);
+    }
+    ++hook::project_calls;
+}
+}  // namespace cv
+
+namespace {
+struct CircleProbe : opengv2::CirclesEventFrame {
+    CircleProbe(opengv2::EventContainer::Ptr c, const std::pair<double, double> &d, CirclePatternParameters::Ptr pattern, Params p)
+        : opengv2::CirclesEventFrame(c, d, pattern, p) {}
+    opengv2::vectorofEigenMatrix<Eigen::Vector2d> &pos() { return positiveEvents_; }
+    opengv2::vectorofEigenMatrix<Eigen::Vector2d> &neg() { return negativeEvents_; }
+    std::vector<opengv2::FeatureBase::Ptr> &feats() { return features_; }
+    void fit(const std::vector<uint> &ps, const std::vector<uint> &ns, Eigen::Vector2d &c, double &r) { fitCircle(ps, ns, c, r); }
+    double rthr() const { return circleRadiusThreshold_; }
+};
+
+std::shared_ptr<CircleProbe> make_frame(const double *t, const double *x, const double *y, const unsigned char *pol, long long n,
+                                        double t0, double t1, int W, int H, const double *prm) {
+    auto container = std::make_shared<opengv2::EventContainer>();
+    container->camera = std::make_shared<opengv2::PinholeCamera>(Eigen::Vector2d(W, H));
+    for (long long i = 0; i < n; ++i)
+        container->container.emplace(t[i], opengv2::Event_loc_pol(Eigen::Vector2d(x[i], y[i]), pol[i] != 0));
+    cv::FileStorage fs;  // the reference's own parameter constructors read these keys (parameters.hpp:15-21, CirclesEventFrame.cpp:42-48)
+    fs.kv = {{"BoardSize_Cols", prm[0]}, {"BoardSize_Rows", prm[1]}, {"Square_Size", prm[2]}, {"Is_Pattern_Asymmetric", prm[3]},
+             {"Circles_Radius", prm[4]}, {"dbscan_eps", prm[5]}, {"dbscan_startMinSample", prm[6]}, {"clusterMinSample", prm[7]},
+             {"knn_num", prm[8]}, {"fitCircle", prm[9]}};
+    auto pattern = std::make_shared<CirclePatternParameters>(fs);
+    opengv2::CirclesEventFrame::Params params(fs);
+    return std::make_shared<CircleProbe>(container, std::make_pair(t0, t1), pattern, params);
+}
+}  // namespace
+
+extern "C" {
+// prm = cols rows square asymmetric radius | eps startMinSample clusterMinSample knn fitCircle.
+// Runs the reference's constructor + extractFeatures().  cand_f32[cap][2]: the candidate centres it handed to findCirclesGrid
+// (cv::Point2f); features[rows*cols][3]: centre and radius of features_ in board order when the grid was found.
+// Returns 1 found / 0 not found; *n_cand = -1 when findCirclesGrid was never reached (too few clusters, :127-129).
+int ref_extract(const double *t, const double *x, const double *y, const unsigned char *pol, long long n, double t0, double t1, int W,
+                int H, const double *prm, float *cand_f32, int cap, int *n_cand, double *features, double *rthr) {
+    auto f = make_frame(t, x, y, pol, n, t0, t1, W, H, prm);
+    hook::grid_points.clear();
+    hook::grid_calls = 0;
+    const bool ok = f->extractFeatures();
+    *rthr = f->rthr();
+    *n_cand = hook::grid_calls ? (int) hook::grid_points.size() : -1;
+    for (size_t i = 0; i < hook::grid_points.size() && (int) i < cap; ++i)
+        cand_f32[2 * i] = hook::grid_points[i].x, cand_f32[2 * i + 1] = hook::grid_points[i].y;
+    if (ok)
+        for (size_t i = 0; i < f->feats().size(); ++i) {
+            auto c = dynamic_cast<opengv2::CalibCircle *>(f->feats()[i].get());
+            features[3 * i] = c->location()[0], features[3 * i + 1] = c->location()[1], features[3 * i + 2] = c->radius;
+        }
+    return ok ? 1 : 0;
+}
+
+// the reference's fitCircle over explicit point sets (+ then -)
+void ref_fit_circle(const double *pxy, int np, const double *nxy, int nn, double *out3) {
+    const double t = 0, xx = 0, yy = 0;
+    const unsigned char pp = 1;
+    const double prm[10] = {4, 9, 5.5, 1, 1.75, 4, 2, 5, 3, 1};
+    auto f = make_frame(&t, &xx, &yy, &pp, 0, 0, 1, 346, 260, prm);
+    std::vector<uint> ps, ns;
+    for (int i = 0; i < np; ++i) f->pos().emplace_back(pxy[2 * i], pxy[2 * i + 1]), ps.push_back((uint) i);
+    for (int i = 0; i < nn; ++i) f->neg().emplace_back(nxy[2 * i], nxy[2 * i + 1]), ns.push_back((uint) i);
+    Eigen::Vector2d c;
+    double r;
+    f->fit(ps, ns, c, r);
+    out3[0] = c[0], out3[1] = c[1], out3[2] = r;
+}
+
+// extractFeatures() then rectifyFeatures() with the caller's projections image_points[rows*cols][5][2] (centre + 4 quadrant
+// points per board circle, :431-456).  out[rows*cols][3]: rectified centre / radius per board circle, radius -1 = deleted.
+// Returns -1 when extractFeatures() fails, else rectifyFeatures()'s verdict (0 / 1); find_xy[n_find][2] -> find_id[n_find]: the
+// landmark findCenter() returns for a pixel afterwards (-1: none), only when the verdict is 1.
+int ref_rectify(const double *t, const double *x, const double *y, const unsigned char *pol, long long n, double t0, double t1, int W,
+                int H, const double *prm, const double *image_points, double *out, const double *find_xy, int n_find, int *find_id) {
+    auto f = make_frame(t, x, y, pol, n, t0, t1, W, H, prm);
+    hook::grid_calls = 0;
+    if (!f->extractFeatures()) return -1;
+    const int nc = (int) f->feats().size();
+    std::vector<opengv2::LandmarkBase::Ptr> lms;  // the board points (EventCalibIni.cpp:99-113), kept alive here
+    const int cols = (int) prm[0];
+    for (int i = 0; i < nc; ++i) {
+        const int r = i / cols, c = i % cols;
+        lms.push_back(std::make_shared<opengv2::LandmarkBase>(i, Eigen::Vector3d((prm[3] != 0 ? (2 * c + r % 2) : c) * prm[2], r * prm[2], 0)));
+        f->feats()[(size_t) i]->setLandmark(lms.back());
+    }
+    for (int i = 0; i < nc; ++i) out[3 * i] = out[3 * i + 1] = 0.0, out[3 * i + 2] = -1.0;
+    hook::image_points = image_points;
+    hook::project_calls = 0;
+    Eigen::Matrix3d R;
+    const bool ok = f->rectifyFeatures(std::unordered_set<int>(), R, Eigen::Vector3d(0, 0, 0));
+    for (auto &fb : f->feats()) {
+        auto c = dynamic_cast<opengv2::CalibCircle *>(fb.get());
+        const int id = c->landmark()->id();
+        out[3 * id] = c->location()[0], out[3 * id + 1] = c->location()[1], out[3 * id + 2] = c->radius;
+    }
+    if (ok)
+        for (int i = 0; i < n_find; ++i) {
+            auto lm = f->findCenter(Eigen::Vector2d(find_xy[2 * i], find_xy[2 * i + 1]));
+            find_id[i] = lm ? lm->id() : -1;
+        }
+    return ok ? 1 : 0;
 }
 }

@@ -1,8 +1,13 @@
-// TEST INFRASTRUCTURE.  Stand-in for <nanoflann.hpp> (external, absent): the reference's utility.hpp names two nanoflann
-// templates in an alias (SO3_KDTree) that the code compiled in place through this directory never instantiates.
+// TEST INFRASTRUCTURE.  Stand-in for <nanoflann.hpp> (external, absent): the names the reference mentions.  The searches
+// themselves are restated in KDTreeVectorOfVectorsAdaptor.h of this directory.
 #ifndef ECB_ORACLE_NANOFLANN_SHIM
 #define ECB_ORACLE_NANOFLANN_SHIM
 namespace nanoflann {
+struct metric_L2 {};
+struct metric_L2_Simple {};
+struct SearchParams {
+    SearchParams(int = 32, float = 0, bool = true) {}
+};
 template <class Distance, class DatasetAdaptor, int DIM = -1, typename IndexType = unsigned long>
 class KDTreeSingleIndexAdaptor;
 template <class T, class DataSource, typename DistanceType = T>

@@ -14,6 +14,13 @@ stand-in Eigen / Ceres / Sophus headers of oracle/shim_functor/ (oracle/Makefile
     element equal between the restatement (oracle/ecb_oracle_frontend.cpp) and the reference's EventFrame.cpp compiled in
     place with its own EigenMatrixHash (utility.hpp:38-51); record reader (a1): Event.hpp's operator>> reads our .bin files
 
+  * extractFeatures / fitCircle / rectifyFeatures / findCenter (a3-a7): the reference's CirclesEventFrame.cpp with its own
+    DBSCAN (dbscan.h + kdtree.cpp) and the real std::nth_element, compiled in place; hooks stand in for the three OpenCV
+    calls (findCirclesGrid = the product's grid finder on the candidate centres the reference hands over, projectPoints =
+    the caller's 5 image points per circle), exhaustive searches for nanoflann.  The restatement (oracle.extract /
+    fit_circle / rectify, what the GPU tests compare with) gives the same candidate lists, and BIT-IDENTICAL feature centres,
+    radii, rectified features and frame verdicts
+
 The library is built in the build container (where /root/reference exists) and travels as a prebuilt file; without it the
 tests skip."""
 import ctypes as C
@@ -179,3 +186,92 @@ def test_event_frame_and_record_reader_vs_reference_source(ref, tmp_path):
     np.testing.assert_array_equal(x1, x)
     np.testing.assert_array_equal(y1, y)
     np.testing.assert_array_equal(p1, p)
+
+
+def _grid():
+    from test_circles_grid import _lib as grid_lib, _order as grid_order
+    return grid_lib(), grid_order
+
+
+def test_extract_features_vs_reference_source(ref):
+    """a3 + a4 + a5 end to end on raw events: reference constructor (window, sets), DBSCAN, cluster filter, nth_element
+    medians, k-NN pairing, memoised Kasa fits, fit-error gates, mutual-best check, grid order -> features_."""
+    from eventcalib_b200 import synth
+    glib, grid_order = _grid()
+    found = total = 0
+    for seed, orbit, amp in ((1001, False, None), (7, True, (0.35, 0.35, 0.3))):
+        ev = synth.make_stream(60000, 346, 260, t0=5.0, duration=0.03, seed=seed, orbit=orbit, rot_amp=amp)
+        t, x, y, p = ev["t"], ev["x"], ev["y"], ev["p"]
+        for fit in (0, 1):
+            for w in synth.tiling_windows(5.0, 5.03, 1.5e-3)[::2]:
+                a, b = float(w[0]), float(w[1])
+                m = (t >= a - 1e-3) & (t <= b + 1e-3)
+                r1 = ref.ref_extract(t[m], x[m], y[m], p[m], a, b, 346, 260, fit)
+                P0, N0, _, _ = ref.event_frame(t, x, y, p, a, b)
+                assert abs(r1["rthr"] - ref.radius_threshold(346, 260, 9, 4, 1, 5.5, 1.75)) == 0
+                r0 = ref.extract(P0, N0, fitCircle=fit, Rthr=r1["rthr"])
+                total += 1
+                if r1["cand_f32"] is None:          # fewer than rows*cols clusters in a polarity (:127-129)
+                    assert not r0["enough"]
+                    continue
+                c0 = r0["cand"]
+                np.testing.assert_array_equal(c0[:, 2:4].astype(np.float32), r1["cand_f32"])
+                ok, order = grid_order(glib, c0[:, 2:4].astype(np.float32).astype(np.float64))
+                assert ok == r1["found"]
+                if ok:
+                    found += 1
+                    np.testing.assert_array_equal(c0[order][:, 2:5], r1["features"])   # centres and radii, bit for bit
+    assert found >= 10 and total >= 30
+
+
+def test_fit_circle_vs_reference_source(ref):
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        c, r = rng.uniform(50, 200, 2), rng.uniform(4, 12)
+        th = rng.uniform(0, 2 * np.pi, 60)
+        pts = np.rint(np.c_[c[0] + r * np.cos(th), c[1] + r * np.sin(th)] + rng.normal(0, 0.5, (60, 2)))
+        np.testing.assert_array_equal(ref.fit_circle(pts[:30], pts[30:]), ref.ref_fit_circle(pts[:30], pts[30:]))
+
+
+def test_rectify_and_find_center_vs_reference_source(ref):
+    """a6 + a7: rectifyFeatures (radius search, quadrant band, cluster expansion, refit, gates, edge scores, 20 % rule) and
+    findCenter on the rectified frame."""
+    from eventcalib_b200 import synth
+    board = synth.Board()
+    cen, sk = board.centres(), board.radius / np.sqrt(2)
+    rng = np.random.default_rng(3)
+    verdicts = {}
+    for seed, fit in ((1001, 0), (1001, 1), (7, 1)):
+        ev = synth.make_stream(60000, 346, 260, t0=5.0, duration=0.03, seed=seed, return_truth=True)
+        cam, traj = ev["camera"], ev["trajectory"]
+        t, x, y, p = ev["t"], ev["x"], ev["y"], ev["p"]
+        for w in synth.tiling_windows(5.0, 5.03, 1.5e-3)[::2]:
+            a, b = float(w[0]), float(w[1])
+            R, tw = traj.pose(np.array([(a + b) / 2]))
+            img = np.zeros((36, 5, 2))
+            for k in range(36):
+                o5 = np.array([cen[k], cen[k] + [sk, sk, 0], cen[k] + [sk, -sk, 0], cen[k] + [-sk, -sk, 0], cen[k] + [-sk, sk, 0]])
+                u, v = synth.project(cam, np.repeat(R, 5, 0), np.repeat(tw, 5, 0), o5)
+                img[k, :, 0], img[k, :, 1] = u, v
+            if rng.uniform() < 0.35:
+                img += rng.normal(0, 3.0, img.shape)          # bad projections: deleted features, rejected frames
+            img = img.astype(np.float32).astype(np.float64)  # vector<cv::Point2f>
+            m = (t >= a - 1e-3) & (t <= b + 1e-3)
+            fxy = np.c_[rng.integers(0, 346, 300), rng.integers(0, 260, 300)].astype(float)
+            rc, out1, fid = ref.ref_rectify(t[m], x[m], y[m], p[m], a, b, 346, 260, fit, img, fxy)
+            if rc < 0:
+                continue
+            P0, N0, _, _ = ref.event_frame(t, x, y, p, a, b)
+            out0, ok0 = ref.rectify(P0, N0, img, 346, 260, fitCircle=fit)
+            assert rc == int(ok0)
+            np.testing.assert_array_equal(out0[:, 2] < 0, out1[:, 2] < 0)
+            keep = out1[:, 2] >= 0
+            np.testing.assert_array_equal(out0[keep], out1[keep])
+            verdicts[rc] = verdicts.get(rc, 0) + 1
+            if rc == 1:   # findCenter: nearest kept circle, accepted iff | ||p - c|| - r | < 5 px -> its landmark (board index)
+                ids = np.nonzero(keep)[0]
+                d2 = ((fxy[:, None, :] - out1[ids][None, :, :2]) ** 2).sum(-1)
+                best = d2.argmin(1)
+                acc = np.abs(np.sqrt(d2[np.arange(len(fxy)), best]) - out1[ids][best, 2]) < 5
+                np.testing.assert_array_equal(fid, np.where(acc, ids[best], -1))
+    assert verdicts.get(1, 0) >= 5 and verdicts.get(0, 0) >= 1
