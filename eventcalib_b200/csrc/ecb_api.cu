@@ -427,6 +427,10 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     pa.knn_num = params->knn_num < 1 ? 1 : params->knn_num;
     pa.rows_cols = params->rows_cols;
     pa.rthr = params->radius_threshold;
+    {   // word 8 of the status block (zeroed at the start of this run) = k_pair's window counter
+        static const int pair_dyn = getenv("ECB_PAIR_DYN") ? atoi(getenv("ECB_PAIR_DYN")) : 1;
+        pa.win_counter = pair_dyn ? (unsigned *) ctx->status.p + 8 : nullptr;
+    }
     if ((rc = ecb_launch_pair(ctx, pa))) return rc;
     ctx->n_win = n_win;
     return ECB_OK;

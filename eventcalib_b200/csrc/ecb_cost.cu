@@ -681,9 +681,14 @@ int prepare_records(ecb_ctx *ctx, CostState *st, bool have_basis = false) {
     int chunk = CHUNK;
     {
         const int64_t warps = (int64_t) ctx->sm_count * (st->so3 ? 1 : 2) * NE_WARPS;
-        const int64_t rounds = std::max<int64_t>(1, (n + warps * CHUNK - 1) / (warps * CHUNK));
+        int64_t rounds = std::max<int64_t>(1, (n + warps * CHUNK - 1) / (warps * CHUNK));
         chunk = (int) (((n + warps * rounds - 1) / (warps * rounds) + 31) / 32 * 32);
         chunk = std::min(std::max(chunk, 256), CHUNK);
+        static const int chunk_cap = getenv("ECB_NE_CHUNK") ? atoi(getenv("ECB_NE_CHUNK")) : 1536;  // shorter items: no partial last round (1.86 -> 1.81 ms)
+        if (chunk_cap >= 256 && chunk > chunk_cap) {
+            rounds = std::max<int64_t>(1, (n + warps * chunk_cap - 1) / (warps * chunk_cap));
+            chunk = std::min((int) (((n + warps * rounds - 1) / (warps * rounds) + 31) / 32 * 32), chunk_cap);
+        }
         for (; chunk < CHUNK; chunk += 32) {  // the partial chunks at span ends add items: grow until the count fits
             int64_t cnt = 0;
             for (int s = 0; s < st->total_spans; ++s)

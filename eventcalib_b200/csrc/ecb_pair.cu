@@ -9,6 +9,8 @@
 // by operation.  The 9 moment sums are exact integers (int64 in k_cluster), so A and b are bit-identical.
 #include <float.h>
 
+#include <algorithm>
+
 #include "ecb_window.cuh"
 
 namespace {
@@ -148,7 +150,15 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
     __shared__ int s_next;  // next unclaimed positive cluster of the window (the clusters' fit work varies: dynamic hand-out)
     const int tid = threadIdx.x, lane = tid & 31;
 
-    for (int w = blockIdx.x; w < a.n_win; w += gridDim.x) {
+    __shared__ int s_win;
+    for (int w = blockIdx.x;; w += gridDim.x) {
+        if (a.win_counter) {  // dynamic hand-out: the windows' pairing work varies by a factor of two
+            __syncthreads();
+            if (tid == 0) s_win = (int) atomicAdd(a.win_counter, 1u);
+            __syncthreads();
+            w = s_win;
+        }
+        if (w >= a.n_win) break;
         const ProbDesc dn = a.prob[2 * w], dp = a.prob[2 * w + 1];
         const ProbHdr hn = a.hdr[2 * w], hp = a.hdr[2 * w + 1];
         const KeptCluster *kn = a.ktab + (size_t) (2 * w) * a.max_k, *kp = a.ktab + (size_t) (2 * w + 1) * a.max_k;
@@ -470,6 +480,7 @@ __global__ void k_fit(const double *__restrict__ xy, const int64_t *__restrict__
 int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     if (a.n_win <= 0) return ECB_OK;
     int grid = a.n_win < ctx->sm_count * 8 ? a.n_win : ctx->sm_count * 8;
+    if (a.win_counter) grid = std::min(a.n_win, ctx->sm_count * 4);  // the resident CTAs (__launch_bounds__(256, 4))
     // stage member pixels in shared memory when both polarities of the largest window fit
     const size_t smem = (size_t) 2 * a.smem_cap * 4;
     const bool direct = a.smem_cap > 0 && smem <= 96 * 1024;

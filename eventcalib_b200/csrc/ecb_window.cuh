@@ -42,6 +42,7 @@ struct PairArgs {
     int fit_circle, knn_num;
     uint32_t rows_cols;
     double rthr;
+    unsigned *win_counter;    // non-null: windows are handed out dynamically (zeroed by the caller), grid = resident CTAs
 };
 
 int ecb_launch_ingest(ecb_ctx *ctx, const void *d_raw, int64_t n);
