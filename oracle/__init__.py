@@ -9,9 +9,10 @@ Libraries (built by ``oracle/Makefile``; see the headers of the .cpp files for w
   * ``_ref/libref_frontend.so``  — restated glue + verbatim reference DBSCAN (the "reference" CPU baseline)
   * ``_ref/libref_functor.so``   — the UNMODIFIED reference residual functor (EventCalibSpline.hpp), B-spline
                                    (BsplineReal.hpp), event window (EventFrame.cpp + utility.hpp hash), record reader
-                                   (Event.hpp) and CirclesEventFrame.cpp (extractFeatures / fitCircle / rectifyFeatures /
-                                   findCenter, with dbscan.h + kdtree.cpp) compiled in place against the stand-in headers
-                                   of ``shim_functor/``
+                                   (Event.hpp), CirclesEventFrame.cpp (extractFeatures / fitCircle / rectifyFeatures /
+                                   findCenter, with dbscan.h + kdtree.cpp) and EventCalibSpline.cpp (constructor: set-up,
+                                   association, Ceres problem assembly into a recording stand-in) compiled in place
+                                   against the stand-in headers of ``shim_functor/``
 """
 import ctypes as C
 import os
@@ -23,7 +24,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _PORT = os.path.join(_HERE, "_build", "libecb_oracle.so")
 _REF_DB = os.path.join(_HERE, "_ref", "libref_dbscan.so")
 _REF_FE = os.path.join(_HERE, "_ref", "libref_frontend.so")
-_REF_FN = os.path.join(_HERE, "_ref", "libref_functor.so")
+_REF_FN = os.environ.get("ECB_REF_FN_OVERRIDE") or os.path.join(_HERE, "_ref", "libref_functor.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -183,6 +184,47 @@ def ref_rectify(t, x, y, pol, t0, t1, W, H, fitCircle, image_points, find_xy=Non
                                        C.c_double(t1), C.c_int(W), C.c_int(H), _p(prm, _dp), _p(img, _dp), _p(out, _dp), _p(fxy, _dp),
                                        C.c_int(len(fxy)), _p(fid, _ip))
     return rc, out, fid[:len(fxy)]
+
+
+def ref_calib_spline(t, x, y, pol, kf_t, kf_q, kf_twb, circles, board, cam9, W, H, step, radius, res_cap=None):
+    """The reference's own EventCalibSpline constructor (event_camera_calib/src/EventCalibSpline.cpp: reduceMap segmentation,
+    spline set-up, intrinsics, association loop, Ceres problem assembly with a recording ceres::Problem and a no-op Solve,
+    updateMap) compiled in place.  Returns a dict, or raises RuntimeError with the std::logic_error text."""
+    t, x, y = (np.ascontiguousarray(v, np.float64) for v in (t, x, y))
+    pol = np.ascontiguousarray(pol, np.uint8)
+    kf_t, kf_q, kf_twb = (np.ascontiguousarray(v, np.float64) for v in (kf_t, kf_q, kf_twb))
+    circles = np.ascontiguousarray(circles, np.float64)
+    board = np.ascontiguousarray(board, np.float64)
+    cam9 = np.ascontiguousarray(cam9, np.float64)
+    K, n_circ = circles.shape[0], circles.shape[1]
+    cap = int(res_cap or len(t))
+    info = np.zeros(8, np.int32)
+    ncp = np.zeros(K + 1, np.int32)
+    knots, rot, trans = np.zeros(K + 64 * 8), np.zeros(4 * (K + 64)), np.zeros(3 * (K + 64))
+    ranges, intr, ht = np.zeros((K + 1, 2)), np.zeros(9), np.zeros(3)
+    obs, lm, basis = np.zeros((cap, 2)), np.zeros((cap, 3)), np.zeros((cap, 4))
+    span, spl, rcp = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros((cap, 2), np.int32)
+    pose = np.zeros((K, 8))
+    err = C.create_string_buffer(256)
+    rc = ref_functor_lib().ref_calib_spline(
+        _p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)), _p(kf_t, _dp), _p(kf_q, _dp), _p(kf_twb, _dp),
+        _p(circles, _dp), C.c_int(K), C.c_int(n_circ), _p(board, _dp), _p(cam9, _dp), C.c_int(W), C.c_int(H), C.c_double(step),
+        C.c_double(radius), _p(info, _ip), _p(ncp, _ip), _p(knots, _dp), _p(rot, _dp), _p(trans, _dp), _p(ranges, _dp), _p(intr, _dp),
+        _p(ht, _dp), C.c_longlong(cap), _p(obs, _dp), _p(lm, _dp), _p(basis, _dp), _p(span, _ip), _p(spl, _ip), _p(rcp, _ip),
+        _p(pose, _dp), err, C.c_int(256))
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    S, n = int(info[0]), int(info[1])
+    ncp = ncp[:S].copy()
+    ko = np.concatenate([[0], np.cumsum(ncp + 4)])
+    co = np.concatenate([[0], np.cumsum(ncp)])
+    return dict(n_splines=S, n_residuals=n, solve_calls=int(info[2]), param_blocks=int(info[3]), quaternion_blocks=int(info[4]),
+                linear_solver=int(info[5]), frames_left=int(info[6]), n_cp=ncp,
+                knots=[knots[ko[s]:ko[s + 1]].copy() for s in range(S)],
+                rot_cp=[rot[4 * co[s]:4 * co[s + 1]].reshape(-1, 4).copy() for s in range(S)],
+                trans_cp=[trans[3 * co[s]:3 * co[s + 1]].reshape(-1, 3).copy() for s in range(S)],
+                ranges=ranges[:S].copy(), intrinsics=intr, huber=ht[0], gradient_tolerance=ht[1], function_tolerance=ht[2],
+                obs=obs[:n], lm=lm[:n], basis=basis[:n], span=span[:n], spline=spl[:n], first_cp=rcp[:n], kf_pose=pose)
 
 
 def ref_dbscan_lib():

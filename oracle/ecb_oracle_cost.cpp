@@ -17,7 +17,9 @@
 // tests/test_oracle_cost.py; (2) the reference's OWN functor and B-spline compiled where they lie against stand-in Eigen
 // headers (oracle/ref_functor_capi.cpp -> oracle/_ref/libref_functor.so): the restated residual() below equals it bit for bit
 // on Jet<37> (value + 37 partials), knots / findSpan / dersBasisFuns are bit-identical (tests/test_oracle_reference_source.py);
-// (3) an independent 40-digit mpmath evaluation (tests/test_oracle_cost.py).  Still PARITY UNPINNED: what Ceres and Sophus do
+// (3) the association (orc_associate) returns the same ordered (event, landmark) list, spans and basis values as the
+// reference's own EventCalibSpline.cpp constructor compiled in place with a recording ceres::Problem; (4) an independent
+// 40-digit mpmath evaluation (tests/test_oracle_cost.py).  Still PARITY UNPINNED: what Ceres and Sophus do
 // (corrector, parameterisations, SO(3) exp / log) — external, restated from their published behaviour.
 #include <algorithm>
 #include <cmath>

@@ -12,6 +12,11 @@
 //                                                                      camera_calibration/event_camera_calib/src/CirclesEventFrame.cpp,
 //                                                                      .../include/opengv2/event_camera_calib/CirclesEventFrame.hpp,
 //                                                                      camera_calibration/dbscan/{include/dbscan.h,src/kdtree.cpp}
+//   opengv2::EventCalibSpline (constructor: reduceMap segmentation, time extension, cpNum rule, spline fits, intrinsics with the
+//   inverse radial polynomial; optimize(): association loop, Ceres problem assembly; updateMap())
+//                                                                      camera_calibration/event_camera_calib/src/EventCalibSpline.cpp
+//     ceres::Problem records what the reference adds and ceres::Solve is a no-op hook (Ceres is absent): the ASSEMBLED problem
+//     (residual list, parameter blocks, loss, solver options) is what is compared, not the solve
 //     hooks (OpenCV is absent): findCirclesGrid = the product's grid finder (include/ecb/circles_grid.hpp) on the candidate
 //     centres the reference hands over; projectPoints = the 5 image points per board circle supplied by the caller
 //
@@ -362,5 +367,168 @@ int ref_rectify(const double *t, const double *x, const double *y, const unsigne
             find_id[i] = lm ? lm->id() : -1;
         }
     return ok ? 1 : 0;
+}
+}
+
+// ---- EventCalibSpline (a7 association, a12 problem assembly, spline set-up) ----
+#include <ceres/ceres.h>
+#include <opengv2/map/MapBase.hpp>
+
+namespace hook {
+struct SolveRecord {
+    int calls = 0;
+    double gradient_tolerance = 0, function_tolerance = 0, huber = 0;
+    int linear_solver = -1, n_param_blocks = 0, n_quaternion_blocks = 0;
+    std::vector<std::vector<double *>> residual_params;
+} solve;
+}  // namespace hook
+
+namespace ceres {
+void Solve(const Solver::Options &options, Problem *problem, Solver::Summary *) {
+    hook::SolveRecord &r = hook::solve;
+    ++r.calls;
+    r.gradient_tolerance = options.gradient_tolerance;
+    r.function_tolerance = options.function_tolerance;
+    r.linear_solver = (int) options.linear_solver_type;
+    r.n_param_blocks = (int) problem->parameters.size();
+    r.n_quaternion_blocks = 0;
+    for (const auto &pb : problem->parameters)
+        if (pb.size == 4 && dynamic_cast<const EigenQuaternionParameterization *>(pb.local)) ++r.n_quaternion_blocks;
+    r.residual_params.clear();
+    r.huber = 0;
+    for (const auto &rb : problem->residuals) {
+        r.residual_params.push_back(rb.params);
+        if (auto h = dynamic_cast<const HuberLoss *>(rb.loss)) r.huber = h->a_;
+    }
+}
+}  // namespace ceres
+
+namespace {
+// a key frame in the state rectifyFeatures() leaves it in (CirclesEventFrame.cpp:628-637): features_ with landmarks, circles_,
+// circleKdTree_
+struct KeyFrameProbe : opengv2::CirclesEventFrame {
+    KeyFrameProbe(opengv2::EventContainer::Ptr c, const std::pair<double, double> &d, CirclePatternParameters::Ptr pattern)
+        : opengv2::CirclesEventFrame(c, d, pattern) {}
+    void setCircles(const double *circ, int n, const std::vector<opengv2::LandmarkBase::Ptr> &lms) {
+        for (int i = 0; i < n; ++i) {
+            if (circ[3 * i + 2] < 0) continue;  // feature deleted by rectifyFeatures
+            auto f = std::make_shared<opengv2::CalibCircle>(Eigen::Vector2d(circ[3 * i], circ[3 * i + 1]), circ[3 * i + 2]);
+            f->setLandmark(lms[(size_t) i]);
+            features_.push_back(f);
+        }
+        circles_.reserve(features_.size());
+        for (const auto &f : features_) circles_.push_back(f->location());
+        circleKdTree_ = std::make_shared<KDTreeVectorOfVectorsAdaptor<opengv2::vectorofEigenMatrix<Eigen::Vector2d>, double, 2>>(2, circles_, 10);
+    }
+};
+struct SplineProbe : opengv2::EventCalibSpline {
+    using opengv2::EventCalibSpline::EventCalibSpline;
+    std::vector<opengv2::BsplineReal<3>> &tw() { return twbSplines_; }
+    std::vector<opengv2::BsplineReal<4>> &qw() { return QwbSplines_; }
+    const std::vector<RelationContainer> &relations() const { return relationContainer_; }
+    const Eigen::Matrix<double, 9, 1> &intr() const { return intrinsics_; }
+    const std::vector<std::pair<double, double>> &ranges() const { return time2splineIdx_; }
+};
+}  // namespace
+
+extern "C" {
+// Runs the reference's EventCalibSpline constructor (set-up + optimize() with the no-op Solve + updateMap()).
+//  events (t, x, y, pol)[n]; key frames: stamp[K], pose q[K][4] (x y z w) / twb[K][3], circles[K][n_circ][3] (r < 0: absent);
+//  board[n_circ][3]; cam = fx fy cx cy k1 k2 p1 p2 k3; W, H; step = MotionTimeStep; radius = Circles_Radius.
+// Outputs (caller-sized): info[8] = n_splines, n_residuals, solve calls, parameter blocks, quaternion blocks, linear solver,
+//  key frames left in the map, 0; ncp[n_splines]; knots / rot_cp / trans_cp concatenated over the splines; ranges[n_splines][2];
+//  intr9; huber_tol[3] = Huber a, gradient tolerance, function tolerance; per residual: obs[2], lm[3], basis[4], span, spline,
+//  and the FIRST control-point index of its 4 rotation / 4 translation blocks (res_cp[2]) as handed to AddResidualBlock;
+//  kf_pose[K][8] = stamp, twb, q (x y z w) of the key frames after updateMap() (NaN rows for frames removed from the map).
+// Returns 0, or -1 with what() in err (the constructor throws std::logic_error like the reference's).
+int ref_calib_spline(const double *t, const double *x, const double *y, const unsigned char *pol, long long n, const double *stamp,
+                     const double *kq, const double *kt, const double *circles, int K, int n_circ, const double *board,
+                     const double *cam, int W, int H, double step, double radius, int *info, int *ncp, double *knots,
+                     double *rot_cp, double *trans_cp, double *ranges, double *intr9, double *huber_tol, long long res_cap,
+                     double *res_obs, double *res_lm, double *res_basis, int *res_span, int *res_spline, int *res_cp,
+                     double *kf_pose, char *err, int err_cap) {
+    auto container = std::make_shared<opengv2::EventContainer>();
+    auto camera = std::make_shared<opengv2::PinholeCamera>(Eigen::Vector2d(W, H));
+    Eigen::Matrix3d Km;
+    Km << cam[0], 0, cam[2], 0, cam[1], cam[3], 0, 0, 1;
+    camera->setK(Km);
+    for (int i = 0; i < 5; ++i) camera->distCoeffs()[i] = cam[4 + i];
+    container->camera = camera;
+    for (long long i = 0; i < n; ++i)
+        container->container.emplace(t[i], opengv2::Event_loc_pol(Eigen::Vector2d(x[i], y[i]), pol[i] != 0));
+    cv::FileStorage fs;
+    fs.kv = {{"BoardSize_Cols", 4}, {"BoardSize_Rows", 9}, {"Square_Size", 5.5}, {"Is_Pattern_Asymmetric", 1}, {"Circles_Radius", radius}};
+    auto pattern = std::make_shared<CirclePatternParameters>(fs);
+    std::vector<opengv2::LandmarkBase::Ptr> lms;
+    for (int i = 0; i < n_circ; ++i)
+        lms.push_back(std::make_shared<opengv2::LandmarkBase>(i, Eigen::Vector3d(board[3 * i], board[3 * i + 1], board[3 * i + 2])));
+    auto map = std::make_shared<opengv2::MapBase>();
+    for (int k = 0; k < K; ++k) {
+        // the frame's own window is irrelevant here (its event sets are released after rectifyFeatures): an empty one
+        auto frame = std::make_shared<KeyFrameProbe>(container, std::make_pair(-2.0, -1.0), pattern);
+        frame->setCircles(circles + (size_t) k * n_circ * 3, n_circ, lms);
+        map->addFrame(std::make_shared<opengv2::Bodyframe>(frame, stamp[k], Eigen::Vector3d(kt[3 * k], kt[3 * k + 1], kt[3 * k + 2]),
+                                                            Eigen::Quaterniond(kq[4 * k + 3], kq[4 * k], kq[4 * k + 1], kq[4 * k + 2])));
+    }
+    hook::solve = hook::SolveRecord();
+    std::unique_ptr<SplineProbe> sp;
+    try {
+        sp.reset(new SplineProbe(map, container, false, false, step, radius));
+    } catch (const std::exception &e) {
+        std::snprintf(err, (size_t) err_cap, "%s", e.what());
+        return -1;
+    }
+    const int S = (int) sp->tw().size();
+    info[0] = S;
+    info[1] = (int) sp->relations().size();
+    info[2] = hook::solve.calls;
+    info[3] = hook::solve.n_param_blocks;
+    info[4] = hook::solve.n_quaternion_blocks;
+    info[5] = hook::solve.linear_solver;
+    info[6] = (int) map->frameNum();
+    info[7] = 0;
+    size_t ko = 0, ro = 0, to = 0;
+    for (int s = 0; s < S; ++s) {
+        const auto &kv = sp->tw()[(size_t) s].getKnotVector();
+        auto &tc = sp->tw()[(size_t) s].getCP();
+        auto &qc = sp->qw()[(size_t) s].getCP();
+        ncp[s] = (int) tc.size();
+        for (double k : kv) knots[ko++] = k;
+        for (auto &c : qc)
+            for (int a = 0; a < 4; ++a) rot_cp[ro++] = c[a];
+        for (auto &c : tc)
+            for (int a = 0; a < 3; ++a) trans_cp[to++] = c[a];
+        ranges[2 * s] = sp->ranges()[(size_t) s].first;
+        ranges[2 * s + 1] = sp->ranges()[(size_t) s].second;
+    }
+    for (int i = 0; i < 9; ++i) intr9[i] = sp->intr()[i];
+    huber_tol[0] = hook::solve.huber;
+    huber_tol[1] = hook::solve.gradient_tolerance;
+    huber_tol[2] = hook::solve.function_tolerance;
+    long long r = 0;
+    for (const auto &rel : sp->relations()) {
+        if (r >= res_cap) break;
+        res_obs[2 * r] = rel.obs[0], res_obs[2 * r + 1] = rel.obs[1];
+        for (int a = 0; a < 3; ++a) res_lm[3 * r + a] = rel.lm[a];
+        for (int a = 0; a < 4; ++a) res_basis[4 * r + a] = (*rel.rBasis)[0][(size_t) a];
+        res_span[r] = (int) rel.rSpanIdx;
+        res_spline[r] = (int) rel.splineIdx;
+        const auto &ps = hook::solve.residual_params[(size_t) r];  // intrinsics, 4 rotation blocks, 4 translation blocks
+        res_cp[2 * r] = (int) ((ps[1] - sp->qw()[rel.splineIdx].getCP()[0].data()) / 4);
+        res_cp[2 * r + 1] = (int) ((ps[5] - sp->tw()[rel.splineIdx].getCP()[0].data()) / 3);
+        ++r;
+    }
+    for (int k = 0; k < K; ++k) {
+        auto bf = map->keyframe(stamp[k]);
+        double *o = kf_pose + 8 * k;
+        if (!bf) {
+            for (int a = 0; a < 8; ++a) o[a] = std::nan("");
+            continue;
+        }
+        o[0] = bf->timeStamp();
+        for (int a = 0; a < 3; ++a) o[1 + a] = bf->twb()[a];
+        for (int a = 0; a < 4; ++a) o[4 + a] = bf->unitQwb().coeffs()[a];
+    }
+    return 0;
 }
 }

@@ -21,6 +21,13 @@ stand-in Eigen / Ceres / Sophus headers of oracle/shim_functor/ (oracle/Makefile
     fit_circle / rectify, what the GPU tests compare with) gives the same candidate lists, and BIT-IDENTICAL feature centres,
     radii, rectified features and frame verdicts
 
+  * spline set-up, association and problem assembly (a7, a12): the reference's EventCalibSpline.cpp constructor compiled in
+    place (reduceMap segmentation, 3-step time extension, cpNum rule, BsplineReal fits, intrinsics with the inverse radial
+    polynomial, association loop, AddParameterBlock / AddResidualBlock calls into a RECORDING ceres::Problem, no-op Solve,
+    updateMap): segments / knots / control points equal the façade's (1e-15), the (event, landmark) residual list, spans and
+    basis values equal the oracle's association exactly, every residual touches control points span-3 .. span, rotation
+    blocks carry EigenQuaternionParameterization, HuberLoss(0.2 r), tolerances 1e-10, SPARSE_NORMAL_CHOLESKY
+
 The library is built in the build container (where /root/reference exists) and travels as a prebuilt file; without it the
 tests skip."""
 import ctypes as C
@@ -275,3 +282,78 @@ def test_rectify_and_find_center_vs_reference_source(ref):
                 acc = np.abs(np.sqrt(d2[np.arange(len(fxy)), best]) - out1[ids][best, 2]) < 5
                 np.testing.assert_array_equal(fid, np.where(acc, ids[best], -1))
     assert verdicts.get(1, 0) >= 5 and verdicts.get(0, 0) >= 1
+
+
+@pytest.mark.parametrize("with_gaps", [False, True])
+def test_calib_spline_setup_association_and_assembly_vs_reference_source(ref, with_gaps):
+    from eventcalib_b200 import synth, calib_problem
+    import eventcalib_b200.build as b
+    b.build()
+    so = os.path.join(ROOT, "tests", "_build", "libfacade_host.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "helpers", "facade_host.cpp"),
+                           "-L" + os.path.join(ROOT, "eventcalib_b200"), "-lecb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "eventcalib_b200")])
+    F = C.CDLL(so)
+    dur = 0.3 if with_gaps else 0.2
+    ev = synth.make_stream(int(1.2e6 * dur), 346, 260, t0=5.0, duration=dur, seed=11, return_truth=True)
+    cam, traj, board = ev["camera"], ev["trajectory"], ev["board"]
+    step = 5e-4
+    pb = calib_problem.build_from_truth(cam, traj, board, 5.0, 5.0 + dur, step=step)
+    kf_t, circ = pb["kf_t"], pb["circles"].copy()
+    if with_gaps:   # a gap > 50 steps -> two segments; a 3-frame island between two gaps -> dropped (reduceMap :319-348)
+        keep = ~(((kf_t > 5.12) & (kf_t < 5.15)) | ((kf_t >= 5.162) & (kf_t < 5.19)))
+        kf_t, circ = kf_t[keep], circ[keep]
+    rng = np.random.default_rng(0)
+    circ[rng.uniform(size=circ.shape[:2]) < 0.05, 2] = -1.0        # features deleted by rectifyFeatures
+    q, tw = traj.quat_xyzw(kf_t)
+    cam9 = np.array([cam.f * 1.01, cam.f * 0.99, cam.cx + 0.5, cam.cy - 0.5, -0.33, -0.02, 0, 0, 0.5])
+    r = ref.ref_calib_spline(ev["t"], ev["x"], ev["y"], ev["p"], kf_t, q, tw, circ, board.centres(), cam9, 346, 260, step, board.radius)
+    assert r["n_splines"] == (2 if with_gaps else 1) and r["solve_calls"] == 1
+    left = ~np.isnan(r["kf_pose"][:, 0])
+    assert left.sum() == r["frames_left"] == (len(kf_t) - 3 if with_gaps else len(kf_t))
+    # ---- spline set-up vs the façade (EventCalibSpline::segmentsFromKeyframes) ----
+    K = len(kf_t)
+    for w in range(r["n_splines"]):
+        ncp = C.c_int()
+        kn, rot, tr = np.zeros(K + 8), np.zeros((K, 4)), np.zeros((K, 3))
+        ns = F.fh_segments(P(kf_t), P(np.ascontiguousarray(q)), P(np.ascontiguousarray(tw)), K, C.c_double(step), w, C.byref(ncp),
+                           P(kn), P(rot), P(tr))
+        n = ncp.value
+        assert ns == r["n_splines"] and n == r["n_cp"][w]
+        np.testing.assert_array_equal(kn[:n + 4], r["knots"][w])
+        np.testing.assert_allclose(rot[:n], r["rot_cp"][w], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(tr[:n], r["trans_cp"][w], rtol=1e-13, atol=1e-13)
+        assert r["ranges"][w, 0] == r["knots"][w][0] and r["ranges"][w, 1] == r["knots"][w][-1]
+    if not with_gaps:   # cpNum = floor(T / (50 step)) with T extended by 3 steps on both sides (:64-85)
+        assert r["n_cp"][0] == int(np.floor((kf_t[-1] - kf_t[0] + 6 * step) / (50 * step)))
+    # ---- intrinsics_ (:94-105): K and the inverse of the radial part (k1, k2, k3 = distCoeffs(4), 0) ----
+    np.testing.assert_array_equal(r["intrinsics"], np.r_[cam9[:4], ref.inverse_radial([cam9[4], cam9[5], cam9[8], 0.0])])
+    # ---- association loop (:157-192) vs the oracle's, on the key frames left in the map ----
+    cp = ref.CostProblem(r["n_cp"], r["knots"], radius=board.radius, huber=0.2 * board.radius)
+    oe, oc = cp.associate(ev["t"], ev["x"], ev["y"], kf_t[left], circ[left], board.centres(), step)
+    assert len(oe) == r["n_residuals"] > 10000
+    np.testing.assert_array_equal(r["obs"], np.c_[ev["x"][oe], ev["y"][oe]])
+    np.testing.assert_array_equal(r["lm"], board.centres()[oc])
+    spl = np.searchsorted(r["ranges"][:, 1], ev["t"][oe], side="left")
+    np.testing.assert_array_equal(r["spline"], spl)
+    for i in range(0, len(oe), 53):
+        sp, N = ref.basis(r["knots"][r["spline"][i]], float(ev["t"][oe[i]]))
+        assert sp == r["span"][i]
+        np.testing.assert_array_equal(N, r["basis"][i])
+    # ---- problem assembly (:116-247) ----
+    np.testing.assert_array_equal(r["first_cp"][:, 0], r["span"] - 3)     # rotation blocks span-3 .. span
+    np.testing.assert_array_equal(r["first_cp"][:, 1], r["span"] - 3)     # translation blocks span-3 .. span
+    assert r["param_blocks"] == r["quaternion_blocks"] == int(r["n_cp"].sum())   # every rotation control point: 4 -> 3
+    assert abs(r["huber"] - 0.2 * board.radius) < 1e-15 and r["gradient_tolerance"] == 1e-10 and r["function_tolerance"] == 1e-10
+    assert r["linear_solver"] == 1    # SPARSE_NORMAL_CHOLESKY
+    # ---- updateMap (:253-317): key-frame poses = the splines at the stamps (no-op solve: the initial fit) ----
+    F.fh_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    for k in np.nonzero(left)[0][::5]:
+        w = int(np.searchsorted(r["ranges"][:, 1], kf_t[k], side="left"))
+        q4, t3 = np.zeros(4), np.zeros(3)
+        assert F.fh_eval(P(r["knots"][w]), int(r["n_cp"][w]), P(np.ascontiguousarray(r["rot_cp"][w])),
+                         P(np.ascontiguousarray(r["trans_cp"][w])), 0, float(kf_t[k]), P(q4), P(t3)) == 1
+        np.testing.assert_allclose(r["kf_pose"][k, 1:4], t3, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(r["kf_pose"][k, 4:8], q4, rtol=1e-12, atol=1e-12)
