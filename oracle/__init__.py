@@ -24,7 +24,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _PORT = os.path.join(_HERE, "_build", "libecb_oracle.so")
 _REF_DB = os.path.join(_HERE, "_ref", "libref_dbscan.so")
 _REF_FE = os.path.join(_HERE, "_ref", "libref_frontend.so")
-_REF_FN = os.environ.get("ECB_REF_FN_OVERRIDE") or os.path.join(_HERE, "_ref", "libref_functor.so")
+_REF_FN = os.path.join(_HERE, "_ref", "libref_functor.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
