@@ -10,8 +10,9 @@ Libraries (built by ``oracle/Makefile``; see the headers of the .cpp files for w
   * ``_ref/libref_functor.so``   — the UNMODIFIED reference residual functor (EventCalibSpline.hpp), B-spline
                                    (BsplineReal.hpp), event window (EventFrame.cpp + utility.hpp hash), record reader
                                    (Event.hpp), CirclesEventFrame.cpp (extractFeatures / fitCircle / rectifyFeatures /
-                                   findCenter, with dbscan.h + kdtree.cpp) and EventCalibSpline.cpp (constructor: set-up,
-                                   association, Ceres problem assembly into a recording stand-in) compiled in place
+                                   findCenter, with dbscan.h + kdtree.cpp), EventCalibSpline.cpp (constructor: set-up,
+                                   association, Ceres problem assembly into a recording stand-in) and EventCalibIni.cpp
+                                   (tracking gate, checkPose, cvCalibration flow) compiled in place
                                    against the stand-in headers of ``shim_functor/``
 """
 import ctypes as C
@@ -225,6 +226,55 @@ def ref_calib_spline(t, x, y, pol, kf_t, kf_q, kf_twb, circles, board, cam9, W, 
                 trans_cp=[trans[3 * co[s]:3 * co[s + 1]].reshape(-1, 3).copy() for s in range(S)],
                 ranges=ranges[:S].copy(), intrinsics=intr, huber=ht[0], gradient_tolerance=ht[1], function_tolerance=ht[2],
                 obs=obs[:n], lm=lm[:n], basis=basis[:n], span=span[:n], spline=spl[:n], first_cp=rcp[:n], kf_pose=pose)
+
+
+class RefIni:
+    """The reference's own EventCalibIni (event_camera_calib/src/EventCalibIni.cpp) compiled in place: tracking gate
+    (TrackingBase::process -> track), checkPose, and the front-to-back flow per window (CirclesEventFrame + extractFeatures,
+    gate, cvCalibration) with the product's host header as the OpenCV hooks."""
+
+    def __init__(self, W, H, step, n_use=200, fitCircle=0, rows=9, cols=4):
+        self.lib = ref_functor_lib()
+        self.lib.ref_ini_new.restype = C.c_void_p
+        self.prm = np.array([cols, rows, 5.5, 1.0, 1.75, 4.0, 2, 5, 3, fitCircle], np.float64)
+        self.n_feat = rows * cols
+        self.fit = int(fitCircle)
+        self.h = C.c_void_p(self.lib.ref_ini_new(C.c_int(W), C.c_int(H), C.c_double(step), _p(self.prm, _dp), C.c_int(n_use)))
+
+    def __del__(self):
+        try:
+            self.lib.ref_ini_free(self.h)
+        except Exception:
+            pass
+
+    def add_events(self, t, x, y, pol):
+        t, x, y = (np.ascontiguousarray(v, np.float64) for v in (t, x, y))
+        pol = np.ascontiguousarray(pol, np.uint8)
+        self.lib.ref_ini_add_events(self.h, _p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)))
+
+    def gate(self, stamp, xy):
+        xy = np.ascontiguousarray(xy, np.float64)
+        return int(self.lib.ref_ini_gate(self.h, C.c_double(stamp), _p(xy, _dp), C.c_int(len(xy))))
+
+    def run(self, windows):
+        """-> dict(ok, cam9, status[w] (0 no features / 1 gate rejected / 2 dropped by cvCalibration / 3 kept), pose[w][7] =
+        twb + Qwb (x y z w), feat[w][n_feat][3], frames_before, frames_after, calibrate_views, calibrate_flags)"""
+        win = np.ascontiguousarray(windows, np.float64)
+        nw = len(win)
+        cam9, status = np.zeros(9), np.zeros(nw, np.int32)
+        pose, feat, counts = np.zeros((nw, 7)), np.zeros((nw, self.n_feat, 3)), np.zeros(4, np.int32)
+        ok = self.lib.ref_ini_run(self.h, _p(win, _dp), C.c_int(nw), C.c_int(self.fit), _p(cam9, _dp), _p(status, _ip), _p(pose, _dp),
+                                  _p(feat, _dp), _p(counts, _ip))
+        return dict(ok=bool(ok), cam9=cam9, status=status, pose=pose, feat=feat, frames_before=int(counts[0]),
+                    frames_after=int(counts[1]), calibrate_views=int(counts[2]), calibrate_flags=int(counts[3]))
+
+
+def ref_check_pose(ref_stamp, ref_q, ref_t, cur_stamp, cur_q, cur_t, step):
+    """The reference's own EventCalibIni::checkPose (EventCalibIni.cpp:328-346) against a map whose last key frame is ref."""
+    a = [np.ascontiguousarray(v, np.float64) for v in (ref_q, ref_t, cur_q, cur_t)]
+    f = ref_functor_lib().ref_check_pose
+    f.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double]
+    return int(f(ref_stamp, a[0].ctypes.data, a[1].ctypes.data, cur_stamp, a[2].ctypes.data, a[3].ctypes.data, step))
 
 
 def ref_dbscan_lib():

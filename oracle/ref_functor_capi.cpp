@@ -15,6 +15,11 @@
 //   opengv2::EventCalibSpline (constructor: reduceMap segmentation, time extension, cpNum rule, spline fits, intrinsics with the
 //   inverse radial polynomial; optimize(): association loop, Ceres problem assembly; updateMap())
 //                                                                      camera_calibration/event_camera_calib/src/EventCalibSpline.cpp
+//   opengv2::EventCalibIni (track = the tracking gate, checkPose, cvCalibration)
+//                                                                      camera_calibration/event_camera_calib/src/EventCalibIni.cpp
+//     hooks: calibrateCamera / solvePnPRansac / projectPoints / Rodrigues = the product's include/ecb/calib_init.hpp, so the
+//     reference's own control flow (frame selection, pose conversion, checkPose chain, rectifyFeatures, counters) runs on the
+//     product's numerics; JacobiSVD of the row fits is restated in the stand-in Eigen
 //     ceres::Problem records what the reference adds and ceres::Solve is a no-op hook (Ceres is absent): the ASSEMBLED problem
 //     (residual list, parameter blocks, loss, solver options) is what is compared, not the solve
 //     hooks (OpenCV is absent): findCirclesGrid = the product's grid finder (include/ecb/circles_grid.hpp) on the candidate
@@ -236,13 +241,15 @@ long long ref_read_bin(const char *path, long long cap, double *t, double *x, do
 #include <opengv2/event_camera_calib/CirclesEventFrame.hpp>
 #include <opengv2/sensor/PinholeCamera.hpp>
 
+#include "../include/ecb/calib_init.hpp"    // the product's OpenCV-free calibration, used as the calibrateCamera / PnP hooks
 #include "../include/ecb/circles_grid.hpp"  // the product's grid finder, used as the findCirclesGrid hook
 
 namespace hook {
 std::vector<cv::Point2f> grid_points;      // candidate centres of the last findCirclesGrid call (cv::Point2f like the reference's)
 int grid_calls = 0;
-const double *image_points = nullptr;      // [features][5][2] for projectPoints
+const double *image_points = nullptr;      // [features][5][2] for projectPoints (null: real projection)
 int project_calls = 0;
+int calibrate_calls = 0, calibrate_views = 0, calibrate_flags = 0;
 }  // namespace hook
 
 namespace cv {
@@ -258,14 +265,82 @@ bool findCirclesGrid(const std::vector<Point2f> &points_, Size patternSize, std:
     for (int idx : order) centers.push_back(points_[(size_t) idx]);
     return true;
 }
-void projectPoints(const std::vector<Point3f> &objectPoints, const Mat &, const Mat &, const Mat &, const Mat &,
-                   std::vector<Point2f> &imagePoints) {
+// projectPoints: with hook::image_points set, the caller's points (rectifyFeatures tests); otherwise the real projection through
+// the product's host header (cvCalibration flow)
+void projectPoints(const std::vector<Point3f> &objectPoints, const Mat &rvec, const Mat &tvec, const Mat &cameraMatrix,
+                   const Mat &distCoeffs, std::vector<Point2f> &imagePoints) {
     imagePoints.clear();
-    for (size_t i = 0; i < objectPoints.size(); ++i) {
-        const double *p = hook::image_points + ((size_t) hook::project_calls * objectPoints.size() + i) * 2;
-        imagePoints.emplace_back(p[0], p[1]);
+    if (hook::image_points) {
+        for (size_t i = 0; i < objectPoints.size(); ++i) {
+            const double *p = hook::image_points + ((size_t) hook::project_calls * objectPoints.size() + i) * 2;
+            imagePoints.emplace_back(p[0], p[1]);
+        }
+        ++hook::project_calls;
+        return;
     }
-    ++hook::project_calls;
+    ecb::CameraModel cam;
+    cam.fx = cameraMatrix.d[0], cam.fy = cameraMatrix.d[4], cam.cx = cameraMatrix.d[2], cam.cy = cameraMatrix.d[5];
+    for (size_t k = 0; k < 5 && k < distCoeffs.d.size(); ++k) cam.dist[k] = distCoeffs.d[k];
+    for (const auto &o : objectPoints) {
+        const double X[3] = {o.x, o.y, o.z};
+        double uv[2];
+        ecb::projectPoints(X, 1, rvec.d.data(), tvec.d.data(), cam, uv);
+        imagePoints.emplace_back(uv[0], uv[1]);
+    }
+}
+void Rodrigues(const Mat &src, Mat &dst) {
+    if (src.d.size() == 9) {
+        dst = Mat::zeros(3, 1, 0);
+        ecb::rodriguesInverse(src.d.data(), dst.d.data());
+    } else {
+        dst = Mat::zeros(3, 3, 0);
+        ecb::rodrigues<double>(src.d.data(), dst.d.data());
+    }
+}
+double calibrateCamera(const std::vector<std::vector<Point3f>> &objectPoints, const std::vector<std::vector<Point2f>> &imagePoints,
+                       Size imageSize, Mat &cameraMatrix, Mat &distCoeffs, std::vector<Mat> &rvecs, std::vector<Mat> &tvecs, int flags) {
+    ++hook::calibrate_calls;
+    hook::calibrate_views = (int) imagePoints.size();
+    hook::calibrate_flags = flags;
+    std::vector<double> obj;
+    for (const auto &o : objectPoints[0]) obj.insert(obj.end(), {(double) o.x, (double) o.y, (double) o.z});
+    std::vector<std::vector<double>> img;
+    for (const auto &v : imagePoints) {
+        img.emplace_back();
+        for (const auto &q : v) img.back().insert(img.back().end(), {(double) q.x, (double) q.y});
+    }
+    ecb::CalibFlags fl;
+    fl.fixPrincipalPoint = flags & CALIB_FIX_PRINCIPAL_POINT;
+    fl.zeroTangentDist = flags & CALIB_ZERO_TANGENT_DIST;
+    fl.fixAspectRatio = flags & CALIB_FIX_ASPECT_RATIO;
+    fl.fixK1 = flags & CALIB_FIX_K1, fl.fixK2 = flags & CALIB_FIX_K2, fl.fixK3 = flags & CALIB_FIX_K3;
+    fl.aspectRatio = cameraMatrix.d[0] / cameraMatrix.d[4];
+    ecb::CameraModel cam;
+    std::vector<std::array<double, 3>> rv, tv;
+    const double rms = ecb::calibrateCamera(obj, img, imageSize.width, imageSize.height, fl, cam, rv, tv);
+    cameraMatrix = Mat::eye(3, 3, 0);
+    cameraMatrix.d[0] = cam.fx, cameraMatrix.d[4] = cam.fy, cameraMatrix.d[2] = cam.cx, cameraMatrix.d[5] = cam.cy;
+    distCoeffs = Mat::zeros(5, 1, 0);  // OpenCV trims the 8 coefficients to 5 without CALIB_RATIONAL_MODEL
+    for (int k = 0; k < 5; ++k) distCoeffs.d[(size_t) k] = cam.dist[k];
+    rvecs.clear(), tvecs.clear();
+    for (size_t v = 0; v < rv.size(); ++v) {
+        Mat r = Mat::zeros(3, 1, 0), t = Mat::zeros(3, 1, 0);
+        for (int k = 0; k < 3; ++k) r.d[(size_t) k] = rv[v][(size_t) k], t.d[(size_t) k] = tv[v][(size_t) k];
+        rvecs.push_back(r), tvecs.push_back(t);
+    }
+    return rms;
+}
+bool solvePnPRansac(const std::vector<Point3f> &objectPoints, const std::vector<Point2f> &imagePoints, const Mat &cameraMatrix,
+                    const Mat &distCoeffs, Mat &rvec, Mat &tvec, bool, int, float reprojectionError, double, std::vector<int> &inliers,
+                    int) {
+    std::vector<double> obj, img;
+    for (const auto &o : objectPoints) obj.insert(obj.end(), {(double) o.x, (double) o.y, (double) o.z});
+    for (const auto &q : imagePoints) img.insert(img.end(), {(double) q.x, (double) q.y});
+    ecb::CameraModel cam;
+    cam.fx = cameraMatrix.d[0], cam.fy = cameraMatrix.d[4], cam.cx = cameraMatrix.d[2], cam.cy = cameraMatrix.d[5];
+    for (size_t k = 0; k < 5 && k < distCoeffs.d.size(); ++k) cam.dist[k] = distCoeffs.d[k];
+    rvec = Mat::zeros(3, 1, 0), tvec = Mat::zeros(3, 1, 0);
+    return ecb::solvePnPPlanar(obj, img, cam, (double) reprojectionError, rvec.d.data(), tvec.d.data(), inliers);
 }
 }  // namespace cv
 
@@ -356,6 +431,7 @@ int ref_rectify(const double *t, const double *x, const double *y, const unsigne
     hook::project_calls = 0;
     Eigen::Matrix3d R;
     const bool ok = f->rectifyFeatures(std::unordered_set<int>(), R, Eigen::Vector3d(0, 0, 0));
+    hook::image_points = nullptr;
     for (auto &fb : f->feats()) {
         auto c = dynamic_cast<opengv2::CalibCircle *>(fb.get());
         const int id = c->landmark()->id();
@@ -530,5 +606,131 @@ int ref_calib_spline(const double *t, const double *x, const double *y, const un
         for (int a = 0; a < 4; ++a) o[4 + a] = bf->unitQwb().coeffs()[a];
     }
     return 0;
+}
+}
+
+// ---- EventCalibIni: tracking gate (f-1), checkPose and cvCalibration flow (f-4) ----
+#include <opengv2/event_camera_calib/EventCalibIni.hpp>
+#include <opengv2/system/SystemBase.hpp>
+
+namespace {
+struct IniSession {
+    std::shared_ptr<opengv2::EventContainer> container;
+    std::shared_ptr<opengv2::PinholeCamera> camera;
+    std::shared_ptr<opengv2::MapBase> map;
+    opengv2::SystemBase system;
+    CalibrationSetting::Ptr setting;
+    std::shared_ptr<opengv2::EventCalibIni> ini;
+    double prm[10];
+    int W, H;
+};
+IniSession *ini_new(int W, int H, double step, const double *prm10, int n_use) {
+    auto *s = new IniSession();
+    s->W = W, s->H = H;
+    for (int i = 0; i < 10; ++i) s->prm[i] = prm10[i];
+    s->container = std::make_shared<opengv2::EventContainer>();
+    s->camera = std::make_shared<opengv2::PinholeCamera>(Eigen::Vector2d(W, H));
+    s->container->camera = s->camera;
+    s->map = std::make_shared<opengv2::MapBase>();
+    s->system.map = s->map;
+    s->system.viewer = std::make_shared<opengv2::ViewerBase>();  // cvCalibration() calls it unconditionally (EventCalibIni.cpp:320)
+    cv::FileStorage fs;  // parameters.hpp:32-46 with the values of example.yaml
+    fs.kv = {{"BoardSize_Cols", prm10[0]}, {"BoardSize_Rows", prm10[1]}, {"Square_Size", prm10[2]}, {"Is_Pattern_Asymmetric", prm10[3]},
+             {"Circles_Radius", prm10[4]}, {"Calibrate_FixAspectRatio", 1}, {"Calibrate_AssumeZeroTangentialDistortion", 1},
+             {"Calibrate_FixPrincipalPointAtTheCenter", 1}, {"Calibrate_UseFisheyeModel", 0}, {"Fix_K1", 0}, {"Fix_K2", 0}, {"Fix_K3", 0},
+             {"Fix_K4", 1}, {"Fix_K5", 1}, {"Calibrate_NrOfFrameToUse", (double) n_use}};
+    s->setting = std::make_shared<CalibrationSetting>(fs);
+    s->ini = std::make_shared<opengv2::EventCalibIni>(s->map, s->setting, step);
+    s->ini->setSystem(&s->system);
+    return s;
+}
+}  // namespace
+
+extern "C" {
+void *ref_ini_new(int W, int H, double step, const double *prm10, int n_use) { return ini_new(W, H, step, prm10, n_use); }
+void ref_ini_free(void *h) { delete (IniSession *) h; }
+void ref_ini_add_events(void *h, const double *t, const double *x, const double *y, const unsigned char *pol, long long n) {
+    auto *s = (IniSession *) h;
+    for (long long i = 0; i < n; ++i)
+        s->container->container.emplace(t[i], opengv2::Event_loc_pol(Eigen::Vector2d(x[i], y[i]), pol[i] != 0));
+}
+// tracking->process(bf) (eventCameraCalib.cpp:60) for a frame whose features are given (board order, centres only): the first
+// frame initialises the map, later ones go through EventCalibIni::track.  Returns 1 accepted / 0 rejected.
+int ref_ini_gate(void *h, double stamp, const double *xy, int n_feat) {
+    auto *s = (IniSession *) h;
+    cv::FileStorage fs;
+    fs.kv = {{"BoardSize_Cols", s->prm[0]}, {"BoardSize_Rows", s->prm[1]}, {"Square_Size", s->prm[2]}, {"Is_Pattern_Asymmetric", s->prm[3]},
+             {"Circles_Radius", s->prm[4]}};
+    auto frame = std::make_shared<KeyFrameProbe>(s->container, std::make_pair(-2.0, -1.0), std::make_shared<CirclePatternParameters>(fs));
+    std::vector<double> circ((size_t) n_feat * 3);
+    for (int i = 0; i < n_feat; ++i) circ[3 * i] = xy[2 * i], circ[3 * i + 1] = xy[2 * i + 1], circ[3 * i + 2] = 1.0;
+    std::vector<opengv2::LandmarkBase::Ptr> none((size_t) n_feat);
+    frame->setCircles(circ.data(), n_feat, none);
+    auto bf = std::make_shared<opengv2::Bodyframe>(frame, stamp, Eigen::Vector3d(0, 0, 0), Eigen::Quaterniond(1, 0, 0, 0));
+    return s->ini->process(bf) ? 1 : 0;
+}
+// EventCalibIni::checkPose(cur) against a map whose last key frame is `ref` (poses: q = x y z w of Qwb, t = twb)
+int ref_check_pose(double ref_stamp, const double *rq, const double *rt, double cur_stamp, const double *cq, const double *ct, double step) {
+    const double prm[10] = {4, 9, 5.5, 1, 1.75, 4, 2, 5, 3, 0};
+    std::unique_ptr<IniSession> s(ini_new(346, 260, step, prm, 200));
+    s->map->addFrame(std::make_shared<opengv2::Bodyframe>(nullptr, ref_stamp, Eigen::Vector3d(rt[0], rt[1], rt[2]),
+                                                           Eigen::Quaterniond(rq[3], rq[0], rq[1], rq[2])));
+    auto cur = std::make_shared<opengv2::Bodyframe>(nullptr, cur_stamp, Eigen::Vector3d(ct[0], ct[1], ct[2]),
+                                                    Eigen::Quaterniond(cq[3], cq[0], cq[1], cq[2]));
+    return s->ini->checkPose(cur) ? 1 : 0;
+}
+// The reference's front-to-back flow on raw events for given windows: per window CirclesEventFrame + extractFeatures(), the
+// tracking gate, then EventCalibIni::cvCalibration().  Outputs: cam9 (fx fy cx cy k1 k2 p1 p2 k3), per input window
+// status[w] = 0 no features / 1 gate rejected / 2 in the map before cvCalibration but dropped by it / 3 kept, pose[w][7] = twb,
+// Qwb (x y z w) and feat[w][n_feat][3] = rectified circles (r < 0: deleted) for kept frames.  Returns cvCalibration()'s bool.
+int ref_ini_run(void *h, const double *windows, int n_win, int fit_circle, double *cam9, int *status, double *pose, double *feat,
+                int *counts) {
+    auto *s = (IniSession *) h;
+    double prm[10];
+    for (int i = 0; i < 10; ++i) prm[i] = s->prm[i];
+    prm[9] = fit_circle;
+    cv::FileStorage fs;
+    fs.kv = {{"BoardSize_Cols", prm[0]}, {"BoardSize_Rows", prm[1]}, {"Square_Size", prm[2]}, {"Is_Pattern_Asymmetric", prm[3]},
+             {"Circles_Radius", prm[4]}, {"dbscan_eps", prm[5]}, {"dbscan_startMinSample", prm[6]}, {"clusterMinSample", prm[7]},
+             {"knn_num", prm[8]}, {"fitCircle", prm[9]}};
+    auto pattern = std::make_shared<CirclePatternParameters>(fs);
+    opengv2::CirclesEventFrame::Params params(fs);
+    const int n_feat = (int) (prm[0] * prm[1]);
+    std::map<double, int> stamp2win;
+    hook::image_points = nullptr;
+    for (int w = 0; w < n_win; ++w) {
+        status[w] = 0;
+        auto frame = std::make_shared<CircleProbe>(s->container, std::make_pair(windows[2 * w], windows[2 * w + 1]), pattern, params);
+        if (!frame->extractFeatures()) continue;
+        const double ts = (windows[2 * w] + windows[2 * w + 1]) / 2;  // Bodyframe time stamp (eventCameraCalib.cpp:57)
+        auto bf = std::make_shared<opengv2::Bodyframe>(frame, ts, Eigen::Vector3d(0, 0, 0), Eigen::Quaterniond(1, 0, 0, 0));
+        status[w] = s->ini->process(bf) ? 2 : 1;
+        if (status[w] == 2) stamp2win[ts] = w;
+    }
+    counts[0] = (int) s->map->frameNum();
+    hook::calibrate_calls = 0;
+    const bool ok = s->ini->cvCalibration();
+    counts[1] = (int) s->map->frameNum();
+    counts[2] = hook::calibrate_views;
+    counts[3] = hook::calibrate_flags;
+    const Eigen::Matrix3d &K = s->camera->K();
+    cam9[0] = K(0, 0), cam9[1] = K(1, 1), cam9[2] = K(0, 2), cam9[3] = K(1, 2);
+    for (int k = 0; k < 5; ++k) cam9[4 + k] = s->camera->distCoeffs().size() > k ? s->camera->distCoeffs()[k] : 0.0;
+    for (const auto &kv : s->map->keyframes()) {
+        const int w = stamp2win[kv.first];
+        status[w] = 3;
+        const auto &bf = kv.second;
+        double *o = pose + 7 * w;
+        for (int a = 0; a < 3; ++a) o[a] = bf->twb()[a];
+        for (int a = 0; a < 4; ++a) o[3 + a] = bf->unitQwb().coeffs()[a];
+        double *f = feat + (size_t) w * n_feat * 3;
+        for (int i = 0; i < n_feat; ++i) f[3 * i] = f[3 * i + 1] = 0.0, f[3 * i + 2] = -1.0;
+        for (auto &fb : bf->frame(0)->features()) {
+            auto c = dynamic_cast<opengv2::CalibCircle *>(fb.get());
+            const int id = c->landmark()->id();
+            f[3 * id] = c->location()[0], f[3 * id + 1] = c->location()[1], f[3 * id + 2] = c->radius;
+        }
+    }
+    return ok ? 1 : 0;
 }
 }

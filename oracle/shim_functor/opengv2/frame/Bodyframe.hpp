@@ -20,6 +20,7 @@ public:
         Qwb_ = Qwb;
     }
     std::shared_ptr<CameraFrame> frame(int) const { return frame_; }
+    int size() const { return 1; }
     static Eigen::Quaterniond unitQsb(int) { return Eigen::Quaterniond(1, 0, 0, 0); }
     static Eigen::Vector3d tsb(int) { return Eigen::Vector3d(0, 0, 0); }
     std::vector<double> optT;

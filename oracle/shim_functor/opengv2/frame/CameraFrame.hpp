@@ -12,6 +12,7 @@ public:
     virtual ~CameraFrame() {}
     std::vector<FeatureBase::Ptr> &features() { return features_; }
     const cv::Mat &image() const { return image_; }
+    CameraBase::Ptr sensor() const { return sensor_; }
 
 protected:
     cv::Mat image_;

@@ -4,16 +4,20 @@
 #include <Eigen/Eigen>
 #include <memory>
 namespace opengv2 {
+struct FeatureIdentifier;
 class LandmarkBase {
 public:
     typedef std::shared_ptr<LandmarkBase> Ptr;
     LandmarkBase(int id, const Eigen::Vector3d &p) : id_(id), position_(p) {}
     Eigen::Vector3d position() const noexcept { return position_; }
     int id() const noexcept { return id_; }
+    void addObservation(const FeatureIdentifier &) { ++observations_; }
+    int observations() const { return observations_; }
 
 private:
     int id_;
     Eigen::Vector3d position_;
+    int observations_ = 0;
 };
 }  // namespace opengv2
 #endif

@@ -5,6 +5,8 @@
 #include <map>
 #include <memory>
 #include <opengv2/frame/Bodyframe.hpp>
+#include <opengv2/landmark/LandmarkBase.hpp>
+#include <vector>
 namespace opengv2 {
 class MapBase {
 public:
@@ -17,11 +19,18 @@ public:
         const auto it = kf_.find(id);
         return it == kf_.end() ? nullptr : it->second;
     }
+    bool empty() const { return kf_.empty(); }
+    Bodyframe::Ptr firstKeyframe() const { return kf_.empty() ? nullptr : kf_.begin()->second; }
+    Bodyframe::Ptr lastKeyframe() const { return kf_.empty() ? nullptr : kf_.rbegin()->second; }
+    std::map<double, Bodyframe::Ptr> copyKeyframes() const { return kf_; }
+    void addLandmark(LandmarkBase::Ptr lm) { landmarks_.push_back(lm); }
+    const std::vector<LandmarkBase::Ptr> &landmarks() const { return landmarks_; }
     void keyframeLockShared() {}
     void keyframeUnlockShared() {}
 
 private:
     std::map<double, Bodyframe::Ptr> kf_;
+    std::vector<LandmarkBase::Ptr> landmarks_;
 };
 }  // namespace opengv2
 #endif

@@ -28,6 +28,12 @@ stand-in Eigen / Ceres / Sophus headers of oracle/shim_functor/ (oracle/Makefile
     basis values equal the oracle's association exactly, every residual touches control points span-3 .. span, rotation
     blocks carry EigenQuaternionParameterization, HuberLoss(0.2 r), tolerances 1e-10, SPARSE_NORMAL_CHOLESKY
 
+  * tracking gate, checkPose and the cvCalibration flow (rows f-1, f-4): the reference's EventCalibIni.cpp compiled in place
+    with the product's host header (include/ecb/calib_init.hpp) behind the calibrateCamera / solvePnPRansac / projectPoints /
+    Rodrigues hooks: the façade's TrackingGate and ecb::checkPose take the same decisions as the reference's own code, and the
+    reference's sequential loop (frame selection, pose conversion, checkPose chain, rectifyFeatures) keeps the same frames
+    with the same features as the batched-then-replayed logic of the façade / CLI
+
 The library is built in the build container (where /root/reference exists) and travels as a prebuilt file; without it the
 tests skip."""
 import ctypes as C
@@ -357,3 +363,147 @@ def test_calib_spline_setup_association_and_assembly_vs_reference_source(ref, wi
                          P(np.ascontiguousarray(r["trans_cp"][w])), 0, float(kf_t[k]), P(q4), P(t3)) == 1
         np.testing.assert_allclose(r["kf_pose"][k, 1:4], t3, rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(r["kf_pose"][k, 4:8], q4, rtol=1e-12, atol=1e-12)
+
+
+def _host_libs():
+    import eventcalib_b200.build as b
+    b.build()
+    os.makedirs(os.path.join(ROOT, "tests", "_build"), exist_ok=True)
+    so = os.path.join(ROOT, "tests", "_build", "libfacade_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "helpers", "facade_host.cpp"),
+                           "-L" + os.path.join(ROOT, "eventcalib_b200"), "-lecb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "eventcalib_b200")])
+    so2 = os.path.join(ROOT, "tests", "_build", "libcalib_init_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so2,
+                           os.path.join(ROOT, "tests", "helpers", "calib_init_host.cpp")])
+    F, CI = C.CDLL(so), C.CDLL(so2)
+    F.fh_gate_new.restype = C.c_void_p
+    CI.ci_calibrate.restype = C.c_double
+    CI.ci_calibrate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 5
+    CI.ci_solve_pnp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 4
+    CI.ci_project.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    CI.ci_check_pose.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double]
+    return F, CI
+
+
+def test_tracking_gate_and_check_pose_vs_reference_source(ref):
+    """f-1: TrackingBase::process + EventCalibIni::track (row directions, median angle / duration < 5e-4 pi / step, reference
+    frame by lower_bound of the time stamp) against the façade's TrackingGate, frames arriving out of order like from the
+    reference's worker threads; f-4: EventCalibIni::checkPose against ecb::checkPose."""
+    from eventcalib_b200 import synth
+    from scipy.spatial.transform import Rotation as Rot
+    F, CI = _host_libs()
+    board, cam, step = synth.Board(), synth.Camera(), 5e-4
+    rng = np.random.default_rng(0)
+    mixed = 0
+    for trial, amp in enumerate((1.0, 2.0, 3.0, 6.0)):
+        traj = synth.Trajectory(5 + trial, board, 78.0, rot_amp=(0.1, 0.1, amp))
+        ini = ref.RefIni(346, 260, step)
+        g = C.c_void_p(F.fh_gate_new(9, 4, C.c_double(step)))
+        ts = np.sort(rng.uniform(5.0, 5.6, 160))
+        rng.shuffle(ts[40:])
+        a1, a2 = [], []
+        for tt in ts:
+            R, tw = traj.pose(np.array([tt]))
+            u, v = synth.project(cam, np.repeat(R, 36, 0), np.repeat(tw, 36, 0), board.centres())
+            xy = np.ascontiguousarray(np.c_[u, v] + rng.normal(0, 0.2, (36, 2)))
+            a1.append(ini.gate(float(tt), xy))
+            a2.append(int(F.fh_gate_process(g, C.c_double(tt), P(xy), 36)))
+        F.fh_gate_free(g)
+        assert a1 == a2
+        mixed += 0 < sum(a1) < len(a1)
+    assert mixed >= 3
+    accepted = 0
+    for it in range(1500):
+        q0, t0 = Rot.random(random_state=it).as_quat(), rng.normal(0, 30, 3)
+        dt = rng.uniform(1e-3, 2e-2)
+        ang = rng.uniform(0, 2.2) * 2 * 5e-4 * np.pi / step * dt
+        dtr = rng.uniform(0, 2.2) * 2 * 0.25 / step * dt
+        q1 = (Rot.from_rotvec(Rot.random(random_state=it + 7).apply([0, 0, 1]) * ang) * Rot.from_quat(q0)).as_quat()
+        t1 = t0 + Rot.random(random_state=it + 9).apply([1, 0, 0]) * dtr
+        a = ref.ref_check_pose(1.0, q0, t0, 1.0 + dt, q1, t1, step)
+        b = CI.ci_check_pose(1.0, P(q0.copy()), P(t0.copy()), 1.0 + dt, P(q1.copy()), P(t1.copy()), step)
+        assert a == b
+        accepted += a
+    assert 100 < accepted < 1400
+
+
+@pytest.mark.parametrize("fit,n_use", [(0, 200), (1, 10)])
+def test_cv_calibration_flow_vs_reference_source(ref, fit, n_use):
+    """f-4: the reference's own loop (eventCameraCalib.cpp:49-62 per window, then EventCalibIni::cvCalibration :143-327) on raw
+    events, with the product's calibrateCamera / PnP / projectPoints as the OpenCV hooks, against the batched-then-replayed
+    logic the façade (opengv2::EventCalibIni::cvCalibration in include/ecb/event_calib.hpp) and the CLI use: frames per
+    status, camera (exact), poses (1e-12: the reference goes through Eigen::Quaterniond(Rsw), the façade through R^T),
+    rectified features (exact)."""
+    from eventcalib_b200 import synth
+    glib, grid_order = _grid()
+    F, CI = _host_libs()
+    step, W, H = 5e-4, 346, 260
+    ev = synth.make_stream(400000, W, H, t0=5.0, duration=0.2, seed=1001, rot_amp=(0.35, 0.35, 0.3), orbit=True)
+    t, x, y, p = ev["t"], ev["x"], ev["y"], ev["p"]
+    wins = np.array([[a, a + 1.5e-3] for a in np.arange(5.0, 5.198, 4e-3)])
+    ini = ref.RefIni(W, H, step, n_use=n_use, fitCircle=fit)
+    ini.add_events(t, x, y, p)
+    r = ini.run(wins)
+    assert r["ok"] and r["calibrate_views"] == min(n_use, r["frames_before"])
+    assert r["calibrate_flags"] == (1 << 17) | 2 | 4 | 8 | 2048 | 4096 | 8192   # CALIB_USE_LU | validate()'s flags (parameters.hpp:49-60)
+    # ---- replay ----
+    board = synth.Board()
+    obj = np.ascontiguousarray(board.centres().astype(np.float32).astype(np.float64))   # cv::Point3f
+    rthr = ref.radius_threshold(W, H, 9, 4, 1, 5.5, 1.75)
+    g = C.c_void_p(F.fh_gate_new(9, 4, C.c_double(step)))
+    st = np.zeros(len(wins), np.int32)
+    frames = {}
+    for w, (a, b) in enumerate(wins):
+        P0, N0, _, _ = ref.event_frame(t, x, y, p, float(a), float(b))
+        c = ref.extract(P0, N0, fitCircle=fit, Rthr=rthr)["cand"]
+        if len(c) < 36:
+            continue
+        okg, order = grid_order(glib, c[:, 2:4].astype(np.float32).astype(np.float64))
+        if not okg:
+            continue
+        f = np.ascontiguousarray(c[order][:, 2:5])
+        ts = (a + b) / 2
+        acc = F.fh_gate_process(g, C.c_double(ts), P(np.ascontiguousarray(f[:, :2])), 36)
+        st[w] = 2 if acc else 1
+        if acc:
+            frames[ts] = (w, f, P0, N0)
+    F.fh_gate_free(g)
+    stamps = sorted(frames)
+    use, stp = n_use, len(stamps) // n_use
+    if stp == 0:
+        use, stp = len(stamps), 1
+    img = np.ascontiguousarray(np.array([frames[stamps[i * stp]][1][:, :2] for i in range(use)]).astype(np.float32).astype(np.float64))
+    c9, rv, tv = np.zeros(9), np.zeros((use, 3)), np.zeros((use, 3))
+    tot, pv = np.zeros(1), np.zeros(use, np.float32)
+    CI.ci_calibrate(P(obj), 36, P(img), use, W, H, 7, 1.0, P(c9), P(rv), P(tv), P(tot), P(pv))
+    np.testing.assert_array_equal(c9, r["cam9"])
+    last, sk = None, 1.75 / np.sqrt(2)
+    for s in stamps:
+        w, f, P0, N0 = frames[s]
+        im = np.ascontiguousarray(f[:, :2].astype(np.float32).astype(np.float64))
+        r3, t3, inl, nin = np.zeros(3), np.zeros(3), np.zeros(36, np.int32), np.zeros(1, np.int32)
+        CI.ci_solve_pnp(P(obj), 36, P(im), P(c9), 4.0, P(r3), P(t3), P(inl), P(nin))
+        q, tw = np.zeros(4), np.zeros(3)
+        CI.ci_body_pose(P(r3), P(t3), P(q), P(tw))
+        if last is not None and not CI.ci_check_pose(last[0], P(last[1]), P(last[2]), s, P(q), P(tw), step):
+            continue
+        ip = np.zeros((36, 5, 2))
+        for k in range(36):
+            o5 = np.array([obj[k], obj[k] + [sk, sk, 0], obj[k] + [sk, -sk, 0], obj[k] + [-sk, -sk, 0], obj[k] + [-sk, sk, 0]])
+            o5 = np.ascontiguousarray(o5.astype(np.float32).astype(np.float64))
+            out = np.zeros((5, 2))
+            CI.ci_project(P(o5), 5, P(r3), P(t3), P(c9), P(out))
+            ip[k] = out
+        o2, ok2 = ref.rectify(P0, N0, ip.astype(np.float32).astype(np.float64), W, H, fitCircle=fit)
+        if not ok2:
+            continue
+        st[w] = 3
+        np.testing.assert_allclose(r["pose"][w], np.r_[tw, q], rtol=0, atol=1e-11)
+        keep = o2[:, 2] >= 0
+        np.testing.assert_array_equal(r["feat"][w][:, 2] < 0, ~keep)
+        np.testing.assert_array_equal(r["feat"][w][keep], o2[keep])
+        last = (s, q.copy(), tw.copy())
+    np.testing.assert_array_equal(st, r["status"])
+    assert (st == 3).sum() == r["frames_after"] >= 10 and (st >= 2).sum() == r["frames_before"]
