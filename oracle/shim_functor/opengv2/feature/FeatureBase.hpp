@@ -1,24 +1,31 @@
-// TEST INFRASTRUCTURE.  Stand-in for core/feature/include/opengv2/feature/FeatureBase.hpp: a 2-d location and a weak
-// landmark link (same accessors as the reference's class).
+// TEST INFRASTRUCTURE.  Stand-in for the reference's feature class (core/feature): this oracle build only needs a 2-d image
+// location and an optional link to a landmark, reachable through the accessor names CirclesEventFrame.cpp uses.
 #ifndef ECB_ORACLE_FEATUREBASE_SHIM
 #define ECB_ORACLE_FEATUREBASE_SHIM
-#include <Eigen/Eigen>
 #include <memory>
+
+#include <Eigen/Eigen>
 #include <opengv2/landmark/LandmarkBase.hpp>
+
 namespace opengv2 {
 class FeatureBase {
+    typedef std::weak_ptr<LandmarkBase> Link;
+
 public:
     typedef std::shared_ptr<FeatureBase> Ptr;
-    explicit FeatureBase(const Eigen::Vector2d &loc) : loc_(loc) {}
-    virtual ~FeatureBase() {}
-    LandmarkBase::Ptr landmark() const noexcept { return landmark_.lock(); }
-    void setLandmark(const LandmarkBase::Ptr &lm) noexcept { landmark_ = lm; }
-    const Eigen::Vector2d &location() const noexcept { return loc_; }
-    virtual void setLocation(const Eigen::Vector2d &loc) noexcept { loc_ = loc; }
 
-protected:
-    std::weak_ptr<LandmarkBase> landmark_;
-    Eigen::Vector2d loc_;
+    explicit FeatureBase(const Eigen::Vector2d &xy) : where_(xy) {}
+    virtual ~FeatureBase() = default;
+
+    const Eigen::Vector2d &location() const { return where_; }
+    virtual void setLocation(const Eigen::Vector2d &xy) { where_ = xy; }
+
+    std::shared_ptr<LandmarkBase> landmark() const { return link_.lock(); }
+    void setLandmark(const std::shared_ptr<LandmarkBase> &target) { link_ = target; }
+
+private:
+    Eigen::Vector2d where_;
+    Link link_;
 };
 }  // namespace opengv2
 #endif
