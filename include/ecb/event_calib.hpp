@@ -551,28 +551,44 @@ public:
                     throw std::runtime_error(ecb_last_error(fe.context()));
             }
             // replay of the sequential loop (:246-300): checkPose against the last frame kept, then the rectify verdict
+            std::vector<const KeyFrame *> seq(all.begin(), all.end());
+            const std::vector<char> keep = replayKeep(seq, verdict, step_, counter1, counter2);
             std::map<double, KeyFrame> kept;
-            const KeyFrame *last = nullptr;
             for (size_t i = 0; i < all.size(); ++i) {
+                if (!keep[i]) continue;
                 KeyFrame &kf = *all[i];
-                if (last && !ecb::checkPose(last->timeStamp, last->unitQwb, last->twb, kf.timeStamp, kf.unitQwb, kf.twb, step_)) {
-                    ++counter1;
-                    continue;
-                }
-                if (!verdict[i]) {
-                    ++counter2;
-                    continue;
-                }
                 kf.circles.resize((size_t) nc);
                 for (int k = 0; k < nc; ++k)
                     for (int a = 0; a < 3; ++a) kf.circles[(size_t) k][(size_t) a] = out[(i * nc + (size_t) k) * 3 + (size_t) a];
-                last = &kept.emplace(kf.timeStamp, kf).first->second;
+                kept.emplace(kf.timeStamp, kf);
             }
             frames.swap(kept);
         }
         os << counter1 << " frames discard by checkPose." << std::endl;
         os << counter2 << " frames discard by rectifyFeature." << std::endl;
         return ok;
+    }
+    // The reference adds the frames back one by one in time order (:246-300): a frame is dropped when checkPose against the
+    // LAST FRAME KEPT fails (counter1), else when its rectifyFeatures verdict is false (counter2).  The verdicts do not depend
+    // on the other frames, so they can be computed for all frames at once and the loop replayed afterwards.
+    static std::vector<char> replayKeep(const std::vector<const KeyFrame *> &framesInTimeOrder, const std::vector<int32_t> &verdict,
+                                        double motionTimeStep, int &counter1, int &counter2) {
+        std::vector<char> keep(framesInTimeOrder.size(), 0);
+        const KeyFrame *last = nullptr;
+        for (size_t i = 0; i < framesInTimeOrder.size(); ++i) {
+            const KeyFrame &kf = *framesInTimeOrder[i];
+            if (last && !ecb::checkPose(last->timeStamp, last->unitQwb, last->twb, kf.timeStamp, kf.unitQwb, kf.twb, motionTimeStep)) {
+                ++counter1;
+                continue;
+            }
+            if (!verdict[i]) {
+                ++counter2;
+                continue;
+            }
+            keep[i] = 1;
+            last = &kf;
+        }
+        return keep;
     }
     ecb::CameraModel camera;  // K and distCoeffs (k1 k2 p1 p2 k3) after cvCalibration
 

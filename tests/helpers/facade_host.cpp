@@ -64,3 +64,19 @@ extern "C" void fh_fit_spline(const double *us, const double *data, int n, int d
     std::copy(k.begin(), k.end(), knots);
     std::copy(c.begin(), c.end(), cp);
 }
+// opengv2::EventCalibIni::replayKeep: the cvCalibration loop replayed over precomputed poses (q = x y z w) and rectify verdicts
+extern "C" void fh_replay_keep(const double *ts, const double *q, const double *t, const int *verdict, int n, double step,
+                               char *keep, int *counters) {
+    std::vector<EventCalibIni::KeyFrame> kf((size_t) n);
+    std::vector<const EventCalibIni::KeyFrame *> seq;
+    std::vector<int32_t> v(verdict, verdict + n);
+    for (int i = 0; i < n; ++i) {
+        kf[(size_t) i].timeStamp = ts[i];
+        for (int a = 0; a < 4; ++a) kf[(size_t) i].unitQwb[a] = q[4 * i + a];
+        for (int a = 0; a < 3; ++a) kf[(size_t) i].twb[a] = t[3 * i + a];
+        seq.push_back(&kf[(size_t) i]);
+    }
+    counters[0] = counters[1] = 0;
+    const std::vector<char> k = EventCalibIni::replayKeep(seq, v, step, counters[0], counters[1]);
+    for (int i = 0; i < n; ++i) keep[i] = k[(size_t) i];
+}

@@ -507,3 +507,25 @@ def test_cv_calibration_flow_vs_reference_source(ref, fit, n_use):
         last = (s, q.copy(), tw.copy())
     np.testing.assert_array_equal(st, r["status"])
     assert (st == 3).sum() == r["frames_after"] >= 10 and (st >= 2).sum() == r["frames_before"]
+    # ---- the façade's own replay (opengv2::EventCalibIni::replayKeep): poses and rectify verdicts of ALL frames first (what
+    # the batched GPU call delivers), then the loop — must keep exactly the frames the reference's sequential loop keeps ----
+    n = len(stamps)
+    qs, tws, verdict = np.zeros((n, 4)), np.zeros((n, 3)), np.zeros(n, np.int32)
+    for i, s_ in enumerate(stamps):
+        w, f, P0, N0 = frames[s_]
+        im = np.ascontiguousarray(f[:, :2].astype(np.float32).astype(np.float64))
+        r3, t3, inl, nin = np.zeros(3), np.zeros(3), np.zeros(36, np.int32), np.zeros(1, np.int32)
+        CI.ci_solve_pnp(P(obj), 36, P(im), P(c9), 4.0, P(r3), P(t3), P(inl), P(nin))
+        CI.ci_body_pose(P(r3), P(t3), P(qs[i]), P(tws[i]))
+        ip = np.zeros((36, 5, 2))
+        for k in range(36):
+            o5 = np.array([obj[k], obj[k] + [sk, sk, 0], obj[k] + [sk, -sk, 0], obj[k] + [-sk, -sk, 0], obj[k] + [-sk, sk, 0]])
+            o5 = np.ascontiguousarray(o5.astype(np.float32).astype(np.float64))
+            out = np.zeros((5, 2))
+            CI.ci_project(P(o5), 5, P(r3), P(t3), P(c9), P(out))
+            ip[k] = out
+        verdict[i] = int(ref.rectify(P0, N0, ip.astype(np.float32).astype(np.float64), W, H, fitCircle=fit)[1])
+    keep, counters = np.zeros(n, np.int8), np.zeros(2, np.int32)
+    F.fh_replay_keep(P(np.ascontiguousarray(np.array(stamps))), P(qs), P(tws), P(verdict), n, C.c_double(step), P(keep), P(counters))
+    np.testing.assert_array_equal(keep.astype(bool), np.array([r["status"][frames[s_][0]] == 3 for s_ in stamps]))
+    assert counters[0] + counters[1] == n - keep.sum()
