@@ -9,6 +9,8 @@ the restatement / the product can be checked against them where /root/reference 
   fit_*       CirclesEventFrame::fitCircle (:361-415)
   rectify_*   rectifyFeatures (:417-638): rectified features, verdict; findCenter (CirclesEventFrame.hpp:50-65)
   spline_*    EventCalibSpline constructor (EventCalibSpline.cpp:14-251): segments, intrinsics, residual list, assembly
+  gate_*      TrackingBase::process + EventCalibIni::track (EventCalibIni.cpp:18-97) on frame sequences arriving out of order
+  pose_*      EventCalibIni::checkPose (:328-346)
 
 Needs /root/reference (build container).  Run from the repo root:  python tests/golden/make_reference_source_golden.py
 """
@@ -124,6 +126,32 @@ out.update(spline_ev_t=ev2["t"], spline_ev_x=ev2["x"].astype(np.int16), spline_e
            spline_huber_tol=np.array([r["huber"], r["gradient_tolerance"], r["function_tolerance"]]))
 for s in range(r["n_splines"]):
     out[f"spline_knots_{s}"], out[f"spline_rot_{s}"], out[f"spline_trans_{s}"] = r["knots"][s], r["rot_cp"][s], r["trans_cp"][s]
+# ---- tracking gate and checkPose ----
+from scipy.spatial.transform import Rotation as Rot  # noqa: E402
+for trial, amp in enumerate((1.0, 3.0)):
+    trj = synth.Trajectory(5 + trial, board, 78.0, rot_amp=(0.1, 0.1, amp))
+    ini = oracle.RefIni(346, 260, 5e-4)
+    ts = np.sort(rng.uniform(5.0, 5.6, 80))
+    rng.shuffle(ts[20:])
+    xs, acc = [], []
+    for tt in ts:
+        R, tw_ = trj.pose(np.array([tt]))
+        u, v = synth.project(cam, np.repeat(R, 36, 0), np.repeat(tw_, 36, 0), board.centres())
+        xy = np.ascontiguousarray(np.c_[u, v] + rng.normal(0, 0.2, (36, 2)))
+        xs.append(xy)
+        acc.append(ini.gate(float(tt), xy))
+    out[f"gate_ts_{trial}"], out[f"gate_xy_{trial}"], out[f"gate_accept_{trial}"] = ts, np.array(xs), np.array(acc, np.int8)
+pc = []
+for it in range(400):
+    q0, t0 = Rot.random(random_state=it).as_quat(), rng.normal(0, 30, 3)
+    dt = rng.uniform(1e-3, 2e-2)
+    ang = rng.uniform(0, 2.2) * 2 * 5e-4 * np.pi / 5e-4 * dt
+    dtr = rng.uniform(0, 2.2) * 2 * 0.25 / 5e-4 * dt
+    q1 = (Rot.from_rotvec(Rot.random(random_state=it + 7).apply([0, 0, 1]) * ang) * Rot.from_quat(q0)).as_quat()
+    t1 = t0 + Rot.random(random_state=it + 9).apply([1, 0, 0]) * dtr
+    pc.append(np.r_[q0, t0, dt, q1, t1, oracle.ref_check_pose(1.0, q0, t0, 1.0 + dt, q1, t1, 5e-4)])
+out["pose_cases"] = np.array(pc)   # q0(4) t0(3) dt q1(4) t1(3) verdict
+
 path = os.path.join(ROOT, "tests", "golden", "reference_source.npz")
 np.savez_compressed(path, **out)
 print("written", len(out), "arrays,", os.path.getsize(path) // 1024, "KiB; residuals", r["n_residuals"])

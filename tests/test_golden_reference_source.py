@@ -177,3 +177,31 @@ def test_calib_spline_golden(oracle_mod):
     pb, qb, solver, calls = (int(v) for v in G["spline_assembly"])
     assert pb == qb == int(n_cp.sum()) and solver == 1 and calls == 1
     assert abs(G["spline_huber_tol"][0] - 0.2 * board.radius) < 1e-15 and G["spline_huber_tol"][1] == 1e-10 and G["spline_huber_tol"][2] == 1e-10
+
+
+def test_gate_and_check_pose_golden():
+    """f-1 / f-4: the façade's TrackingGate and ecb::checkPose against the decisions of the reference's EventCalibIni."""
+    import eventcalib_b200.build as b
+    b.build()
+    os.makedirs(os.path.join(ROOT, "tests", "_build"), exist_ok=True)
+    so = os.path.join(ROOT, "tests", "_build", "libfacade_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "helpers", "facade_host.cpp"),
+                           "-L" + os.path.join(ROOT, "eventcalib_b200"), "-lecb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "eventcalib_b200")])
+    so2 = os.path.join(ROOT, "tests", "_build", "libcalib_init_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so2,
+                           os.path.join(ROOT, "tests", "helpers", "calib_init_host.cpp")])
+    F, CI = C.CDLL(so), C.CDLL(so2)
+    F.fh_gate_new.restype = C.c_void_p
+    CI.ci_check_pose.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double]
+    for trial in (0, 1):
+        g = C.c_void_p(F.fh_gate_new(9, 4, C.c_double(5e-4)))
+        acc = [int(F.fh_gate_process(g, C.c_double(float(tt)), P(np.ascontiguousarray(xy)), 36))
+               for tt, xy in zip(G["gate_ts_%d" % trial], G["gate_xy_%d" % trial])]
+        F.fh_gate_free(g)
+        np.testing.assert_array_equal(acc, G["gate_accept_%d" % trial])
+        assert 0 < sum(acc) < len(acc)
+    for row in G["pose_cases"]:
+        q0, t0, dt, q1, t1, verdict = row[:4].copy(), row[4:7].copy(), float(row[7]), row[8:12].copy(), row[12:15].copy(), int(row[15])
+        assert CI.ci_check_pose(1.0, P(q0), P(t0), 1.0 + dt, P(q1), P(t1), 5e-4) == verdict
