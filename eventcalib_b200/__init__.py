@@ -147,7 +147,7 @@ def _ptr(a):
 
 
 def default_params(eps=4.0, min_pts=2, cluster_min=5, knn_num=3, fit_circle=0, radius_threshold=15.511363636363637,
-                   rows_cols=36, order_mode=0, max_clusters=128, median_mode=0):
+                   rows_cols=36, order_mode=0, max_clusters=0, median_mode=0):
     """CirclesEventFrame::Params defaults + parameter/event_calibration/example.yaml.
     order_mode=1, median_mode=1 reproduce the reference's pid order and std::nth_element medians."""
     return FrontendParams(eps, min_pts, cluster_min, knn_num, fit_circle, radius_threshold, rows_cols, order_mode,

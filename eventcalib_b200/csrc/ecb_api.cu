@@ -280,8 +280,11 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     int rc;
     ctx->fp = *params;
     ctx->n_win = 0;
-    int max_k = params->max_clusters ? (int) params->max_clusters : 128;
-    if (max_k > ECB_MAXK_LIMIT) max_k = ECB_MAXK_LIMIT;
+    // kept-cluster table capacity per (window, polarity): fixed when the caller names one (overflow -> ECB_PB_CLUSTER_CAP),
+    // else automatic — the cluster / pair stages are repeated with a larger table when a window overflows (the reference
+    // has no cap, CirclesEventFrame.cpp:89-117), and the context remembers the capacity for the next run
+    const bool auto_k = params->max_clusters == 0;
+    int max_k = auto_k ? ctx->max_k_auto : (int) std::min<uint32_t>(params->max_clusters, 1u << 20);
     ClusterArgs ca;
     memset(&ca, 0, sizeof ca);
     if ((rc = fill_stencil(ctx, ca, params->dbscan_eps))) return rc;
@@ -316,11 +319,8 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
     if ((rc = ecb_reserve(ctx, ctx->kmem, 2 * slots * 4))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->db_dims, (size_t) 2 * n_win * sizeof(ProbDesc)))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->db_hdr, (size_t) 2 * n_win * sizeof(ProbHdr)))) return rc;
-    if ((rc = ecb_reserve(ctx, ctx->ktab, (size_t) 2 * n_win * max_k * sizeof(KeptCluster)))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->summary, (size_t) n_win * sizeof(ecb_window_summary)))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->status, 64))) return rc;
-    ctx->cand_stride = max_k;
-    if ((rc = ecb_reserve(ctx, ctx->cand, (size_t) n_win * ctx->cand_stride * 5 * 8))) return rc;
 
     WindowArgs wa;
     wa.xyp = (const uint32_t *) ctx->ev_xyp.p;
@@ -354,6 +354,12 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
         if ((rc = ecb_launch_order(ctx, oa, (int) max_nm[1]))) return rc;
     }
 
+  for (int attempt = 0;; ++attempt) {  // repeated (rarely) with a larger kept-cluster table in the automatic mode
+    if ((rc = ecb_reserve(ctx, ctx->ktab, (size_t) 2 * n_win * max_k * sizeof(KeptCluster)))) return rc;
+    ctx->cand_stride = max_k;
+    if ((rc = ecb_reserve(ctx, ctx->cand, (size_t) n_win * ctx->cand_stride * 5 * 8))) return rc;
+    uint32_t *const d_max_kept = (uint32_t *) ctx->status.p + 12;
+    ca.max_kept = d_max_kept;
     ca.prob = (const ProbDesc *) ctx->db_dims.p;
     ca.n_prob = 2 * n_win;
     ca.work_counter = (unsigned *) ctx->status.p;
@@ -432,6 +438,15 @@ int ecb_frontend_run(ecb_ctx *ctx, const double *windows, int n_win, const ecb_f
         pa.win_counter = pair_dyn ? (unsigned *) ctx->status.p + 8 : nullptr;
     }
     if ((rc = ecb_launch_pair(ctx, pa))) return rc;
+    if (!auto_k) break;
+    uint32_t max_kept = 0;
+    if ((rc = ecb_d2h(ctx, &max_kept, d_max_kept, 4))) return rc;
+    if (max_kept <= (uint32_t) max_k) break;
+    if (attempt >= 2) return ecb_fail(ctx, ECB_ERR_STATE, "kept-cluster table still too small after resizing (%u > %d)", max_kept, max_k);
+    max_k = (int) ((max_kept + 63u) & ~63u);
+    ctx->max_k_auto = max_k;
+    ECB_CUDA(ctx, cudaMemsetAsync((uint32_t *) ctx->status.p + 8, 0, 32, ctx->stream));  // pair window counter, max_kept
+  }
     ctx->n_win = n_win;
     return ECB_OK;
 }
@@ -624,7 +639,7 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
         max_n = std::max(max_n, d.n);
     }
     const size_t slots = (size_t) std::max<int64_t>(total, 1);
-    const int max_k = 128;
+    const int max_k = 1;  // no kept-cluster tables on this path (cluster_min below)
     if ((rc = ecb_reserve(ctx, ctx->db_pix, slots * 4))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->db_labels, slots * 4))) return rc;
     if ((rc = ecb_reserve(ctx, ctx->db_scratch, slots * 4))) return rc;
@@ -650,6 +665,7 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
     ca.PH = ca.H + 2 * ca.E;
     ca.min_pts = min_pts;
     ca.cluster_min = 0x7FFFFFFF;  // no kept-cluster tables on this path
+    ca.max_kept = nullptr;
     if (ordered) {
         if ((rc = ecb_reserve(ctx, ctx->kd_tree, 4 * slots * 4))) return rc;
         ca.exact_order = 1;

@@ -66,7 +66,6 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ uint32_t ws[33];
     __shared__ uint32_t s_pb, s_status, s_chunk;
-    __shared__ int32_t k_raw[ECB_MAXK_LIMIT], k_size[ECB_MAXK_LIMIT], k_off[ECB_MAXK_LIMIT + 1];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     const int PW = a.PW, PH = a.PH, E = a.E, NW = PW * PH;
@@ -89,6 +88,9 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
     s.r_kd = arr + 2 * NC;  // 2*NC words
     s.r_st = arr + 4 * NC;
     s.r_flag = reinterpret_cast<uint8_t *>(arr + 5 * NC);  // NC bytes, indexed by rank: kd tie flags (bit0 x, bit1 y)
+    // kept-cluster scratch tables (raw id, size, member-list offset), max_k entries each (+1 for the end offset)
+    int32_t *k_raw = reinterpret_cast<int32_t *>(arr + 5 * NC + ((NC + 3) >> 2));
+    int32_t *k_size = k_raw + a.max_k, *k_off = k_size + a.max_k;
 
     for (;;) {
         __syncthreads();
@@ -484,7 +486,10 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             }
         }
         if (n_kept > (uint32_t) a.max_k) {
-            if (tid == 0) atomicOr(&s_status, ECB_PB_CLUSTER_CAP);
+            if (tid == 0) {
+                atomicOr(&s_status, ECB_PB_CLUSTER_CAP);
+                if (a.max_kept) atomicMax(a.max_kept, n_kept);  // the caller re-runs with a table of that capacity
+            }
             n_kept = a.max_k;
         }
         __syncthreads();
@@ -678,10 +683,13 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
 
 }  // namespace
 
-size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, bool arrays_in_smem, bool rank32) {
+// words of the per-point arrays + the kept-cluster scratch tables of one CTA
+static size_t cluster_array_words(int n_cap, int max_k) { return (size_t) 5 * n_cap + ((size_t) n_cap + 3) / 4 + (size_t) 3 * max_k + 1; }
+
+size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, int max_k, bool arrays_in_smem, bool rank32) {
     size_t NW = (size_t) PW * PH;
     size_t b = 2 * NW * 4 + ((NW * (rank32 ? 4 : 2) + 3) / 4) * 4;
-    if (arrays_in_smem) b += (size_t) 5 * n_cap * 4 + (((size_t) n_cap + 3) / 4) * 4;
+    if (arrays_in_smem) b += cluster_array_words(n_cap, max_k) * 4;
     return b;
 }
 
@@ -692,8 +700,8 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     // static shared + reserve; also the (constant) dynamic-smem attribute value, so that concurrent launches from several
     // host threads with different sizes cannot race on cudaFuncSetAttribute
     const size_t limit = (size_t) ctx->smem_optin - 9 * 1024;
-    size_t planes = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, false, rank32);
-    size_t with_arrays = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, true, rank32);
+    size_t planes = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, a.max_k, false, rank32);
+    size_t with_arrays = ecb_cluster_smem_bytes(a.PW, a.PH, a.n_cap, a.max_k, true, rank32);
     // sensors whose bit planes exceed one CTA's shared memory (e.g. 1280x720) run with the planes in per-CTA L2 scratch
     a.planes_in_smem = planes <= limit;
     a.arrays_in_smem = with_arrays <= limit;  // else the per-point arrays live in per-CTA L2 scratch
@@ -715,7 +723,7 @@ int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n) {
     int grid = ctx->sm_count * per_sm;
     if (grid > a.n_prob) grid = a.n_prob;
     if (!a.arrays_in_smem) {
-        a.gscratch_stride = (size_t) 5 * a.n_cap + (a.n_cap + 3) / 4 + (a.planes_in_smem ? 0 : (planes + 3) / 4);
+        a.gscratch_stride = cluster_array_words(a.n_cap, a.max_k) + (a.planes_in_smem ? 0 : (planes + 3) / 4);
         int rc = ecb_reserve(ctx, ctx->scratch, (size_t) grid * a.gscratch_stride * 4);
         if (rc) return rc;
         a.gscratch = (uint32_t *) ctx->scratch.p;

@@ -3,7 +3,6 @@
 #include "ecb_common.cuh"
 
 #define ECB_CL_THREADS 512
-#define ECB_MAXK_LIMIT 512
 
 // one clustering problem = one (window, polarity) point set, or one ecb_dbscan_run input
 struct ProbDesc {
@@ -50,6 +49,7 @@ struct ClusterArgs {
     ProbHdr *hdr;
     KeptCluster *ktab;
     int max_k;
+    uint32_t *max_kept;         // device word (may be null): atomicMax of the kept-cluster count of problems that overflow max_k
     uint32_t *gscratch;         // per-CTA global scratch when the per-point arrays do not fit shared memory
     size_t gscratch_stride;     // words per CTA
     int arrays_in_smem;
@@ -85,7 +85,7 @@ struct BfsArgs {
     double eps;
 };
 
-size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, bool arrays_in_smem, bool rank32);
+size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, int max_k, bool arrays_in_smem, bool rank32);
 int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n);
 int ecb_launch_bfs(ecb_ctx *ctx, BfsArgs &a);
 // every cluster of every problem -> BfsItem (ecb_dbscan_run_ordered): csize/cseed/coff are per point slot (index off + cid)

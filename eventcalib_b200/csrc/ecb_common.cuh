@@ -42,7 +42,8 @@ struct ecb_ctx {
     // front end
     int n_win = 0;
     ecb_frontend_params fp{};
-    DevBuf win_t, win_lohi, win_ptoff, summary, arrive, pts[2], labels[2], scratch, ktab, kmem, cand, status;
+    DevBuf win_t, win_lohi, win_ptoff, summary, arrive, pts[2], labels[2], scratch, ktab, kmem, cand, status, pair_tab;
+    int max_k_auto = 128;     // kept-cluster table capacity of the automatic mode (max_clusters = 0): grows with the data, sticky
     std::vector<int64_t> h_lohi, h_ptoff;
     int64_t total_points = 0;
     int cand_stride = 0;

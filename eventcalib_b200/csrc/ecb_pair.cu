@@ -140,12 +140,19 @@ __device__ __noinline__ void warp_knn(const int *mx, const int *my, int n, int q
     }
 }
 
-template <bool DIRECT, bool FIT>
+// Per-CTA tables over the kept clusters (max_k entries each): accepted circle (3 doubles), medians of both polarities,
+// accepted negative partner.  GT = false: in dynamic shared memory (pointers derived from the shared array only);
+// GT = true (very many kept clusters, e.g. noisy 1280x720 windows): in per-CTA global scratch.
+template <bool DIRECT, bool FIT, bool GT>
 __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
-    extern __shared__ __align__(16) uint32_t sm_pix[];  // DIRECT: member pixels of both polarities
-    __shared__ int mx[2][ECB_MAXK_LIMIT], my[2][ECB_MAXK_LIMIT];
-    __shared__ int acc_ni[ECB_MAXK_LIMIT];
-    __shared__ double acc_c[ECB_MAXK_LIMIT][3];
+    extern __shared__ __align__(16) uint32_t sm_dyn[];
+    double (*acc_c)[3];
+    if constexpr (GT) acc_c = reinterpret_cast<double (*)[3]>(a.gtab + (size_t) blockIdx.x * a.gtab_stride);
+    else acc_c = reinterpret_cast<double (*)[3]>(sm_dyn);
+    int *const tab_i = reinterpret_cast<int *>(acc_c + a.max_k);
+    int *const mx[2] = {tab_i, tab_i + a.max_k}, *const my[2] = {tab_i + 2 * a.max_k, tab_i + 3 * a.max_k};
+    int *const acc_ni = tab_i + 4 * a.max_k;
+    uint32_t *const sm_pix = GT ? sm_dyn : reinterpret_cast<uint32_t *>(acc_ni + a.max_k);  // DIRECT: member pixels of both polarities
     __shared__ uint32_t ws[33];
     __shared__ int s_next;  // next unclaimed positive cluster of the window (the clusters' fit work varies: dynamic hand-out)
     const int tid = threadIdx.x, lane = tid & 31;
@@ -363,8 +370,10 @@ struct RectifyArgs {
 constexpr int RECT_WARPS = 4;
 
 __global__ void __launch_bounds__(RECT_WARPS * 32) k_rectify(const RectifyArgs a) {
-    __shared__ uint32_t mask[RECT_WARPS][2][ECB_MAXK_LIMIT / 32];
+    extern __shared__ uint32_t mask_dyn[];  // [RECT_WARPS][2][mw] bit masks over the kept-cluster tables
+    const int mw = (a.max_k + 31) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t *const mask[2] = {mask_dyn + (size_t) (2 * wib) * mw, mask_dyn + (size_t) (2 * wib + 1) * mw};
     const int item = blockIdx.x * RECT_WARPS + wib;
     if (item >= a.n_frames * a.n_feat) return;
     const int fr = item / a.n_feat;
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__(RECT_WARPS * 32) k_rectify(const RectifyArgs a
         if (radius[i - 1] > maxRadius) maxRadius = radius[i - 1];
     }
     const double R2 = (maxRadius + a.thr) * (maxRadius + a.thr);
-    for (int i = lane; i < 2 * (ECB_MAXK_LIMIT / 32); i += 32) (&mask[wib][0][0])[i] = 0;
+    for (int i = lane; i < 2 * mw; i += 32) mask[0][i] = 0;  // both polarities (contiguous)
     __syncwarp();
     double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int cnt[2] = {0, 0};
@@ -410,11 +419,11 @@ __global__ void __launch_bounds__(RECT_WARPS * 32) k_rectify(const RectifyArgs a
                 const int mid = (lo + hi) >> 1;
                 if (kt[mid].raw_id < l) lo = mid + 1; else hi = mid;
             }
-            if (lo < nk && kt[lo].raw_id == l) atomicOr(&mask[wib][pol][lo >> 5], 1u << (lo & 31));
+            if (lo < nk && kt[lo].raw_id == l) atomicOr(&mask[pol][lo >> 5], 1u << (lo & 31));
         }
         __syncwarp();
         for (int k = lane; k < nk; k += 32)
-            if ((mask[wib][pol][k >> 5] >> (k & 31)) & 1u) {
+            if ((mask[pol][k >> 5] >> (k & 31)) & 1u) {
                 cnt[pol] += kt[k].size;
 #pragma unroll
                 for (int q = 0; q < 9; ++q) m[q] += kt[k].m[q];
@@ -481,14 +490,28 @@ int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     if (a.n_win <= 0) return ECB_OK;
     int grid = a.n_win < ctx->sm_count * 8 ? a.n_win : ctx->sm_count * 8;
     if (a.win_counter) grid = std::min(a.n_win, ctx->sm_count * 4);  // the resident CTAs (__launch_bounds__(256, 4))
-    // stage member pixels in shared memory when both polarities of the largest window fit
-    const size_t smem = (size_t) 2 * a.smem_cap * 4;
-    const bool direct = a.smem_cap > 0 && smem <= 96 * 1024;
+    // kept-cluster tables: 44 bytes per entry, in shared memory unless there are very many kept clusters; member pixels are
+    // staged in shared memory as well when both polarities of the largest window fit next to the tables
+    const size_t tab = (((size_t) a.max_k * 44) + 15) & ~(size_t) 15;
+    const size_t pix = (size_t) 2 * a.smem_cap * 4;
+    const size_t cap = 96 * 1024;
+    const bool gt = tab > cap;
+    const bool direct = !gt && a.smem_cap > 0 && tab + pix <= cap;
+    const size_t smem = gt ? 0 : tab + (direct ? pix : 0);
+    a.gtab = nullptr;
+    a.gtab_stride = 0;
+    if (gt) {
+        a.gtab_stride = tab / 8;
+        int rc = ecb_reserve(ctx, ctx->pair_tab, (size_t) grid * tab);
+        if (rc) return rc;
+        a.gtab = (double *) ctx->pair_tab.p;
+    }
     ECB_PROF_BEGIN(ctx, ECB_STAGE_PAIR);
-    void (*kern)(const PairArgs) = direct ? (a.fit_circle ? k_pair<true, true> : k_pair<true, false>)
-                                          : (a.fit_circle ? k_pair<false, true> : k_pair<false, false>);
-    ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)  /* constant: race-free */);
-    kern<<<grid, PAIR_THREADS, direct ? smem : 0, ctx->stream>>>(a);
+    void (*kern)(const PairArgs) = gt ? (a.fit_circle ? k_pair<false, true, true> : k_pair<false, false, true>)
+                                   : direct ? (a.fit_circle ? k_pair<true, true, false> : k_pair<true, false, false>)
+                                            : (a.fit_circle ? k_pair<false, true, false> : k_pair<false, false, false>);
+    ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cap)  /* constant: race-free */);
+    kern<<<grid, PAIR_THREADS, smem, ctx->stream>>>(a);
     ECB_PROF_END(ctx, ECB_STAGE_PAIR);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_pair launch");
@@ -523,7 +546,10 @@ int ecb_launch_rectify(ecb_ctx *ctx, const int32_t *d_win, int n_frames, int n_f
     a.H = ctx->height;
     a.thr = thr;
     const int items = n_frames * n_feat;
-    k_rectify<<<(items + RECT_WARPS - 1) / RECT_WARPS, RECT_WARPS * 32, 0, ctx->stream>>>(a);
+    const size_t smem = (size_t) RECT_WARPS * 2 * ((a.max_k + 31) / 32) * 4;
+    if (smem > 200 * 1024) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "rectify: %d kept clusters per window", a.max_k);
+    ECB_CUDA(ctx, cudaFuncSetAttribute(k_rectify, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_rectify<<<(items + RECT_WARPS - 1) / RECT_WARPS, RECT_WARPS * 32, smem, ctx->stream>>>(a);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_rectify launch");
 }

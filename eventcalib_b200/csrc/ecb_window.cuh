@@ -43,6 +43,8 @@ struct PairArgs {
     uint32_t rows_cols;
     double rthr;
     unsigned *win_counter;    // non-null: windows are handed out dynamically (zeroed by the caller), grid = resident CTAs
+    double *gtab;             // per-CTA kept-cluster tables in global scratch when max_k is too large for shared memory
+    size_t gtab_stride;       // doubles per CTA
 };
 
 int ecb_launch_ingest(ecb_ctx *ctx, const void *d_raw, int64_t n);

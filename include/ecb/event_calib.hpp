@@ -17,6 +17,7 @@
 #ifndef ECB_EVENT_CALIB_HPP
 #define ECB_EVENT_CALIB_HPP
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <fstream>
@@ -198,27 +199,37 @@ public:
         if (ecb_frontend_run(c_->ctx, w.data(), (int) windows.size(), &fp) != ECB_OK)
             throw std::runtime_error(ecb_last_error(c_->ctx));
         summary_.resize(windows.size());
-        cand_.assign(windows.size() * kMaxCand * 5, 0.0);
+        stride_ = 1;
         if (!windows.empty()) {
-            ecb_frontend_summary(c_->ctx, summary_.data(), (int) windows.size());
-            ecb_frontend_candidates(c_->ctx, cand_.data(), kMaxCand);
+            if (ecb_frontend_summary(c_->ctx, summary_.data(), (int) windows.size()) != ECB_OK)
+                throw std::runtime_error(ecb_last_error(c_->ctx));
+            // max_clusters = 0: the kept-cluster tables grow with the data, so a window is never truncated
+            // (CirclesEventFrame.cpp:89-312 has no cap); anything else the kernels flag is an error, not a shorter list
+            for (const auto &s : summary_) {
+                if (s.status & (ECB_PB_CLUSTER_CAP | ECB_PB_RANGE))
+                    throw std::runtime_error("front end: window result incomplete (status bits " + std::to_string(s.status) + ")");
+                stride_ = std::max(stride_, (int) s.n_candidates);
+            }
         }
+        cand_.assign(windows.size() * (size_t) stride_ * 5, 0.0);
+        if (!windows.empty() && ecb_frontend_candidates(c_->ctx, cand_.data(), stride_) != ECB_OK)
+            throw std::runtime_error(ecb_last_error(c_->ctx));
     }
     const ecb_window_summary &summary(size_t w) const { return summary_[w]; }
     int eventsNum(size_t w) const { return summary_[w].n_points[0] + summary_[w].n_points[1]; }
     std::vector<CalibCircleLite> candidates(size_t w) const {
         std::vector<CalibCircleLite> out;
-        for (int k = 0; k < summary_[w].n_candidates && k < kMaxCand; ++k) {
-            const double *c = &cand_[(w * kMaxCand + k) * 5];
+        for (int k = 0; k < summary_[w].n_candidates && k < stride_; ++k) {
+            const double *c = &cand_[(w * (size_t) stride_ + k) * 5];
             out.push_back(CalibCircleLite{{{c[2], c[3]}}, c[4], (int) c[0], (int) c[1]});
         }
         return out;
     }
     double circleRadiusThreshold() const { return rthr_; }
     ecb_ctx *context() const { return c_->ctx; }
-    static constexpr int kMaxCand = 128;
 
 private:
+    int stride_ = 1;  // candidate slots per window of the last run = its largest candidate count
     EventContainer::Ptr c_;
     CirclePatternParameters::Ptr pattern_;
     Params p_;

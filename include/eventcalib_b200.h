@@ -94,7 +94,11 @@ typedef struct {
     uint32_t rows_cols;         /* pattern rows*cols (need that many kept clusters per polarity, :127-129) */
     int32_t order_mode;         /* 0: pid = first-arrival order; 1: libstdc++ unordered_set iteration order
                                    (the reference's order, EventFrame.cpp:12-35) */
-    uint32_t max_clusters;      /* kept-cluster table capacity per (window,polarity); 0 -> 128 */
+    uint32_t max_clusters;      /* kept-cluster table capacity per (window,polarity).  0 (recommended): automatic — the
+                                   tables grow until every window fits (the reference has no cap,
+                                   CirclesEventFrame.cpp:89-117) and the context keeps the capacity for later runs;
+                                   > 0: fixed capacity, windows with more kept clusters are truncated and flagged
+                                   ECB_PB_CLUSTER_CAP */
     uint32_t median_mode;       /* cluster centre = member with the median norm (CirclesEventFrame.cpp:137-147):
                                    0: slot size/2 of the members sorted by (norm, pid) — order independent;
                                    1: the reference's pick: std::nth_element (libstdc++) over the members in DBSCAN's

@@ -434,6 +434,29 @@ def frontend_windows(t, x, y, pol, windows, eps=4.0, minS=2, clusterMin=5, knn_n
     return int(tot), int(nev.value), per[:len(win)].copy()
 
 
+def frontend_windows_detail(t, x, y, pol, windows, eps=4.0, minS=2, clusterMin=5, knn_num=3, fitCircle=0, Rthr=15.51,
+                            rows_cols=36, threads=1, ref=True, cand_cap=64):
+    """frontend_windows with the per-window results kept: returns (events, counts [n_win][6] = points -, +, raw clusters
+    -, +, kept clusters -, +; candidates per window; cand [n_win][cand_cap][5] = pi, ni, cx, cy, r)."""
+    lib = ref_frontend_lib() if (ref and os.path.exists(_REF_FE)) else port()
+    lib.orc_frontend_windows_detail.restype = C.c_int64
+    t = np.ascontiguousarray(t, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    pol = np.ascontiguousarray(pol, np.uint8)
+    win = np.ascontiguousarray(windows, np.float64).reshape(-1, 2)
+    nev = C.c_int64(0)
+    per = np.zeros(max(len(win), 1), np.int32)
+    counts = np.zeros((max(len(win), 1), 6), np.int32)
+    cand = np.zeros((max(len(win), 1), cand_cap, 5))
+    lib.orc_frontend_windows_detail(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_int64(len(t)), _p(win, _dp),
+                                    C.c_int(len(win)), C.c_double(eps), C.c_uint(minS), C.c_uint(clusterMin),
+                                    C.c_int(knn_num), C.c_int(fitCircle), C.c_double(Rthr), C.c_uint(rows_cols),
+                                    C.c_int(threads), C.byref(nev), _p(per, _ip), _p(counts, _ip), _p(cand, _dp),
+                                    C.c_int(cand_cap))
+    return int(nev.value), counts[:len(win)].copy(), per[:len(win)].copy(), cand[:len(win)]
+
+
 # ------------------------------------------------------------------------------- cost evaluation ----
 def inverse_radial(k4):
     k = np.ascontiguousarray(k4, np.float64)

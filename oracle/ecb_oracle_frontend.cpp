@@ -674,10 +674,36 @@ extern "C" {
 #include <atomic>
 #include <thread>
 
+// Same loop with the per-window results kept (bench.py's full-size parity check): counts[w] = points -, points +, raw
+// clusters -, +, kept clusters -, + ; cand_out[w][k] = pi, ni, cx, cy, r of the first cand_cap candidates.
+static int64_t frontend_windows_impl(const double *t, const double *x, const double *y, const uint8_t *pol,
+                                     int64_t n, const double *win, int n_win, double eps, unsigned minS,
+                                     unsigned clusterMin, int knn_num, int fitCircleFlag, double Rthr,
+                                     unsigned rows_cols, int threads, int64_t *n_events_out, int *cand_per_win,
+                                     int *counts, double *cand_out, int cand_cap);
+
+extern "C" int64_t orc_frontend_windows_detail(const double *t, const double *x, const double *y, const uint8_t *pol,
+                                               int64_t n, const double *win, int n_win, double eps, unsigned minS,
+                                               unsigned clusterMin, int knn_num, int fitCircleFlag, double Rthr,
+                                               unsigned rows_cols, int threads, int64_t *n_events_out, int *cand_per_win,
+                                               int *counts, double *cand_out, int cand_cap) {
+    return frontend_windows_impl(t, x, y, pol, n, win, n_win, eps, minS, clusterMin, knn_num, fitCircleFlag, Rthr, rows_cols,
+                                 threads, n_events_out, cand_per_win, counts, cand_out, cand_cap);
+}
+
 extern "C" int64_t orc_frontend_windows(const double *t, const double *x, const double *y, const uint8_t *pol,
                                         int64_t n, const double *win, int n_win, double eps, unsigned minS,
                                         unsigned clusterMin, int knn_num, int fitCircleFlag, double Rthr,
                                         unsigned rows_cols, int threads, int64_t *n_events_out, int *cand_per_win) {
+    return frontend_windows_impl(t, x, y, pol, n, win, n_win, eps, minS, clusterMin, knn_num, fitCircleFlag, Rthr, rows_cols,
+                                 threads, n_events_out, cand_per_win, nullptr, nullptr, 0);
+}
+
+static int64_t frontend_windows_impl(const double *t, const double *x, const double *y, const uint8_t *pol,
+                                     int64_t n, const double *win, int n_win, double eps, unsigned minS,
+                                     unsigned clusterMin, int knn_num, int fitCircleFlag, double Rthr,
+                                     unsigned rows_cols, int threads, int64_t *n_events_out, int *cand_per_win,
+                                     int *counts, double *cand_out, int cand_cap) {
     std::atomic<int> next(0);
     std::atomic<int64_t> total(0), nev(0);
     auto work = [&]() {
@@ -691,6 +717,24 @@ extern "C" int64_t orc_frontend_windows(const double *t, const double *x, const 
             extract(f, eps, minS, clusterMin, knn_num, fitCircleFlag, Rthr, rows_cols, false);
             total += (int64_t) f.cand.size();
             if (cand_per_win) cand_per_win[w] = (int) f.cand.size();
+            if (counts) {
+                int *c = counts + (size_t) 6 * w;
+                c[0] = (int) f.neg.size();
+                c[1] = (int) f.pos.size();
+                c[2] = (int) f.ndb.clusters.size();
+                c[3] = (int) f.pdb.clusters.size();
+                c[4] = (int) f.ncl.size();
+                c[5] = (int) f.pcl.size();
+            }
+            if (cand_out)
+                for (size_t k = 0; k < f.cand.size() && (int) k < cand_cap; ++k) {
+                    double *o = cand_out + ((size_t) w * cand_cap + k) * 5;
+                    o[0] = f.cand[k].pi;
+                    o[1] = f.cand[k].ni;
+                    o[2] = f.cand[k].cx;
+                    o[3] = f.cand[k].cy;
+                    o[4] = f.cand[k].r;
+                }
         }
     };
     if (threads <= 1)

@@ -30,7 +30,7 @@ def _first_arrival(ev, lo, hi, pol):
 
 
 def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4.0, min_pts=2, order_mode=0,
-                  median_mode=0):
+                  median_mode=0, cluster_min=5, stats=None):
     import eventcalib_b200 as ecb
     from eventcalib_b200 import synth
     ctx.set_sensor(width, height)
@@ -38,11 +38,13 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
     assert n == len(ev["t"])
     rthr = ecb.radius_threshold(width, height, 9, 4, True, 5.5, 1.75)
     prm = ecb.default_params(eps=eps, min_pts=min_pts, fit_circle=fit_circle, radius_threshold=rthr,
-                             order_mode=order_mode, median_mode=median_mode)
+                             order_mode=order_mode, median_mode=median_mode, cluster_min=cluster_min)
     ctx.frontend_run(windows, prm)
     summ = ctx.summary()
     pts = [ctx.points(0), ctx.points(1)]
-    cand = ctx.candidates(64)
+    cand = ctx.candidates(max(64, int(summ["n_candidates"].max())))
+    if stats is not None:
+        stats["max_kept"] = max(stats.get("max_kept", 0), int(summ["n_kept"].max()))
     n_cand_total = 0
     for w, (t0, t1) in enumerate(windows):
         P, N, lo, hi = oracle_mod.event_frame(ev["t"], ev["x"], ev["y"], ev["p"], t0, t1)
@@ -62,12 +64,12 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
             V.append(xy)
         # median_mode 1: the oracle runs the real std::nth_element over the BFS-ordered member lists, like the reference
         r = oracle_mod.extract(V[1], V[0], eps=eps, minS=min_pts, fitCircle=fit_circle, Rthr=rthr,
-                               canonical_median=(median_mode == 0))
+                               canonical_median=(median_mode == 0), clusterMin=cluster_min)
         for pol, key in ((0, "n"), (1, "p")):
             o, k = int(s["point_offset"][pol]), int(s["n_points"][pol])
             assert np.array_equal(pts[pol][1][o:o + k], r[key + "_labels"]), "labels differ window %d pol %d" % (w, pol)
             assert s["n_clusters"][pol] == len(r[key + "_clusters"])
-            raw, size, med = ctx.clusters(w, pol)
+            raw, size, med = ctx.clusters(w, pol, cap=max(512, int(s["n_kept"][pol])))
             assert np.array_equal(raw, r["kept_" + key])
             assert np.array_equal(size, [len(r[key + "_clusters"][c]) for c in raw])
             if r["enough"]:
@@ -144,6 +146,29 @@ def test_hd_sensor_noise_sweep(ctx, oracle_mod):
     _check_stream(ctx, oracle_mod, ev, win, 1280, 720, 1, order_mode=1, median_mode=1)
     for eps, mp in ((2, 2), (3, 5), (6, 3), (8, 8)):
         _check_stream(ctx, oracle_mod, ev, win, 1280, 720, 0, eps=float(eps), min_pts=mp)
+
+
+def test_many_kept_clusters_grow_the_tables(ctx, oracle_mod):
+    """The reference has no cap on the clusters a window keeps (CirclesEventFrame.cpp:89-117).  max_clusters = 0 sizes the
+    kept-cluster tables from the data: noisy windows with hundreds of kept clusters come back complete (status 0, every
+    kept cluster / median / candidate equal to the oracle's); a fixed capacity truncates and says so."""
+    import eventcalib_b200 as ecb
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(120000, 1280, 720, t0=0.0, duration=0.002, seed=77, noise_frac=0.6, flip_frac=0.05)
+    win = synth.tiling_windows(0.0, 0.002, 1e-3)
+    st = {}
+    _check_stream(ctx, oracle_mod, ev, win, 1280, 720, 1, eps=8.0, min_pts=2, cluster_min=2, order_mode=1, median_mode=1, stats=st)
+    _check_stream(ctx, oracle_mod, ev, win, 1280, 720, 0, eps=3.0, min_pts=2, cluster_min=2, stats=st)
+    assert st["max_kept"] > 512, st   # beyond the old static limits (128 default, 512 maximum)
+    ev = synth.make_stream(60000, 346, 260, t0=0.0, duration=0.003, seed=78, noise_frac=0.7, flip_frac=0.1)
+    win = synth.tiling_windows(0.0, 0.003, 1.5e-3)
+    st = {}
+    _check_stream(ctx, oracle_mod, ev, win, 346, 260, 1, eps=2.0, min_pts=2, cluster_min=2, order_mode=1, median_mode=1, stats=st)
+    assert st["max_kept"] > 128, st
+    # fixed capacity: truncated tables are flagged
+    prm = ecb.default_params(eps=2.0, min_pts=2, cluster_min=2, max_clusters=16)
+    ctx.frontend_run(win, prm)
+    assert all(int(v) & ecb.PB_CLUSTER_CAP for v in ctx.summary()["status"])
 
 
 def test_eps_minpts_sweep(ctx, oracle_mod):
