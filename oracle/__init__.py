@@ -95,6 +95,49 @@ def ref_residual_jac(intr, rcp, tcp, obs, lm, radius, b):
     return r, jac, rd
 
 
+def ref_residual_jac_so3(intr, rcp, tcp, obs, lm, radius, beta3, basis4):
+    """The reference's own CalibReprojectionError_SO3::operator() (EventCalibSpline.hpp:65-156) on Jet<37> and on double,
+    compiled where it lies against the stand-in Sophus (oracle/shim_functor/sophus/so3.hpp): (value on Jet, 1x37 ambient
+    Jacobian, value on double).  beta3: the cumulative rotation basis, basis4: the translation basis."""
+    a = [np.ascontiguousarray(v, np.float64) for v in (intr, rcp, tcp, obs, lm, beta3, basis4)]
+    jac = np.zeros(37)
+    lib = ref_functor_lib()
+    lib.ref_residual_jac_so3.restype = C.c_double
+    lib.ref_residual_so3.restype = C.c_double
+    r = lib.ref_residual_jac_so3(_p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), _p(a[3], _dp), _p(a[4], _dp), C.c_double(radius),
+                                 _p(a[5], _dp), _p(a[6], _dp), _p(jac, _dp))
+    rd = lib.ref_residual_so3(_p(a[0], _dp), _p(a[1], _dp), _p(a[2], _dp), _p(a[3], _dp), _p(a[4], _dp), C.c_double(radius),
+                              _p(a[5], _dp), _p(a[6], _dp))
+    return r, jac, rd
+
+
+def ref_so3_basis(knots, u):
+    """The reference's BsplineSO3::findSpan + derBasisFuns(u, span, 0) (core/spline/src/BsplineSO3.cpp:73-109, compiled where
+    it lies): (span, the 3 cumulative basis values)."""
+    kn = np.ascontiguousarray(knots, np.float64)
+    span = C.c_int()
+    b = np.zeros(3)
+    ref_functor_lib().ref_so3_basis(_p(kn, _dp), C.c_int(len(kn)), C.c_double(u), C.byref(span), _p(b, _dp))
+    return span.value, b
+
+
+def ref_so3_plus(x, d):
+    """The reference's LocalParameterizationSO3::Plus (BsplineSO3.hpp:196-204): T * exp(delta)."""
+    x = np.ascontiguousarray(x, np.float64)
+    d = np.ascontiguousarray(d, np.float64)
+    out = np.zeros(4)
+    ref_functor_lib().ref_so3_plus(_p(x, _dp), _p(d, _dp), _p(out, _dp))
+    return out
+
+
+def ref_so3_plus_jacobian(x):
+    """The reference's LocalParameterizationSO3::ComputeJacobian (BsplineSO3.hpp:209-217), 4 x 3."""
+    x = np.ascontiguousarray(x, np.float64)
+    J = np.zeros(12)
+    ref_functor_lib().ref_so3_plus_jacobian(_p(x, _dp), _p(J, _dp))
+    return J.reshape(4, 3)
+
+
 def ref_undistort(intr, obs):
     a = [np.ascontiguousarray(v, np.float64) for v in (intr, obs)]
     out = np.zeros(3)

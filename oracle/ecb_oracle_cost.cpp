@@ -188,23 +188,32 @@ T residual(const T *intr, const T *const r_cp[4], const T *const t_cp[4], const 
     return jsqrt(d[0] * d[0] + (d[1] * d[1] + d[2] * d[2])) - radius;
 }
 
-// ---- Sophus::SO3 pieces used by CalibReprojectionError_SO3  [external: Sophus 1.x so3.hpp, NOT in /root/reference] ----
-// storage = Eigen quaternion coefficients x y z w
+// ---- Sophus::SO3 pieces used by CalibReprojectionError_SO3  [external: Sophus 1.0 so3.hpp, NOT in /root/reference] ----
+// storage = Eigen quaternion coefficients x y z w.  Every SO3 built from a quaternion is normalised by Sophus' constructor
+// (coeffs /= norm, Eigen's reduction order (x^2 + y^2) + (z^2 + w^2)); that includes the results of operator* and inverse().
+// The same semantics are written out in the stand-in oracle/shim_functor/sophus/so3.hpp the reference's own SO(3) functor is
+// compiled against (oracle/_ref/libref_functor.so) — tests/test_oracle_reference_source.py holds the two bit-identical.
+template <class T> void so3_normalize(T r[4]) {
+    const T n = jsqrt((r[0] * r[0] + r[1] * r[1]) + (r[2] * r[2] + r[3] * r[3]));
+    for (int c = 0; c < 4; ++c) r[c] = r[c] / n;
+}
 template <class T> void so3_mul(const T a[4], const T b[4], T r[4]) {  // SO3::operator*
     r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
     r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
     r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
     r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    so3_normalize(r);
 }
-template <class T> void so3_inverse(const T a[4], T r[4]) {  // conjugate
+template <class T> void so3_inverse(const T a[4], T r[4]) {  // SO3(conjugate)
     r[0] = -a[0];
     r[1] = -a[1];
     r[2] = -a[2];
     r[3] = a[3];
+    so3_normalize(r);
 }
 template <class T> void so3_log(const T q[4], T t[3]) {  // SO3::logAndTheta
     const double eps = 1e-10;  // Sophus::Constants<double>::epsilon()
-    T squared_n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    T squared_n = q[0] * q[0] + (q[1] * q[1] + q[2] * q[2]);  // vec().squaredNorm(), Eigen's reduction order
     T w = q[3];
     T two_atan_nbyw_by_n;
     if (jval(squared_n) < eps * eps) {
@@ -222,7 +231,7 @@ template <class T> void so3_log(const T q[4], T t[3]) {  // SO3::logAndTheta
 }
 template <class T> void so3_exp(const T o[3], T q[4]) {  // SO3::expAndTheta
     const double eps = 1e-10;
-    T theta_sq = o[0] * o[0] + o[1] * o[1] + o[2] * o[2];
+    T theta_sq = o[0] * o[0] + (o[1] * o[1] + o[2] * o[2]);
     T imag, real;
     if (jval(theta_sq) < eps * eps) {
         T theta_po4 = theta_sq * theta_sq;

@@ -81,6 +81,33 @@ template <int NP> Jet<NP> &operator*=(Jet<NP> &f, const Jet<NP> &g) { return f =
 template <int NP> Jet<NP> &operator+=(Jet<NP> &f, const Jet<NP> &g) { return f = f + g; }
 template <int NP> bool operator>(const Jet<NP> &f, const Jet<NP> &g) { return f.a > g.a; }
 template <int NP> bool operator!=(const Jet<NP> &f, const Jet<NP> &g) { return f.a != g.a; }
+template <int NP> bool operator<(const Jet<NP> &f, const Jet<NP> &g) { return f.a < g.a; }
+template <int NP> Jet<NP> operator/(const Jet<NP> &f, double s) { return f / Jet<NP>(s); }
+template <int NP> Jet<NP> operator/(double s, const Jet<NP> &f) { return Jet<NP>(s) / f; }
+template <int NP> Jet<NP> &operator/=(Jet<NP> &f, const Jet<NP> &g) { return f = f / g; }
+// ceres/jet.h: abs, sin, cos, atan of a dual number
+template <int NP> Jet<NP> abs(const Jet<NP> &f) { return f.a < 0.0 ? -f : f; }
+template <int NP> Jet<NP> sin(const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = std::sin(f.a);
+    const double c = std::cos(f.a);
+    for (int i = 0; i < NP; ++i) h.v[i] = c * f.v[i];
+    return h;
+}
+template <int NP> Jet<NP> cos(const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = std::cos(f.a);
+    const double s = -std::sin(f.a);
+    for (int i = 0; i < NP; ++i) h.v[i] = s * f.v[i];
+    return h;
+}
+template <int NP> Jet<NP> atan(const Jet<NP> &f) {
+    Jet<NP> h;
+    h.a = std::atan(f.a);
+    const double t = 1.0 / (1.0 + f.a * f.a);
+    for (int i = 0; i < NP; ++i) h.v[i] = t * f.v[i];
+    return h;
+}
 template <int NP> Jet<NP> sqrt(const Jet<NP> &f) {  // ceres/jet.h
     Jet<NP> h;
     h.a = std::sqrt(f.a);
@@ -139,6 +166,73 @@ void ref_undistort(const double *intr, const double *obs, double *Xc3) {
     EventCalibSpline::unDistort<double>(intr[0], intr[1], intr[2], intr[3], intr[4], intr[5], intr[6], intr[7], intr[8],
                                         Eigen::Vector2d(obs[0], obs[1]), Xc);
     for (int k = 0; k < 3; ++k) Xc3[k] = Xc[k];
+}
+}
+
+// ---- a11: the SO(3) variant (useSO3: 1) — CalibReprojectionError_SO3 (EventCalibSpline.hpp:65-156), the cumulative basis of
+// BsplineSO3::derBasisFuns (core/spline/src/BsplineSO3.cpp:73-109, compiled where it lies) and LocalParameterizationSO3
+// (core/spline/include/opengv2/spline/BsplineSO3.hpp:190-221), against the stand-in Sophus of shim_functor/sophus/so3.hpp ----
+namespace {
+template <class T>
+T run_functor_so3(const T *intr, const T *rcp16, const T *tcp12, const double *obs, const double *lm, double radius,
+                  const double *beta3, const double *basis4) {
+    const Eigen::Vector2d o(obs[0], obs[1]);
+    const Eigen::Vector3d l(lm[0], lm[1], lm[2]);
+    const Eigen::Quaterniond Qbs(1, 0, 0, 0);
+    const Eigen::Vector3d tbs(0, 0, 0);
+    auto rB = std::make_shared<std::vector<std::vector<double>>>(1, std::vector<double>(beta3, beta3 + 3));
+    auto tB = std::make_shared<std::vector<std::vector<double>>>(1, std::vector<double>(basis4, basis4 + 4));
+    EventCalibSpline::CalibReprojectionError_SO3 f(&o, &l, &radius, &Qbs, &tbs, rB, tB);
+    T res;
+    f(intr, rcp16, rcp16 + 4, rcp16 + 8, rcp16 + 12, tcp12, tcp12 + 3, tcp12 + 6, tcp12 + 9, &res);
+    return res;
+}
+struct SO3SplineProbe : opengv2::BsplineSO3 {
+    SO3SplineProbe() : opengv2::BsplineSO3(3) {}
+    void setKnots(const double *k, int nk) { knotVector_.assign(k, k + nk); }
+};
+}  // namespace
+
+extern "C" {
+double ref_residual_so3(const double *intr, const double *rcp16, const double *tcp12, const double *obs, const double *lm,
+                        double radius, const double *beta3, const double *basis4) {
+    return run_functor_so3<double>(intr, rcp16, tcp12, obs, lm, radius, beta3, basis4);
+}
+// value and 1 x 37 ambient Jacobian (9 intrinsics | 4 x 4 SO3 control-point coefficients x y z w | 4 x 3 translation control points)
+double ref_residual_jac_so3(const double *intr, const double *rcp16, const double *tcp12, const double *obs, const double *lm,
+                            double radius, const double *beta3, const double *basis4, double *jac37) {
+    typedef jet::Jet<37> J;
+    J p[37];
+    for (int k = 0; k < 9; ++k) p[k] = J(intr[k]);
+    for (int k = 0; k < 16; ++k) p[9 + k] = J(rcp16[k]);
+    for (int k = 0; k < 12; ++k) p[25 + k] = J(tcp12[k]);
+    for (int k = 0; k < 37; ++k) p[k].v[k] = 1.0;
+    const J r = run_functor_so3<J>(p, p + 9, p + 25, obs, lm, radius, beta3, basis4);
+    for (int k = 0; k < 37; ++k) jac37[k] = r.v[k];
+    return r.a;
+}
+// BsplineSO3::findSpan + derBasisFuns(u, span, 0) on a given knot vector: the 3 cumulative basis values beta_{k,k-p+j}
+void ref_so3_basis(const double *knots, int nk, double u, int *span, double *beta3) {
+    SO3SplineProbe sp;
+    sp.setKnots(knots, nk);
+    const size_t s = sp.findSpan(u);
+    std::vector<std::vector<double>> ders;
+    sp.derBasisFuns(u, s, 0, ders);
+    *span = (int) s;
+    for (int j = 0; j < 3; ++j) beta3[j] = ders[0][(size_t) j];
+}
+// LocalParameterizationSO3::Plus (T * exp(delta)) and ::ComputeJacobian (4 x 3, row major)
+void ref_so3_plus(const double *x4, const double *delta3, double *out4) {
+    opengv2::LocalParameterizationSO3 lp;
+    lp.Plus(x4, delta3, out4);
+}
+void ref_so3_plus_jacobian(const double *x4, double *J12) {
+    opengv2::LocalParameterizationSO3 lp;
+    lp.ComputeJacobian(x4, J12);
+}
+int ref_so3_sizes(void) {
+    opengv2::LocalParameterizationSO3 lp;
+    return lp.GlobalSize() * 10 + lp.LocalSize();
 }
 }
 

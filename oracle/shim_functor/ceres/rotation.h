@@ -33,6 +33,11 @@ public:
 class LocalParameterization {
 public:
     virtual ~LocalParameterization() {}
+    // the interface the reference's LocalParameterizationSO3 overrides (BsplineSO3.hpp:190-221)
+    virtual bool Plus(const double *, const double *, double *) const { return false; }
+    virtual bool ComputeJacobian(const double *, double *) const { return false; }
+    virtual int GlobalSize() const { return 0; }
+    virtual int LocalSize() const { return 0; }
 };
 class EigenQuaternionParameterization : public LocalParameterization {};
 enum LinearSolverType { DENSE_QR, SPARSE_NORMAL_CHOLESKY };
@@ -54,6 +59,8 @@ public:
     void AddParameterBlock(double *values, int size, LocalParameterization *local = nullptr) {
         parameters.push_back(RecordedParameter{values, size, local});
     }
+    void SetParameterBlockConstant(double *values) { constant.push_back(values); }
+    std::vector<double *> constant;
     template <class... Ps> void AddResidualBlock(CostFunction *cost, LossFunction *loss, Ps... ps) {
         residuals.push_back(RecordedResidual{cost, loss, std::vector<double *>{ps...}});
     }
@@ -67,6 +74,7 @@ struct Options {
     int num_threads = 1, num_linear_solver_threads = 1, max_num_iterations = 50;
 };
 struct Summary {
+    std::string BriefReport() const { return "ceres stand-in: Solve() is a no-op"; }
     std::string FullReport() const { return "ceres stand-in: Solve() is a no-op (oracle/shim_functor/ceres/rotation.h)"; }
 };
 }  // namespace Solver

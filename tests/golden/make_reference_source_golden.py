@@ -9,6 +9,8 @@ the restatement / the product can be checked against them where /root/reference 
   fit_*       CirclesEventFrame::fitCircle (:361-415)
   rectify_*   rectifyFeatures (:417-638): rectified features, verdict; findCenter (CirclesEventFrame.hpp:50-65)
   spline_*    EventCalibSpline constructor (EventCalibSpline.cpp:14-251): segments, intrinsics, residual list, assembly
+  so3_*       CalibReprojectionError_SO3::operator() on Jet<37> (EventCalibSpline.hpp:65-156) for the residual blocks of a small
+              calibration problem, BsplineSO3::derBasisFuns (BsplineSO3.cpp:73-109), LocalParameterizationSO3 (BsplineSO3.hpp:190-221)
   gate_*      TrackingBase::process + EventCalibIni::track (EventCalibIni.cpp:18-97) on frame sequences arriving out of order
   pose_*      EventCalibIni::checkPose (:328-346)
 
@@ -126,6 +128,34 @@ out.update(spline_ev_t=ev2["t"], spline_ev_x=ev2["x"].astype(np.int16), spline_e
            spline_huber_tol=np.array([r["huber"], r["gradient_tolerance"], r["function_tolerance"]]))
 for s in range(r["n_splines"]):
     out[f"spline_knots_{s}"], out[f"spline_rot_{s}"], out[f"spline_trans_{s}"] = r["knots"][s], r["rot_cp"][s], r["trans_cp"][s]
+# ---- a11: the SO(3) variant — CalibReprojectionError_SO3 on Jet<37>, BsplineSO3::derBasisFuns, LocalParameterizationSO3 ----
+ev3 = synth.make_stream(1500, 346, 260, t0=5.0, duration=0.1, seed=21, return_truth=True)
+pb3 = calib_problem.build(ev3, seed=3)
+P3 = oracle.CostProblem([pb3["n_cp"]], [pb3["knots"]], pb3["radius"], pb3["huber"], so3=True)
+oe3, oc3 = P3.associate(ev3["t"], ev3["x"], ev3["y"], pb3["kf_t"], pb3["circles"], pb3["landmarks"], pb3["step"])
+S = dict(span=[], beta=[], N=[], r=[], jac=[], rd=[])
+for e_, c_ in zip(oe3, oc3):
+    u = float(ev3["t"][e_])
+    sp_r, N4 = oracle.ref_basis(pb3["knots"], u)
+    sp_s, beta = oracle.ref_so3_basis(pb3["knots"], u)
+    assert sp_r == sp_s
+    r_, jac_, rd_ = oracle.ref_residual_jac_so3(pb3["intrinsics"], pb3["rot_cp"][sp_s - 3:sp_s + 1], pb3["trans_cp"][sp_s - 3:sp_s + 1],
+                                                np.array([ev3["x"][e_], ev3["y"][e_]]), pb3["landmarks"][c_], pb3["radius"], beta, N4)
+    for k, v in zip(S, (sp_s, beta, N4, r_, jac_, rd_)):
+        S[k].append(v)
+out.update(so3_ev_t=ev3["t"], so3_ev_x=ev3["x"].astype(np.int16), so3_ev_y=ev3["y"].astype(np.int16), so3_ev_p=ev3["p"].astype(np.uint8),
+           so3_kf_t=pb3["kf_t"], so3_circles=pb3["circles"], so3_landmarks=pb3["landmarks"], so3_knots=pb3["knots"],
+           so3_rot_cp=pb3["rot_cp"], so3_trans_cp=pb3["trans_cp"], so3_intrinsics=pb3["intrinsics"], so3_step=np.array(pb3["step"]),
+           so3_event=oe3, so3_circle=oc3.astype(np.int8))
+for k, v in S.items():
+    out["so3_" + k] = np.array(v)
+out["so3_plus_jac"] = np.array([oracle.ref_so3_plus_jacobian(q_) for q_ in pb3["rot_cp"]])
+px = rng.normal(size=(40, 4))
+px /= np.linalg.norm(px, axis=1, keepdims=True)
+pd = rng.normal(size=(40, 3)) * 10.0 ** rng.uniform(-12, 0, (40, 1))
+out["so3_plus_x"], out["so3_plus_d"] = px, pd
+out["so3_plus_out"] = np.array([oracle.ref_so3_plus(a_, b_) for a_, b_ in zip(px, pd)])
+
 # ---- tracking gate and checkPose ----
 from scipy.spatial.transform import Rotation as Rot  # noqa: E402
 for trial, amp in enumerate((1.0, 3.0)):

@@ -52,6 +52,63 @@ def test_product_residual_header_golden():
         assert np.abs(J - Jr).max() <= 1e-9 * np.abs(Jr).max()
 
 
+def _so3_golden_rows():
+    """per residual of the golden SO(3) problem: (span, 1 x 33 tangent Jacobian row, residual) from the reference functor's
+    Jet<37> output and the reference's LocalParameterizationSO3 Jacobians"""
+    span, jac, r = G["so3_span"], G["so3_jac"], G["so3_r"]
+    PJ = G["so3_plus_jac"]
+    rows = np.zeros((len(r), 33))
+    rows[:, :9] = jac[:, :9]
+    for k in range(4):
+        rows[:, 9 + 3 * k: 12 + 3 * k] = np.einsum("na,nab->nb", jac[:, 9 + 4 * k: 13 + 4 * k], PJ[span - 3 + k])
+    rows[:, 21:] = jac[:, 25:]
+    return span, rows, r
+
+
+def so3_golden_normal_equations(huber=0.35):
+    """J^T J / J^T r per span and the cost as Ceres builds them from the reference functor's rows (Huber corrector: residual and
+    row scaled by sqrt(rho'), rho'' <= 0 for Huber)"""
+    span, rows, r = _so3_golden_rows()
+    n_spans = len(G["so3_knots"]) - 4 - 3
+    H, g, cost = np.zeros((n_spans, 33, 33)), np.zeros((n_spans, 33)), 0.0
+    for k in range(len(r)):
+        s2 = r[k] * r[k]
+        rho1 = 1.0 if s2 <= huber ** 2 else huber / np.sqrt(s2)
+        cost += 0.5 * (s2 if s2 <= huber ** 2 else 2 * huber * np.sqrt(s2) - huber ** 2)
+        row, rr = rows[k] * np.sqrt(rho1), r[k] * np.sqrt(rho1)
+        H[span[k] - 3] += np.outer(row, row)
+        g[span[k] - 3] += row * rr
+    return H, g, cost
+
+
+def test_so3_functor_golden(oracle_mod):
+    """a11: restated SO(3) functor on Jet<37> == the reference's CalibReprojectionError_SO3 (value and 37 partials), the
+    cumulative basis and LocalParameterizationSO3, bit for bit; the oracle's normal equations of the whole golden problem
+    equal the ones assembled from the reference functor's rows (1e-12)."""
+    kn, Q, T, intr = G["so3_knots"], G["so3_rot_cp"], G["so3_trans_cp"], G["so3_intrinsics"]
+    ev_t, ev_x, ev_y = G["so3_ev_t"], G["so3_ev_x"].astype(np.float64), G["so3_ev_y"].astype(np.float64)
+    for k in range(0, len(G["so3_r"]), 3):
+        e, sp = int(G["so3_event"][k]), int(G["so3_span"][k])
+        r, jac = oracle_mod.residual_jac_so3(intr, Q[sp - 3:sp + 1], T[sp - 3:sp + 1], np.array([ev_x[e], ev_y[e]]),
+                                             G["so3_landmarks"][G["so3_circle"][k]], 1.75, G["so3_N"][k])
+        assert r == G["so3_r"][k]
+        np.testing.assert_array_equal(jac, G["so3_jac"][k])
+        N = G["so3_N"][k]
+        np.testing.assert_array_equal(G["so3_beta"][k], [(N[3] + N[2]) + N[1], N[3] + N[2], N[3]])
+    for x, d, o in zip(G["so3_plus_x"], G["so3_plus_d"], G["so3_plus_out"]):
+        np.testing.assert_array_equal(oracle_mod.so3_plus(x, d), o)
+    for q, J in zip(Q, G["so3_plus_jac"]):
+        np.testing.assert_array_equal(oracle_mod.so3_plus_jacobian(q), J)
+    Pc = oracle_mod.CostProblem([len(Q)], [kn], 1.75, 0.35, so3=True)
+    oe, oc = Pc.associate(ev_t, ev_x, ev_y, G["so3_kf_t"], G["so3_circles"], G["so3_landmarks"], float(G["so3_step"]))
+    np.testing.assert_array_equal(oe, G["so3_event"])
+    np.testing.assert_array_equal(oc, G["so3_circle"].astype(oc.dtype))
+    c, H, g = Pc.normal_eq(intr, Q, T)
+    Hg, gg, cg = so3_golden_normal_equations()
+    assert abs(c - cg) <= 1e-12 * cg
+    assert np.abs(H - Hg).max() <= 1e-12 * np.abs(Hg).max() and np.abs(g - gg).max() <= 1e-12 * np.abs(gg).max()
+
+
 def test_spline_golden(oracle_mod):
     """a8 + spline set-up: knots, spans, basis bit-exact; façade fit 1e-12."""
     from eventcalib_b200 import spline

@@ -65,3 +65,31 @@ def test_association_vs_reference_source_golden(ctx):
     oe, oc = ctx.cost_association()
     np.testing.assert_array_equal(np.c_[ev["x"][oe], ev["y"][oe]], G["spline_obs"].astype(np.float64))
     np.testing.assert_array_equal(oc, G["spline_lm_idx"].astype(np.int32))
+
+
+def test_so3_variant_vs_reference_source_golden(ctx):
+    """a11 on the GPU (k_normal_eq<SO3>, k_cost<SO3>, association) against the reference's own CalibReprojectionError_SO3 /
+    BsplineSO3::derBasisFuns / LocalParameterizationSO3 compiled in place: residual list exact; J^T J, J^T r and the cost of the
+    golden problem within 1e-9 relative of the ones assembled from the reference functor's Jet<37> rows."""
+    from eventcalib_b200 import synth
+    from test_golden_reference_source import so3_golden_normal_equations
+    ev = dict(t=G["so3_ev_t"], x=G["so3_ev_x"].astype(np.float64), y=G["so3_ev_y"].astype(np.float64), p=G["so3_ev_p"])
+    Q, T, intr = G["so3_rot_cp"], G["so3_trans_cp"], G["so3_intrinsics"]
+    ctx.set_sensor(346, 260)
+    ctx.load_events(synth.to_records(ev))
+    ctx.cost_setup([len(Q)], [G["so3_knots"]], 1.75, 0.35)
+    ctx.cost_set_rotation_model(1)
+    try:
+        n = ctx.cost_associate(G["so3_kf_t"], G["so3_circles"], G["so3_landmarks"], float(G["so3_step"]))
+        assert n == len(G["so3_r"])
+        oe, oc = ctx.cost_association()
+        np.testing.assert_array_equal(oe, G["so3_event"])
+        np.testing.assert_array_equal(oc, G["so3_circle"].astype(np.int32))
+        c, H, g = ctx.cost_normal_eq(intr, Q, T)
+        c2 = ctx.cost_eval(intr, Q, T)
+    finally:
+        ctx.cost_set_rotation_model(0)
+    Hg, gg, cg = so3_golden_normal_equations()
+    assert abs(c - cg) <= 1e-9 * cg and abs(c2 - cg) <= 1e-9 * cg
+    assert np.abs(H - Hg).max() <= 1e-9 * np.abs(Hg).max()
+    assert np.abs(g - gg).max() <= 1e-9 * np.abs(gg).max()
