@@ -385,14 +385,22 @@ def run_c4(args, cfg, rank, world, local):
         tot_res = int(t.item())
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        # the device LM loop against the host state machine (ecb_lm_*) driving the same GPU evaluations: same accept / reject
-        # sequence, final intrinsics 1e-9 (the Ceres solve itself is external: DESIGN.md §5)
-        i2, r2, t2, s2, tr2 = ctx.calibrate([pb["n_cp"]], pb["intrinsics"], pb["rot_cp"], pb["trans_cp"],
-                                            ecb.lm_options(max_iterations=iters, fixed_iterations=1))
-        rel = float(np.max(np.abs(summ["intrinsics"] - i2) / np.abs(i2)))
-        parity = {"windows": 0, "mismatches": int(not (rel <= RTOL and summ["successful_steps"] == s2["successful_steps"])),
-                  "checked": "device LM loop vs the host LM state machine on the same GPU evaluations: accepted steps %d / %d, "
-                             "final intrinsics max rel. diff %.2e" % (summ["successful_steps"], s2["successful_steps"], rel)}
+        # the device LM loop against the host state machine (ecb_lm_*) driving the same GPU evaluations, over the first 12
+        # iterations (before convergence: afterwards both wander along the weakly determined k3..k5 directions at round-off
+        # level, and rounding differences of the two solves are amplified by the conditioning, not by an error): same accept /
+        # reject sequence, cost trajectory and intrinsics within 1e-9 (the Ceres solve itself is external: DESIGN.md §5)
+        K = min(12, iters)
+        i2, r2, t2, s2, tr2 = ctx.calibrate([pb["n_cp"]], pb["intrinsics"], pb["rot_cp"], pb["trans_cp"], ecb.lm_options(max_iterations=K))
+        lm2 = ecb.DeviceLm(ctx, [pb["n_cp"]], ecb.lm_options(max_iterations=K))
+        o2 = lm2.run(pb["intrinsics"], pb["rot_cp"], pb["trans_cp"])
+        lm2.close()
+        rel = float(np.max(np.abs(o2["intrinsics"] - i2) / np.abs(i2)))
+        same = len(o2["trace"]) == len(tr2) and bool(np.array_equal(o2["trace"][:, 3], tr2[:, 3]))
+        relc = float(np.max(np.abs(o2["trace"][:, 0] - tr2[:, 0]) / tr2[:, 0])) if same else float("inf")
+        parity = {"windows": 0, "mismatches": int(not (rel <= RTOL and relc <= RTOL and same)), "rtol": RTOL,
+                  "checked": "device LM loop (state machine + band-arrow Cholesky on the GPU) vs the host LM state machine on the same GPU "
+                             "evaluations, first %d iterations: accept / reject sequence %s, cost trajectory max rel. diff %.1e, "
+                             "intrinsics max rel. diff %.1e" % (K, "equal" if same else "DIFFERS", relc, rel)}
     if rank == 0:
         it = summ["iterations"]
         unit = "residuals x LM iterations / s"
@@ -409,7 +417,8 @@ def run_c4(args, cfg, rank, world, local):
                            "parallelism": "residuals sharded by time x%d (strong scaling)" % world,
                            "l2": "residual records %.0f MB per GPU per evaluation" % (n_res * 56 / 1e6)},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "lm": {k: (float(v) if isinstance(v, float) else v) for k, v in summ.items() if k != "intrinsics"},
+                "lm": {k: (float(v) if isinstance(v, float) else int(v)) for k, v in summ.items()
+                       if k in ("iterations", "successful_steps", "termination", "initial_cost", "final_cost", "gradient_max_norm", "radius")},
                 "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
                         "note": "the LM loop runs from device-resident residuals; per iteration only the accept / reject scalars "
                                 "cross PCIe"}}
@@ -419,6 +428,7 @@ def run_c4(args, cfg, rank, world, local):
         if parity:
             line["parity"] = parity
         print_json(line)
+    solver.close()
     if world > 1:
         teardown_exchange(ctx, xch, rank, dist, torch)
         dist.destroy_process_group()

@@ -62,9 +62,11 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_set_rotation_model", "ecb_cost_layout",
            "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq",
            "ecb_exchange_buffer_bytes", "ecb_cost_normal_eq_exchange", "ecb_device_alloc", "ecb_device_free", "ecb_ipc_export",
-           "ecb_ipc_open", "ecb_ipc_close", "ecb_lm_default_options", "ecb_lm_create",
+           "ecb_ipc_open", "ecb_ipc_close", "ecb_enable_peer_access", "ecb_lm_default_options", "ecb_lm_create",
            "ecb_lm_destroy", "ecb_lm_dimension", "ecb_lm_begin", "ecb_lm_propose", "ecb_lm_feedback", "ecb_lm_update",
-           "ecb_lm_state", "ecb_lm_trace", "ecb_calibrate"]
+           "ecb_lm_state", "ecb_lm_trace", "ecb_calibrate", "ecb_lm_device_create", "ecb_lm_device_destroy",
+           "ecb_lm_device_set_exchange", "ecb_lm_device_begin", "ecb_lm_device_iterate", "ecb_lm_device_running",
+           "ecb_lm_device_result", "ecb_calibrate_device"]
 
 _lib = None
 
@@ -74,9 +76,10 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("ECB_LIBRARY", LIB_PATH)  # A/B builds of the same library (profiles/tools/ab_build.py)
+    if not os.path.exists(path):
         raise EcbError(ERR_CUDA, "libecb.so not built (run `python -m eventcalib_b200.build`); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, u32, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_double
     lib.ecb_ctx_create.argtypes = [i32, vp, C.POINTER(vp)]
     lib.ecb_ctx_destroy.argtypes = [vp]
@@ -110,6 +113,7 @@ def load_library():
     lib.ecb_ipc_export.argtypes = [vp, vp, vp]
     lib.ecb_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
     lib.ecb_ipc_close.argtypes = [vp, vp]
+    lib.ecb_enable_peer_access.argtypes = [vp, i32]
     lib.ecb_dbscan_run.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32)]
     lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
     lib.ecb_dbscan_run_ordered.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32), vp, vp]
@@ -138,6 +142,15 @@ def load_library():
     lib.ecb_lm_state.argtypes = [vp, vp, vp, vp, C.POINTER(LmSummary)]
     lib.ecb_lm_trace.argtypes = [vp, vp, i32]
     lib.ecb_calibrate.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(LmOptions), C.POINTER(LmSummary), vp, i32]
+    lib.ecb_lm_device_create.argtypes = [vp, i32, vp, C.POINTER(LmOptions), C.POINTER(vp)]
+    lib.ecb_lm_device_destroy.argtypes = [vp]
+    lib.ecb_lm_device_destroy.restype = None
+    lib.ecb_lm_device_set_exchange.argtypes = [vp, i32, i32, vp]
+    lib.ecb_lm_device_begin.argtypes = [vp, vp, vp, vp]
+    lib.ecb_lm_device_iterate.argtypes = [vp, i32]
+    lib.ecb_lm_device_running.argtypes = [vp]
+    lib.ecb_lm_device_result.argtypes = [vp, vp, vp, vp, C.POINTER(LmSummary), vp, i32]
+    lib.ecb_calibrate_device.argtypes = [vp, vp, vp, vp, C.POINTER(LmSummary), vp, i32]
     _lib = lib
     return lib
 
@@ -377,6 +390,10 @@ class Context:
         self._chk(self.lib.ecb_ipc_open(self.h, _ptr(h), C.byref(p)))
         return p.value
 
+    def enable_peer_access(self, peer_device):
+        """several GPUs driven from ONE process: lets this context's kernels store into buffers of `peer_device`"""
+        self._chk(self.lib.ecb_enable_peer_access(self.h, int(peer_device)))
+
     def ipc_close(self, ptr):
         self._chk(self.lib.ecb_ipc_close(self.h, C.c_void_p(ptr)))
 
@@ -465,6 +482,77 @@ def lm_options(**kw):
     for k, v in kw.items():
         setattr(o, k, v)
     return o
+
+
+class DeviceLm:
+    """EventCalibSpline::optimize with the LM state machine and the band-arrow Cholesky solve on the device (ecb_lm_device_*):
+    the host enqueues the iterations and reads the result once.  ctx must hold the residual set (cost_setup + association)."""
+
+    def __init__(self, ctx, n_cp, options=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.n_cp = np.ascontiguousarray(np.atleast_1d(n_cp), np.int32)
+        self.C = int(self.n_cp.sum())
+        self.opt = options or lm_options()
+        h = C.c_void_p()
+        ctx._chk(self.lib.ecb_lm_device_create(ctx.h, len(self.n_cp), _ptr(self.n_cp), C.byref(self.opt), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            if getattr(self.ctx, "h", None):   # the context owns the device: destroy before it (a closed context took it along)
+                self.lib.ecb_lm_device_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_exchange(self, rank, recv_ptrs):
+        """several GPUs: device pointers of every rank's receive buffer (own buffer at [rank]), see Context.exchange_buffer_bytes"""
+        ptrs = (C.c_void_p * len(recv_ptrs))(*[C.c_void_p(p) for p in recv_ptrs])
+        self._keep = ptrs
+        self.ctx._chk(self.lib.ecb_lm_device_set_exchange(self.h, rank, len(recv_ptrs), ptrs))
+
+    def begin(self, intr, rot, trans):
+        a = [np.ascontiguousarray(v, np.float64) for v in (intr, rot, trans)]
+        self.ctx._chk(self.lib.ecb_lm_device_begin(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])))
+
+    def iterate(self, n):
+        self.ctx._chk(self.lib.ecb_lm_device_iterate(self.h, int(n)))
+
+    def running(self):
+        rc = self.lib.ecb_lm_device_running(self.h)
+        if rc < 0:
+            self.ctx._chk(rc)
+        return rc == 1
+
+    def result(self, trace_rows=256):
+        i, r, t = np.zeros(9), np.zeros((self.C, 4)), np.zeros((self.C, 3))
+        s = LmSummary()
+        tr = np.zeros((trace_rows, 4))
+        self.ctx._chk(self.lib.ecb_lm_device_result(self.h, _ptr(i), _ptr(r), _ptr(t), C.byref(s), _ptr(tr), trace_rows))
+        out = {f[0]: getattr(s, f[0]) for f in LmSummary._fields_}
+        out.update(intrinsics=i, rot_cp=r, trans_cp=t, trace=tr[:int(np.count_nonzero(tr[:, 2]))])
+        return out
+
+    def run(self, intr, rot, trans, trace_rows=256):
+        """begin + all iterations + result; with fixed_iterations the whole loop is enqueued without a host round trip"""
+        self.begin(intr, rot, trans)
+        total = self.opt.max_iterations + 1
+        if self.opt.fixed_iterations:
+            self.iterate(total)
+        else:
+            done = 0
+            while done < total:
+                k = min(8, total - done)
+                self.iterate(k)
+                done += k
+                if done < total and not self.running():
+                    break
+        return self.result(trace_rows)
 
 
 class LmState:

@@ -801,6 +801,21 @@ int ecb_ipc_open(ecb_ctx *ctx, const void *handle64, void **d_ptr) {
     return ecb_check(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
 }
 
+int ecb_enable_peer_access(ecb_ctx *ctx, int peer_device) {
+    if (!ctx || peer_device < 0) return ECB_ERR_ARG;
+    if (peer_device == ctx->device) return ECB_OK;
+    cudaSetDevice(ctx->device);
+    int can = 0;
+    ECB_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", ctx->device, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return ECB_OK;
+    }
+    return ecb_check(ctx, e, "cudaDeviceEnablePeerAccess");
+}
+
 int ecb_ipc_close(ecb_ctx *ctx, void *d_ptr) {
     if (!ctx) return ECB_ERR_ARG;
     cudaSetDevice(ctx->device);

@@ -32,6 +32,17 @@ struct Smem {
     uint8_t *r_flag;
 };
 
+// A/B switches of the round-2 changes (profiles/tools/ab_build.py builds variants with -D...=0)
+#ifndef ECB_CL_AGG
+#define ECB_CL_AGG 0        // warp-aggregated atomicMin in the first kd rounds: measured SLOWER (+0.18 ms on C2, MATCH.ANY costs more than the serialised atomics; profiles/r2d_ab_cluster.jsonl)
+#endif
+#ifndef ECB_CL_RANKORDER
+#define ECB_CL_RANKORDER 1  // steps 5 - 6 walk the points in row-major rank order instead of pid order
+#endif
+#ifndef ECB_CL_UNSET
+#define ECB_CL_UNSET 1      // planes cleared once per CTA, every problem un-sets the words it touched
+#endif
+
 constexpr int KD_PT = 6;  // points per thread kept in registers during the kd rounds (fast path: n <= KD_PT * threads)
 
 __device__ __forceinline__ uint32_t find_root(volatile uint32_t *parent, uint32_t a) {
@@ -92,7 +103,13 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
     int32_t *k_raw = reinterpret_cast<int32_t *>(arr + 5 * NC + ((NC + 3) >> 2));
     int32_t *k_size = k_raw + a.max_k, *k_off = k_size + a.max_k;
 
+    // ---- 0. clear planes: once per CTA; every problem un-sets the words it touched when it is done with them (step 8) ----
+    for (int i = tid; i < 2 * NW; i += nthr) s.U[i] = 0;
     for (;;) {
+#if !ECB_CL_UNSET
+        __syncthreads();
+        for (int i = tid; i < 2 * NW; i += nthr) s.U[i] = 0;
+#endif
         __syncthreads();
         if (tid == 0) {
             s_pb = atomicAdd(a.work_counter, 1u);
@@ -105,10 +122,6 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         const int n = d.n;
         const uint32_t *gpix = a.pix[d.pol] + d.off;
         int32_t *glab = a.labels[d.pol] + d.off;
-
-        // ---- 0. clear planes -----------------------------------------------------------------
-        for (int i = tid; i < 2 * NW; i += nthr) s.U[i] = 0;
-        __syncthreads();
         // ---- 1. occupancy bitmap ---------------------------------------------------------------
         for (int pid = tid; pid < n; pid += nthr) {
             uint32_t p = gpix[pid];
@@ -130,13 +143,13 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         }
         __syncthreads();
         // ---- 2. word-prefix popcounts: rank(x,y) = wrank[word] + popc(bits below) ---------------
+        uint32_t n_ranked;  // distinct in-range pixels = set bits of U (== n unless the input is flagged)
         {
             const int per = (NW + nthr - 1) / nthr;
             const int b = tid * per, e = min(NW, b + per);
             uint32_t c = 0;
             for (int i = b; i < e; ++i) c += __popc(s.U[i]);
-            uint32_t tot;
-            uint32_t ex = block_excl_scan(c, ws, &tot);
+            uint32_t ex = block_excl_scan(c, ws, &n_ranked);
             for (int i = b; i < e; ++i) {
                 s.wrank[i] = (RankT) ex;
                 ex += __popc(s.U[i]);
@@ -150,6 +163,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         // ---- 4. kd insertion-order emulation -> tie flags ---------------------------------------
         // NOTE: the root is pid 0 like kd_insert's first insertion.
         uint32_t *child = s.r_kd;
+        uint32_t *rloc = s.r_lab;  // [rank] -> packed pixel; r_lab is not needed before step 7
         for (int i = tid; i < 2 * n; i += nthr) child[i] = ECB_NONE;
         if (n <= KD_PT * nthr) {
             // fast path: each thread keeps its <= KD_PT points (pixel, current node, flags) in registers
@@ -166,14 +180,27 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                 const int dsh = (round & 1) ? 16 : 0;
                 bool any = false;
                 uint32_t slot[KD_PT];
+                // the first levels of the tree have few nodes: all lanes of a warp hit the same <= 2^(round+1) child slots and
+                // the shared-memory atomics serialise (ncu: 37 % of the kernel's excess wavefronts).  There the lanes are
+                // grouped by slot first and only the lowest lane of a group — the lowest pid, pids ascend with the lane —
+                // issues the atomicMin.
+                const bool aggregate = ECB_CL_AGG && round < 5;
 #pragma unroll
                 for (int k = 0; k < KD_PT; ++k) {
-                    if (cur[k] == ECB_NONE) continue;
-                    any = true;
-                    const uint32_t ci = (mypix[k] >> dsh) & 0xFFFF, ca = (s.r_pix[cur[k]] >> dsh) & 0xFFFF;
-                    if (ci == ca) fl[k] |= 1u << (round & 1);
-                    slot[k] = 2 * cur[k] + (ci < ca ? 0 : 1);
-                    atomicMin(&child[slot[k]], (uint32_t) (tid + k * nthr));
+                    const bool act = cur[k] != ECB_NONE;
+                    slot[k] = ECB_NONE;
+                    if (act) {
+                        any = true;
+                        const uint32_t ci = (mypix[k] >> dsh) & 0xFFFF, ca = (s.r_pix[cur[k]] >> dsh) & 0xFFFF;
+                        if (ci == ca) fl[k] |= 1u << (round & 1);
+                        slot[k] = 2 * cur[k] + (ci < ca ? 0 : 1);
+                    }
+                    if (aggregate) {
+                        const uint32_t peers = __match_any_sync(0xffffffffu, slot[k]);
+                        if (act && (peers & ((1u << lane) - 1u)) == 0) atomicMin(&child[slot[k]], (uint32_t) (tid + k * nthr));
+                    } else if (act) {
+                        atomicMin(&child[slot[k]], (uint32_t) (tid + k * nthr));
+                    }
                 }
                 if (!__syncthreads_or(any)) break;
 #pragma unroll
@@ -187,7 +214,12 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             }
 #pragma unroll
             for (int k = 0; k < KD_PT; ++k)
-                if (mypix[k] != ECB_NONE) s.r_flag[rank_of(mypix[k] & 0xFFFF, mypix[k] >> 16)] = (uint8_t) fl[k];
+                if (mypix[k] != ECB_NONE) {
+                    const uint32_t rk = rank_of(mypix[k] & 0xFFFF, mypix[k] >> 16);
+                    s.r_flag[rk] = (uint8_t) fl[k];
+                    rloc[rk] = mypix[k];          // pixel of every rank: steps 5 - 6 walk the points in row-major order
+                    s.r_st[tid + k * nthr] = rk;  // rank of every pid: step 7
+                }
         } else {
             uint32_t *state = s.r_st;
             const uint32_t DONE = 0x3FFFFFFFu;
@@ -218,7 +250,12 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             }
             for (int pid = tid; pid < n; pid += nthr) {
                 const uint32_t loc = s.r_pix[pid];
-                if (loc != ECB_NONE) s.r_flag[rank_of(loc & 0xFFFF, loc >> 16)] = (uint8_t) (state[pid] >> 30);
+                if (loc != ECB_NONE) {
+                    const uint32_t rk = rank_of(loc & 0xFFFF, loc >> 16);
+                    s.r_flag[rk] = (uint8_t) (state[pid] >> 30);
+                    rloc[rk] = loc;
+                    state[pid] = rk;  // r_st: same thread, same index as the read above
+                }
             }
         }
         __syncthreads();
@@ -238,10 +275,17 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         // tie flag of the (occupied) pixel (x,y): bit0 = FX, bit1 = FY
         auto flag_of = [&](int x, int y) -> uint32_t { return s.r_flag[rank_of(x, y)]; };
         // ---- 5. neighbour count, core flag -----------------------------------------------------------
+        // (steps 5, 6a, 6b take the points in row-major RANK order: neighbouring lanes then read the same or adjacent bitmap
+        // words — broadcasts instead of the bank conflicts of the pid order, which is the hash-set order, i.e. random)
         const int ei = a.eps_int;
-        for (int pid = tid; pid < n; pid += nthr) {
-            uint32_t loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
+        const int m = (int) n_ranked;
+        for (int it5 = tid; it5 < (ECB_CL_RANKORDER ? m : n); it5 += nthr) {
+            int rk = it5;
+            if (!ECB_CL_RANKORDER) {
+                if (s.r_pix[it5] == ECB_NONE) continue;
+                rk = (int) s.r_st[it5];
+            }
+            const uint32_t loc = rloc[rk];
             const int x = loc & 0xFFFF, y = loc >> 16;
             int cnt = -1;  // self
             for (int dy = -E; dy <= E; ++dy) {
@@ -266,9 +310,13 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         // found with bit scans — no atomics, depth-1 trees.  6b/6c: runs are then united across rows (and across an
         // exact-eps in-row gap) with a lock-free union-find whose chains start at run heads.
         const int gap = (ei > 0 ? ei : E + 1) - 1;  // pixels whose distance is <= gap are unconditionally adjacent in-row
-        for (int pid = tid; pid < n; pid += nthr) {
-            const uint32_t loc = s.r_pix[pid];
-            if (loc == ECB_NONE) continue;
+        for (int it6 = tid; it6 < (ECB_CL_RANKORDER ? m : n); it6 += nthr) {
+            int rk = it6;
+            if (!ECB_CL_RANKORDER) {
+                if (s.r_pix[it6] == ECB_NONE) continue;
+                rk = (int) s.r_st[it6];
+            }
+            const uint32_t loc = rloc[rk];
             const int x = loc & 0xFFFF, y = loc >> 16;
             if (!test_bit(s.C + y * PW, x)) continue;
             int p = x;
@@ -278,7 +326,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                     if (!wbits) break;
                     p = p - gap + (__ffs(wbits) - 1);
                 }
-            if (p != x) parent[rank_of(x, y)] = rank_of(p, y);
+            if (p != x) parent[rk] = rank_of(p, y);
         }
         if (tid == 0) s_chunk = 0;
         __syncthreads();
@@ -298,20 +346,25 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                 }
                 return gap > 0 ? sm << 1 : 0ull;
             };
-            // Load balance: warps draw chunks of 32 pids from a shared counter, and inside a warp the (sub-run head, dy) pairs
+            // Load balance: warps draw chunks of 32 ranks from a shared counter, and inside a warp the (sub-run head, dy) pairs
             // of the chunk are dealt out evenly to the lanes (the union cost per pair varies a lot).
             const uint32_t invE = (65536u + (uint32_t) E - 1u) / (uint32_t) E;  // it / E == (it * invE) >> 16 for it < 512
             for (;;) {
                 int base = 0;
                 if (lane == 0) base = (int) atomicAdd(&s_chunk, 32u);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= n) break;
-                const int pid = base + lane;
+                if (base >= (ECB_CL_RANKORDER ? m : n)) break;
+                int rk = base + lane;
                 bool head = false;
                 uint32_t h_xy = 0, h_sub = 0, h_rf = 0;
-                if (pid < n) {
-                    const uint32_t loc = s.r_pix[pid];
-                    if (loc != ECB_NONE) {
+                bool have = rk < m;
+                if (!ECB_CL_RANKORDER) {
+                    have = rk < n && s.r_pix[rk] != ECB_NONE;
+                    if (have) rk = (int) s.r_st[rk];
+                }
+                if (have) {
+                    const uint32_t loc = rloc[rk];
+                    {
                         const int x = loc & 0xFFFF, y = loc >> 16;
                         const int j = x >> 5, f = x & 31;
                         const uint32_t *crow = s.C + y * PW;
@@ -320,7 +373,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                             // q = p - eps*e_x with nothing in between: mutual unless the kd query misses q -> p (FX(p))
                             if (ei > 0 && test_bit(crow, x + ei) && !row_bits(crow, x + 1, ei - 1) &&
                                 !(flag_of(x + ei, y) & 1u))
-                                unite(parent, rank_of(x, y), rank_of(x + ei, y));
+                                unite(parent, (uint32_t) rk, rank_of(x + ei, y));
                             const uint32_t F = src & ~(uint32_t) smear(src);  // first pixel of every sub-run of the word
                             if ((F >> f) & 1u) {
                                 const uint32_t Fup = f < 31 ? F >> (f + 1) : 0u;  // next sub-run start above f
@@ -328,7 +381,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                                 head = true;
                                 h_xy = loc;
                                 h_sub = src & upto & ~((1u << f) - 1u);
-                                h_rf = rank_of(x, y);
+                                h_rf = (uint32_t) rk;
                             }
                         }
                     }
@@ -380,18 +433,16 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                 const int x = loc & 0xFFFF, y = loc >> 16;
                 if (test_bit(s.C + y * PW, x)) {
                     ++n_core_local;
-                    root = find_root(parent, rank_of(x, y));
+                    root = find_root(parent, s.r_st[pid]);
                     atomicMin(&glabel[root], (uint32_t) pid);
                 }
             }
-            s.r_lab[pid] = root;  // stash: root rank of the point's group (ECB_NONE for non-core)
+            s.r_lab[pid] = root;  // stash: root rank of the point's group (ECB_NONE for non-core); rloc is dead since 6b's barrier
         }
         __syncthreads();
         for (int pid = tid; pid < n; pid += nthr) {  // full flatten: parent[rank] = root for every core point
             const uint32_t root = s.r_lab[pid];
-            if (root == ECB_NONE) continue;
-            const uint32_t loc = s.r_pix[pid];
-            parent[rank_of(loc & 0xFFFF, loc >> 16)] = root;
+            if (root != ECB_NONE) parent[s.r_st[pid]] = root;
         }
         __syncthreads();
         if (ei > 0) {
@@ -456,6 +507,12 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             }
             s.r_lab[pid] = (uint32_t) lab;
             glab[pid] = lab;
+            const uint32_t loc = s.r_pix[pid];  // U and C are dead: leave the planes empty for the CTA's next problem
+            if (ECB_CL_UNSET && loc != ECB_NONE) {
+                const int w = (int) (loc >> 16) * PW + (int) ((loc & 0xFFFF) >> 5);
+                s.U[w] = 0;
+                s.C[w] = 0;
+            }
         }
         __syncthreads();
         // ---- 9. cluster sizes, size filter, member lists, moments, medians ----------------------------

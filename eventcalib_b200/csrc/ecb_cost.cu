@@ -47,6 +47,8 @@ struct CostState {
     DevBuf span_start, items, part, out, params, cost_part, flags;
     DevBuf ev_flag, ev_cnt, ev_tag, kf_t, kf_circ, kf_c32, lm_tab, sel_event, sel_circle;
     std::vector<int64_t> h_span_start;
+    uint64_t xch_last_epoch = 0;   // ecb_cost_normal_eq_exchange: last epoch sent / generation of the caller's sequence
+    uint32_t xch_generation = 0;
 };
 
 CostState *state(ecb_ctx *ctx) {
@@ -160,6 +162,7 @@ struct NeArgs {
     int total_cp;
     double radius, huber;
     double *part;
+    const int *go;         // device flag (may be null): 0 = the launch is a no-op (device-side LM loop: step rejected / finished)
 };
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
@@ -171,6 +174,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 template <int MINB, bool SO3>
 __global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) {
     extern __shared__ __align__(16) double sm_tiles[];
+    if (a.go && *a.go == 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *tile = sm_tiles + (size_t) wid * TILE_ROWS * TILE_LD;
     const int g = lane >> 2, t = lane & 3;
@@ -265,9 +269,9 @@ __global__ void __launch_bounds__(NE_THREADS, MINB) k_normal_eq(const NeArgs a) 
 
 // out[s] = sum over the span's work items, fixed order; tiles -> full symmetric 33x33 + gradient
 __global__ void k_reduce_spans(const double *__restrict__ part, const int *__restrict__ item_start, int n_spans,
-                               double *__restrict__ out) {
+                               double *__restrict__ out, const int *__restrict__ go = nullptr) {
     const int s = blockIdx.x;
-    if (s >= n_spans) return;
+    if (s >= n_spans || (go && *go == 0)) return;
     const int i0 = item_start[s], i1 = item_start[s + 1];
     double *o = out + (size_t) s * OUT_STRIDE;
     for (int e = threadIdx.x; e < PART_SC + 2; e += blockDim.x) {
@@ -318,11 +322,25 @@ struct XPeers {
     int n_ranks, rank;
 };
 
+// Where an exchange lives in the receive buffers: the epoch comes from the host (ecb_cost_normal_eq_exchange) or from a device
+// counter (device-side LM loop, ecb_lmdev.cu: the host enqueues many iterations ahead and does not know which of them exchange).
+struct XCtl {
+    const int *go;                        // device flag (may be null): 0 = no-op
+    const unsigned long long *d_epoch;    // device epoch counter, or null: use `epoch`
+    unsigned long long epoch;
+    size_t slot;                          // doubles per slot
+    int n_ranks, rank;
+    __device__ __forceinline__ unsigned long long e() const { return d_epoch ? *d_epoch : epoch; }
+    __device__ __forceinline__ size_t parity_off() const { return (size_t) (e() & 1ull) * (size_t) n_ranks * slot; }
+    __device__ __forceinline__ size_t my_slot_off() const { return parity_off() + (size_t) rank * slot; }
+};
+
 // k_reduce_spans whose stores go to the slot of this rank in every peer's buffer
 __global__ void k_reduce_spans_push(const double *__restrict__ part, const int *__restrict__ item_start, int span_lo, int span_hi,
-                                    XPeers peers, size_t slot_off) {
+                                    XPeers peers, XCtl x) {
     const int s = span_lo + blockIdx.x;
-    if (s > span_hi) return;
+    if (s > span_hi || (x.go && *x.go == 0)) return;
+    const size_t slot_off = x.my_slot_off();
     const int i0 = item_start[s], i1 = item_start[s + 1];
     for (int e = threadIdx.x; e < PART_SC + 2; e += blockDim.x) {
         double v = 0.0;
@@ -362,27 +380,29 @@ __global__ void k_reduce_spans_push(const double *__restrict__ part, const int *
 }
 
 // after the pushes (stream order): publish this rank's header to every peer
-__global__ void k_exchange_signal(XPeers peers, size_t slot_off, unsigned long long epoch, int span_lo, int span_hi,
-                                  const double *__restrict__ cost) {
+__global__ void k_exchange_signal(XPeers peers, XCtl x, int span_lo, int span_hi, const double *__restrict__ cost) {
     const int p = threadIdx.x;
-    if (p >= peers.n_ranks) return;
-    double *h = peers.base[p] + slot_off;
+    if (p >= peers.n_ranks || (x.go && *x.go == 0)) return;
+    double *h = peers.base[p] + x.my_slot_off();
     h[1] = (double) span_lo;
     h[2] = (double) span_hi;
     h[3] = *cost;
     __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long *>(h) = epoch;
+    *reinterpret_cast<volatile unsigned long long *>(h) = x.e();
 }
 
-// one warp: wait until every rank's header of this parity carries `epoch` (bounded spin: ~2 s, then an error flag)
-__global__ void k_exchange_wait(const double *__restrict__ recv, size_t parity_off, size_t slot_stride, int n_ranks,
-                                unsigned long long epoch, unsigned *err) {
+// one warp: wait until every rank's header of this parity carries the epoch.  The spin is bounded (ECB_EXCHANGE_TIMEOUT_S
+// seconds, default 30: lazy module loads or host pauses of a peer process must not trip it) and a timeout raises a sticky
+// error bit per rank that k_exchange_sum turns into a NaN cost, so no caller can mistake a partial sum for a result.
+__global__ void k_exchange_wait(const double *__restrict__ recv, XCtl x, long long timeout_clocks, unsigned *err) {
     const int r = threadIdx.x;
-    if (r >= n_ranks) return;
-    const volatile unsigned long long *f = reinterpret_cast<const volatile unsigned long long *>(recv + parity_off + (size_t) r * slot_stride);
+    if (r >= x.n_ranks || (x.go && *x.go == 0)) return;
+    const unsigned long long epoch = x.e();
+    const volatile unsigned long long *f =
+        reinterpret_cast<const volatile unsigned long long *>(recv + x.parity_off() + (size_t) r * x.slot);
     const long long t0 = clock64();
     while (*f != epoch) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (clock64() - t0 > timeout_clocks) {
             atomicOr(err, 1u << r);
             break;
         }
@@ -392,13 +412,17 @@ __global__ void k_exchange_wait(const double *__restrict__ recv, size_t parity_o
 }
 
 // out[s] = sum over the ranks whose range holds s, in rank order; out[n_spans*OUT_STRIDE] = sum of the costs
-__global__ void k_exchange_sum(const double *__restrict__ recv, size_t parity_off, size_t slot_stride, int n_ranks, int n_spans,
-                               double *__restrict__ out) {
+__global__ void k_exchange_sum(const double *__restrict__ recv, XCtl x, int n_spans, double *__restrict__ out,
+                               const unsigned *__restrict__ err) {
     const int s = blockIdx.x;
+    if (x.go && *x.go == 0) return;
+    const size_t parity_off = x.parity_off(), slot_stride = x.slot;
+    const int n_ranks = x.n_ranks;
     if (s == n_spans) {
         if (threadIdx.x == 0) {
             double c = 0.0;
             for (int r = 0; r < n_ranks; ++r) c += recv[parity_off + (size_t) r * slot_stride + 3];
+            if (err && *err) c = __longlong_as_double(0x7FF8000000000000ll);  // a rank never arrived: no result
             out[(size_t) n_spans * OUT_STRIDE] = c;
             out[(size_t) n_spans * OUT_STRIDE + 1] = 0.0;
         }
@@ -414,9 +438,44 @@ __global__ void k_exchange_sum(const double *__restrict__ recv, size_t parity_of
     }
 }
 
-__global__ void k_reduce_cost(const double *__restrict__ part, int n, int stride, int offset, double *__restrict__ out) {
+// Scalar all-reduce over the same peer buffers (device-side LM loop: the candidate cost of every iteration): rank r stores
+// (value, epoch) into slot r of every peer's scalar area, waits for all slots of this epoch and adds them in rank order.
+// One warp; *value is replaced by the sum.  The scalar area follows the two parity blocks of the span slots.
+__global__ void k_exchange_scalar(XPeers peers, XCtl x, size_t scalar_off, double *value, long long timeout_clocks, unsigned *err) {
+    const int p = threadIdx.x;
+    if (x.go && *x.go == 0) return;
+    const unsigned long long epoch = x.e();
+    const size_t par = scalar_off + (size_t) (epoch & 1ull) * 2 * (size_t) x.n_ranks;
+    if (p < x.n_ranks) {
+        double *h = peers.base[p] + par + 2 * (size_t) x.rank;
+        h[1] = *value;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(h) = epoch;
+        const volatile unsigned long long *f = reinterpret_cast<const volatile unsigned long long *>(peers.base[x.rank] + par + 2 * (size_t) p);
+        const long long t0 = clock64();
+        while (*f != epoch) {
+            if (clock64() - t0 > timeout_clocks) {
+                atomicOr(err, 1u << p);
+                break;
+            }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (p == 0) {
+        double c = 0.0;
+        for (int r = 0; r < x.n_ranks; ++r) c += *reinterpret_cast<const volatile double *>(peers.base[x.rank] + par + 2 * (size_t) r + 1);
+        if (*err) c = __longlong_as_double(0x7FF8000000000000ll);
+        *value = c;
+    }
+}
+
+__global__ void k_reduce_cost(const double *__restrict__ part, int n, int stride, int offset, double *__restrict__ out,
+                              const int *__restrict__ go = nullptr) {
     // single block, fixed order: thread-strided partial sums, then a shared-memory tree
     __shared__ double sh[256];
+    if (go && *go == 0) return;
     double v = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) v += part[(size_t) i * stride + offset];
     sh[threadIdx.x] = v;
@@ -433,8 +492,9 @@ __global__ void __launch_bounds__(256, MINB) k_cost(const double *__restrict__ o
                                              const int *__restrict__ circ, const double *__restrict__ lm_tab,
                                              const double *__restrict__ basis, const int *__restrict__ cp0, int64_t n,
                                              const double *__restrict__ params, int total_cp, double radius, double huber,
-                                             double *__restrict__ block_part) {
+                                             double *__restrict__ block_part, const int *__restrict__ go = nullptr) {
     __shared__ double sh[256];
+    if (go && *go == 0) return;
     const double *intr = params, *rot = params + 9, *trans = params + 9 + 4 * (size_t) total_cp;
     double c = 0.0;
     for (int64_t k = (int64_t) blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t) gridDim.x * 256) {
@@ -929,6 +989,182 @@ int ecb_cost_get_association(ecb_ctx *ctx, int64_t *event_index, int32_t *circle
     return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "association copy");
 }
 
+// ---- launches shared by the host-parameter entry points and the device-side LM loop (ecb_lmdev.cu) ----
+}  // extern "C"
+
+static long long exchange_timeout_clocks(ecb_ctx *ctx) {
+    static const double secs = getenv("ECB_EXCHANGE_TIMEOUT_S") ? atof(getenv("ECB_EXCHANGE_TIMEOUT_S")) : 30.0;
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    return (long long) (secs * 1e3 * (double) khz);
+}
+
+static void fill_ne_args(CostState *st, NeArgs &a, const double *d_params, const int *d_go) {
+    a.obs = (const double *) st->obs.p;
+    a.lm = (const double *) st->lm.p;
+    a.circ = st->use_circ ? (const int *) st->sel_circle.p : nullptr;
+    a.lm_tab = (const double *) st->lm_tab.p;
+    a.basis = (const double *) st->basis.p;
+    a.cp0 = (const int *) st->cp0.p;
+    a.items = (const Item *) st->items.p;
+    a.n_items = st->n_items;
+    a.params = d_params;
+    a.total_cp = st->total_cp;
+    a.radius = st->radius;
+    a.huber = st->huber;
+    a.part = (double *) st->part.p;
+    a.go = d_go;
+}
+
+// k_normal_eq over the residual set with the parameters at d_params (device: intr 9 | rot 4C | trans 3C)
+static int launch_normal_eq_kernel(ecb_ctx *ctx, CostState *st, const double *d_params, const int *d_go) {
+    NeArgs a;
+    fill_ne_args(st, a, d_params, d_go);
+    const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
+    static const int variant = getenv("ECB_NE_VARIANT") ? atoi(getenv("ECB_NE_VARIANT")) : 2;
+    void (*kern)(const NeArgs) = st->so3 ? k_normal_eq<1, true> : (variant == 1 ? k_normal_eq<1, false> : k_normal_eq<2, false>);
+    ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * ((variant == 1 || st->so3) ? 1 : 2));
+    kern<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
+    ECB_LAUNCHED(ctx);
+    return ECB_OK;
+}
+
+static const int *item_start_of(CostState *st) {
+    return (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
+}
+
+// the span range this rank's residuals contribute to
+static void span_range(CostState *st, int &lo, int &hi) {
+    lo = 0;
+    hi = -1;
+    for (int s = 0; s < st->total_spans; ++s)
+        if (st->h_span_start[(size_t) s + 1] > st->h_span_start[(size_t) s]) {
+            if (hi < 0) lo = s;
+            hi = s;
+        }
+}
+
+// cost-only evaluation at d_params -> *d_cost (device scalar); async
+int ecb_cost_dev_eval(ecb_ctx *ctx, const double *d_params, const int *d_go, double *d_cost) {
+    CostState *st = (CostState *) ctx->cost;
+    int rc;
+    if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
+    if (st->n_res == 0) {
+        ECB_CUDA(ctx, cudaMemsetAsync(d_cost, 0, 8, ctx->stream));
+        return ECB_OK;
+    }
+    const int grid = (int) std::min<int64_t>((st->n_res + 255) / 256, (int64_t) ctx->sm_count * 8);
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_COST);
+    static const int cost_minb = getenv("ECB_COST_MINB") ? atoi(getenv("ECB_COST_MINB")) : 4;  // 64 registers, 32 warps / SM: 0.35 -> 0.33 ms
+    (st->so3 ? k_cost<true, 2> : (cost_minb >= 4 ? k_cost<false, 4> : k_cost<false, 3>))<<<grid, 256, 0, ctx->stream>>>(
+        (const double *) st->obs.p, (const double *) st->lm.p, st->use_circ ? (const int *) st->sel_circle.p : nullptr,
+        (const double *) st->lm_tab.p, (const double *) st->basis.p, (const int *) st->cp0.p, st->n_res, d_params, st->total_cp,
+        st->radius, st->huber, (double *) st->cost_part.p, d_go);
+    ECB_LAUNCHED(ctx);
+    k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->cost_part.p, grid, 1, 0, d_cost, d_go);
+    ECB_LAUNCHED(ctx);
+    ECB_PROF_END(ctx, ECB_STAGE_COST);
+    return ecb_check(ctx, cudaGetLastError(), "cost kernels");
+}
+
+// normal equations at d_params -> d_out (packed, this rank's residuals only); async
+int ecb_cost_dev_normal_eq(ecb_ctx *ctx, const double *d_params, const int *d_go, double *d_out) {
+    CostState *st = (CostState *) ctx->cost;
+    if (st->n_items <= 0) return ECB_OK;
+    int rc;
+    ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
+    if ((rc = launch_normal_eq_kernel(ctx, st, d_params, d_go))) return rc;
+    k_reduce_spans<<<st->total_spans, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start_of(st), st->total_spans, d_out, d_go);
+    ECB_LAUNCHED(ctx);
+    k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, PART_SC + 3,
+                                              d_out + (size_t) st->total_spans * OUT_STRIDE, d_go);
+    ECB_LAUNCHED(ctx);
+    ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);
+    return ecb_check(ctx, cudaGetLastError(), "normal equation kernels");
+}
+
+// the same with the inter-GPU sum fused in (all ranks' residuals -> d_out on every rank); the epoch is a device counter
+// (d_epoch, already advanced for this exchange) or a host value.  phases as in ecb_cost_normal_eq_exchange.  d_err: sticky
+// timeout bits (device word).
+int ecb_cost_dev_normal_eq_exchange(ecb_ctx *ctx, const double *d_params, const int *d_go, int rank, int n_ranks,
+                                    void *const *recv_buffers, const unsigned long long *d_epoch, unsigned long long epoch,
+                                    int phases, double *d_out, unsigned *d_err) {
+    CostState *st = (CostState *) ctx->cost;
+    int rc;
+    if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
+    XPeers peers;
+    memset(&peers, 0, sizeof peers);
+    peers.n_ranks = n_ranks;
+    peers.rank = rank;
+    for (int p = 0; p < n_ranks; ++p) {
+        if (!recv_buffers[p]) return ECB_ERR_ARG;
+        peers.base[p] = (double *) recv_buffers[p];
+    }
+    XCtl x;
+    x.go = d_go;
+    x.d_epoch = d_epoch;
+    x.epoch = epoch;
+    x.slot = xslot_doubles(st->total_spans);
+    x.n_ranks = n_ranks;
+    x.rank = rank;
+    int lo, hi;
+    span_range(st, lo, hi);
+    double *d_cost = (double *) st->cost_part.p + 4001;
+    if (phases & ECB_EXCHANGE_SEND) {
+        ECB_CUDA(ctx, cudaMemsetAsync(d_cost, 0, 8, ctx->stream));  // (harmless when the launch is gated off)
+        if (st->n_items > 0 && hi >= lo) {
+            ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
+            if ((rc = launch_normal_eq_kernel(ctx, st, d_params, d_go))) return rc;
+            k_reduce_spans_push<<<hi - lo + 1, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start_of(st), lo, hi, peers, x);
+            ECB_LAUNCHED(ctx);
+            k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, PART_SC + 3, d_cost, d_go);
+            ECB_LAUNCHED(ctx);
+            ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);
+        }
+        k_exchange_signal<<<1, 32, 0, ctx->stream>>>(peers, x, lo, hi, d_cost);
+        ECB_LAUNCHED(ctx);
+    }
+    if (phases & ECB_EXCHANGE_RECV) {
+        k_exchange_wait<<<1, 32, 0, ctx->stream>>>(peers.base[rank], x, exchange_timeout_clocks(ctx), d_err);
+        ECB_LAUNCHED(ctx);
+        k_exchange_sum<<<st->total_spans + 1, 192, 0, ctx->stream>>>(peers.base[rank], x, st->total_spans, d_out, d_err);
+        ECB_LAUNCHED(ctx);
+    }
+    return ecb_check(ctx, cudaGetLastError(), "exchange kernels");
+}
+
+// scalar sum over the ranks (device-side LM loop); *d_value: this rank's part in, the sum out
+int ecb_cost_dev_scalar_exchange(ecb_ctx *ctx, const int *d_go, int rank, int n_ranks, void *const *recv_buffers,
+                                 const unsigned long long *d_epoch, double *d_value, unsigned *d_err) {
+    CostState *st = (CostState *) ctx->cost;
+    XPeers peers;
+    memset(&peers, 0, sizeof peers);
+    peers.n_ranks = n_ranks;
+    peers.rank = rank;
+    for (int p = 0; p < n_ranks; ++p) peers.base[p] = (double *) recv_buffers[p];
+    XCtl x;
+    x.go = d_go;
+    x.d_epoch = d_epoch;
+    x.epoch = 0;
+    x.slot = xslot_doubles(st->total_spans);
+    x.n_ranks = n_ranks;
+    x.rank = rank;
+    k_exchange_scalar<<<1, 32, 0, ctx->stream>>>(peers, x, 2 * (size_t) n_ranks * x.slot, d_value, exchange_timeout_clocks(ctx), d_err);
+    ECB_LAUNCHED(ctx);
+    return ecb_check(ctx, cudaGetLastError(), "scalar exchange");
+}
+
+double *ecb_cost_params_buffer(ecb_ctx *ctx, size_t *doubles) {  // the context's parameter upload buffer (intr | rot | trans)
+    CostState *st = (CostState *) ctx->cost;
+    const size_t n = 9 + 7 * (size_t) st->total_cp;
+    if (ecb_reserve(ctx, st->params, n * 8)) return nullptr;
+    if (doubles) *doubles = n;
+    return (double *) st->params.p;
+}
+
+extern "C" {
+
 int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, double *cost) {
     if (!ctx || !ctx->cost || !intrinsics || !rot_cp || !trans_cp || !cost) return ECB_ERR_ARG;
     cudaSetDevice(ctx->device);
@@ -938,18 +1174,7 @@ int ecb_cost_eval(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, 
     if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
     *cost = 0.0;
     if (st->n_res == 0) return ECB_OK;
-    int grid = (int) std::min<int64_t>((st->n_res + 255) / 256, (int64_t) ctx->sm_count * 8);
-    ECB_PROF_BEGIN(ctx, ECB_STAGE_COST);
-    static const int cost_minb = getenv("ECB_COST_MINB") ? atoi(getenv("ECB_COST_MINB")) : 4;  // 64 registers, 32 warps / SM: 0.35 -> 0.33 ms
-    (st->so3 ? k_cost<true, 2> : (cost_minb >= 4 ? k_cost<false, 4> : k_cost<false, 3>))<<<grid, 256, 0, ctx->stream>>>((const double *) st->obs.p, (const double *) st->lm.p,
-                                          st->use_circ ? (const int *) st->sel_circle.p : nullptr, (const double *) st->lm_tab.p,
-                                          (const double *) st->basis.p,
-                                          (const int *) st->cp0.p, st->n_res, (const double *) st->params.p, st->total_cp,
-                                          st->radius, st->huber, (double *) st->cost_part.p);
-    ECB_LAUNCHED(ctx);
-    k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->cost_part.p, grid, 1, 0, (double *) st->cost_part.p + 4000);
-    ECB_LAUNCHED(ctx);
-    ECB_PROF_END(ctx, ECB_STAGE_COST);
+    if ((rc = ecb_cost_dev_eval(ctx, (const double *) st->params.p, nullptr, (double *) st->cost_part.p + 4000))) return rc;
     return ecb_d2h(ctx, cost, (double *) st->cost_part.p + 4000, 8);
 }
 
@@ -966,38 +1191,7 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
     if ((rc = ecb_reserve(ctx, st->out, (n_out + 8) * 8))) return rc;
     double *out = d_out ? (double *) d_out : (double *) st->out.p;
     ECB_CUDA(ctx, cudaMemsetAsync(out, 0, n_out * 8, ctx->stream));
-    if (st->n_items > 0) {
-        NeArgs a;
-        a.obs = (const double *) st->obs.p;
-        a.lm = (const double *) st->lm.p;
-        a.circ = st->use_circ ? (const int *) st->sel_circle.p : nullptr;
-        a.lm_tab = (const double *) st->lm_tab.p;
-        a.basis = (const double *) st->basis.p;
-        a.cp0 = (const int *) st->cp0.p;
-        a.items = (const Item *) st->items.p;
-        a.n_items = st->n_items;
-        a.params = (const double *) st->params.p;
-        a.total_cp = st->total_cp;
-        a.radius = st->radius;
-        a.huber = st->huber;
-        a.part = (double *) st->part.p;
-        const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
-        static const int variant = getenv("ECB_NE_VARIANT") ? atoi(getenv("ECB_NE_VARIANT")) : 2;
-        void (*kern)(const NeArgs) = st->so3 ? k_normal_eq<1, true> : (variant == 1 ? k_normal_eq<1, false> : k_normal_eq<2, false>);
-        ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * ((variant == 1 || st->so3) ? 1 : 2));
-        ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
-        kern<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
-        ECB_LAUNCHED(ctx);
-        const int *item_start = (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
-        k_reduce_spans<<<st->total_spans, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start, st->total_spans, out);
-        ECB_LAUNCHED(ctx);
-        k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, PART_SC + 3,
-                                                  out + (size_t) st->total_spans * OUT_STRIDE);
-        ECB_LAUNCHED(ctx);
-        ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);
-        if ((rc = ecb_check(ctx, cudaGetLastError(), "normal equation kernels"))) return rc;
-    }
+    if ((rc = ecb_cost_dev_normal_eq(ctx, (const double *) st->params.p, nullptr, out))) return rc;
     if (h_out) {
         if ((rc = ecb_d2h(ctx, h_out, out, n_out * 8))) return rc;
         if (cost) *cost = h_out[(size_t) st->total_spans * OUT_STRIDE];
@@ -1011,7 +1205,8 @@ int ecb_cost_normal_eq(ecb_ctx *ctx, const double *intrinsics, const double *rot
 size_t ecb_exchange_buffer_bytes(ecb_ctx *ctx, int n_ranks) {
     if (!ctx || !ctx->cost || n_ranks < 1) return 0;
     CostState *st = (CostState *) ctx->cost;
-    return 2 * (size_t) n_ranks * xslot_doubles(st->total_spans) * 8;
+    // two parity blocks of n_ranks span slots, then two parity blocks of n_ranks (epoch, value) scalar slots
+    return (2 * (size_t) n_ranks * xslot_doubles(st->total_spans) + 4 * (size_t) n_ranks + 8) * 8;
 }
 
 int ecb_cost_normal_eq_exchange(ecb_ctx *ctx, const double *intrinsics, const double *rot_cp, const double *trans_cp, int rank,
@@ -1024,68 +1219,20 @@ int ecb_cost_normal_eq_exchange(ecb_ctx *ctx, const double *intrinsics, const do
     int rc;
     if ((rc = upload_params(ctx, st, intrinsics, rot_cp, trans_cp))) return rc;
     if ((rc = ecb_reserve(ctx, st->cost_part, 4096 * 8))) return rc;
-    XPeers peers;
-    memset(&peers, 0, sizeof peers);
-    peers.n_ranks = n_ranks;
-    peers.rank = rank;
-    for (int p = 0; p < n_ranks; ++p) {
-        if (!recv_buffers[p]) return ECB_ERR_ARG;
-        peers.base[p] = (double *) recv_buffers[p];
-    }
-    const size_t slot = xslot_doubles(st->total_spans);
-    const size_t parity_off = (size_t) (epoch & 1) * n_ranks * slot;
-    const size_t my_slot_off = parity_off + (size_t) rank * slot;
-    // span range this rank contributes to (host knows the work items)
-    int lo = 0, hi = -1;
-    for (int s = 0; s < st->total_spans; ++s)
-        if (st->h_span_start[(size_t) s + 1] > st->h_span_start[(size_t) s]) {
-            if (hi < 0) lo = s;
-            hi = s;
-        }
-    double *d_cost = (double *) st->cost_part.p + 4001;
-    if (phases & ECB_EXCHANGE_SEND) ECB_CUDA(ctx, cudaMemsetAsync(d_cost, 0, 8, ctx->stream));
+    // Epochs on the wire never repeat for a receive buffer: a caller that restarts its sequence (a second LM run on the same
+    // buffers begins at 1 again) starts a new generation, so a header left over from the previous run cannot satisfy the wait.
+    // Every rank sees the same epoch sequence, hence the same generations.  (SEND and RECV of one exchange carry one epoch.)
+    if ((phases & ECB_EXCHANGE_SEND) && epoch <= st->xch_last_epoch) ++st->xch_generation;
+    if (phases & ECB_EXCHANGE_SEND) st->xch_last_epoch = epoch;
+    const unsigned long long wire = ((unsigned long long) st->xch_generation << 40) | (unsigned long long) (epoch & 0xFFFFFFFFFFull);
+    // the parity must follow the caller's epoch (double buffering), generations keep it: shift left by one, parity in bit 0
+    const unsigned long long wire_epoch = (wire << 1) | (epoch & 1ull);
     unsigned *d_err = (unsigned *) ((double *) st->cost_part.p + 4002);
-    if (phases & ECB_EXCHANGE_SEND) {
-    if (st->n_items > 0 && hi >= lo) {
-        NeArgs a;
-        a.obs = (const double *) st->obs.p;
-        a.lm = (const double *) st->lm.p;
-        a.circ = st->use_circ ? (const int *) st->sel_circle.p : nullptr;
-        a.lm_tab = (const double *) st->lm_tab.p;
-        a.basis = (const double *) st->basis.p;
-        a.cp0 = (const int *) st->cp0.p;
-        a.items = (const Item *) st->items.p;
-        a.n_items = st->n_items;
-        a.params = (const double *) st->params.p;
-        a.total_cp = st->total_cp;
-        a.radius = st->radius;
-        a.huber = st->huber;
-        a.part = (double *) st->part.p;
-        const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
-        void (*kern)(const NeArgs) = st->so3 ? k_normal_eq<1, true> : k_normal_eq<2, false>;
-        ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        const int grid = std::min((st->n_items + NE_WARPS - 1) / NE_WARPS, ctx->sm_count * (st->so3 ? 1 : 2));
-        ECB_PROF_BEGIN(ctx, ECB_STAGE_NORMAL_EQ);
-        kern<<<grid, NE_THREADS, smem, ctx->stream>>>(a);
-        ECB_LAUNCHED(ctx);
-        const int *item_start = (const int *) ((const char *) st->items.p + (size_t) std::max(st->n_items, 1) * sizeof(Item));
-        k_reduce_spans_push<<<hi - lo + 1, 192, 0, ctx->stream>>>((const double *) st->part.p, item_start, lo, hi, peers, my_slot_off);
-        ECB_LAUNCHED(ctx);
-        k_reduce_cost<<<1, 256, 0, ctx->stream>>>((const double *) st->part.p, st->n_items, PART_STRIDE, PART_SC + 3, d_cost);
-        ECB_LAUNCHED(ctx);
-        ECB_PROF_END(ctx, ECB_STAGE_NORMAL_EQ);
-    }
-    ECB_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, ctx->stream));
-    k_exchange_signal<<<1, 32, 0, ctx->stream>>>(peers, my_slot_off, (unsigned long long) epoch, lo, hi, d_cost);
-    ECB_LAUNCHED(ctx);
-    }
-    if (!(phases & ECB_EXCHANGE_RECV)) return ecb_check(ctx, cudaGetLastError(), "exchange kernels");
-    k_exchange_wait<<<1, 32, 0, ctx->stream>>>(peers.base[rank], parity_off, slot, n_ranks, (unsigned long long) epoch, d_err);
-    ECB_LAUNCHED(ctx);
-    k_exchange_sum<<<st->total_spans + 1, 192, 0, ctx->stream>>>(peers.base[rank], parity_off, slot, n_ranks, st->total_spans,
-                                                                 (double *) d_out);
-    ECB_LAUNCHED(ctx);
-    if ((rc = ecb_check(ctx, cudaGetLastError(), "exchange kernels"))) return rc;
+    if (phases & ECB_EXCHANGE_SEND) ECB_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+    if ((rc = ecb_cost_dev_normal_eq_exchange(ctx, (const double *) st->params.p, nullptr, rank, n_ranks, recv_buffers, nullptr,
+                                              wire_epoch, phases, (double *) d_out, d_err)))
+        return rc;
+    if (!(phases & ECB_EXCHANGE_RECV)) return ECB_OK;
     if (cost) {
         double hc[2];
         if ((rc = ecb_d2h(ctx, hc, (double *) d_out + (size_t) st->total_spans * OUT_STRIDE, 8))) return rc;
@@ -1094,6 +1241,8 @@ int ecb_cost_normal_eq_exchange(ecb_ctx *ctx, const double *intrinsics, const do
         if (herr) return ecb_fail(ctx, ECB_ERR_STATE, "normal-equation exchange timed out waiting for ranks (mask 0x%x)", herr);
         *cost = hc[0];
     }
+    // cost == NULL: nothing is read back here; a timeout leaves NaN in the cost slot of d_out (k_exchange_sum), which every
+    // consumer of the packed buffer sees
     return ECB_OK;
 }
 

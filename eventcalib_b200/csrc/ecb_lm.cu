@@ -409,7 +409,10 @@ int ecb_lm_feedback(ecb_lm *lm, double candidate_cost) {
     lm->decrease_factor *= 2.0;
     lm->reuse_diagonal = true;
     lm->record(0.0);
-    if (lm->radius < lm->opt.min_radius) return lm->termination = ECB_LM_MIN_RADIUS;
+    if (lm->radius < lm->opt.min_radius) {
+        if (!lm->opt.fixed_iterations) return lm->termination = ECB_LM_MIN_RADIUS;
+        lm->radius = lm->opt.min_radius;  // benchmark mode (config C4): exactly max_iterations iterations, no early exit
+    }
     return 0;
 }
 

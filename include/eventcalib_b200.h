@@ -228,6 +228,9 @@ int ecb_device_free(ecb_ctx *ctx, void *d_ptr);
 int ecb_ipc_export(ecb_ctx *ctx, void *d_ptr, void *handle64);          /* 64-byte cudaIpcMemHandle_t */
 int ecb_ipc_open(ecb_ctx *ctx, const void *handle64, void **d_ptr);     /* maps a peer's buffer (enables peer access) */
 int ecb_ipc_close(ecb_ctx *ctx, void *d_ptr);
+/* several GPUs driven from ONE process (one context per device): lets ctx's kernels store into ecb_device_alloc buffers of
+ * peer_device (cudaDeviceEnablePeerAccess); receive buffers are then passed to the exchange as plain device pointers */
+int ecb_enable_peer_access(ecb_ctx *ctx, int peer_device);
 
 /* ---- a12: the LM step around the GPU normal equations (EventCalibSpline::optimize, src/EventCalibSpline.cpp:197-247) ---- */
 typedef struct {
@@ -274,6 +277,34 @@ int ecb_lm_trace(const ecb_lm *lm, double *out, int cap_rows);
 /* single-GPU driver of the whole loop; parameters are updated in place */
 int ecb_calibrate(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, double *intrinsics, double *rot_cp, double *trans_cp,
                   const ecb_lm_options *opt, ecb_lm_summary *summary, double *trace, int trace_rows);
+
+/* ---- the same loop with the state machine AND the linear solve on the device --------------------------------------------
+ * The host only enqueues kernels: per iteration a band-arrow Cholesky of the damped system (one CTA per spline segment, the 9
+ * intrinsics and the right-hand side as arrow rows), the candidate's cost, the accept / reject decision and — only if the step
+ * was accepted, decided by a device flag — the normal equations at the new point.  Nothing crosses PCIe until the result is
+ * read.  Several GPUs (one process per GPU, or several contexts of one process): every rank runs the same replicated state
+ * machine on its own share of the residuals; the packed normal equations and the candidate costs are summed over the ranks
+ * inside the kernels through the peer-mapped receive buffers of ecb_cost_normal_eq_exchange (sized by
+ * ecb_exchange_buffer_bytes, zero-filled once), in rank order, so all ranks take bit-identical decisions.
+ * fixed_iterations != 0 runs exactly max_iterations iterations (benchmark config C4): no convergence test, no MIN_RADIUS exit.
+ * Call order: create (after ecb_cost_setup + association) -> [set_exchange] -> begin -> iterate(n) ... -> result. */
+typedef struct ecb_lm_device ecb_lm_device;
+int ecb_lm_device_create(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const ecb_lm_options *opt, ecb_lm_device **out);
+void ecb_lm_device_destroy(ecb_lm_device *lm);
+int ecb_lm_device_set_exchange(ecb_lm_device *lm, int rank, int n_ranks, void *const *recv_buffers);
+/* uploads x, evaluates the normal equations at x, initialises the trust region (asynchronous) */
+int ecb_lm_device_begin(ecb_lm_device *lm, const double *intrinsics, const double *rot_cp, const double *trans_cp);
+/* enqueues n_iterations LM iterations (asynchronous; no-ops on the device once the state machine has terminated) */
+int ecb_lm_device_iterate(ecb_lm_device *lm, int n_iterations);
+/* synchronises: 1 while the state machine is running, 0 when it has terminated, < 0 on error */
+int ecb_lm_device_running(ecb_lm_device *lm);
+/* synchronises and reads back the parameters, the summary and up to trace_rows rows of (cost, gradient_max_norm, radius,
+ * accepted 1 / rejected 0 / invalid -1) */
+int ecb_lm_device_result(ecb_lm_device *lm, double *intrinsics, double *rot_cp, double *trans_cp, ecb_lm_summary *summary,
+                         double *trace, int trace_rows);
+/* begin + iterations until termination + result; parameters are updated in place */
+int ecb_calibrate_device(ecb_lm_device *lm, double *intrinsics, double *rot_cp, double *trans_cp, ecb_lm_summary *summary,
+                         double *trace, int trace_rows);
 
 #ifdef __cplusplus
 }

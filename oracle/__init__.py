@@ -76,6 +76,19 @@ def have_ref_functor():
     return os.path.exists(_REF_FN)
 
 
+_REF_DROPIN = os.path.join(_HERE, "_ref", "libref_dropin.so")
+
+
+def have_ref_dropin():
+    return os.path.exists(_REF_DROPIN)
+
+
+def ref_dropin_lib():
+    """The reference's sources compiled where they lie with `#include <dbscan.h>` resolved to the PRODUCT's include/ecb/dbscan.h:
+    its DBSCAN::Run calls run on the GPU through libecb.so (oracle/Makefile, target _ref/libref_dropin.so)."""
+    return C.CDLL(_REF_DROPIN)
+
+
 def ref_functor_lib():
     lib = _load(_REF_FN)
     lib.ref_residual.restype = C.c_double
@@ -187,7 +200,7 @@ def ref_read_bin(path, cap):
 
 
 def ref_extract(t, x, y, pol, t0, t1, W, H, fitCircle, eps=4.0, minS=2, clusterMin=5, knn_num=3, rows=9, cols=4, asym=True,
-                square=5.5, radius=1.75):
+                square=5.5, radius=1.75, lib=None):
     """The reference's own CirclesEventFrame constructor + extractFeatures() (event_camera_calib/src/CirclesEventFrame.cpp:16-359,
     with its DBSCAN) on raw events.  Returns dict(found, cand_f32 = the candidate centres handed to findCirclesGrid as
     cv::Point2f (None when :127-129 returned before), features = rows*cols x (cx, cy, r) in board order when found, rthr)."""
@@ -198,7 +211,7 @@ def ref_extract(t, x, y, pol, t0, t1, W, H, fitCircle, eps=4.0, minS=2, clusterM
     cand = np.zeros((cap, 2), np.float32)
     n_cand, rthr = C.c_int(), C.c_double()
     feats = np.zeros((rows * cols, 3))
-    ok = ref_functor_lib().ref_extract(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)), C.c_double(t0),
+    ok = (lib or ref_functor_lib()).ref_extract(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)), C.c_double(t0),
                                        C.c_double(t1), C.c_int(W), C.c_int(H), _p(prm, _dp), cand.ctypes.data_as(C.c_void_p),
                                        C.c_int(cap), C.byref(n_cand), _p(feats, _dp), C.byref(rthr))
     return dict(found=bool(ok), cand_f32=cand[:n_cand.value].copy() if n_cand.value >= 0 else None, features=feats, rthr=rthr.value)
@@ -213,7 +226,7 @@ def ref_fit_circle(pxy, nxy):
     return out
 
 
-def ref_rectify(t, x, y, pol, t0, t1, W, H, fitCircle, image_points, find_xy=None, rows=9, cols=4):
+def ref_rectify(t, x, y, pol, t0, t1, W, H, fitCircle, image_points, find_xy=None, rows=9, cols=4, lib=None):
     """The reference's own extractFeatures() + rectifyFeatures() (CirclesEventFrame.cpp:417-638) with the caller's projections
     image_points[rows*cols][5][2]; then findCenter() (CirclesEventFrame.hpp:50-65) for the pixels find_xy.
     Returns (verdict: -1 extractFeatures failed / 0 / 1, out[rows*cols][3] with r = -1 for deleted features, landmark ids)."""
@@ -224,7 +237,7 @@ def ref_rectify(t, x, y, pol, t0, t1, W, H, fitCircle, image_points, find_xy=Non
     out = np.zeros((rows * cols, 3))
     fxy = np.ascontiguousarray(find_xy if find_xy is not None else np.zeros((0, 2)), np.float64)
     fid = np.full(max(len(fxy), 1), -2, np.int32)
-    rc = ref_functor_lib().ref_rectify(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)), C.c_double(t0),
+    rc = (lib or ref_functor_lib()).ref_rectify(_p(t, _dp), _p(x, _dp), _p(y, _dp), _p(pol, _bp), C.c_longlong(len(t)), C.c_double(t0),
                                        C.c_double(t1), C.c_int(W), C.c_int(H), _p(prm, _dp), _p(img, _dp), _p(out, _dp), _p(fxy, _dp),
                                        C.c_int(len(fxy)), _p(fid, _ip))
     return rc, out, fid[:len(fxy)]
