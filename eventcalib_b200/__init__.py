@@ -58,7 +58,7 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_set_sensor", "ecb_load_events_host", "ecb_load_events_device", "ecb_num_events", "ecb_frontend_run",
            "ecb_frontend_summary", "ecb_frontend_total_points", "ecb_frontend_points", "ecb_frontend_candidates",
            "ecb_frontend_clusters", "ecb_frontend_rectify", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
-           "ecb_dbscan_run_ordered", "ecb_dbscan_run_batch_ordered",
+           "ecb_dbscan_run_ordered", "ecb_dbscan_run_batch_ordered", "ecb_dbscan_run_nd",
            "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_set_rotation_model", "ecb_cost_layout",
            "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq",
            "ecb_exchange_buffer_bytes", "ecb_cost_normal_eq_exchange", "ecb_device_alloc", "ecb_device_free", "ecb_ipc_export",
@@ -118,6 +118,7 @@ def load_library():
     lib.ecb_dbscan_run_batch.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp]
     lib.ecb_dbscan_run_ordered.argtypes = [vp, vp, i32, dbl, u32, vp, C.POINTER(C.c_int32), vp, vp]
     lib.ecb_dbscan_run_batch_ordered.argtypes = [vp, vp, vp, i32, dbl, u32, vp, vp, vp, vp, vp]
+    lib.ecb_dbscan_run_nd.argtypes = [vp, vp, i32, i32, dbl, u32, vp, C.POINTER(C.c_int32), vp, vp]
     lib.ecb_fit_circles.argtypes = [vp, vp, vp, i32, vp]
     lib.ecb_set_profiling.argtypes = [vp, i32]
     lib.ecb_stage_ms.argtypes = [vp, vp]
@@ -317,6 +318,23 @@ class Context:
         self._chk(rc)
         off = np.concatenate([[0], np.cumsum(sizes[:nc.value])])
         clusters = [members[off[c]:off[c + 1]].copy() for c in range(nc.value)]
+        return OK, labels[:n], clusters, np.nonzero(labels[:n] < 0)[0].astype(np.uint32)
+
+    def dbscan_nd(self, pts, eps, min_pts, ordered=True):
+        """DBSCAN<T,Float>::Run(V, dim, eps, min) for dim = pts.shape[1] (1..4): (status, labels, clusters, noise)."""
+        pts = np.ascontiguousarray(pts, np.float64)
+        n, dim = pts.shape
+        labels = np.full(max(n, 1), -1, np.int32)
+        sizes = np.zeros(max(n, 1), np.int32)
+        members = np.zeros(max(n, 1), np.uint32)
+        nc = C.c_int32(0)
+        rc = self.lib.ecb_dbscan_run_nd(self.h, _ptr(pts), n, dim, float(eps), int(min_pts), _ptr(labels), C.byref(nc),
+                                        _ptr(sizes) if ordered else None, _ptr(members) if ordered else None)
+        if rc == FAILED:
+            return FAILED, labels[:0], [], labels[:0]
+        self._chk(rc)
+        off = np.concatenate([[0], np.cumsum(sizes[:nc.value])])
+        clusters = [members[off[c]:off[c + 1]].copy() for c in range(nc.value)] if ordered else nc.value
         return OK, labels[:n], clusters, np.nonzero(labels[:n] < 0)[0].astype(np.uint32)
 
     def dbscan_batch_ordered(self, xy, offsets, eps, min_pts):

@@ -161,6 +161,8 @@ void ecb_ctx_destroy(ecb_ctx *c) {
                       &c->bfs_items, &c->bfs_front, &c->bfs_tab};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (DevBuf &b : c->gh)
+        if (b.p) cudaFree(b.p);
     for (int i = 0; i < ECB_N_STAGES; ++i)
         for (int j = 0; j < 2; ++j)
             if (c->pev[i][j]) cudaEventDestroy(c->pev[i][j]);
@@ -222,13 +224,15 @@ static int unpack_events(ecb_ctx *ctx, const void *d_raw, int64_t n) {
     uint32_t flag = 0;
     if ((rc = ecb_d2h(ctx, &flag, ctx->ev_flag.p, 4))) return rc;
     ctx->n_events = n;
-    if (flag & 2u) {
-        ctx->n_events = 0;
-        return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "event stream is not sorted by time stamp");
-    }
     if (flag & 1u) {
         ctx->n_events = 0;
         return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "event stream holds non-integer or out-of-sensor pixel coordinates");
+    }
+    // an unsorted file: the reference's multimap load orders it by stamp, file order among equal stamps
+    // (eventCameraCalib.cpp:154-163) — a stable device radix sort here
+    if ((flag & 2u) && (rc = ecb_sort_events_by_time(ctx, n))) {
+        ctx->n_events = 0;
+        return rc;
     }
     return ECB_OK;
 }
@@ -600,8 +604,16 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
     int rc;
     ClusterArgs ca;
     memset(&ca, 0, sizeof ca);
-    if ((rc = fill_stencil(ctx, ca, eps))) return rc;
     if (n_problems == 0) return ECB_OK;
+    // Inputs outside the bitmap kernel's domain (distinct integer pixels, 1 <= eps <= 15, bounded extent) take the general
+    // grid-hash path (ecb_gridhash.cu) — same results as the reference on everything it accepts (dbscan.h:40,70,115-177).
+    auto general = [&]() {
+        if (status)
+            for (int k = 0; k < n_problems; ++k) status[k] = 0;
+        return ecb_dbscan_general(ctx, xy, 2, offsets, n_problems, eps, min_pts, labels, n_clusters, cluster_sizes, members);
+    };
+    if (!(eps >= 1.0) || eps > ECB_MAX_EPS) return general();
+    if ((rc = fill_stencil(ctx, ca, eps))) return rc;
     const int64_t total = offsets[n_problems];
     // host-side packing: integer check, bounding boxes (the window path does this on the device in k_ingest)
     std::vector<uint32_t> pix((size_t) std::max<int64_t>(total, 1));
@@ -615,11 +627,7 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
         for (int64_t i = b; i < e; ++i) {
             const double x = xy[2 * i], y = xy[2 * i + 1];
             const int xi = (int) x, yi = (int) y;
-            if (!((double) xi == x && (double) yi == y && xi >= 0 && xi < 32768 && yi >= 0 && yi < 32768))
-                return ecb_fail(ctx, ECB_ERR_UNSUPPORTED,
-                                "problem %d point %lld = (%g, %g): only integer pixel coordinates in [0, 32767] are "
-                                "supported by the device DBSCAN",
-                                k, (long long) (i - b), x, y);
+            if (!(x >= 0.0 && x < 32768.0 && y >= 0.0 && y < 32768.0 && (double) xi == x && (double) yi == y)) return general();
             pix[(size_t) i] = (uint32_t) xi | ((uint32_t) yi << 15);
             xmin = std::min(xmin, xi);
             ymin = std::min(ymin, yi);
@@ -638,6 +646,7 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
         Hmax = std::max(Hmax, ymax - ymin + 1);
         max_n = std::max(max_n, d.n);
     }
+    if ((int64_t) (Wmax + 2 * ca.E + 64) * (Hmax + 2 * ca.E) > (1ll << 21)) return general();  // bit planes beyond 256 KB
     const size_t slots = (size_t) std::max<int64_t>(total, 1);
     const int max_k = 1;  // no kept-cluster tables on this path (cluster_min below)
     if ((rc = ecb_reserve(ctx, ctx->db_pix, slots * 4))) return rc;
@@ -715,8 +724,9 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
     for (int k = 0; k < n_problems; ++k) {
         if (n_clusters) n_clusters[k] = hdr[(size_t) k].n_clusters;
         if (status) status[k] = hdr[(size_t) k].status;
-        if ((hdr[(size_t) k].status & ECB_PB_DUPLICATE) && !status)
-            return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "problem %d holds duplicate points (the reference path never does)", k);
+        // duplicate points are distinct pids and neighbours of each other in the reference (dbscan.h:218): the bitmap cannot
+        // hold them, the general path can
+        if (hdr[(size_t) k].status & ECB_PB_DUPLICATE) return general();
     }
     return ECB_OK;
 }
@@ -739,6 +749,16 @@ int ecb_dbscan_run_ordered(ecb_ctx *ctx, const double *xy, int n, double eps, ui
     if (n < 1 || min_pts < 1) return ECB_FAILED;  // dbscan.h:121-123
     const int64_t off[2] = {0, n};
     return dbscan_batch(ctx, xy, off, 1, eps, min_pts, labels, n_clusters, nullptr, cluster_sizes, members);
+}
+
+int ecb_dbscan_run_nd(ecb_ctx *ctx, const double *pts, int n, int dim, double eps, uint32_t min_pts, int32_t *labels,
+                      int32_t *n_clusters, int32_t *cluster_sizes, uint32_t *members) {
+    if (!ctx || (!pts && n > 0) || ((cluster_sizes == nullptr) != (members == nullptr))) return ECB_ERR_ARG;
+    if (n < 1 || dim < 1 || min_pts < 1) return ECB_FAILED;  // dbscan.h:121-123
+    const int64_t off[2] = {0, n};
+    if (dim == 2) return dbscan_batch(ctx, pts, off, 1, eps, min_pts, labels, n_clusters, nullptr, cluster_sizes, members);
+    cudaSetDevice(ctx->device);
+    return ecb_dbscan_general(ctx, pts, dim, off, 1, eps, min_pts, labels, n_clusters, cluster_sizes, members);
 }
 
 int ecb_dbscan_run(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t min_pts, int32_t *labels,

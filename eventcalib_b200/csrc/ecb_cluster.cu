@@ -33,9 +33,8 @@ struct Smem {
 };
 
 // A/B switches of the round-2 changes (profiles/tools/ab_build.py builds variants with -D...=0)
-#ifndef ECB_CL_AGG
-#define ECB_CL_AGG 0        // warp-aggregated atomicMin in the first kd rounds: measured SLOWER (+0.18 ms on C2, MATCH.ANY costs more than the serialised atomics; profiles/r2d_ab_cluster.jsonl)
-#endif
+// (warp-aggregated atomicMin in the first kd rounds was measured SLOWER: +0.18 ms on C2, MATCH.ANY costs more than the
+// serialised atomics; profiles/r2d_ab_cluster.jsonl)
 #ifndef ECB_CL_RANKORDER
 #define ECB_CL_RANKORDER 1  // steps 5 - 6 walk the points in row-major rank order instead of pid order
 #endif
@@ -76,7 +75,8 @@ template <typename RankT, bool SM>
 __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs a) {
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ uint32_t ws[33];
-    __shared__ uint32_t s_pb, s_status, s_chunk;
+    __shared__ uint32_t s_nextpb[2], s_status, s_chunk;
+    __shared__ uint8_t s_own[ECB_CL_THREADS / 32][32];  // 6b: lane of the k-th sub-run head of the warp's chunk
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     const int PW = a.PW, PH = a.PH, E = a.E, NW = PW * PH;
@@ -105,19 +105,22 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
 
     // ---- 0. clear planes: once per CTA; every problem un-sets the words it touched when it is done with them (step 8) ----
     for (int i = tid; i < 2 * NW; i += nthr) s.U[i] = 0;
-    for (;;) {
+    // Problems are drawn from a global counter.  The draw for the NEXT problem is issued at the start of the current one and
+    // parked in a register of thread 0 until the header is written, so its latency (an L2 round trip per problem) is hidden.
+    if (tid == 0) {
+        s_nextpb[0] = atomicAdd(a.work_counter, 1u);
+        s_status = 0;
+    }
+    for (int iter = 0;; ++iter) {
 #if !ECB_CL_UNSET
         __syncthreads();
         for (int i = tid; i < 2 * NW; i += nthr) s.U[i] = 0;
 #endif
         __syncthreads();
-        if (tid == 0) {
-            s_pb = atomicAdd(a.work_counter, 1u);
-            s_status = 0;
-        }
-        __syncthreads();
-        const uint32_t pb = s_pb;
+        const uint32_t pb = s_nextpb[iter & 1];
         if (pb >= (uint32_t) a.n_prob) break;
+        uint32_t next_pb = 0;
+        if (tid == 0) next_pb = atomicAdd(a.work_counter, 1u);
         const ProbDesc d = a.prob[pb];
         const int n = d.n;
         const uint32_t *gpix = a.pix[d.pol] + d.off;
@@ -166,7 +169,9 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         uint32_t *rloc = s.r_lab;  // [rank] -> packed pixel; r_lab is not needed before step 7
         for (int i = tid; i < 2 * n; i += nthr) child[i] = ECB_NONE;
         if (n <= KD_PT * nthr) {
-            // fast path: each thread keeps its <= KD_PT points (pixel, current node, flags) in registers
+            // fast path: each thread keeps its <= KD_PT points (pixel, current node, flags) in registers.
+            // (Handing the last walkers of the late rounds over to one thread each was measured SLOWER: the rounds are bound by
+            // the barrier + shared-memory latency chain, not by issue slots; profiles/r2s_ab_cluster_compact.jsonl.)
             uint32_t mypix[KD_PT], cur[KD_PT], fl[KD_PT];
 #pragma unroll
             for (int k = 0; k < KD_PT; ++k) {
@@ -180,27 +185,14 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                 const int dsh = (round & 1) ? 16 : 0;
                 bool any = false;
                 uint32_t slot[KD_PT];
-                // the first levels of the tree have few nodes: all lanes of a warp hit the same <= 2^(round+1) child slots and
-                // the shared-memory atomics serialise (ncu: 37 % of the kernel's excess wavefronts).  There the lanes are
-                // grouped by slot first and only the lowest lane of a group — the lowest pid, pids ascend with the lane —
-                // issues the atomicMin.
-                const bool aggregate = ECB_CL_AGG && round < 5;
 #pragma unroll
                 for (int k = 0; k < KD_PT; ++k) {
-                    const bool act = cur[k] != ECB_NONE;
-                    slot[k] = ECB_NONE;
-                    if (act) {
-                        any = true;
-                        const uint32_t ci = (mypix[k] >> dsh) & 0xFFFF, ca = (s.r_pix[cur[k]] >> dsh) & 0xFFFF;
-                        if (ci == ca) fl[k] |= 1u << (round & 1);
-                        slot[k] = 2 * cur[k] + (ci < ca ? 0 : 1);
-                    }
-                    if (aggregate) {
-                        const uint32_t peers = __match_any_sync(0xffffffffu, slot[k]);
-                        if (act && (peers & ((1u << lane) - 1u)) == 0) atomicMin(&child[slot[k]], (uint32_t) (tid + k * nthr));
-                    } else if (act) {
-                        atomicMin(&child[slot[k]], (uint32_t) (tid + k * nthr));
-                    }
+                    if (cur[k] == ECB_NONE) continue;
+                    any = true;
+                    const uint32_t ci = (mypix[k] >> dsh) & 0xFFFF, ca = (s.r_pix[cur[k]] >> dsh) & 0xFFFF;
+                    if (ci == ca) fl[k] |= 1u << (round & 1);
+                    slot[k] = 2 * cur[k] + (ci < ca ? 0 : 1);
+                    atomicMin(&child[slot[k]], (uint32_t) (tid + k * nthr));
                 }
                 if (!__syncthreads_or(any)) break;
 #pragma unroll
@@ -387,13 +379,15 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                     }
                 }
                 const uint32_t hm = __ballot_sync(0xffffffffu, head);
+                if (head) s_own[wid][__popc(hm & ((1u << lane) - 1u))] = (uint8_t) lane;
+                __syncwarp();
                 const int n_it = __popc(hm) * E;
                 for (int it0 = 0; it0 < n_it; it0 += 32) {
                     const int it = it0 + lane;
                     const bool act = it < n_it;
                     const int hi = act ? (int) (((uint32_t) it * invE) >> 16) : 0;
                     const int dy = it - hi * E + 1;
-                    const int owner = (int) __fns(hm, 0, hi + 1);
+                    const int owner = (int) s_own[wid][hi];
                     const uint32_t loc = __shfl_sync(0xffffffffu, h_xy, owner);
                     const uint32_t sub = __shfl_sync(0xffffffffu, h_sub, owner);
                     const uint32_t rf = __shfl_sync(0xffffffffu, h_rf, owner);
@@ -421,6 +415,7 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                         unite(parent, rf, rank_of(nx, y + dy));
                     }
                 }
+                __syncwarp();  // s_own is rewritten by the next chunk
             }
         }
         __syncthreads();
@@ -637,24 +632,26 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         for (int k = wid; k < (int) n_kept; k += nwarp) {
             const int32_t cid = k_raw[k];
             const int base = k_off[k], sz = k_size[k];
-            long long S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            // pixel coordinates are in [0, 32767]: squares and x*y are exact in 32 bits, cubes are one 32 x 32 -> 64 multiply-add
+            unsigned long long S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             int med = -1;
             uint32_t *mnorm = s.r_kd;  // csize / keptidx are dead: squared norms of the members, same indexing as `members`
             for (int i = lane; i < sz; i += 32) {
                 const uint32_t pid = members[base + i];
                 gmem[base + i] = pid;
                 const uint32_t loc = s.r_pix[pid];
-                const long long x = (int) (loc & 0xFFFF) - E + d.x0, y = (int) (loc >> 16) - E + d.y0;
+                const uint32_t x = (uint32_t) ((int) (loc & 0xFFFF) - E + d.x0), y = (uint32_t) ((int) (loc >> 16) - E + d.y0);
+                const uint32_t xx = x * x, yy = y * y, xy = x * y;
                 S[0] += x;
                 S[1] += y;
-                S[2] += x * x;
-                S[3] += y * y;
-                S[4] += x * y;
-                S[5] += x * x * x;
-                S[6] += y * y * y;
-                S[7] += x * y * y;
-                S[8] += x * x * y;
-                mnorm[base + i] = (uint32_t) (x * x + y * y);
+                S[2] += xx;
+                S[3] += yy;
+                S[4] += xy;
+                S[5] += (unsigned long long) xx * x;
+                S[6] += (unsigned long long) yy * y;
+                S[7] += (unsigned long long) xy * y;
+                S[8] += (unsigned long long) xx * y;
+                mnorm[base + i] = xx + yy;
             }
             __syncwarp();
             bool tie = false;
@@ -704,10 +701,15 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                     a.bfs_items[slot] = it;
                 }
             }
+            // warp sums with the integer reduction unit: three 21-bit limbs per 64-bit partial sum (each < 2^63)
 #pragma unroll
-            for (int q = 0; q < 9; ++q)
-                for (int o = 16; o > 0; o >>= 1) S[q] += __shfl_down_sync(0xffffffffu, S[q], o);
-            for (int o = 16; o > 0; o >>= 1) med = max(med, __shfl_down_sync(0xffffffffu, med, o));
+            for (int q = 0; q < 9; ++q) {
+                const uint32_t l0 = __reduce_add_sync(0xffffffffu, (uint32_t) S[q] & 0x1FFFFFu);
+                const uint32_t l1 = __reduce_add_sync(0xffffffffu, (uint32_t) (S[q] >> 21) & 0x1FFFFFu);
+                const uint32_t l2 = __reduce_add_sync(0xffffffffu, (uint32_t) (S[q] >> 42));
+                S[q] = (unsigned long long) l0 + ((unsigned long long) l1 << 21) + ((unsigned long long) l2 << 42);
+            }
+            med = __reduce_max_sync(0xffffffffu, med);
             if (lane == 0) {
                 KeptCluster kc;
                 kc.raw_id = cid;
@@ -733,6 +735,8 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                 h.n_core = (int32_t) tot;
                 h.status = s_status;
                 a.hdr[pb] = h;
+                s_status = 0;
+                s_nextpb[(iter + 1) & 1] = next_pb;
             }
         }
     }

@@ -88,6 +88,13 @@ struct BfsArgs {
 size_t ecb_cluster_smem_bytes(int PW, int PH, int n_cap, int max_k, bool arrays_in_smem, bool rank32);
 int ecb_launch_cluster(ecb_ctx *ctx, ClusterArgs &a, int max_n);
 int ecb_launch_bfs(ecb_ctx *ctx, BfsArgs &a);
+// general points: the tree is {left, right, parent, depth << 1 | side} and coordinates come from P[n][dim] (ecb_gridhash.cu)
+int ecb_launch_bfs_general(ecb_ctx *ctx, BfsArgs &a, const double *P, int dim);
+// stable device sort of the loaded events (ev_t, ev_xyp) by time stamp: the reference's multimap load accepts any file order
+int ecb_sort_events_by_time(ecb_ctx *ctx, int64_t n);
+// DBSCAN::Run for any input (non-integer coordinates, duplicates, any eps, dim <= ECB_GH_MAXD): grid hash + radix sort
+int ecb_dbscan_general(ecb_ctx *ctx, const double *pts, int dim, const int64_t *offsets, int n_problems, double eps,
+                       uint32_t min_pts, int32_t *labels, int32_t *n_clusters, int32_t *cluster_sizes, uint32_t *members);
 // every cluster of every problem -> BfsItem (ecb_dbscan_run_ordered): csize/cseed/coff are per point slot (index off + cid)
 int ecb_launch_bfs_all_items(ecb_ctx *ctx, const ProbDesc *prob, const ProbHdr *hdr, int n_prob, const int32_t *labels,
                              uint32_t *csize, uint32_t *cseed, uint32_t *coff, BfsItem *items, unsigned *count, int cap);

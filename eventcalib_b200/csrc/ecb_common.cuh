@@ -10,6 +10,8 @@
 
 #define ECB_MAX_EPS 15      // stencil rows fit a 64-bit funnel window (2*15+1 = 31 bits)
 #define ECB_NONE 0xFFFFFFFFu
+#define ECB_GH_MAXD 4       // largest point dimension of the general (grid-hash) DBSCAN path
+#define ECB_GH_NBUF 32      // device buffers of that path
 
 // packed event / pixel word:  x bits 0..14, y bits 15..29, bit 30 invalid, bit 31 polarity
 #define ECB_PIX_X(p) ((p) & 0x7FFFu)
@@ -51,6 +53,7 @@ struct ecb_ctx {
     DevBuf kd_tree, bfs_key, bfs_items, bfs_front, bfs_tab;
     // dbscan boundary
     DevBuf db_pix, db_off, db_labels, db_hdr, db_scratch, db_dims, db_hdr_b, db_ktab, db_counter;
+    DevBuf gh[ECB_GH_NBUF];   // general path (ecb_gridhash.cu)
     // fit
     DevBuf fit_in, fit_off, fit_out;
     // pinned staging (device -> host), and mapped pinned staging the device pulls small uploads from

@@ -6,10 +6,13 @@
 //               returns 0 SUCCESS / 1 FAILED when V->size()<1 || dim<1 || min<1, never throws                       :121-123
 //               public: std::vector<std::vector<uint>> Clusters; std::vector<uint> Noise;                            :92-93
 //
-// Differences: only dim == 2 with integer-valued, distinct points is supported by the device path
-// (that is the reference's only instantiation, CirclesEventFrame.cpp:66-70) — anything else returns FAILED and
-// `last_error()` says why.  `Clusters` (discovery order, members in the reference's BFS pop order) and `Noise` are
-// identical to the reference's as ordered lists.  `disfunc` is accepted and ignored exactly like the reference's kd-tree build.
+// Any T with operator[] convertible to double (dbscan.h:40-41,192), dim = 1 .. 4, any finite coordinates (duplicates
+// included) and any eps are clustered on the device: distinct integer pixels with 1 <= eps <= 15 — what
+// CirclesEventFrame.cpp:66-70 hands over — on the sensor-plane bitmap kernel, everything else on the general grid-hash path
+// (DESIGN.md §2).  `Clusters` (discovery order, members in the reference's BFS pop order) and `Noise` are identical to the
+// reference's as ordered lists.  FAILED beyond the reference's own conditions only for dim > 4, NaN / infinite input or
+// a missing CUDA device (`last_error()` says which).  `disfunc` is accepted and ignored exactly like the reference's kd-tree
+// build (dbscan.h:16,64).
 // Thread model: one lazily created context per host thread (the reference runs Run() on hardware_concurrency()-2 threads).
 #ifndef ECB_DBSCAN_H
 #define ECB_DBSCAN_H
@@ -65,26 +68,20 @@ public:
         if (min < 1) return ERROR_TYPE::FAILED;
         Clusters.clear();
         Noise.clear();
-        if (dim != 2) {
-            err_ = "device DBSCAN supports dim == 2 only";
-            return ERROR_TYPE::FAILED;
-        }
         ecb_ctx *ctx = ecb::thread_context();
         if (!ctx) {
             err_ = "no CUDA device (there is no CPU fallback)";
             return ERROR_TYPE::FAILED;
         }
         const int n = (int) V->size();
-        std::vector<double> xy(2 * (size_t) n);
-        for (int i = 0; i < n; ++i) {
-            xy[2 * i] = (double) (*V)[i][0];
-            xy[2 * i + 1] = (double) (*V)[i][1];
-        }
+        std::vector<double> xy((size_t) dim * (size_t) n);  // kdtree only supports double (dbscan.h:190-193)
+        for (int i = 0; i < n; ++i)
+            for (uint c = 0; c < dim; ++c) xy[(size_t) dim * i + c] = (double) (*V)[i][c];
         std::vector<int32_t> labels((size_t) n), sizes((size_t) n);
         std::vector<uint32_t> members((size_t) n);
         int32_t nc = 0;
-        const int rc = ecb_dbscan_run_ordered(ctx, xy.data(), n, (double) eps, min, labels.data(), &nc, sizes.data(),
-                                              members.data());
+        const int rc = ecb_dbscan_run_nd(ctx, xy.data(), n, (int) dim, (double) eps, min, labels.data(), &nc, sizes.data(),
+                                         members.data());
         if (rc != ECB_OK) {
             err_ = ecb_last_error(ctx);
             return ERROR_TYPE::FAILED;

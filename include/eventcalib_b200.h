@@ -42,7 +42,8 @@ typedef enum {
 
 /* per-problem status bits reported by the device kernels */
 #define ECB_PB_OK 0u
-#define ECB_PB_DUPLICATE 2u     /* duplicate points handed to ecb_dbscan_run (the reference path never does) */
+#define ECB_PB_DUPLICATE 2u     /* duplicate pixels inside one front-end problem (cannot happen after the per-pixel dedupe);
+                                   ecb_dbscan_run* re-runs such inputs on the general path instead of reporting this */
 #define ECB_PB_CLUSTER_CAP 4u   /* more kept clusters than max_clusters: tables truncated, labels still exact */
 #define ECB_PB_RANGE 8u         /* pixel outside the sensor / bitmap */
 
@@ -144,9 +145,14 @@ int ecb_frontend_rectify(ecb_ctx *ctx, const int32_t *window_index, int n_frames
 int ecb_frontend_device_ptrs(ecb_ctx *ctx, void **d_summary, void **d_candidates, int *cand_stride);
 
 /* ---- a3: the DBSCAN::Run boundary ---------------------------------------------------------------- */
-/* xy: n x 2 doubles in pid order (integer-valued pixel coordinates, all distinct, bounding box within the
- * shared-memory bitmap budget).  labels[n]: cluster id in the reference's discovery order, -1 = Noise.
- * Returns ECB_FAILED for n<1 or min_pts<1 exactly like the reference. */
+/* xy: n x 2 doubles in pid order — ANY finite doubles, duplicates included, any eps (the reference's template takes every
+ * T with operator[], dbscan.h:40,70).  Distinct integer pixels with 1 <= eps <= 15 (what the calibration front end
+ * produces) run on the sensor-plane bitmap kernel; everything else runs on the general path (grid hash: cell =
+ * floor((p - min) / eps), in-tree radix sort by cell key, 3 x 3 cell search, the kd query's strict pruning rule replayed on
+ * the emulated insertion tree for the pairs it can affect).  Both give the reference's labels.
+ * labels[n]: cluster id in the reference's discovery order, -1 = Noise.
+ * Returns ECB_FAILED for n<1 or min_pts<1 exactly like the reference; ECB_ERR_UNSUPPORTED only for NaN / infinite
+ * coordinates, NaN eps and problems of 2^21 points or more. */
 int ecb_dbscan_run(ecb_ctx *ctx, const double *xy, int n, double eps, uint32_t min_pts, int32_t *labels,
                    int32_t *n_clusters);
 /* batch: problem k is xy[offsets[k] .. offsets[k+1]); labels is flat; n_clusters[n_problems]; status
@@ -165,6 +171,11 @@ int ecb_dbscan_run_ordered(ecb_ctx *ctx, const double *xy, int n, double eps, ui
 int ecb_dbscan_run_batch_ordered(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int n_problems, double eps,
                                  uint32_t min_pts, int32_t *labels, int32_t *n_clusters, uint32_t *status,
                                  int32_t *cluster_sizes, uint32_t *members);
+
+/* DBSCAN<T,Float>::Run(V, dim, eps, min) for dim = 1 .. 4 (dbscan.h:115-177): pts = n x dim doubles.  cluster_sizes and
+ * members are optional (both or neither): ordered `Clusters` as above.  dim < 1 returns ECB_FAILED like the reference. */
+int ecb_dbscan_run_nd(ecb_ctx *ctx, const double *pts, int n, int dim, double eps, uint32_t min_pts, int32_t *labels,
+                      int32_t *n_clusters, int32_t *cluster_sizes, uint32_t *members);
 
 /* ---- a5: batched circle fit ---------------------------------------------------------------------- */
 /* set k = points xy[offsets[k]..offsets[k+1]) (union of a + and a - index set); out[k] = cx, cy, r */

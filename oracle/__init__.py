@@ -368,6 +368,23 @@ def ref_dbscan(xy, eps, minpts):
     return _dbscan(ref_dbscan_lib().ref_dbscan_run, xy, eps, minpts)
 
 
+def ref_dbscan_nd(pts, eps, minpts):
+    """The unmodified reference DBSCAN<T,double>::Run(V, dim, ...) on n x dim points, dim = 1..4 (oracle/_ref)."""
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    n, dim = pts.shape
+    labels = np.full(max(n, 1), -1, np.int32)
+    members = np.zeros(max(n, 1), np.uint32)
+    off = np.zeros(n + 2, np.uint32)
+    noise = np.zeros(max(n, 1), np.uint32)
+    nc = C.c_int(0)
+    nn = C.c_int(0)
+    rc = ref_dbscan_lib().ref_dbscan_run_nd(_p(pts, _dp), C.c_int(n), C.c_int(dim), C.c_double(eps), C.c_uint(minpts),
+                                            _p(labels, _ip), C.byref(nc), _p(members, _up), _p(off, _up), _p(noise, _up),
+                                            C.byref(nn))
+    clusters = [members[off[c]:off[c + 1]].copy() for c in range(nc.value)]
+    return dict(rc=rc, labels=labels[:n].copy(), clusters=clusters, noise=noise[:nn.value].copy())
+
+
 def kd_range(xy, q, eps, ref=False):
     xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
     out = np.zeros(xy.shape[0], np.uint32)

@@ -13,6 +13,41 @@
 #include <cstring>
 #include <vector>
 
+// The same template for other point types / dimensions (dbscan.h:40-41: any T with operator[] convertible to double).
+//   pts  n x dim doubles, dim in 1..4
+template <int D>
+struct PointN {
+    double v[D];
+    double operator[](int i) const { return v[i]; }
+};
+
+template <int D>
+static int run_nd(const double *pts, int n, double eps, unsigned minpts, int *labels, int *n_clusters, unsigned *members,
+                  unsigned *cluster_off, unsigned *noise, int *n_noise) {
+    std::vector<PointN<D>, Eigen::aligned_allocator<PointN<D>>> V((size_t) (n > 0 ? n : 0));
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < D; ++d) V[i].v[d] = pts[(size_t) i * D + d];
+    DBSCAN<PointN<D>, double> db;
+    int rc = db.Run(&V, D, eps, minpts);
+    *n_clusters = 0;
+    *n_noise = 0;
+    if (rc != 0) return rc;
+    for (int i = 0; i < n; ++i) labels[i] = -1;
+    unsigned off = 0;
+    cluster_off[0] = 0;
+    for (size_t c = 0; c < db.Clusters.size(); ++c) {
+        for (uint pid : db.Clusters[c]) {
+            labels[pid] = (int) c;
+            members[off++] = pid;
+        }
+        cluster_off[c + 1] = off;
+    }
+    *n_clusters = (int) db.Clusters.size();
+    for (size_t i = 0; i < db.Noise.size(); ++i) noise[i] = db.Noise[i];
+    *n_noise = (int) db.Noise.size();
+    return rc;
+}
+
 extern "C" {
 
 // Runs DBSCAN<Eigen::Vector2d,double>::Run exactly as
@@ -47,6 +82,17 @@ int ref_dbscan_run(const double *xy, int n, double eps, unsigned minpts, int *la
     for (size_t i = 0; i < db.Noise.size(); ++i) noise[i] = db.Noise[i];
     *n_noise = (int) db.Noise.size();
     return rc;
+}
+
+int ref_dbscan_run_nd(const double *pts, int n, int dim, double eps, unsigned minpts, int *labels, int *n_clusters,
+                      unsigned *members, unsigned *cluster_off, unsigned *noise, int *n_noise) {
+    switch (dim) {
+        case 1: return run_nd<1>(pts, n, eps, minpts, labels, n_clusters, members, cluster_off, noise, n_noise);
+        case 2: return run_nd<2>(pts, n, eps, minpts, labels, n_clusters, members, cluster_off, noise, n_noise);
+        case 3: return run_nd<3>(pts, n, eps, minpts, labels, n_clusters, members, cluster_off, noise, n_noise);
+        case 4: return run_nd<4>(pts, n, eps, minpts, labels, n_clusters, members, cluster_off, noise, n_noise);
+    }
+    return -1;
 }
 
 // Raw kd_nearest_range result order for one query (used to pin the restated

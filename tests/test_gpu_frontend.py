@@ -180,6 +180,12 @@ def test_eps_minpts_sweep(ctx, oracle_mod):
             _check_stream(ctx, oracle_mod, ev, win, 346, 260, 0, eps=float(eps), min_pts=mp)
 
 
+def ecb_params(ctx):
+    import eventcalib_b200 as ecb
+    return ecb.default_params(fit_circle=1, radius_threshold=ecb.radius_threshold(346, 260, 9, 4, True, 5.5, 1.75), order_mode=1,
+                              median_mode=1)
+
+
 def test_rejects_bad_streams(ctx):
     import eventcalib_b200 as ecb
     from eventcalib_b200 import synth
@@ -190,11 +196,37 @@ def test_rejects_bad_streams(ctx):
     bad["x"][10] = 12.5
     with pytest.raises(ecb.EcbError):
         ctx.load_events(synth.to_records(bad))
-    bad = dict(ev)
-    bad["t"] = ev["t"].copy()
-    bad["t"][500] = 0.0
-    with pytest.raises(ecb.EcbError):
-        ctx.load_events(synth.to_records(bad))
+
+
+def test_unsorted_stream_is_ordered_like_the_multimap_load(ctx, oracle_mod):
+    """The reference loads the records into a std::multimap keyed by the stamp (eventCameraCalib.cpp:154-163): any file
+    order is accepted and equal stamps keep their file order.  Device: a stable radix sort by stamp in ecb_load_events_*."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(40000, 346, 260, t0=5.0, duration=0.015, seed=31)
+    ev["t"] = np.round(ev["t"], 5)  # many equal stamps: stability matters (first arrival decides the pid order)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(ev["t"]))
+    shuf = {k: (v[perm] if isinstance(v, np.ndarray) and len(v) == len(perm) else v) for k, v in ev.items()}
+    order = np.argsort(shuf["t"], kind="stable")  # what the multimap iteration yields
+    srt = {k: (v[order] if isinstance(v, np.ndarray) and len(v) == len(perm) else v) for k, v in shuf.items()}
+    win = synth.tiling_windows(5.0, 5.015, 1.5e-3)
+    ctx.set_sensor(346, 260)
+    prm = ecb_params(ctx)
+    ctx.load_events(synth.to_records(shuf))
+    ctx.frontend_run(win, prm)
+    got = (ctx.summary().copy(), ctx.points(0), ctx.points(1), ctx.candidates(64).copy())
+    ctx.load_events(synth.to_records(srt))
+    ctx.frontend_run(win, prm)
+    ref = (ctx.summary().copy(), ctx.points(0), ctx.points(1), ctx.candidates(64).copy())
+    assert np.array_equal(got[0], ref[0])
+    for a, b in zip(got[1] + got[2], ref[1] + ref[2]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got[3], ref[3])
+    # and against the oracle's window on the stably sorted stream
+    s0 = got[0][0]
+    P, N, lo, hi = oracle_mod.event_frame(srt["t"], srt["x"], srt["y"], srt["p"], win[0, 0], win[0, 1])
+    assert (int(s0["ev_lo"]), int(s0["ev_hi"])) == (lo, hi)
+    assert np.array_equal(got[2][0][:len(P)], P) and np.array_equal(got[1][0][:len(N)], N)
 
 
 def test_fit_circles_api(ctx, oracle_mod):
