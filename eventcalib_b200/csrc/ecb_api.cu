@@ -119,6 +119,15 @@ extern "C" {
 
 const char *ecb_version(void) { return "eventcalib_b200 0.1 (sm_100a)"; }
 
+int ecb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int ecb_ctx_create(int device, void *stream, ecb_ctx **out) {
     if (!out) return ECB_ERR_ARG;
     *out = nullptr;

@@ -15,6 +15,11 @@
 // shared map, here the pieces of one round are gated in piece order).  The initialisation (EventCalibIni::cvCalibration)
 // runs without OpenCV (include/ecb/calib_init.hpp); the ordered circles of the key frames are also written to
 // SavePath/candidates.txt.
+//
+// Several GPUs (ECB_DEVICES, default: all visible): the reference's time pieces are dealt out to the GPUs in contiguous blocks,
+// every GPU holds the records of its block, one host thread + context per GPU (include/ecb/multi_gpu.hpp); the spline
+// optimisation shards the residuals the same way and sums the normal equations over NVLink inside the kernels.  The frames,
+// candidates and key-frame map do not depend on the number of GPUs.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +32,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/ecb/event_calib.hpp"
+#include "../../include/ecb/multi_gpu.hpp"
 
 using namespace opengv2;
 
@@ -117,16 +122,8 @@ int main(int argc, char **argv) {
         std::cerr << "no events in [StartTime, EndTime)" << std::endl;
         return 1;
     }
-    std::shared_ptr<EventContainer> container;
-    try {
-        container = std::make_shared<EventContainer>(getenv("ECB_DEVICE") ? atoi(getenv("ECB_DEVICE")) : 0, width, height);
-        container->load(rec.data() + b, e - b);
-    } catch (const std::exception &ex) {
-        std::cerr << "ecb: " << ex.what() << std::endl;
-        return 1;
-    }
-    endTime = container->lastTime;
-    std::cout << "Events from " << startTime << " second to " << endTime << " second loaded." << std::endl;
+    // the reference sets endTime to the last loaded stamp (:165) and cuts [startTime, endTime] into its time pieces (:172-180)
+    endTime = rec[(size_t) e - 1].t;
 
     FrontEnd::Params params;
     params.dbscan_eps = fs.num("dbscan_eps", 4);
@@ -158,7 +155,22 @@ int main(int argc, char **argv) {
     }
     typedef EventCalibIni::KeyFrame Frame;
     std::map<double, Frame> frames;  // MapBase keeps key frames ordered by time stamp
-    FrontEnd fe(container, pattern, params);
+    // GPUs: contiguous blocks of pieces (piece k covers [endTime - (k+1) pstep, endTime - k pstep): ascending time = descending k)
+    std::vector<int> devices = ecbDevices();
+    if ((int) devices.size() > pieceNum) devices.resize((size_t) pieceNum);
+    const int G = (int) devices.size();
+    std::vector<double> cuts;
+    for (int g = 1; g < G; ++g) cuts.push_back(pieces[(size_t) (pieceNum - (int) ((int64_t) g * pieceNum / G))].hi);
+    ShardedEventContainer::Ptr container;
+    try {
+        container = std::make_shared<ShardedEventContainer>(devices, width, height);
+        container->load(rec.data() + b, e - b, cuts);
+    } catch (const std::exception &ex) {
+        std::cerr << "ecb: " << ex.what() << std::endl;
+        return 1;
+    }
+    std::cout << "Events from " << startTime << " second to " << endTime << " second loaded." << std::endl;
+    ShardedFrontEnd fe(container, pattern, params);
     TrackingGate gate(pattern->rows, pattern->cols, motionTimeStep);  // EventCalibIni::track; pieces of one round in piece order
     size_t rounds = 0, evaluated = 0;
     for (;;) {
@@ -216,7 +228,7 @@ int main(int argc, char **argv) {
                 << f.features[k].radius << "\n";
     }
     out.close();
-    std::cerr << evaluated << " windows evaluated on the GPU in " << rounds << " batched rounds over " << pieceNum
+    std::cerr << evaluated << " windows evaluated on " << G << " GPU(s) in " << rounds << " batched rounds over " << pieceNum
               << " time pieces" << std::endl;
 
     // EventCalibIni::cvCalibration (eventCameraCalib.cpp:199): intrinsics, frame poses, checkPose, rectifyFeatures
@@ -266,14 +278,24 @@ int main(int argc, char **argv) {
         std::cout << std::endl << "Intrinsics before optimization:";
         printEigenLike(std::cout, intrinsics.data(), 1, 9);
         std::cout << std::endl;
-        EventCalibSpline spline(container, segments, intrinsics, motionTimeStep, pattern->circleRadius, useSO3);
+        // distinct devices: residuals sharded like the events; the same device listed several times (tests of the sharding
+        // logic on a one-GPU box): the optimisation runs on one context holding the whole stream
+        bool distinct = true;
+        for (int g = 0; g < G; ++g)
+            for (int h = 0; h < g; ++h) distinct = distinct && devices[(size_t) g] != devices[(size_t) h];
+        ShardedEventContainer::Ptr opt_events = container;
+        if (!distinct) {
+            opt_events = std::make_shared<ShardedEventContainer>(std::vector<int>(1, devices[0]), width, height);
+            opt_events->load(rec.data() + b, e - b, {});
+        }
+        ShardedCalibSpline spline(opt_events, segments, intrinsics, motionTimeStep, pattern->circleRadius, useSO3);
         std::vector<std::array<double, 3>> landmarks;
         const std::vector<double> board = ini.boardPoints();
         for (size_t k = 0; k + 2 < board.size(); k += 3) landmarks.push_back({board[k], board[k + 1], board[k + 2]});
         const int64_t n_res = spline.associate(kfs, landmarks);
         ecb_lm_summary sum;
         if (!spline.optimize(&sum)) {
-            std::cerr << "ecb: " << ecb_last_error(container->ctx) << std::endl;
+            std::cerr << "ecb: " << spline.lastError() << std::endl;
             return 1;
         }
         // in place of ceres::Solver::Summary::FullReport() (EventCalibSpline.cpp:248)

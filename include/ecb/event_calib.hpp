@@ -227,6 +227,17 @@ public:
     }
     double circleRadiusThreshold() const { return rthr_; }
     ecb_ctx *context() const { return c_->ctx; }
+    // rectifyFeatures (CirclesEventFrame.cpp:417-609) for windows of the last run, batched: image_points = 5 projected points
+    // (landmark + four quadrant points, :431-456) per frame and circle; out[frame][circle] = cx, cy, r (r < 0: deleted)
+    void rectify(const std::vector<int32_t> &window_index, int n_circles, const std::vector<double> &image_points, double inlier,
+                 int rows, int cols, bool asymmetric, std::vector<double> &out, std::vector<int32_t> &verdict) {
+        out.assign(window_index.size() * (size_t) n_circles * 3, 0.0);
+        verdict.assign(window_index.size(), 0);
+        if (window_index.empty()) return;
+        if (ecb_frontend_rectify(c_->ctx, window_index.data(), (int) window_index.size(), n_circles, image_points.data(), inlier, rows,
+                                 cols, asymmetric ? 1 : 0, out.data(), verdict.data()) != ECB_OK)
+            throw std::runtime_error(ecb_last_error(c_->ctx));
+    }
 
 private:
     int stride_ = 1;  // candidate slots per window of the last run = its largest candidate count
@@ -478,7 +489,9 @@ public:
     // cvCalibration(): intrinsics from NumOfFrameToUse evenly spaced key frames, then for every key frame in time order the
     // planar PnP pose, checkPose against the last frame kept, rectifyFeatures (one batched GPU call over all frames — its
     // verdict does not depend on the other frames) -> `frames` is replaced by the frames that stay in the map.
-    bool cvCalibration(FrontEnd &fe, std::map<double, KeyFrame> &frames, std::ostream &os) {
+    // FE: FrontEnd (one GPU) or ShardedFrontEnd (multi_gpu.hpp)
+    template <class FE>
+    bool cvCalibration(FE &fe, std::map<double, KeyFrame> &frames, std::ostream &os) {
         if (setting_.useFisheye) {
             os << "Calibration failed: the fisheye model (cv::fisheye::calibrate) is not part of this build" << std::endl;
             return false;
@@ -557,9 +570,7 @@ public:
             if (!all.empty()) {
                 fe.run(windows);
                 for (size_t i = 0; i < all.size(); ++i) widx[i] = (int32_t) i;
-                if (ecb_frontend_rectify(fe.context(), widx.data(), (int) all.size(), nc, img.data(), 3.0, pat.rows, pat.cols,
-                                         pat.isAsymmetric ? 1 : 0, out.data(), verdict.data()) != ECB_OK)
-                    throw std::runtime_error(ecb_last_error(fe.context()));
+                fe.rectify(widx, nc, img, 3.0, pat.rows, pat.cols, pat.isAsymmetric, out, verdict);
             }
             // replay of the sequential loop (:246-300): checkPose against the last frame kept, then the rectify verdict
             std::vector<const KeyFrame *> seq(all.begin(), all.end());

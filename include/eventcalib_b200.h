@@ -71,6 +71,8 @@ int ecb_synchronize(ecb_ctx *ctx);
 int ecb_set_profiling(ecb_ctx *ctx, int on);
 int ecb_stage_ms(ecb_ctx *ctx, float *out);
 const char *ecb_version(void);
+/* number of CUDA devices visible to the process (0 without a driver / device): a multi-GPU host creates one context per device */
+int ecb_device_count(void);
 
 /* ---- a1: event ingest ---------------------------------------------------------------------------- */
 /* Sensor size in pixels (Camera.width / Camera.height of the YAML). Must be set before loading events. */
