@@ -944,6 +944,22 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     // basis pass (k_prepare) is folded into the record write; otherwise k_prepare runs and checks the order
     bool fused = true;
     {
+        // The reference adds one residual block per spline whose [front, back] holds the event (EventCalibSpline.cpp:157-192);
+        // assoc_one emits at most one.  The two agree while the ranges are disjoint — the reference's own segmentation always
+        // is (segments split at gaps > 50 steps, extended by 3 steps) — so overlapping ranges are refused instead of silently
+        // dropping the second residual.
+        std::vector<std::pair<double, double>> rg;
+        size_t ko2 = 0;
+        for (int q = 0; q < st->n_splines; ++q) {
+            rg.emplace_back(st->knots[ko2], st->knots[ko2 + (size_t) st->n_cp[(size_t) q] + 3]);
+            ko2 += (size_t) st->n_cp[(size_t) q] + 4;
+        }
+        std::sort(rg.begin(), rg.end());
+        for (size_t q = 1; q < rg.size(); ++q)
+            if (!(rg[q].first > rg[q - 1].second))
+                return ecb_fail(ctx, ECB_ERR_UNSUPPORTED,
+                                "spline knot ranges overlap ([%g, %g] and [%g, %g]): an event inside both would need one residual "
+                                "per spline", rg[q - 1].first, rg[q - 1].second, rg[q].first, rg[q].second);
         size_t ko = 0;
         double prev_end = -1e300;
         for (int q = 0; q < st->n_splines; ++q) {

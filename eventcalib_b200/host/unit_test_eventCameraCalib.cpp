@@ -204,7 +204,7 @@ int main(int argc, char **argv) {
                 f.duration = {pc.first, pc.second};
                 f.eventsNum = events_num;
                 f.features = c;
-                frames[ts] = f;
+                frames.emplace(ts, f);  // MapBase::addFrame through TrackingBase (an existing stamp is kept)
                 pc.first = pc.second + frameGap;  // :60-62
                 pc.second = pc.first + len;
             } else if (events_num > frameEventNumThreshold || (pc.second - pc.first) > 3 * len) {  // :66-68,75-77

@@ -8,7 +8,8 @@
 // alignment of the labelled lattice with the board rectangle under the 8 lattice symmetries, then a homography check.
 // Checked against cv2.findCirclesGrid on rendered candidates (tests/golden/circles_grid.npz).  Host only; <= ~100 points.
 // Differences: the accept / reject decision in hard cases (clutter next to the grid, missing circles) is OpenCV's own
-// heuristic and is NOT reproduced — this returns false whenever no complete, consistent labelling exists.
+// heuristic and is NOT reproduced — this returns false whenever no complete, consistent labelling exists.  The reference's
+// CALIB_CB_CLUSTERING retry is find_asymmetric_circles_grid_clustering() at the end of this file.
 #ifndef ECB_CIRCLES_GRID_HPP
 #define ECB_CIRCLES_GRID_HPP
 
@@ -234,6 +235,71 @@ inline bool find_asymmetric_circles_grid(const std::vector<Pt2> &points, int row
             }
     }
     return false;
+}
+
+// The reference's SECOND attempt, `findCirclesGrid(..., CALIB_CB_ASYMMETRIC_GRID | CALIB_CB_CLUSTERING)`
+// (CirclesEventFrame.cpp:334-336 -> cv_calib.cpp:24-31 -> CirclesGridClusterFinder::findGrid, circlesgrid.cpp:132-176).
+// Its first stage decides WHICH candidates form the pattern and is restated step by step (hierarchicalClustering,
+// circlesgrid.cpp:72-130): single-linkage agglomeration on the float distance matrix — always the globally smallest
+// remaining distance (first one in row-major order, like minMaxLoc), the higher index merged into the lower — until the
+// cluster just grown holds rows * cols points; more than that means "not found".  The following stages of OpenCV (convex
+// hull corners, rectification, parsing) only label the selected points; the label set is canonical, so the selected points
+// are labelled by the lattice finder above.
+inline bool hierarchical_cluster_select(const std::vector<Pt2> &points, size_t pn, std::vector<int> &selected) {
+    const int n = (int) points.size();
+    selected.clear();
+    if (pn >= points.size()) {
+        if (pn == points.size())
+            for (int i = 0; i < n; ++i) selected.push_back(i);
+        return !selected.empty();
+    }
+    std::vector<float> dists((size_t) n * n, 0.0f);
+    std::vector<unsigned char> mask((size_t) n * n, 0);
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            // norm(Point2f - Point2f): float difference, double accumulation and sqrt, stored as float
+            const float dx = (float) points[(size_t) i].x - (float) points[(size_t) j].x, dy = (float) points[(size_t) i].y - (float) points[(size_t) j].y;
+            const float d = (float) std::sqrt((double) dx * dx + (double) dy * dy);
+            dists[(size_t) i * n + j] = dists[(size_t) j * n + i] = d;
+            mask[(size_t) i * n + j] = mask[(size_t) j * n + i] = 255;
+        }
+    std::vector<std::vector<int>> clusters((size_t) n);
+    for (int i = 0; i < n; ++i) clusters[(size_t) i].push_back(i);
+    int pattern = 0;
+    while (clusters[(size_t) pattern].size() < pn) {
+        int br = -1, bc = -1;
+        float best = 0;
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < n; ++c)
+                if (mask[(size_t) r * n + c] && (br < 0 || dists[(size_t) r * n + c] < best)) best = dists[(size_t) r * n + c], br = r, bc = c;
+        if (br < 0) return false;
+        const int lo = std::min(br, bc), hi = std::max(br, bc);
+        for (int k = 0; k < n; ++k) mask[(size_t) hi * n + k] = mask[(size_t) k * n + hi] = 0;
+        for (int k = 0; k < n; ++k) {  // row lo = min(row minLoc.x, row minLoc.y), mirrored into column lo
+            const float v = std::min(dists[(size_t) bc * n + k], dists[(size_t) br * n + k]);
+            dists[(size_t) lo * n + k] = v;
+        }
+        for (int k = 0; k < n; ++k) dists[(size_t) k * n + lo] = dists[(size_t) lo * n + k];
+        clusters[(size_t) lo].insert(clusters[(size_t) lo].end(), clusters[(size_t) hi].begin(), clusters[(size_t) hi].end());
+        clusters[(size_t) hi].clear();
+        pattern = lo;
+    }
+    if (clusters[(size_t) pattern].size() != pn) return false;  // the cluster overshot the pattern size
+    selected = clusters[(size_t) pattern];
+    return true;
+}
+
+inline bool find_asymmetric_circles_grid_clustering(const std::vector<Pt2> &points, int rows, int cols, std::vector<int> &order_out,
+                                                    double max_err = 0.25) {
+    std::vector<int> sel;
+    order_out.clear();
+    if (points.empty() || !hierarchical_cluster_select(points, (size_t) rows * (size_t) cols, sel)) return false;
+    std::vector<Pt2> sub;
+    for (int k : sel) sub.push_back(points[(size_t) k]);
+    std::vector<int> o;
+    if (!find_asymmetric_circles_grid(sub, rows, cols, o, max_err)) return false;
+    for (int k : o) order_out.push_back(sel[(size_t) k]);
+    return true;
 }
 
 }  // namespace ecb

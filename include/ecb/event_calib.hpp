@@ -268,11 +268,14 @@ public:
     static bool orderFeatures(const std::vector<CalibCircleLite> &cand, const CirclePatternParameters &pattern,
                               std::vector<CalibCircleLite> &features) {
         features.clear();
-        if ((int) cand.size() < pattern.rows * pattern.cols || !pattern.isAsymmetric) return false;
+        // the reference calls findCirclesGrid with CALIB_CB_ASYMMETRIC_GRID whatever Is_Pattern_Asymmetric says (:332-336)
+        if ((int) cand.size() < pattern.rows * pattern.cols) return false;
         std::vector<ecb::Pt2> pts;
         for (const auto &c : cand) pts.push_back(ecb::Pt2{(double) (float) c.center[0], (double) (float) c.center[1]});  // cv::Point2f (:322-324)
         std::vector<int> order;
-        if (!ecb::find_asymmetric_circles_grid(pts, pattern.rows, pattern.cols, order)) return false;
+        if (!ecb::find_asymmetric_circles_grid(pts, pattern.rows, pattern.cols, order) &&
+            !ecb::find_asymmetric_circles_grid_clustering(pts, pattern.rows, pattern.cols, order))  // the CALIB_CB_CLUSTERING retry (:334-336)
+            return false;
         for (int idx : order) features.push_back(cand[(size_t) idx]);
         return true;
     }
