@@ -1010,9 +1010,16 @@ int ecb_cost_get_association(ecb_ctx *ctx, int64_t *event_index, int32_t *circle
 
 static long long exchange_timeout_clocks(ecb_ctx *ctx) {
     static const double secs = getenv("ECB_EXCHANGE_TIMEOUT_S") ? atof(getenv("ECB_EXCHANGE_TIMEOUT_S")) : 30.0;
-    int khz = 1965000;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
-    return (long long) (secs * 1e3 * (double) khz);
+    // cudaDevAttrClockRate is a live driver query (~1 ms, much more while nvidia-smi polls the device): asked once per device,
+    // not per exchange — it was 60 % of a multi-GPU LM iteration (profiles/r2s_lm_exchange_timing.md)
+    static int khz_of[64] = {0};
+    const int d = ctx->device & 63;
+    if (khz_of[d] == 0) {
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        khz_of[d] = khz > 0 ? khz : 1965000;
+    }
+    return (long long) (secs * 1e3 * (double) khz_of[d]);
 }
 
 static void fill_ne_args(CostState *st, NeArgs &a, const double *d_params, const int *d_go) {
@@ -1037,6 +1044,9 @@ static int launch_normal_eq_kernel(ecb_ctx *ctx, CostState *st, const double *d_
     NeArgs a;
     fill_ne_args(st, a, d_params, d_go);
     const size_t smem = (size_t) NE_WARPS * TILE_ROWS * TILE_LD * 8;
+    // 2 CTAs x 8 warps per SM at 128 registers.  More resident warps for the latency-bound residual / Jacobian phase were tried
+    // with 4-warp CTAs: 5 per SM at 96 registers (more spills) 2.10 ms, 4 per SM at 128 registers 1.87 ms, against 1.81 ms
+    // (profiles/r2s_ab_normal_eq.jsonl).
     static const int variant = getenv("ECB_NE_VARIANT") ? atoi(getenv("ECB_NE_VARIANT")) : 2;
     void (*kern)(const NeArgs) = st->so3 ? k_normal_eq<1, true> : (variant == 1 ? k_normal_eq<1, false> : k_normal_eq<2, false>);
     ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

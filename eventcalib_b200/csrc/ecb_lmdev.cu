@@ -618,7 +618,12 @@ struct ecb_lm_device {
     double *d_cand_cost = nullptr;
     uint32_t generation = 0;
     bool begun = false;
+    // ECB_LM_TIMING=1: CUDA events around the phases of every enqueued iteration (solve | candidate cost | scalar exchange |
+    // decide + commit | normal equations (+ exchange) | assemble), averaged and printed to stderr by ecb_lm_device_result
+    std::vector<cudaEvent_t> tev;
+    int t_iters = 0;
 };
+constexpr int LM_TPH = 7;  // events per timed iteration
 
 extern "C" {
 
@@ -765,7 +770,17 @@ int ecb_lm_device_iterate(ecb_lm_device *lm, int n_iterations) {
     LmScalars *s = lm->bufs.s;
     const int blocks = ctx->sm_count * 2;
     int rc;
+    static const bool timing = getenv("ECB_LM_TIMING") && atoi(getenv("ECB_LM_TIMING")) != 0;
+    auto mark = [&](int k) {
+        if (!timing || lm->t_iters >= 64) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        lm->tev.push_back(e);
+        if (k == LM_TPH - 1) ++lm->t_iters;
+    };
     for (int it = 0; it < n_iterations; ++it) {
+        mark(0);
         k_lm_iter_begin<<<1, 1, 0, ctx->stream>>>(lm->bufs, lm->opt);
         k_lm_build<<<blocks, 256, 0, ctx->stream>>>(lm->dims, lm->bufs, lm->opt);
         k_lm_factor<<<lm->dims.n_seg, FACTOR_THREADS, 0, ctx->stream>>>(lm->dims, lm->bufs);
@@ -773,21 +788,27 @@ int ecb_lm_device_iterate(ecb_lm_device *lm, int n_iterations) {
         k_lm_backsub<<<lm->dims.n_seg, 32, 0, ctx->stream>>>(lm->dims, lm->bufs);
         k_lm_step<<<1, 1024, 0, ctx->stream>>>(lm->dims, lm->bufs, lm->opt);
         ctx->launches += 6;
+        mark(1);
         if ((rc = ecb_cost_dev_eval(ctx, lm->bufs.cand, &s->go_cost, lm->d_cand_cost))) return rc;
+        mark(2);
         if (lm->n_ranks > 1) {
             k_lm_epoch<<<1, 1, 0, ctx->stream>>>(&s->go_cost, &s->epoch_sc);
             ECB_LAUNCHED(ctx);
             if ((rc = ecb_cost_dev_scalar_exchange(ctx, &s->go_cost, lm->rank, lm->n_ranks, lm->recv, &s->epoch_sc, lm->d_cand_cost, &s->xerr)))
                 return rc;
         }
+        mark(3);
         k_lm_set_cost<<<1, 1, 0, ctx->stream>>>(lm->bufs, lm->d_cand_cost);
         k_lm_decide<<<1, 1, 0, ctx->stream>>>(lm->bufs, lm->opt);
         k_lm_commit<<<std::min(blocks, (int) ((lm->n_params + 255) / 256)), 256, 0, ctx->stream>>>(lm->bufs, lm->n_params);
         ctx->launches += 3;
+        mark(4);
         if ((rc = lmdev_normal_eq(lm))) return rc;
+        mark(5);
         k_lm_assemble<<<blocks, 256, 0, ctx->stream>>>(lm->dims, lm->bufs, &s->accepted);
         k_lm_gradnorm<<<1, 1024, 0, ctx->stream>>>(lm->dims, lm->bufs, lm->opt, &s->accepted);
         ctx->launches += 2;
+        mark(6);
     }
     return ecb_check(ctx, cudaGetLastError(), "device LM iteration");
 }
@@ -829,6 +850,27 @@ int ecb_lm_device_result(ecb_lm_device *lm, double *intrinsics, double *rot_cp, 
     if (trace && trace_rows > 0) {
         const int rows = std::min(std::min(h.trace_rows, TRACE_CAP), trace_rows);
         if (rows > 0 && (rc = ecb_d2h(ctx, trace, lm->bufs.trace, (size_t) rows * 32))) return rc;
+    }
+    if (!lm->tev.empty()) {
+        static const char *name[LM_TPH - 1] = {"solve", "candidate cost", "scalar exchange", "decide + commit", "normal equations", "assemble"};
+        double sum[LM_TPH - 1] = {0};
+        const bool each = atoi(getenv("ECB_LM_TIMING")) > 1;
+        for (int it = 0; it < lm->t_iters; ++it) {
+            if (each) fprintf(stderr, "[ecb lm timing] rank %d it %2d:", lm->rank, it);
+            for (int k = 0; k + 1 < LM_TPH; ++k) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, lm->tev[(size_t) it * LM_TPH + k], lm->tev[(size_t) it * LM_TPH + k + 1]);
+                sum[k] += ms;
+                if (each) fprintf(stderr, " %.3f", ms);
+            }
+            if (each) fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "[ecb lm timing] rank %d of %d, %d iterations, ms / iteration:", lm->rank, lm->n_ranks, lm->t_iters);
+        for (int k = 0; k + 1 < LM_TPH; ++k) fprintf(stderr, " %s %.4f |", name[k], sum[k] / std::max(lm->t_iters, 1));
+        fprintf(stderr, "\n");
+        for (cudaEvent_t e : lm->tev) cudaEventDestroy(e);
+        lm->tev.clear();
+        lm->t_iters = 0;
     }
     if (h.xerr) return ecb_fail(ctx, ECB_ERR_STATE, "device LM: inter-GPU exchange timed out waiting for ranks (mask 0x%x)", h.xerr);
     return ECB_OK;
