@@ -91,6 +91,34 @@ def frontend_params(cfg, eps=4.0, min_pts=2, order_mode=1, median_mode=1):
                               rows_cols=36, order_mode=order_mode, median_mode=median_mode), rthr
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process (and the pinned host buffers it allocates afterwards: first touch) to the CPUs of the NUMA node the
+    GPU hangs off, so that 8 ranks x 500 MB of records per step do not all cross one node's memory controllers and the
+    inter-socket link.  Returns {"node": n, "cpus": k} or None when the box exposes no NUMA topology (VMs report -1)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -528,6 +556,8 @@ def main():
     ev, win = make_workload(cfg, args.events, rank)
     n = len(ev["t"])
     rec = synth.to_records(ev)
+    # N > 1: host threads and the pinned record buffers of this rank on the GPU's own NUMA node (ECB_BENCH_NO_NUMA=1: off)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("ECB_BENCH_NO_NUMA") else None
     pinned = torch.empty(n * 25, dtype=torch.uint8, pin_memory=True)
     pinned.numpy()[:] = rec.view(np.uint8).reshape(-1)
     d_raw = torch.empty(n * 25 + 16, dtype=torch.uint8, device="cuda")
@@ -819,6 +849,7 @@ def main():
                         "h2d_copy_gbs": h2d_gbs, "pcie_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3 if h2d_gbs > 0 else None}}
         if world > 1:
             floor = n * 25 * world / (h2d_all_gbs * 1e9) * 1e3
+            line["e2e"]["numa"] = numa if numa else "not bound (single NUMA node or topology not exposed)"
             line["e2e"].update({"h2d_copy_gbs_all_ranks_concurrent": h2d_all_gbs, "host_floor_ms": floor,
                                 "frac_of_host_ceiling": floor / (ms_e2e / args.steps)})
         rc = 0

@@ -6,7 +6,8 @@
 // before / after the optimisation) and the same SavePath/TrajectoryByEvent.txt — with the window loop running as ONE batched
 // GPU launch per lattice instead of hardware_concurrency()-2 CPU threads, rectifyFeatures batched over all key frames, and the
 // spline optimisation's residuals / Jacobians / normal equations on the GPU.  Headless (the reference opens a Pangolin
-// viewer, :129; the per-frame debug PNGs of :214-227 are not written).
+// viewer, :129).  SavePath/image/<timestamp>.png holds every key frame's debug image like :214-227 (cluster colours, medians,
+// candidate and rectified circles; include/ecb/image_lite.hpp — ECB_NO_IMAGES=1 skips them).
 //
 // The window loop is the reference's adaptive one (accept -> jump by length + 5 steps, else grow by one step until the
 // window holds FrameEventNumThreshold events or exceeds 3 lengths, then slide; :49-81) over the reference's time pieces.
@@ -273,11 +274,13 @@ int main(int argc, char **argv) {
         const std::array<double, 4> radial = {cam.dist[0], cam.dist[1], cam.dist[4], 0.0};
         const std::array<double, 5> inv = inverseRadialDistortion(radial);
         const std::array<double, 9> intrinsics = {cam.fx, cam.fy, cam.cx, cam.cy, inv[0], inv[1], inv[2], inv[3], inv[4]};
-        std::cout << "OpenCV Distortion before optimization:";
-        printEigenLike(std::cout, radial.data(), 1, 4);
-        std::cout << std::endl << "Intrinsics before optimization:";
-        printEigenLike(std::cout, intrinsics.data(), 1, 9);
-        std::cout << std::endl;
+        if (!getenv("ECB_REFERENCE_SIGNATURES")) {  // (the all-in-one constructor below prints them itself, like the reference's)
+            std::cout << "OpenCV Distortion before optimization:";
+            printEigenLike(std::cout, radial.data(), 1, 4);
+            std::cout << std::endl << "Intrinsics before optimization:";
+            printEigenLike(std::cout, intrinsics.data(), 1, 9);
+            std::cout << std::endl;
+        }
         // distinct devices: residuals sharded like the events; the same device listed several times (tests of the sharding
         // logic on a one-GPU box): the optimisation runs on one context holding the whole stream
         bool distinct = true;
@@ -287,6 +290,77 @@ int main(int argc, char **argv) {
         if (!distinct) {
             opt_events = std::make_shared<ShardedEventContainer>(std::vector<int>(1, devices[0]), width, height);
             opt_events->load(rec.data() + b, e - b, {});
+        }
+        if (getenv("ECB_REFERENCE_SIGNATURES")) {
+            // The same back half through the reference's OWN argument lists (EventCalibSpline.hpp:19, CirclesEventFrame.hpp:43-65;
+            // compat types of include/ecb/compat/): a MapBase of Bodyframes + landmarks + camera, the all-in-one constructor, and
+            // for the first key frame CirclesEventFrame::rectifyFeatures(outlierIdxs, Rcw, tcw) / findCenter(Eigen::Vector2d).
+            EventContainer::Ptr one = opt_events->shards() == 1 ? opt_events->shard[0] : nullptr;
+            if (!one) {
+                one = std::make_shared<EventContainer>(devices[0], width, height);
+                one->load(rec.data() + b, e - b);
+            }
+            auto map = std::make_shared<MapBase>();
+            map->camera = ini.camera;
+            std::vector<LandmarkBase::Ptr> lms;
+            const std::vector<double> bp = ini.boardPoints();
+            for (size_t k = 0; k + 2 < bp.size(); k += 3) {
+                lms.push_back(std::make_shared<LandmarkBase>((int) (k / 3), Eigen::Vector3d(bp[k], bp[k + 1], bp[k + 2])));
+                map->addLandmark(lms.back());
+            }
+            for (const auto &kv : frames) {
+                const Frame &f = kv.second;
+                auto bf = std::make_shared<Bodyframe>(f.timeStamp, Eigen::Quaterniond(f.unitQwb[3], f.unitQwb[0], f.unitQwb[1], f.unitQwb[2]),
+                                                      Eigen::Vector3d(f.twb[0], f.twb[1], f.twb[2]));
+                bf->circles = f.circles;
+                map->addFrame(bf);
+            }
+            {   // per-frame class with the reference's signatures on the first key frame
+                const Frame &f = frames.begin()->second;
+                CirclesEventFrame cf(one, f.duration, pattern, params);
+                const bool found = cf.extractFeatures();
+                cf.setSensor(ini.camera);
+                cf.setLandmarks(lms);
+                const Eigen::Quaterniond Qwb(f.unitQwb[3], f.unitQwb[0], f.unitQwb[1], f.unitQwb[2]);
+                const Eigen::Matrix3d Rwb = Qwb.toRotationMatrix();
+                Eigen::Matrix3d Rcw;
+                Eigen::Vector3d tcw;
+                for (int r = 0; r < 3; ++r) {
+                    for (int c = 0; c < 3; ++c) Rcw(r, c) = Rwb(c, r);
+                }
+                for (int r = 0; r < 3; ++r) tcw[r] = -(Rcw(r, 0) * f.twb[0] + Rcw(r, 1) * f.twb[1] + Rcw(r, 2) * f.twb[2]);
+                const bool ok2 = found && cf.rectifyFeatures(std::unordered_set<int>(), Rcw, tcw);
+                double worst = 0;
+                size_t alive = 0, fi = 0;
+                for (const auto &c : f.circles) {
+                    if (c[2] < 0) continue;
+                    ++alive;
+                    if (fi < cf.features().size()) {
+                        const CalibCircleLite &g = cf.features()[fi++];
+                        worst = std::max(worst, std::max(std::abs(g.center[0] - c[0]), std::max(std::abs(g.center[1] - c[1]), std::abs(g.radius - c[2]))));
+                    }
+                }
+                int hits = 0;
+                for (const auto &g : cf.features()) {
+                    const LandmarkBase::Ptr lm = cf.findCenter(Eigen::Vector2d(g.center[0] + g.radius, g.center[1]));
+                    hits += lm != nullptr;
+                }
+                std::cerr << "reference signatures: rectifyFeatures(outlierIdxs, Rcw, tcw) " << (ok2 ? "true" : "false") << ", "
+                          << cf.features().size() << " of " << alive << " features, max |diff| to the batched result " << worst
+                          << ", findCenter(Eigen::Vector2d) -> landmark for " << hits << " rim points" << std::endl;
+            }
+            EventCalibSpline spline(map, one, useSO3, fs.num("reduceMap", 0) != 0, motionTimeStep, pattern->circleRadius);
+            std::ofstream tum(std::string(argv[3]) + "/TrajectoryByEvent.txt");
+            tum << std::fixed;
+            for (const auto &kv : map->keyframes()) {  // SystemBase::saveKeyFrameTrajectoryTUM on the updated map
+                const Eigen::Quaterniond q = kv.second->unitQwb();
+                const Eigen::Vector3d t = kv.second->twb();
+                tum << std::setprecision(10) << kv.first << " " << t[0] << " " << t[1] << " " << t[2] << " " << q.x() << " " << q.y() << " "
+                    << q.z() << " " << q.w() << std::endl;
+            }
+            std::cout << "press Enter to exit..." << std::endl;
+            std::cin.ignore();
+            return 0;
         }
         ShardedCalibSpline spline(opt_events, segments, intrinsics, motionTimeStep, pattern->circleRadius, useSO3);
         std::vector<std::array<double, 3>> landmarks;
@@ -307,6 +381,18 @@ int main(int argc, char **argv) {
         printEigenLike(std::cout, spline.intrinsics().data(), 1, 9);
         std::cout << std::endl;
         spline.saveKeyFrameTrajectoryTUM(std::string(argv[3]) + "/TrajectoryByEvent.txt", stamps);  // eventCameraCalib.cpp:212
+        if (!getenv("ECB_NO_IMAGES")) {  // :214-227: SavePath/image/<timestamp>.png = cf->image() of every key frame
+            const std::string dir = std::string(argv[3]) + "/image/";
+            mkdir(dir.c_str(), 0755);
+            std::vector<std::pair<double, double>> kw;
+            for (const auto &kv : frames) kw.push_back(kv.second.duration);
+            fe.run(kw);
+            size_t w = 0;
+            for (const auto &kv : frames) {
+                const ecb::Image8UC3 img = renderFrameImage(fe, w++, &kv.second.circles);
+                ecb::write_png(dir + std::to_string(kv.second.timeStamp) + ".png", img);
+            }
+        }
     } catch (const std::logic_error &ex) {
         std::cerr << "terminate called after throwing an instance of 'std::logic_error'\n  what():  " << ex.what() << std::endl;
         return 134;  // the reference aborts on the uncaught exception

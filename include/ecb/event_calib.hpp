@@ -31,6 +31,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <unordered_set>
 #include <utility>
 #include <vector>
 
@@ -38,7 +39,9 @@
 #include "../../eventcalib_b200/csrc/ecb_so3.h"  // plain host/device header: the SO(3) spline of the useSO3 variant
 #include "calib_init.hpp"
 #include "circles_grid.hpp"
+#include "compat/opengv2_lite.hpp"
 #include "dbscan.h"
+#include "image_lite.hpp"
 
 namespace opengv2 {
 
@@ -198,6 +201,7 @@ public:
         }
         if (ecb_frontend_run(c_->ctx, w.data(), (int) windows.size(), &fp) != ECB_OK)
             throw std::runtime_error(ecb_last_error(c_->ctx));
+        pts_valid_[0] = pts_valid_[1] = false;
         summary_.resize(windows.size());
         stride_ = 1;
         if (!windows.empty()) {
@@ -227,6 +231,31 @@ public:
     }
     double circleRadiusThreshold() const { return rthr_; }
     ecb_ctx *context() const { return c_->ctx; }
+    int width() const { return c_->width; }
+    int height() const { return c_->height; }
+    // positiveEvents_ / negativeEvents_ of window w (pol 1 / 0) in pid order with their raw DBSCAN labels (-1 = Noise)
+    void windowPoints(size_t w, int pol, std::vector<Vec2> &xy, std::vector<int32_t> &labels) {
+        if (!pts_valid_[pol]) {
+            const int64_t n = ecb_frontend_total_points(c_->ctx, pol);
+            pts_xy_[pol].assign((size_t) std::max<int64_t>(n, 1) * 2, 0.0);
+            pts_lab_[pol].assign((size_t) std::max<int64_t>(n, 1), -1);
+            if (ecb_frontend_points(c_->ctx, pol, pts_xy_[pol].data(), pts_lab_[pol].data()) != ECB_OK)
+                throw std::runtime_error(ecb_last_error(c_->ctx));
+            pts_valid_[pol] = true;
+        }
+        const size_t off = (size_t) summary_[w].point_offset[pol], n = (size_t) summary_[w].n_points[pol];
+        xy.resize(n);
+        labels.assign(pts_lab_[pol].begin() + off, pts_lab_[pol].begin() + off + n);
+        for (size_t i = 0; i < n; ++i) xy[i] = Vec2{{pts_xy_[pol][2 * (off + i)], pts_xy_[pol][2 * (off + i) + 1]}};
+    }
+    // clusters that pass clusterMinSample (CirclesEventFrame.cpp:89-117), in kept order: raw cluster id, size, median pid
+    void keptClusters(size_t w, int pol, std::vector<int32_t> &raw_id, std::vector<int32_t> &size, std::vector<int32_t> &median_pid) {
+        const int cap = std::max(1, (int) summary_[w].n_kept[pol]);
+        raw_id.assign((size_t) cap, 0), size.assign((size_t) cap, 0), median_pid.assign((size_t) cap, 0);
+        const int n = ecb_frontend_clusters(c_->ctx, (int) w, pol, raw_id.data(), size.data(), median_pid.data(), cap);
+        if (n < 0) throw std::runtime_error(ecb_last_error(c_->ctx));
+        raw_id.resize((size_t) n), size.resize((size_t) n), median_pid.resize((size_t) n);
+    }
     // rectifyFeatures (CirclesEventFrame.cpp:417-609) for windows of the last run, batched: image_points = 5 projected points
     // (landmark + four quadrant points, :431-456) per frame and circle; out[frame][circle] = cx, cy, r (r < 0: deleted)
     void rectify(const std::vector<int32_t> &window_index, int n_circles, const std::vector<double> &image_points, double inlier,
@@ -247,7 +276,51 @@ private:
     double rthr_;
     std::vector<ecb_window_summary> summary_;
     std::vector<double> cand_;
+    std::vector<double> pts_xy_[2];
+    std::vector<int32_t> pts_lab_[2];
+    bool pts_valid_[2] = {false, false};
 };
+
+// The reference's debug rendering of a frame (CirclesEventFrame.cpp:74-126,150-157,314-318,623-627): kept clusters coloured
+// by their index (20 * k -> B = c / 256, G = c % 256, R = 200 for positive / 100 for negative clusters), white radius-2 circles
+// at the cluster medians, green candidate circles, and — after rectifyFeatures — white circles at the rectified features.
+// eventImage (positive events red, negative green) and clusterImage (the clusters alone) are the public debug members of
+// CirclesEventFrame.hpp:69.  FE: FrontEnd or ShardedFrontEnd.
+template <class FE>
+inline ecb::Image8UC3 renderFrameImage(FE &fe, size_t w, const std::vector<std::array<double, 3>> *rectified = nullptr,
+                                       ecb::Image8UC3 *eventImage = nullptr, ecb::Image8UC3 *clusterImage = nullptr) {
+    ecb::Image8UC3 img(fe.height(), fe.width());
+    std::vector<Vec2> xy[2];
+    std::vector<int32_t> lab[2], raw[2], size[2], med[2];
+    for (int pol = 0; pol < 2; ++pol) {
+        fe.windowPoints(w, pol, xy[pol], lab[pol]);
+        fe.keptClusters(w, pol, raw[pol], size[pol], med[pol]);
+    }
+    if (eventImage) {
+        *eventImage = ecb::Image8UC3(fe.height(), fe.width());
+        for (const Vec2 &p : xy[1]) eventImage->set((int) p[0], (int) p[1], 0, 0, 255);
+        for (const Vec2 &p : xy[0]) eventImage->set((int) p[0], (int) p[1], 0, 255, 0);
+    }
+    for (int pol = 1; pol >= 0; --pol) {  // positive clusters first (:89-102), then negative (:104-117)
+        std::map<int32_t, unsigned> kept_of;
+        for (size_t k = 0; k < raw[pol].size(); ++k) kept_of[raw[pol][k]] = (unsigned) k;
+        for (size_t i = 0; i < xy[pol].size(); ++i) {
+            const auto it = kept_of.find(lab[pol][i]);
+            if (lab[pol][i] < 0 || it == kept_of.end()) continue;
+            const unsigned color = 20 * it->second;
+            img.set((int) xy[pol][i][0], (int) xy[pol][i][1], (uint8_t) (color / 256), (uint8_t) (color % 256), pol ? 200 : 100);
+        }
+    }
+    if (clusterImage) *clusterImage = img;
+    for (int pol = 1; pol >= 0; --pol)
+        for (int32_t m : med[pol])
+            if (m >= 0 && (size_t) m < xy[pol].size()) img.circle((int) xy[pol][(size_t) m][0], (int) xy[pol][(size_t) m][1], 2, 255, 255, 255);
+    for (const CalibCircleLite &c : fe.candidates(w)) img.circle((int) c.center[0], (int) c.center[1], (int) c.radius, 0, 255, 0);
+    if (rectified)
+        for (const auto &c : *rectified)
+            if (c[2] >= 0) img.circle((int) c[0], (int) c[1], (int) c[2], 255, 255, 255);
+    return img;
+}
 
 // ---- per-frame class with the reference's interface ----
 class CirclesEventFrame {
@@ -261,8 +334,17 @@ public:
     bool extractFeatures() {  // CirclesEventFrame.cpp:61-359
         const ecb_window_summary &s = fe_.summary(0);
         if (s.n_points[0] == 0 || s.n_points[1] == 0) return false;  // :62-64
-        return orderFeatures(fe_.candidates(0), *pattern_, features_);
+        if (debugImages) image_ = renderFrameImage(fe_, 0, nullptr, &eventImage, &clusterImage);
+        const bool found = orderFeatures(fe_.candidates(0), *pattern_, features_);
+        lm_of_feature_.clear();
+        for (size_t k = 0; k < features_.size(); ++k) lm_of_feature_.push_back((int) k);  // feature k observes board point k (:340-352)
+        return found;
     }
+    // DEBUG images like the reference's public members (CirclesEventFrame.hpp:69) and Bodyframe's image(); filled by
+    // extractFeatures / rectifyFeatures when debugImages is set (they cost a device -> host copy of the frame's points)
+    bool debugImages = false;
+    ecb::Image8UC3 eventImage, clusterImage;
+    const ecb::Image8UC3 &image() const { return image_; }
     // :320-356: the candidates in pattern order (findCirclesGrid, CALIB_CB_ASYMMETRIC_GRID) -> features_; false when the grid
     // is not found.  Grid ordering: include/ecb/circles_grid.hpp (the canonical RESULT of OpenCV's finder).
     static bool orderFeatures(const std::vector<CalibCircleLite> &cand, const CirclePatternParameters &pattern,
@@ -297,11 +379,61 @@ public:
                                  pattern_->isAsymmetric ? 1 : 0, out.data(), &ok) != ECB_OK)
             return false;
         std::vector<CalibCircleLite> kept;
-        for (int k = 0; k < n; ++k)
-            if (out[(size_t) k * 3 + 2] >= 0)
+        std::vector<int> lm_kept;
+        std::vector<std::array<double, 3>> circles;
+        for (int k = 0; k < n; ++k) {
+            circles.push_back({out[(size_t) k * 3], out[(size_t) k * 3 + 1], out[(size_t) k * 3 + 2]});
+            if (out[(size_t) k * 3 + 2] >= 0) {
                 kept.push_back(CalibCircleLite{{{out[(size_t) k * 3], out[(size_t) k * 3 + 1]}}, out[(size_t) k * 3 + 2], -1, -1});
+                lm_kept.push_back((size_t) k < lm_of_feature_.size() ? lm_of_feature_[(size_t) k] : k);
+            }
+        }
         features_ = kept;
+        lm_of_feature_ = lm_kept;
+        if (debugImages && ok) image_ = renderFrameImage(fe_, 0, &circles);  // :623-627
         return ok != 0;
+    }
+    // ---- the reference's own argument lists (CirclesEventFrame.hpp:43-65) ----
+    // The reference reaches the camera through the frame's sensor_ and the board points through each feature's landmark();
+    // here both are handed over once.  Landmark k belongs to feature k of the ordered grid (EventCalibIni.cpp:99-113).
+    void setSensor(const ecb::CameraModel &camera) { camera_ = camera; }
+    void setLandmarks(const std::vector<LandmarkBase::Ptr> &landmarks) { landmarks_ = landmarks; }
+    // CirclesEventFrame.cpp:417-456: Rcw / tcw -> rvec / tvec, the landmark and its four quadrant points (cv::Point3f) projected
+    // with the camera (cv::projectPoints, cv::Point2f), then the batched GPU part.  outlierIdxs is not read by the reference's
+    // implementation either.
+    bool rectifyFeatures(const std::unordered_set<int> &outlierIdxs, const Eigen::Ref<const Eigen::Matrix3d> &Rcw,
+                         const Eigen::Ref<const Eigen::Vector3d> &tcw) {
+        (void) outlierIdxs;
+        double R[9], rvec[3], tvec[3] = {tcw[0], tcw[1], tcw[2]};
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) R[3 * r + c] = Rcw(r, c);
+        ecb::rodriguesInverse(R, rvec);
+        const double skewR = pattern_->circleRadius / std::sqrt(2.0);
+        std::vector<std::array<Vec2, 5>> imagePoints;
+        for (size_t k = 0; k < features_.size(); ++k) {
+            const int li = k < lm_of_feature_.size() ? lm_of_feature_[k] : (int) k;
+            if (li < 0 || (size_t) li >= landmarks_.size() || !landmarks_[(size_t) li])
+                throw std::logic_error("CirclesEventFrame::rectifyFeatures: setLandmarks() first (one landmark per board point)");
+            const Eigen::Vector3d c = landmarks_[(size_t) li]->position();
+            const double o5[15] = {(double) (float) c[0], (double) (float) c[1], (double) (float) c[2],
+                                   (double) (float) (c[0] + skewR), (double) (float) (c[1] + skewR), (double) (float) c[2],
+                                   (double) (float) (c[0] + skewR), (double) (float) (c[1] - skewR), (double) (float) c[2],
+                                   (double) (float) (c[0] - skewR), (double) (float) (c[1] - skewR), (double) (float) c[2],
+                                   (double) (float) (c[0] - skewR), (double) (float) (c[1] + skewR), (double) (float) c[2]};
+            double p5[10];
+            ecb::projectPoints(o5, 5, rvec, tvec, camera_, p5);
+            std::array<Vec2, 5> ip;
+            for (int i = 0; i < 5; ++i) ip[(size_t) i] = Vec2{{(double) (float) p5[2 * i], (double) (float) p5[2 * i + 1]}};
+            imagePoints.push_back(ip);
+        }
+        return rectifyFeatures(imagePoints);
+    }
+    // CirclesEventFrame.hpp:50-65: the landmark of the nearest feature if the event lies within 5 px of its rim, else nullptr
+    LandmarkBase::Ptr findCenter(const Eigen::Vector2d &p) const {
+        const int k = findCenter(Vec2{{p[0], p[1]}});
+        if (k < 0) return nullptr;
+        const int li = (size_t) k < lm_of_feature_.size() ? lm_of_feature_[(size_t) k] : k;
+        return li >= 0 && (size_t) li < landmarks_.size() ? landmarks_[(size_t) li] : nullptr;
     }
     int eventsNum() const { return fe_.eventsNum(0); }
     const std::vector<CalibCircleLite> &features() const { return features_; }
@@ -325,6 +457,10 @@ private:
     std::pair<double, double> duration_;
     CirclePatternParameters::Ptr pattern_;
     std::vector<CalibCircleLite> features_;
+    std::vector<int> lm_of_feature_;  // board point / landmark index of every feature still alive
+    std::vector<LandmarkBase::Ptr> landmarks_;
+    ecb::CameraModel camera_;
+    ecb::Image8UC3 image_;
 };
 
 // ---- the tracking gate: TrackingBase::process (core/tracking/src/TrackingBase.cpp:16-46) + EventCalibIni::track
@@ -660,6 +796,48 @@ public:
         double unitQwb[4];  // x y z w
         double twb[3];
     };
+    // The reference's constructor, argument for argument (EventCalibSpline.hpp:19, EventCalibSpline.cpp:14-113): frame-count
+    // check, reduceMap() (segments at gaps > 50 steps; segments with fewer than degree + 1 frames are REMOVED from the map),
+    // spline fits, intrinsics_ from the camera (K + 5-term inverse of the radial part of distCoeffs), the two report lines,
+    // optimize() (association + LM on the GPU) and updateMap() (K, inverseRadialPoly, every key frame's pose <- spline pose).
+    // The camera and the board landmarks come from the map (compat/opengv2_lite.hpp); `reduceMap` only enables the part of
+    // reduceMap() the reference itself has disabled (:346-348), so it is accepted and has no further effect.
+    EventCalibSpline(MapBase::Ptr map, EventContainer::Ptr eventContainer, bool useSO3, bool reduceMap, double motionTimeStep,
+                     double circleRadius)
+        : EventCalibSpline(eventContainer, segmentsOfMap(map, motionTimeStep, useSO3), intrinsicsOfMap(map), motionTimeStep, circleRadius,
+                           useSO3) {
+        (void) reduceMap;
+        map_ = map;
+        std::vector<KeyFrame> kfs;
+        for (const auto &kv : map->keyframes()) kfs.push_back(KeyFrame{kv.second->timeStamp(), kv.second->circles});
+        std::vector<std::array<double, 3>> landmarks;
+        for (const auto &kv : map->landmarks()) {
+            const Eigen::Vector3d p = kv.second->position();
+            landmarks.push_back({p[0], p[1], p[2]});
+        }
+        associate(kfs, landmarks);
+        if (!optimize()) throw std::runtime_error(ecb_last_error(ev_->ctx));
+        updateMap();
+    }
+    void updateMap() {  // EventCalibSpline.cpp:253-317
+        if (!map_) return;
+        map_->camera.fx = intr_[0], map_->camera.fy = intr_[1], map_->camera.cx = intr_[2], map_->camera.cy = intr_[3];
+        for (int k = 0; k < 5; ++k) map_->inverseRadialPoly[(size_t) k] = intr_[(size_t) (4 + k)];
+        std::cout.precision(12);
+        std::cout << "Intrinsics after optimization:";
+        printEigenLikeRow(std::cout, intr_.data(), 9);
+        std::cout << std::endl;
+        for (const auto &kv : map_->keyframes()) {
+            Bodyframe &bf = *kv.second;
+            double q[4], t[3];
+            if (!evaluate(bf.timeStamp(), q, t)) continue;  // time2splineIdx < 0
+            const Eigen::Quaterniond Qwb_old = bf.unitQwb();
+            const Eigen::Vector3d twb_old = bf.twb();
+            bf.setPose(Eigen::Vector3d(t[0], t[1], t[2]), Eigen::Quaterniond(q[3], q[0], q[1], q[2]));
+            const Eigen::Quaterniond Qbw_old = Qwb_old.conjugate();  // real -> opt (:310-315)
+            bf.optT = {Qbw_old.x(), Qbw_old.y(), Qbw_old.z(), Qbw_old.w(), twb_old[0], twb_old[1], twb_old[2]};
+        }
+    }
     // reduceMap() :319-348: segments at gaps > 50 * MotionTimeStep, segments with fewer than degree + 1 frames dropped
     static std::vector<std::vector<KeyPose>> segmentKeyframes(const std::vector<KeyPose> &kf, double motionTimeStep) {
         std::vector<std::vector<KeyPose>> sets(1);
@@ -739,8 +917,9 @@ public:
     // Spline segments from the map's key frames like the reference constructor (:25-91): frame count check, segmentation,
     // time bounds extended by 3 steps, cpNum = floor(T / (50 step)) clamped, spline fits.  useSO3: the reference fits the
     // SO(3) control points with Ceres (BsplineSO3::optimizeCP); here they start from the normalised quaternion-spline fit.
-    static std::vector<Segment> segmentsFromKeyframes(const std::vector<KeyPose> &kf, double motionTimeStep, bool useSO3 = false) {
-        if (kf.size() <= 10) throw std::logic_error("too few frames in the map.");
+    static std::vector<Segment> segmentsFromKeyframes(const std::vector<KeyPose> &kf, double motionTimeStep, bool useSO3 = false,
+                                                      bool checkFrameCount = true) {
+        if (checkFrameCount && kf.size() <= 10) throw std::logic_error("too few frames in the map.");
         std::vector<Segment> out;
         for (auto &set : segmentKeyframes(kf, motionTimeStep)) {
             std::vector<double> us, tw, qw;
@@ -865,6 +1044,50 @@ public:
     }
 
 private:
+    static void printEigenLikeRow(std::ostream &os, const double *v, int n);
+    // reduceMap() :319-344 + the set-up of :36-91 on the map's key frames
+    static std::vector<Segment> segmentsOfMap(const MapBase::Ptr &map, double motionTimeStep, bool useSO3) {
+        if (!map || map->frameNum() <= 10) throw std::logic_error("too few frames in the map.");
+        std::vector<KeyPose> kf;
+        for (const auto &kv : map->keyframes()) {
+            const Eigen::Quaterniond q = kv.second->unitQwb();
+            const Eigen::Vector3d t = kv.second->twb();
+            kf.push_back(KeyPose{kv.second->timeStamp(), {q.x(), q.y(), q.z(), q.w()}, {t[0], t[1], t[2]}});
+        }
+        std::vector<double> drop;  // frames of segments shorter than degree + 1 leave the map
+        {
+            std::vector<std::vector<double>> sets(1);
+            double last = kf.front().timeStamp;
+            for (const auto &k : kf) {
+                if (k.timeStamp - last > 50 * motionTimeStep) sets.emplace_back();
+                sets.back().push_back(k.timeStamp);
+                last = k.timeStamp;
+            }
+            for (const auto &st : sets)
+                if (st.size() < 4) drop.insert(drop.end(), st.begin(), st.end());
+        }
+        for (double id : drop) map->removeFrame(id);
+        for (size_t i = 1; i < kf.size(); ++i) {  // one sign per quaternion so that the real-valued spline fit sees a continuous curve
+            double d = 0;
+            for (int a = 0; a < 4; ++a) d += kf[i].unitQwb[a] * kf[i - 1].unitQwb[a];
+            if (d < 0)
+                for (int a = 0; a < 4; ++a) kf[i].unitQwb[a] = -kf[i].unitQwb[a];
+        }
+        return segmentsFromKeyframes(kf, motionTimeStep, useSO3, false);
+    }
+    static std::array<double, 9> intrinsicsOfMap(const MapBase::Ptr &map) {  // :93-108
+        const ecb::CameraModel &cam = map->camera;
+        const std::array<double, 4> radial = {cam.dist[0], cam.dist[1], cam.dist[4], 0.0};
+        const std::array<double, 5> inv = inverseRadialDistortion(radial);
+        const std::array<double, 9> intrinsics = {cam.fx, cam.fy, cam.cx, cam.cy, inv[0], inv[1], inv[2], inv[3], inv[4]};
+        std::cout << "OpenCV Distortion before optimization:";
+        printEigenLikeRow(std::cout, radial.data(), 4);
+        std::cout << std::endl << "Intrinsics before optimization:";
+        printEigenLikeRow(std::cout, intrinsics.data(), 9);
+        std::cout << std::endl;
+        return intrinsics;
+    }
+    MapBase::Ptr map_;
     EventContainer::Ptr ev_;
     std::vector<Segment> seg_;
     std::vector<int32_t> n_cp_;
@@ -872,6 +1095,7 @@ private:
     double step_, radius_;
     bool useSO3_ = false;
 };
+inline void EventCalibSpline::printEigenLikeRow(std::ostream &os, const double *v, int n) { printEigenLike(os, v, 1, n); }
 
 }  // namespace opengv2
 #endif  // ECB_EVENT_CALIB_HPP

@@ -159,6 +159,14 @@ public:
             }
     }
     int shards() const { return c_->shards(); }
+    int width() const { return c_->width; }
+    int height() const { return c_->height; }
+    void windowPoints(size_t w, int pol, std::vector<Vec2> &xy, std::vector<int32_t> &labels) {
+        fe_[(size_t) where_[w].first]->windowPoints((size_t) where_[w].second, pol, xy, labels);
+    }
+    void keptClusters(size_t w, int pol, std::vector<int32_t> &raw_id, std::vector<int32_t> &size, std::vector<int32_t> &median_pid) {
+        fe_[(size_t) where_[w].first]->keptClusters((size_t) where_[w].second, pol, raw_id, size, median_pid);
+    }
 
 private:
     ShardedEventContainer::Ptr c_;

@@ -245,3 +245,41 @@ def test_cli_two_real_gpus(built, tmp_path):
     np.testing.assert_allclose(a2[:4], a1[:4], rtol=1e-7)   # host LM on one GPU vs replicated device LM on two
     t1, t2 = np.loadtxt(str(tmp_path / "out1" / "TrajectoryByEvent.txt")), np.loadtxt(str(tmp_path / "out2" / "TrajectoryByEvent.txt"))
     np.testing.assert_allclose(t2, t1, rtol=0, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_cli_reference_signatures_and_images(built, tmp_path):
+    """The reference's own argument lists on the façade (include/ecb/compat/): `EventCalibSpline(MapBase::Ptr, EventContainer::Ptr,
+    bool useSO3, bool reduceMap, double, double)` (EventCalibSpline.hpp:19) does what the CLI's step-by-step path does — same
+    report lines, same intrinsics, same trajectory; `CirclesEventFrame::rectifyFeatures(const std::unordered_set<int>&, Rcw, tcw)`
+    and `findCenter(const Eigen::Vector2d&) -> LandmarkBase::Ptr` (CirclesEventFrame.hpp:43-65) reproduce the batched result;
+    and SavePath/image/<timestamp>.png exists for every key frame (eventCameraCalib.cpp:214-227)."""
+    from eventcalib_b200 import synth
+    ev = synth.make_stream(1000000, 346, 260, t0=5.0, duration=0.5, seed=1001, return_truth=True, workers=4,
+                           rot_amp=(0.35, 0.35, 0.3), orbit=True)
+    synth.write_bin(str(tmp_path / "ev.bin"), ev)
+    (tmp_path / "cfg.yaml").write_text(YAML.replace("fitCircle: 0", "fitCircle: 1"))
+    a = _run_cli(built, tmp_path / "cfg.yaml", tmp_path / "ev.bin", tmp_path / "outA", "0")
+    env = dict(os.environ, ECB_PIECES="6", ECB_DEVICES="0", ECB_REFERENCE_SIGNATURES="1")
+    b = subprocess.run([built, str(tmp_path / "cfg.yaml"), str(tmp_path / "ev.bin"), str(tmp_path / "outB")], capture_output=True,
+                       text=True, stdin=subprocess.DEVNULL, timeout=900, env=env)
+    assert b.returncode == 0, b.stdout[-2000:] + b.stderr
+    keep = lambda out: [l for l in out.splitlines() if not l.startswith("Solver Summary:")]
+    assert keep(a.stdout) == keep(b.stdout)                      # report lines incl. the intrinsics before / after, 12 digits
+    ta, tb = np.loadtxt(str(tmp_path / "outA" / "TrajectoryByEvent.txt")), np.loadtxt(str(tmp_path / "outB" / "TrajectoryByEvent.txt"))
+    np.testing.assert_allclose(tb, ta, rtol=0, atol=2e-10)       # written with 10 decimals
+    msg = [l for l in b.stderr.splitlines() if l.startswith("reference signatures:")][0]
+    assert "rectifyFeatures(outlierIdxs, Rcw, tcw) true" in msg
+    n_feat, n_alive = int(msg.split("true, ")[1].split()[0]), int(msg.split(" of ")[1].split()[0])
+    assert n_feat == n_alive >= 29
+    assert float(msg.split("batched result ")[1].split(",")[0]) < 1e-5    # same circles (image points pass through float)
+    assert int(msg.split("landmark for ")[1].split()[0]) == n_feat
+    # per-key-frame debug images
+    kept = int([l for l in a.stdout.splitlines() if l.endswith("frames in Map after Initialization.")][0].split()[0])
+    pngs = sorted((tmp_path / "outA" / "image").glob("*.png"))
+    assert len(pngs) == kept
+    import cv2
+    im = cv2.imread(str(pngs[0]))
+    assert im.shape == (260, 346, 3)
+    assert (im.reshape(-1, 3) == (255, 255, 255)).all(1).sum() > 200    # white rectified circles / median marks
+    assert ((im[:, :, 2] == 200) | (im[:, :, 2] == 100)).sum() > 300    # cluster pixels (R = 200 positive, 100 negative)
