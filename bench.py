@@ -684,11 +684,14 @@ def main():
     pool = ThreadPoolExecutor(S)
 
     trace = os.environ.get("ECB_BENCH_TRACE")
+    stagger = float(os.environ.get("ECB_BENCH_STAGGER_US", "0")) * 1e-6
     t_origin = [0.0]
 
     def slice_work(j):
         sl = slices[j]
         c = sl["ctx"]
+        if stagger:  # uploads enter the copy queue in slice order (the threads race otherwise): slice plans can then shape the ramp
+            time.sleep(j * stagger)
         tm = [time.perf_counter()]
         c.load_events_ptr(pinned.data_ptr() + sl["lo"] * 25, sl["hi"] - sl["lo"])
         tm.append(time.perf_counter())

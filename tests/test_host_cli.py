@@ -178,6 +178,17 @@ def test_cli_end_to_end_calibration(built, tmp_path):
     # principal point within 2 px, and it is closer than the frame-based initialisation was
     assert abs(after[0] / truth[0] - 1) < 1e-2 and abs(after[1] / truth[1] - 1) < 1e-2, (before, after, truth)
     assert abs(after[2] - truth[2]) < 2 and abs(after[3] - truth[3]) < 2
+    # The distortion terms after[4:9] (inverse radial polynomial k1 .. k5) are NOT asserted: on a 1 s stream with the board near
+    # the image centre only their combined effect on the rim points is observable, the individual coefficients of r^4 .. r^10
+    # are determined to no better than their own magnitude (the LM stops with k2 .. k5 far from the generator's values while
+    # the reprojection cost and the poses below agree with the ground truth; profiles/r1e_cli_c1_fitcircle0.log).  Whether
+    # Ceres would stop elsewhere on the same data cannot be known here (a12's solve is unpinned).  What is
+    # checked instead is the thing they model: the undistortion they encode, at the pixels the rims occupy.
+    x = np.linspace(-0.35, 0.35, 15)               # normalised radius range covered by the board in this stream
+    r2 = x * x
+    s_after = 1 + sum(after[4 + k] * r2 ** (k + 1) for k in range(5))
+    s_truth = 1 + sum(truth[4 + k] * r2 ** (k + 1) for k in range(5))
+    assert np.max(np.abs(s_after / s_truth - 1)) < 5e-3
     summ = line("Solver Summary:")
     c0, c1 = (float(x) for x in summ.split("cost")[1].split(",")[0].split("->"))
     assert c1 < c0
