@@ -47,7 +47,7 @@ constexpr int NB = 24;               // band rows per column (half bandwidth 23 
 constexpr int NI = 9;                // intrinsics
 constexpr int NA = NI + 1;           // arrow rows of the factorisation: intrinsics + right-hand side
 constexpr int OUT_STRIDE = 33 * 33 + 33;
-constexpr int FACTOR_THREADS = 608;  // 300 band + 240 arrow + 55 corner elements
+constexpr int FACTOR_THREADS = 256;  // 595 window elements (300 band + 240 arrow + 55 corner), up to 3 per thread
 constexpr int TRACE_CAP = 1024;
 
 struct LmScalars {
@@ -68,7 +68,7 @@ struct LmBufs {
     double *x, *cand, *ne;            // parameters (intr 9 | rot 4C | trans 3C) at x / candidate; packed normal equations at x
     double *Hb, *Ha, *Hc, *g;         // J^T J (band column major, arrow 9 x n, corner 9 x 9 full) and J^T r at x, unscaled
     double *scale, *diag, *step, *delta;
-    double *Lb, *La, *Cc0, *dC, *Lc, *xi, *ysol;  // factorisation workspace
+    double *Lb, *La, *Cc0, *dC, *Lc, *xi, *ysol;  // factorisation workspace (Lc: 1 / L(j, j) of the band)
     double *trace;
     LmScalars *s;
 };
@@ -285,91 +285,155 @@ __global__ void k_lm_build(LmDims d, LmBufs b, ecb_lm_options o) {
     }
 }
 
-// Banded Cholesky of one segment's block of the band with the arrow rows carried along.  Thread-elements: the lower triangle
-// of the 24 x 24 window (300), the 10 x 24 arrow window (240), the lower triangle of the 10 x 10 corner update (55, registers).
+// Banded Cholesky of one segment's block of the band with the arrow rows carried along — BLOCKED by control point (6 columns
+// per step; a residual couples 4 consecutive control points, so the band is block-banded: column 6 jb + k has no entry below
+// row 6 jb + 23 and a 24-row window holds everything a block column touches).  Per block step:
+//   1. warp 0 factorises the 6-column panel in registers: lane = one window row (24 band rows, 10 arrow rows; lanes 0 and 1
+//      carry the two extra arrow rows), row-wise Crout — for column k the pivot row's entries are broadcast by shuffles,
+//      l_rk = (a_rk - sum_{m<k} l_rm l_km) / sqrt(pivot) — no shared memory, no CTA barrier inside the panel;
+//   2. all threads apply the rank-6 update to the trailing 18 x 18 band window, the 10 x 18 arrow window and the 10 x 10
+//      corner sum, shifted by 6 into the other buffer, while the 6 entering rows / columns (raw entries, loaded one step
+//      ahead during the panel phase) are appended.
+// The updates are subtracted in ascending column order like a column-by-column right-looking factorisation, which this
+// replaces (one column and one CTA barrier per step: 0.62 ms at D = 843; blocked: 139 steps instead of 834,
+// profiles/r2s_lm_exchange_timing.md).  1 / L(j, j) is kept for the back substitution.
+constexpr int FB = 6;                         // block = the 6 tangent parameters of one control point
+constexpr int PANEL_ROWS = NB + NA;           // 24 band rows + 10 arrow rows
+constexpr int N_ELEM = 300 + 240 + 55;        // window elements: band lower triangle, arrow, corner lower triangle
+constexpr int EPT = (N_ELEM + FACTOR_THREADS - 1) / FACTOR_THREADS;
+
 __global__ void __launch_bounds__(FACTOR_THREADS) k_lm_factor(LmDims d, LmBufs b) {
     __shared__ double W[2][NB * NB];
     __shared__ double A[2][NA * NB];
+    __shared__ double P[PANEL_ROWS * FB];  // the factorised panel: P[row * 6 + k]; rows 0..23 band (0..5 = L11), 24..33 arrow
+    __shared__ int s_fail;
     LmScalars *s = b.s;
     if (!s->running) return;
-    const int sg = blockIdx.x, tid = threadIdx.x;
+    const int sg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int j0 = 6 * d.seg_cp_off[sg], ns = 6 * d.seg_ncp[sg], n = d.n;
-    int kind = 3, r = 0, c = 0;  // 0 band (r >= c), 1 arrow (r = arrow row, c = column), 2 corner (r >= c)
-    if (tid < 300) {
-        kind = 0;
-        r = (int) ((sqrt(8.0 * tid + 1.0) - 1.0) * 0.5);
-        while (r * (r + 1) / 2 > tid) --r;
-        while ((r + 1) * (r + 2) / 2 <= tid) ++r;
-        c = tid - r * (r + 1) / 2;
-    } else if (tid < 540) {
-        kind = 1;
-        r = (tid - 300) / NB;
-        c = (tid - 300) % NB;
-    } else if (tid < 595) {
-        kind = 2;
-        const int q = tid - 540;
-        r = (int) ((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
-        while (r * (r + 1) / 2 > q) --r;
-        while ((r + 1) * (r + 2) / 2 <= q) ++r;
-        c = q - r * (r + 1) / 2;
-    }
     double *Lb = b.Lb + (size_t) j0 * NB;
-    // initial window: columns 0 .. 23 of the segment
-    if (kind == 0) W[0][r * NB + c] = r < ns ? Lb[(size_t) c * NB + (r - c)] : 0.0;
-    if (kind == 1) A[0][r * NB + c] = c < ns ? b.La[(size_t) r * n + j0 + c] : 0.0;
-    double acc = 0.0;  // corner update  sum_j a_r a_c
-    // raw entries that enter the window at the end of step j: band row i = j + 24 (columns j+1 .. j+24), arrow column j + 24;
-    // loaded PF steps ahead (they do not depend on the factorisation)
-    constexpr int PF = 4;
-    double pre[PF];
-    auto raw = [&](int j) -> double {
-        const int i = j + NB;  // row / column that enters
-        if (i >= ns) return 0.0;
-        if (kind == 0 && r == NB - 1) return Lb[(size_t) (j + 1 + c) * NB + (NB - 1 - c)];
-        if (kind == 1 && c == NB - 1) return b.La[(size_t) r * n + j0 + i];
+    // this thread's window elements: kind 0 band (r >= c), 1 arrow (r = arrow row, c = column), 2 corner (r >= c)
+    int kind[EPT], er[EPT], ec[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        const int e = tid + q * FACTOR_THREADS;
+        kind[q] = 3, er[q] = 0, ec[q] = 0;
+        if (e < 300 || (e >= 540 && e < N_ELEM)) {
+            const int t = e < 300 ? e : e - 540;
+            int r = (int) ((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while (r * (r + 1) / 2 > t) --r;
+            while ((r + 1) * (r + 2) / 2 <= t) ++r;
+            kind[q] = e < 300 ? 0 : 2, er[q] = r, ec[q] = t - r * (r + 1) / 2;
+        } else if (e < 540) {
+            kind[q] = 1, er[q] = (e - 300) / NB, ec[q] = (e - 300) % NB;
+        }
+    }
+    // raw entries of the 6 rows / columns that enter the window after block step jb (global rows j + 24 .. j + 29)
+    auto raw = [&](int q, int j) -> double {
+        if (kind[q] == 0 && er[q] >= NB - FB) {
+            const int i = j + FB + er[q];  // global row
+            return i < ns ? Lb[(size_t) (j + FB + ec[q]) * NB + (er[q] - ec[q])] : 0.0;
+        }
+        if (kind[q] == 1 && ec[q] >= NB - FB) {
+            const int c = j + FB + ec[q];
+            return c < ns ? b.La[(size_t) er[q] * n + j0 + c] : 0.0;
+        }
         return 0.0;
     };
-    const bool loader = (kind == 0 && r == NB - 1) || (kind == 1 && c == NB - 1);
+    if (tid == 0) s_fail = 0;
 #pragma unroll
-    for (int p = 0; p < PF; ++p) pre[p] = loader ? raw(p) : 0.0;
+    for (int q = 0; q < EPT; ++q) {  // initial window: rows / columns 0 .. 23 of the segment
+        if (kind[q] == 0) W[0][er[q] * NB + ec[q]] = er[q] < ns ? Lb[(size_t) ec[q] * NB + (er[q] - ec[q])] : 0.0;
+        if (kind[q] == 1) A[0][er[q] * NB + ec[q]] = ec[q] < ns ? b.La[(size_t) er[q] * n + j0 + ec[q]] : 0.0;
+    }
+    double acc = 0.0;  // corner update sum_j a_r a_c (the thread's kind-2 element, if any)
     __syncthreads();
     int cur = 0;
-    bool fail = false;
-    for (int j = 0; j < ns; ++j) {
+    for (int j = 0; j < ns; j += FB) {
         const double *Wc = W[cur], *Ac = A[cur];
         double *Wn = W[cur ^ 1], *An = A[cur ^ 1];
-        const double w00 = Wc[0];
-        if (!(w00 > 0.0)) {  // not positive definite (uniform: every thread reads the same value)
-            fail = true;
-            break;
-        }
-        const double rs = 1.0 / sqrt(w00);
-        if (kind == 0) {
-            if (c == 0 && j + r < ns) Lb[(size_t) j * NB + r] = Wc[r * NB] * rs;  // column j of L: L(j + r, j)
-            double v;
-            if (r < NB - 1) v = Wc[(r + 1) * NB + (c + 1)] - (Wc[(r + 1) * NB] * rs) * (Wc[(c + 1) * NB] * rs);
-            else v = pre[0];
-            Wn[r * NB + c] = v;
-        } else if (kind == 1) {
-            const double ar = Ac[r * NB] * rs;
-            if (c == 0) b.La[(size_t) r * n + j0 + j] = ar;
-            double v;
-            if (c < NB - 1) v = Ac[r * NB + c + 1] - ar * (Wc[(c + 1) * NB] * rs);
-            else v = pre[0];
-            An[r * NB + c] = v;
-        } else if (kind == 2) {
-            acc += (Ac[r * NB] * rs) * (Ac[c * NB] * rs);
-        }
-        if (loader) {
+        double pre[EPT];
 #pragma unroll
-            for (int p = 0; p + 1 < PF; ++p) pre[p] = pre[p + 1];
-            pre[PF - 1] = raw(j + PF);
+        for (int q = 0; q < EPT; ++q) pre[q] = raw(q, j);  // in flight during the panel phase
+        if (tid < 32) {
+            // ---- 1. panel: lane -> window row (band rows 0..23 | arrow rows 0..7), second row of lanes 0, 1: arrow rows 8, 9
+            const bool band = lane < NB;
+            double a1[FB], a2[FB];
+#pragma unroll
+            for (int k = 0; k < FB; ++k) {
+                a1[k] = band ? (k <= lane ? Wc[lane * NB + k] : 0.0) : Ac[(lane - NB) * NB + k];
+                a2[k] = lane < 2 ? Ac[(8 + lane) * NB + k] : 0.0;
+            }
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < FB; ++k) {
+                const double piv = __shfl_sync(0xffffffffu, a1[k], k);
+                if (!(piv > 0.0)) bad = true;  // not positive definite (uniform)
+                const double rs = rsqrt(piv);  // <= 1 ulp; sqrt + division were 3/4 of the panel's dependent chain
+                a1[k] *= rs;  // rows above the diagonal of a band column hold zeros: harmless
+                a2[k] *= rs;
+                if (lane == 0) b.Lc[j0 + j + k] = rs;  // 1 / L(j + k, j + k)
+#pragma unroll
+                for (int m = k + 1; m < FB; ++m) {
+                    const double lmk = __shfl_sync(0xffffffffu, a1[k], m);  // L(j + m, j + k): row m of the diagonal block
+                    if (!band || lane >= m) a1[m] -= a1[k] * lmk;
+                    a2[m] -= a2[k] * lmk;
+                }
+            }
+            if (bad) s_fail = 1;
+#pragma unroll
+            for (int k = 0; k < FB; ++k) {
+                P[lane * FB + k] = (band && k > lane) ? 0.0 : a1[k];
+                if (lane < 2) P[(32 + lane) * FB + k] = a2[k];
+                if (band) {  // column j + k of L: L(j + r, j + k) at band offset r - k
+                    if (lane >= k && j + lane < ns) Lb[(size_t) (j + k) * NB + (lane - k)] = a1[k];
+                } else {
+                    b.La[(size_t) (lane - NB) * n + j0 + j + k] = a1[k];
+                }
+                if (lane < 2) b.La[(size_t) (8 + lane) * n + j0 + j + k] = a2[k];
+            }
+        }
+        __syncthreads();
+        if (s_fail) break;
+        // ---- 2. rank-6 update of the trailing window, shifted by one block into the other buffer
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int r = er[q], c = ec[q];
+            if (kind[q] == 0) {
+                double v;
+                if (r < NB - FB) {
+                    v = Wc[(r + FB) * NB + (c + FB)];
+                    const double *pr = P + (r + FB) * FB, *pc = P + (c + FB) * FB;
+#pragma unroll
+                    for (int k = 0; k < FB; ++k) v -= pr[k] * pc[k];
+                } else {
+                    v = pre[q];
+                }
+                Wn[r * NB + c] = v;
+            } else if (kind[q] == 1) {
+                double v;
+                if (c < NB - FB) {
+                    v = Ac[r * NB + c + FB];
+                    const double *pr = P + (NB + r) * FB, *pc = P + (c + FB) * FB;
+#pragma unroll
+                    for (int k = 0; k < FB; ++k) v -= pr[k] * pc[k];
+                } else {
+                    v = pre[q];
+                }
+                An[r * NB + c] = v;
+            } else if (kind[q] == 2) {
+                const double *pr = P + (NB + r) * FB, *pc = P + (NB + c) * FB;
+#pragma unroll
+                for (int k = 0; k < FB; ++k) acc += pr[k] * pc[k];
+            }
         }
         __syncthreads();
         cur ^= 1;
     }
-    if (fail && tid == 0) atomicExch(&s->factor_fail, 1);
-    if (kind == 2) b.dC[(size_t) sg * NA * NA + r * NA + c] = acc;
+    if (s_fail && tid == 0) atomicExch(&s->factor_fail, 1);
+#pragma unroll
+    for (int q = 0; q < EPT; ++q)
+        if (kind[q] == 2) b.dC[(size_t) sg * NA * NA + er[q] * NA + ec[q]] = acc;
 }
 
 // Schur complement of the intrinsics, its Cholesky factor with the right-hand side row, and the intrinsics part of M^-1 gs
@@ -411,38 +475,76 @@ __global__ void k_lm_corner(LmDims d, LmBufs b) {
     for (int r = 0; r < NI; ++r) b.xi[r] = xi[r];
 }
 
-// back substitution of one segment: L^T x = y - (arrow part); lanes 0..22 hold the band terms, lanes 23..31 the arrow terms
-__global__ void __launch_bounds__(32) k_lm_backsub(LmDims d, LmBufs b) {
+// back substitution of one segment, L^T x = y - A^T xi, column oriented: as soon as x_j is known every lane adds its term
+// L(j, j - 1 - r) x_j to the pending sum of row j - 1 - r and the sums move down one lane — one shuffle and three FP64
+// operations on the critical path per unknown instead of a five-level shuffle tree and a division.  Warp 0 runs the
+// recurrence out of shared memory; warps 1 .. 3 stage the next chunk of L, y and 1 / L(j, j) meanwhile (coalesced loads,
+// two buffers), so no global-memory latency sits on the sequential chain (0.35 ms at D = 843 before, ncu).
+constexpr int BS_THREADS = 128, BS_CHUNK = 64, BS_ROW = NB + 1;  // per step: 23 band terms, y, 1 / diag  (25 doubles)
+
+__global__ void __launch_bounds__(BS_THREADS) k_lm_backsub(LmDims d, LmBufs b) {
+    __shared__ double buf[2][BS_CHUNK * BS_ROW];
     const LmScalars *s = b.s;
     if (!s->running || s->factor_fail) return;
-    const int sg = blockIdx.x, lane = threadIdx.x;
+    const int sg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int j0 = 6 * d.seg_cp_off[sg], ns = 6 * d.seg_ncp[sg], n = d.n;
     const double *Lb = b.Lb + (size_t) j0 * NB;
-    const double xa = lane >= NB - 1 ? b.xi[lane - (NB - 1)] : 0.0;  // lanes 23 .. 31: intrinsics 0 .. 8
-    double xr = 0.0;  // lane r < 23: x_{j + 1 + r}
-    constexpr int PF = 6;
-    double lv[PF], yv[PF], dv[PF];
-    auto load = [&](int j, double &l, double &y, double &dg) {
-        l = 0.0, y = 0.0, dg = 1.0;
-        if (j < 0) return;
-        if (lane < NB - 1) l = (j + 1 + lane < ns) ? Lb[(size_t) j * NB + 1 + lane] : 0.0;
-        else l = b.La[(size_t) (lane - (NB - 1)) * n + j0 + j];
-        y = b.La[(size_t) NI * n + j0 + j];
-        dg = Lb[(size_t) j * NB];
+    // right-hand side with the arrow part taken out:  ya_j = y_j - sum_k A(k, j) xi_k   (y = arrow row 9 after the factorisation)
+    {
+        double xi[NI];
+#pragma unroll
+        for (int k = 0; k < NI; ++k) xi[k] = b.xi[k];
+        for (int j = tid; j < ns; j += BS_THREADS) {
+            double v = b.La[(size_t) NI * n + j0 + j];
+#pragma unroll
+            for (int k = 0; k < NI; ++k) v -= b.La[(size_t) k * n + j0 + j] * xi[k];
+            b.ysol[j0 + j] = v;
+        }
+    }
+    __syncthreads();
+    // chunk q covers the unknowns j = hi(q) - 1 ... hi(q) - BS_CHUNK (descending), hi(q) = ns - q * BS_CHUNK
+    const int n_chunks = (ns + BS_CHUNK - 1) / BS_CHUNK;
+    auto stage = [&](int q, int first_thread, int n_threads) {  // slot t of the chunk = unknown j = hi - 1 - t
+        const int hi = ns - q * BS_CHUNK;
+        double *o = buf[q & 1];
+        for (int e = tid - first_thread; e < BS_CHUNK * BS_ROW; e += n_threads) {
+            const int t = e / BS_ROW, r = e - t * BS_ROW, j = hi - 1 - t;
+            double v = 0.0;
+            if (j >= 0) {
+                if (r < NB - 1) {  // L(j, j - 1 - r): column j - 1 - r, band offset 1 + r
+                    const int c = j - 1 - r;
+                    if (c >= 0) v = Lb[(size_t) c * NB + 1 + r];
+                } else if (r == NB - 1) {
+                    v = b.ysol[j0 + j];
+                } else {
+                    v = b.Lc[j0 + j];
+                }
+            }
+            o[e] = v;
+        }
     };
-#pragma unroll
-    for (int p = 0; p < PF; ++p) load(ns - 1 - p, lv[p], yv[p], dv[p]);
-    for (int j = ns - 1; j >= 0; --j) {
-        double t = lv[0] * (lane < NB - 1 ? xr : xa);
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o2);
-        const double xj = (yv[0] - t) / dv[0];
-        if (lane == 0) b.ysol[j0 + j] = xj;
-        xr = __shfl_up_sync(0xffffffffu, xr, 1);
-        if (lane == 0) xr = xj;
-#pragma unroll
-        for (int p = 0; p + 1 < PF; ++p) lv[p] = lv[p + 1], yv[p] = yv[p + 1], dv[p] = dv[p + 1];
-        load(j - PF, lv[PF - 1], yv[PF - 1], dv[PF - 1]);
+    stage(0, 0, BS_THREADS);
+    __syncthreads();
+    double acc = 0.0;  // warp 0, at the start of step j: lane r holds sum_{i > row} L(i, row) x_i collected so far for row = j - r
+    for (int q = 0; q < n_chunks; ++q) {
+        if (tid >= 32) {
+            if (q + 1 < n_chunks) stage(q + 1, 32, BS_THREADS - 32);
+        } else {
+            const double *c = buf[q & 1];
+            const int hi = ns - q * BS_CHUNK, steps = min(BS_CHUNK, hi);
+            double l = lane < NB - 1 ? c[lane] : 0.0, y = c[NB - 1], rd = c[NB];
+            for (int t = 0; t < steps; ++t) {
+                const double *nx = c + (t + 1 < BS_CHUNK ? (t + 1) * BS_ROW : 0);  // next step's operands, loaded ahead of the chain
+                const double l1 = lane < NB - 1 ? nx[lane] : 0.0, y1 = nx[NB - 1], rd1 = nx[NB];
+                const double xj = (y - __shfl_sync(0xffffffffu, acc, 0)) * rd;
+                if (lane == 0) b.ysol[j0 + hi - 1 - t] = xj;
+                acc = __shfl_down_sync(0xffffffffu, acc, 1);  // lane r: row j - 1 - r (independent of x_j: off the critical path)
+                if (lane == 31) acc = 0.0;
+                acc += l * xj;                                // + L(j, j - 1 - r) x_j
+                l = l1, y = y1, rd = rd1;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -686,7 +788,7 @@ int ecb_lm_device_create(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const
     const size_t o_Hb = take((size_t) n * NB), o_Ha = take((size_t) NI * n), o_Hc = take(NI * NI), o_g = take(D);
     const size_t o_scale = take(D), o_diag = take(D), o_step = take(D), o_delta = take(D);
     const size_t o_Lb = take((size_t) n * NB), o_La = take((size_t) NA * n), o_Cc0 = take(NA * NA);
-    const size_t o_dC = take((size_t) n_splines * NA * NA), o_Lc = take(NA * NA), o_xi = take(NI + 1), o_ysol = take(D);
+    const size_t o_dC = take((size_t) n_splines * NA * NA), o_Lc = take((size_t) std::max(n, NA * NA)), o_xi = take(NI + 1), o_ysol = take(D);
     const size_t o_trace = take((size_t) TRACE_CAP * 4), o_cc = take(2), o_s = take((sizeof(LmScalars) + 7) / 8 + 2);
     if ((rc = ecb_reserve(ctx, lm->mem, off * 8))) {
         delete lm;
@@ -785,7 +887,7 @@ int ecb_lm_device_iterate(ecb_lm_device *lm, int n_iterations) {
         k_lm_build<<<blocks, 256, 0, ctx->stream>>>(lm->dims, lm->bufs, lm->opt);
         k_lm_factor<<<lm->dims.n_seg, FACTOR_THREADS, 0, ctx->stream>>>(lm->dims, lm->bufs);
         k_lm_corner<<<1, 32, 0, ctx->stream>>>(lm->dims, lm->bufs);
-        k_lm_backsub<<<lm->dims.n_seg, 32, 0, ctx->stream>>>(lm->dims, lm->bufs);
+        k_lm_backsub<<<lm->dims.n_seg, BS_THREADS, 0, ctx->stream>>>(lm->dims, lm->bufs);
         k_lm_step<<<1, 1024, 0, ctx->stream>>>(lm->dims, lm->bufs, lm->opt);
         ctx->launches += 6;
         mark(1);
