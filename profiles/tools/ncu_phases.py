@@ -18,7 +18,7 @@ src_csv, sass, func = sys.argv[1:4]
 src = open(os.path.join(ROOT, "eventcalib_b200", "csrc", "ecb_cluster.cu")).read().splitlines()
 marks = [(1, "helpers (union-find)")]
 for i, l in enumerate(src, 1):
-    m = re.match(r"\s*// ---- (\d+\w*\.[^-]*?) -+", l)
+    m = re.match(r"\s*// ---- (\d+\w*\. .*?) -{3,}\s*$", l)
     if m:
         marks.append((i, m.group(1).strip()))
     elif "__global__ void" in l and "k_cluster" in l:

@@ -30,6 +30,17 @@ for r in rows[2:]:
          "warps_active_pct": f("sm__warps_active.avg.pct_of_peak_sustained_active"),
          "dram_throughput_pct": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
          "fp64_pipe_active_pct": f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")}
+    for key, metric in (("inst_executed", "smsp__inst_executed.sum"), ("smem_wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+                        ("smem_bank_conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+                        ("dmma_pipe_active_pct", "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active")):
+        if metric in hdr and r[hdr.index(metric)] not in ("", "n/a"):
+            try:
+                e[key] = float(r[hdr.index(metric)].replace(",", ""))
+            except ValueError:
+                pass
+    if e.get("smem_wavefronts"):
+        e["smem_bank_conflict_pct"] = 100.0 * e.get("smem_bank_conflicts", 0.0) / e["smem_wavefronts"]
     if name not in out or e["duration_ms_under_ncu"] > out[name]["duration_ms_under_ncu"]:
         out[name] = e
-print(json.dumps({"events": int(sys.argv[2]), "source": sys.argv[3], "kernels": out}, indent=1))
+print(json.dumps({"events": int(sys.argv[2]), "config": sys.argv[4] if len(sys.argv) > 4 else "C2", "source": sys.argv[3], "kernels": out},
+                 indent=1))
