@@ -40,5 +40,22 @@ ctx.cost_eval(*x)
 ctx.cost_set_rotation_model(1)
 ctx.cost_normal_eq(*x)
 ctx.cost_set_rotation_model(0)
+# round 2: the device LM loop (blocked band Cholesky, staged back substitution) ...
+lm = ecb.DeviceLm(ctx, [pb["n_cp"]], ecb.lm_options(max_iterations=3))
+out = lm.run(pb["intrinsics"], pb["rot_cp"], pb["trans_cp"])
+lm.close()
+# ... the general (grid-hash) DBSCAN path: float coordinates, duplicates on an integer grid (tie rule + tree), 3-D, a batch ...
+rng = np.random.default_rng(0)
+ctx.dbscan_ordered(rng.uniform(0, 20, (400, 2)), 1.3, 3)
+ctx.dbscan(rng.uniform(0, 20, (400, 2)), 1.3, 3)
+ctx.dbscan_ordered(rng.integers(0, 14, (300, 2)).astype(np.float64), 3.0, 2)
+ctx.dbscan_nd(rng.uniform(0, 8, (300, 3)), 1.2, 3)
+ctx.dbscan_nd(rng.uniform(0, 8, (200, 4)), 1.5, 3)
+sets = [rng.uniform(0, 15, (int(rng.integers(1, 120)), 2)) for _ in range(6)]
+ctx.dbscan_batch_ordered(np.concatenate(sets), np.concatenate([[0], np.cumsum([len(q) for q in sets])]), 2.0, 3)
+# ... and an unsorted event file (stable device sort by stamp)
+perm = rng.permutation(len(ev["t"]))
+ctx.load_events(synth.to_records({k: (v[perm] if isinstance(v, np.ndarray) and len(v) == len(perm) else v) for k, v in ev.items()}))
+ctx.frontend_run(win, ecb.default_params(fit_circle=1, radius_threshold=rthr, order_mode=1, median_mode=1))
 ctx.close()
-print("sanitize run ok: %d windows, %d clusters" % (len(win), len(clusters)))
+print("sanitize run ok: %d windows, %d clusters, LM iterations %d" % (len(win), len(clusters), out["iterations"]))
