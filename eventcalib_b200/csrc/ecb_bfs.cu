@@ -13,13 +13,17 @@
 //
 // Consumers: (a) kept clusters whose median norm is tied — std::nth_element (restated in ecb_nth_element.h) then picks
 // the same pixel as CirclesEventFrame.cpp:140-147; (b) ecb_dbscan_run_ordered: `Clusters` as ordered lists.
+#include <algorithm>
+
 #include "ecb_cluster.cuh"
 #include "ecb_nth_element.h"
 
 namespace {
 
-constexpr int BFS_THREADS = 128;
+constexpr int BFS_THREADS = 64;  // two clusters per CTA: the small-cluster scratch is 20 KB of shared memory per warp
 constexpr int BFS_WARPS = BFS_THREADS / 32;
+constexpr int BFSG_THREADS = 128;  // k_bfs_order_general
+constexpr int BFSG_WARPS = BFSG_THREADS / 32;
 
 // ---- tree policies -------------------------------------------------------------------------------------------------------
 // PixTree: integer pixels, one 16-byte node {pixel, left, right, parent} (exported by k_cluster), 2-D.
@@ -255,8 +259,190 @@ __device__ __forceinline__ int bfs_cluster(const Tree &tr, uint32_t root, const 
     return le;
 }
 
+// ---- small clusters: neighbour lists from root paths, all (member, neighbour) pairs at once -----------------------------------
+// The level-synchronous walk above keeps ~4 lanes busy (a ring cluster's frontier) and repeats a ~100-node tree walk per level:
+// ncu counted 29 k warp instructions per 30-member cluster, all on one warp's critical path (0.27 ms per launch however small
+// the batch).  For the usual kept cluster (<= 48 members, tree depth <= 48) the walk is replaced by what it computes:
+//   * v is met by u's query iff d(u, v) <= eps and every ancestor a of v that has v on its FAR side as seen from u passes
+//     find_nearest's pruning test |u[axis(a)] - a[axis(a)]| < eps (kdtree.cpp:166-171);
+//   * the query meets nodes in pre-order, near subtree first.  Two met nodes are therefore visited in the order of their root
+//     paths written as bits (0 near / 1 far per ancestor), compared left-aligned; when one path is a prefix of the other and
+//     the rest is all "near", the shorter path (the ancestor) comes first.
+// A0: every member climbs to the root once and stages its ancestors (coordinate on the ancestor's axis + its own side).
+// A1: the in-range (u, v) pairs of the cluster are listed.  A2: one lane per PAIR evaluates visibility and the path key
+// against v's staged chain.  A3: one lane per member ranks its visible neighbours, later visit first (the reference's list
+// order: head insertion, kdtree.cpp:469-486).  B: the FIFO of expandCluster is replayed from the lists, one warp step per
+// popped member.  Anything that does not fit falls back to the walk.
+#ifndef ECB_BFS_SMALL
+#define ECB_BFS_SMALL 1
+#endif
+constexpr int SM_MAXM = 48;      // members
+constexpr int SM_MAXDEG = 32;    // visible neighbours of one member inside the cluster (one lane each when the member is popped)
+constexpr int SM_MAXDEPTH = 48;  // tree depth of a member: 48 path bits + 6 depth bits in one 64-bit key
+constexpr int SM_MAXPAIR = SM_MAXM * SM_MAXDEG;  // in-range ordered pairs of the cluster
+constexpr unsigned long long SM_UNSEEN = ~0ull;
+
+struct SmallScratch {
+    uint32_t pix[SM_MAXM], node[SM_MAXM];
+    uint8_t depth[SM_MAXM], deg[SM_MAXM], order[SM_MAXM];
+    uint16_t pbase[SM_MAXM + 1];
+    uint8_t nbr[SM_MAXM][SM_MAXDEG];
+    uint8_t pair_v[SM_MAXPAIR];
+    unsigned long long pair_key[SM_MAXPAIR];
+    union {
+        uint16_t chain[SM_MAXM][SM_MAXDEPTH];  // ancestors of member i, parent first: coordinate on the ancestor's axis | (i is on its right) << 15
+        unsigned long long sel[SM_MAXM];       // afterwards: std::nth_element staging, norm^2 << 32 | node
+    };
+};
+
+// returns the number of members placed in O (== sz on success), or -1 when the cluster does not fit the fast path
+__device__ __forceinline__ int bfs_small(const PixTree &tr, const BfsItem &it, uint32_t *O, SmallScratch &w, int lane) {
+    const int sz = it.size;
+    if (sz > SM_MAXM) return -1;
+    bool bad = false;
+    // A0
+    for (int i = lane; i < sz; i += 32) {
+        const uint32_t nd = O[i];
+        w.node[i] = nd;
+        w.pix[i] = tr.pix[nd];
+        int dep = 0;  // depth first (an ancestor's axis is the parity of ITS depth), then the chain; the second climb hits L1
+        for (uint32_t c = __ldg(tr.nodes + nd).w; c != ECB_NONE && dep <= SM_MAXDEPTH; c = __ldg(tr.nodes + c).w) ++dep;
+        bad |= dep > SM_MAXDEPTH;
+        w.depth[i] = (uint8_t) dep;
+        if (dep <= SM_MAXDEPTH) {
+            uint32_t child = nd, anc = __ldg(tr.nodes + nd).w;
+            for (int st = 0; st < dep; ++st) {
+                const uint4 an = __ldg(tr.nodes + anc);
+                const uint32_t c = ((dep - 1 - st) & 1) ? ECB_PIX_Y(an.x) : ECB_PIX_X(an.x);
+                w.chain[i][st] = (uint16_t) (c | (child == an.z ? 0x8000u : 0u));
+                child = anc;
+                anc = an.w;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad)) return -2;
+    __syncwarp();
+    // A1: in-range pairs, grouped by u
+    int cnt[2] = {0, 0};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = lane + 32 * r;
+        if (i < sz) {
+            const uint32_t pu = w.pix[i];
+            const int ux = (int) ECB_PIX_X(pu), uy = (int) ECB_PIX_Y(pu);
+            for (int j = 0; j < sz; ++j) {
+                const uint32_t pv = w.pix[j];
+                const int ex = (int) ECB_PIX_X(pv) - ux, ey = (int) ECB_PIX_Y(pv) - uy;
+                cnt[r] += (j != i) && (ex * ex + ey * ey <= tr.eps2i);
+            }
+        }
+    }
+    const uint32_t inc0 = warp_incl_scan((uint32_t) cnt[0]);
+    const uint32_t tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+    const uint32_t inc1 = warp_incl_scan((uint32_t) cnt[1]);
+    const int n_pair = (int) (tot0 + __shfl_sync(0xffffffffu, inc1, 31));
+    if (n_pair > SM_MAXPAIR) return -3;
+    {
+        const int base[2] = {(int) (inc0 - cnt[0]), (int) (tot0 + inc1 - cnt[1])};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = lane + 32 * r;
+            if (i < sz) {
+                w.pbase[i] = (uint16_t) base[r];
+                const uint32_t pu = w.pix[i];
+                const int ux = (int) ECB_PIX_X(pu), uy = (int) ECB_PIX_Y(pu);
+                int o = base[r];
+                for (int j = 0; j < sz; ++j) {
+                    const uint32_t pv = w.pix[j];
+                    const int ex = (int) ECB_PIX_X(pv) - ux, ey = (int) ECB_PIX_Y(pv) - uy;
+                    if ((j != i) && (ex * ex + ey * ey <= tr.eps2i)) {
+                        w.pair_v[o] = (uint8_t) j;
+                        w.pair_key[o] = (unsigned long long) i;  // u, replaced by the key in A2
+                        ++o;
+                    }
+                }
+            }
+        }
+        if (lane == 0) w.pbase[sz] = (uint16_t) n_pair;
+    }
+    __syncwarp();
+    // A2: one lane per pair
+    for (int p = lane; p < n_pair; p += 32) {
+        const int u = (int) w.pair_key[p], v = (int) w.pair_v[p];
+        const uint32_t pu = w.pix[u];
+        const int ux = (int) ECB_PIX_X(pu), uy = (int) ECB_PIX_Y(pu);
+        const int dv = (int) w.depth[v];
+        unsigned long long bits = 0;
+        bool seen = true;
+        for (int st = dv - 1; st >= 0; --st) {  // root first
+            const uint32_t e = w.chain[v][st];
+            const int dx = (((dv - 1 - st) & 1) ? uy : ux) - (int) (e & 0x7FFFu);
+            const bool far = (dx <= 0) == (bool) (e >> 15);  // the near child is the left one iff dx <= 0
+            if (far && !tr.far_ok(dx)) {
+                seen = false;
+                break;
+            }
+            bits = (bits << 1) | (far ? 1ull : 0ull);
+        }
+        w.pair_key[p] = seen ? (((bits << (SM_MAXDEPTH - dv)) << 6) | (unsigned long long) dv) : SM_UNSEEN;
+    }
+    __syncwarp();
+    // A3: rank the visible neighbours of every member by descending key (keys of one member are distinct)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = lane + 32 * r;
+        if (i < sz) {
+            const int b = w.pbase[i], e = w.pbase[i + 1];
+            int deg = 0;
+            for (int k = b; k < e; ++k) {
+                const unsigned long long kk = w.pair_key[k];
+                if (kk == SM_UNSEEN) continue;
+                ++deg;
+                int rk = 0;
+                for (int q = b; q < e; ++q) {
+                    const unsigned long long kq = w.pair_key[q];
+                    rk += kq != SM_UNSEEN && kq > kk;
+                }
+                if (rk < SM_MAXDEG) w.nbr[i][rk] = w.pair_v[k];
+            }
+            bad |= deg > SM_MAXDEG;
+            w.deg[i] = (uint8_t) deg;
+        }
+    }
+    if (__any_sync(0xffffffffu, bad)) return -4;
+    __syncwarp();
+    // B: the FIFO of expandCluster, the unseen neighbours of the popped member appended in list order
+    uint32_t seen_lo = 1u, seen_hi = 0u;  // member 0 = the seed (lowest pid)
+    if (lane == 0) w.order[0] = 0;
+    int tail = 1;
+    for (int h = 0; h < tail; ++h) {
+        __syncwarp();
+        const int u = w.order[h];
+        const int d = w.deg[u];
+        int v = 0;
+        bool fresh = false;
+        if (lane < d) {
+            v = w.nbr[u][lane];
+            fresh = !(((v < 32 ? seen_lo : seen_hi) >> (v & 31)) & 1u);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, fresh);
+        if (!bal) continue;
+        if (fresh) w.order[tail + __popc(bal & ((1u << lane) - 1u))] = (uint8_t) v;
+        seen_lo |= __reduce_or_sync(0xffffffffu, (fresh && v < 32) ? 1u << v : 0u);
+        if (sz > 32) seen_hi |= __reduce_or_sync(0xffffffffu, (fresh && v >= 32) ? 1u << (v - 32) : 0u);
+        tail += __popc(bal);
+    }
+    __syncwarp();
+    for (int i = lane; i < tail; i += 32) O[i] = w.node[w.order[i]];
+    __syncwarp();
+    return tail;
+}
+
 __global__ void __launch_bounds__(BFS_THREADS) k_bfs_order(const BfsArgs a) {
     __shared__ unsigned s_cnt[BFS_WARPS];
+#if ECB_BFS_SMALL
+    __shared__ SmallScratch s_small[BFS_WARPS];
+#endif
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned n_items = min(*a.count, (unsigned) a.max_items);
 
@@ -273,32 +459,58 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs_order(const BfsArgs a) {
         tr.pix = pix;
         tr.nodes = a.kd_nodes[d.pol] + d.off;  // one 16-byte load per node visit
         tr.set_eps(a.eps);
-        const int le = bfs_cluster(tr, 0u, it, lab, O, F, key, a.init_keys != 0, &s_cnt[wib], lane);
+        int le = -1;
+#if ECB_BFS_SMALL
+        if (a.init_keys) le = bfs_small(tr, it, O, s_small[wib], lane);  // O holds the member list (front-end items) only then
+#endif
+        const bool small = le >= 0;
+        if (!small) le = bfs_cluster(tr, 0u, it, lab, O, F, key, a.init_keys != 0, &s_cnt[wib], lane);
         // the reference's median: nth_element over the member list by norm (CirclesEventFrame.cpp:137-147)
-        if (it.kept >= 0 && a.ktab && lane == 0 && le == sz) {
-            auto less = [&](uint32_t l, uint32_t r) {
-                const uint32_t pl = pix[l], pr = pix[r];
-                const uint32_t nl = ECB_PIX_X(pl) * ECB_PIX_X(pl) + ECB_PIX_Y(pl) * ECB_PIX_Y(pl);
-                const uint32_t nr = ECB_PIX_X(pr) * ECB_PIX_X(pr) + ECB_PIX_Y(pr) * ECB_PIX_Y(pr);
-                return nl < nr;
+        if (it.kept >= 0 && a.ktab && le == sz) {
+            uint32_t med = 0;
+            auto norm2 = [&](uint32_t m) {
+                const uint32_t p = pix[m];
+                return ECB_PIX_X(p) * ECB_PIX_X(p) + ECB_PIX_Y(p) * ECB_PIX_Y(p);
             };
-            ecb_nth::nth_element(O, (long) sz, (long) (sz / 2), less);
-            const uint32_t med = O[sz / 2];
-            KeptCluster *kc = a.ktab + (size_t) it.pb * a.max_k + it.kept;
-            kc->med_pid = (int32_t) med;
-            kc->med_x = (int32_t) ECB_PIX_X(pix[med]) + 0;
-            kc->med_y = (int32_t) ECB_PIX_Y(pix[med]) + 0;
+#if ECB_BFS_SMALL
+            if (small) {  // the selection is sequential: run it on a shared-memory copy, put the permuted list back in parallel
+                unsigned long long *x = s_small[wib].sel;
+                for (int i = lane; i < sz; i += 32) {
+                    const uint32_t m = O[i];
+                    x[i] = ((unsigned long long) norm2(m) << 32) | m;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    auto less = [](unsigned long long l, unsigned long long r) { return (uint32_t) (l >> 32) < (uint32_t) (r >> 32); };
+                    ecb_nth::nth_element(x, (long) sz, (long) (sz / 2), less);
+                }
+                __syncwarp();
+                for (int i = lane; i < sz; i += 32) O[i] = (uint32_t) x[i];
+                med = (uint32_t) x[sz / 2];
+            } else
+#endif
+            if (lane == 0) {
+                auto less = [&](uint32_t l, uint32_t r) { return norm2(l) < norm2(r); };
+                ecb_nth::nth_element(O, (long) sz, (long) (sz / 2), less);
+                med = O[sz / 2];
+            }
+            if (lane == 0) {
+                KeptCluster *kc = a.ktab + (size_t) it.pb * a.max_k + it.kept;
+                kc->med_pid = (int32_t) med;
+                kc->med_x = (int32_t) ECB_PIX_X(pix[med]) + 0;
+                kc->med_y = (int32_t) ECB_PIX_Y(pix[med]) + 0;
+            }
         }
         __syncwarp();
     }
 }
 
 // general points (ecb_gridhash.cu): same BFS over the emulated tree of double coordinates
-__global__ void __launch_bounds__(BFS_THREADS) k_bfs_order_general(const BfsArgs a, const double *__restrict__ P, int dim) {
-    __shared__ unsigned s_cnt[BFS_WARPS];
+__global__ void __launch_bounds__(BFSG_THREADS) k_bfs_order_general(const BfsArgs a, const double *__restrict__ P, int dim) {
+    __shared__ unsigned s_cnt[BFSG_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned n_items = min(*a.count, (unsigned) a.max_items);
-    for (unsigned item = blockIdx.x * BFS_WARPS + wib; item < n_items; item += gridDim.x * BFS_WARPS) {
+    for (unsigned item = blockIdx.x * BFSG_WARPS + wib; item < n_items; item += gridDim.x * BFSG_WARPS) {
         BfsItem it = a.items[item];
         const ProbDesc d = a.prob[it.pb];
         // the emulated tree of the general path links points by their index in the whole batch: the walk runs in that index
@@ -383,16 +595,18 @@ int ecb_launch_bfs_all_items(ecb_ctx *ctx, const ProbDesc *prob, const ProbHdr *
 int ecb_launch_bfs_general(ecb_ctx *ctx, BfsArgs &a, const double *P, int dim) {
     if (a.max_items <= 0) return ECB_OK;
     int grid = ctx->sm_count * 8;
-    const int need = (a.max_items + BFS_WARPS - 1) / BFS_WARPS;
+    const int need = (a.max_items + BFSG_WARPS - 1) / BFSG_WARPS;
     if (grid > need) grid = need;
-    k_bfs_order_general<<<grid, BFS_THREADS, 0, ctx->stream>>>(a, P, dim);
+    k_bfs_order_general<<<grid, BFSG_THREADS, 0, ctx->stream>>>(a, P, dim);
     ECB_LAUNCHED(ctx);
     return ecb_check(ctx, cudaGetLastError(), "k_bfs_order_general launch");
 }
 
 int ecb_launch_bfs(ecb_ctx *ctx, BfsArgs &a) {
     if (a.max_items <= 0) return ECB_OK;
-    int grid = ctx->sm_count * 8;
+    int per_sm = 8;  // resident CTAs (the small-cluster scratch in shared memory decides); items are strided over the grid
+    ECB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bfs_order, BFS_THREADS, 0));
+    int grid = ctx->sm_count * std::max(per_sm, 1);
     const int need = (a.max_items + BFS_WARPS - 1) / BFS_WARPS;
     if (grid > need) grid = need;
     ECB_PROF_BEGIN(ctx, ECB_STAGE_BFS);

@@ -51,6 +51,9 @@ struct ecb_ctx {
     int cand_stride = 0;
     // exact member order / medians (ecb_bfs.cu): exported kd-tree, claim keys, work items, frontier scratch
     DevBuf kd_tree, bfs_key, bfs_items, bfs_front, bfs_tab;
+    // k_uset_order: std::hash<double> of every integer coordinate of the sensor (+ the hash_combine constant)
+    DevBuf ord_htab;
+    int ord_htab_n = 0;
     // dbscan boundary
     DevBuf db_pix, db_off, db_labels, db_hdr, db_scratch, db_dims, db_hdr_b, db_ktab, db_counter;
     DevBuf gh[ECB_GH_NBUF];   // general path (ecb_gridhash.cu)

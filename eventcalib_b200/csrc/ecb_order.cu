@@ -17,6 +17,11 @@
 // costs about two passes over the final set.  Checked against the real std::unordered_set in tests/test_gpu_frontend.py.
 //
 // One CTA per (window, polarity); all arrays in shared memory when they fit, else in per-CTA L2 scratch.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "ecb_window.cuh"
 
 namespace {
@@ -29,12 +34,22 @@ __constant__ uint32_t c_prime[ORD_NSTAGE] = {13,    29,     59,     127,    257,
 static const uint32_t h_prime[ORD_NSTAGE] = {13,    29,     59,     127,    257,    541,     1109,   2357,   5087,
                                              10273, 20753,  42043,  85229,  172933, 351061,  712697, 1447153};
 
+#ifndef ECB_ORD_HTAB
+#define ECB_ORD_HTAB 1  // coordinate hashes from a table (one entry per sensor column / row) instead of two murmur rounds per pixel
+#endif
+
 // std::hash<double> of libstdc++: 0 for +-0.0, else _Hash_bytes(&v, 8, 0xc70f6907) (64-bit murmur variant)
-__device__ __forceinline__ uint64_t hash_double(double v) {
+__host__ __device__ __forceinline__ uint64_t hash_double(double v) {
     if (v == 0.0) return 0;
     const uint64_t mul = (0xc6a4a793ull << 32) + 0x5bd1e995ull;
     uint64_t h = 0xc70f6907ull ^ (8ull * mul);
+#ifdef __CUDA_ARCH__
     uint64_t d = (uint64_t) __double_as_longlong(v) * mul;
+#else
+    uint64_t d;
+    memcpy(&d, &v, 8);
+    d *= mul;
+#endif
     d ^= d >> 47;
     d *= mul;
     h ^= d;
@@ -51,6 +66,12 @@ __device__ __forceinline__ uint64_t hash_pixel(uint32_t pix) {
     seed ^= hash_double((double) ECB_PIX_X(pix)) + 0x9e3779b9ull + (seed << 6) + (seed >> 2);
     seed ^= hash_double((double) ECB_PIX_Y(pix)) + 0x9e3779b9ull + (seed << 6) + (seed >> 2);
     return seed;
+}
+
+// the same with tab[v] = hash_double((double) v) + 0x9e3779b9 (the seed starts at 0, so the first combine is the table entry)
+__device__ __forceinline__ uint64_t hash_pixel_tab(uint32_t pix, const unsigned long long *__restrict__ tab) {
+    const uint64_t seed = __ldg(tab + ECB_PIX_X(pix));
+    return seed ^ (__ldg(tab + ECB_PIX_Y(pix)) + (seed << 6) + (seed >> 2));
 }
 
 // h % c_prime[stage] with compile-time divisors (the stage is uniform across the CTA)
@@ -120,7 +141,8 @@ __global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_ord
             for (int p = tid; p < newN; p += nthr) {
                 const uint32_t e = p < prevN ? cur[p] : (uint32_t) p;
                 if (p >= prevN) cur[p] = e;
-                const uint32_t b = bucket_of(hash_pixel(arr[e] & 0x3FFFFFFFu), stage);
+                const uint32_t px = arr[e] & 0x3FFFFFFFu;
+                const uint32_t b = bucket_of((ECB_ORD_HTAB && a.htab) ? hash_pixel_tab(px, a.htab) : hash_pixel(px), stage);
                 bk[p] = b;
                 atomicMin(&first[b], (uint32_t) p);
                 chain[p] = atomicExch(&head[b], (uint32_t) p);
@@ -205,6 +227,20 @@ int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
     if (max_m > (int) h_prime[ORD_NSTAGE - 1]) return ecb_fail(ctx, ECB_ERR_UNSUPPORTED, "window with %d distinct pixels", max_m);
     int st = 0;
     while ((int) h_prime[st] < max_m) ++st;
+    a.htab = nullptr;
+    if (ECB_ORD_HTAB) {  // the coordinate hashes of this sensor, uploaded once per context
+        const int nt = std::max(ctx->width, ctx->height);
+        if (nt > 0 && ctx->ord_htab_n != nt) {
+            std::vector<unsigned long long> tab((size_t) nt);
+            for (int v = 0; v < nt; ++v) tab[(size_t) v] = hash_double((double) v) + 0x9e3779b9ull;
+            int rc = ecb_reserve(ctx, ctx->ord_htab, (size_t) nt * 8);
+            if (rc) return rc;
+            ECB_CUDA(ctx, cudaMemcpyAsync(ctx->ord_htab.p, tab.data(), (size_t) nt * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->ord_htab_n = nt;
+        }
+        if (ctx->ord_htab_n == nt && nt > 0) a.htab = (const unsigned long long *) ctx->ord_htab.p;
+    }
     a.m_cap = (max_m + 3) & ~3;
     a.b_cap = ((int) h_prime[st] + 3) & ~3;
     const size_t words = (size_t) 4 * a.m_cap + (size_t) 3 * a.b_cap;

@@ -26,6 +26,7 @@ struct OrderArgs {
     uint32_t *gscratch;
     size_t gscratch_stride;
     int arrays_in_smem, m_cap, b_cap;
+    const unsigned long long *htab;  // [max(W, H)] hash_double((double) v) + 0x9e3779b9 (NULL: hash computed per pixel)
 };
 
 struct PairArgs {
