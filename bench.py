@@ -660,6 +660,16 @@ def main():
         args.slices = 8 if world == 1 else max(2, min(8, (os.cpu_count() or 16) // world))
     plan = [float(v) for v in args.slice_plan.split(",")] if args.slice_plan else [1.0] * max(1, min(args.slices, len(win)))
     S = len(plan)
+    # Host waits: a slice thread spins in cudaStreamSynchronize by default.  When the ranks' slice threads outnumber the host
+    # cores (8 ranks x 4 slices on the 32-core 8-GPU box) the spinning threads starve each other, so the slice contexts then
+    # sleep on an event instead (ECB_BLOCKING_SYNC, read by ecb_ctx_create).  ECB_BENCH_SYNC=spin|block|yield overrides (yield: poll + sched_yield).
+    sync_mode = os.environ.get("ECB_BENCH_SYNC", "auto")
+    if sync_mode == "auto":
+        # (8 ranks x 4 slices on 32 cores, e2e ms per step: yield 29.8, spin 30.4, block 31.9; 1 rank on 16 cores: spin 12.3,
+        #  block 14.4 — profiles/r2t_n8_e2e_trace.md)
+        sync_mode = "yield" if world * (S + 1) > (os.cpu_count() or 16) else "spin"
+    if sync_mode in ("block", "yield"):
+        os.environ["ECB_BLOCKING_SYNC"] = "1" if sync_mode == "block" else "2"
     cuts = np.round(np.cumsum([0.0] + plan) / sum(plan) * len(win)).astype(int)
     slices = []
     for j in range(S):
@@ -686,6 +696,8 @@ def main():
     trace = os.environ.get("ECB_BENCH_TRACE")
     stagger = float(os.environ.get("ECB_BENCH_STAGGER_US", "0")) * 1e-6
     t_origin = [0.0]
+    load_done = [0.0] * S
+    h2d_done = []   # per step: host time at which the LAST slice's records had arrived, relative to the step start
 
     def slice_work(j):
         sl = slices[j]
@@ -706,13 +718,15 @@ def main():
             cost = c.cost_eval(intr, rot, trans)       # synchronises the slice's stream
         tm.append(time.perf_counter())
         if trace:
-            sys.stderr.write("slice %d: start %.2f load_end %.2f frontend_end %.2f cost_end %.2f ms\n" % (
-                (j,) + tuple((x - t_origin[0]) * 1e3 for x in tm)))
+            sys.stderr.write("rank %d slice %d: start %.2f load_end %.2f frontend_end %.2f cost_end %.2f ms\n" % (
+                (rank, j) + tuple((x - t_origin[0]) * 1e3 for x in tm)))
+        load_done[j] = tm[1] - t_origin[0]   # when this slice's records (H2D + unpack) were on the device
         return out + (cost,)
 
     def step_e2e():
         t_origin[0] = time.perf_counter()
         res = list(pool.map(slice_work, range(S)))
+        h2d_done.append(max(load_done))
         if do_res:
             torch.sum(d_parts, dim=0, out=d_ne)   # the packed buffer ends with the cost: summed with the rest
             if world > 1:
@@ -763,7 +777,13 @@ def main():
     # end to end through the C ABI with host buffers
     s, c = step_e2e()
     step_e2e()
+    del h2d_done[:]
     ms_e2e = timed(step_e2e, args.steps)
+    h2d_done_ms = float(np.mean(h2d_done)) * 1e3 if h2d_done else 0.0
+    if world > 1:   # the step lasts as long as its slowest rank: report that rank's arrival time
+        t_ = torch.tensor([h2d_done_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        h2d_done_ms = float(t_.item())
     clocks = sampler.stop() if sampler else None
     e2e_value = world * n_pass * args.steps / (ms_e2e * 1e-3)
     h2d = n * 25 + win.nbytes * len(sweep) + ((9 + 7 * len(rot)) * 8 * 2 if do_res else 0)
@@ -848,8 +868,11 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "pipeline": "%d time slices (relative sizes %s), one context/stream/host thread each "
-                        "(H2D of slice k+1 overlaps the kernels of slice k)" % (S, ":".join("%g" % v for v in plan)),
-                        "h2d_copy_gbs": h2d_gbs, "pcie_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3 if h2d_gbs > 0 else None}}
+                        "(H2D of slice k+1 overlaps the kernels of slice k); host waits: %s" % (S, ":".join("%g" % v for v in plan), sync_mode),
+                        "h2d_copy_gbs": h2d_gbs, "pcie_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3 if h2d_gbs > 0 else None,
+                        # measured inside the timed steps: when the last record of the step had reached the (slowest) GPU; the
+                        # rest of the step is the last slice's kernels + result copies
+                        "h2d_done_ms": h2d_done_ms, "frac_h2d_done": h2d_done_ms / (ms_e2e / args.steps)}}
         if world > 1:
             floor = n * 25 * world / (h2d_all_gbs * 1e9) * 1e3
             line["e2e"]["numa"] = numa if numa else "not bound (single NUMA node or topology not exposed)"

@@ -1,5 +1,6 @@
 // C ABI of libecb: context, ingest, batched front end, DBSCAN::Run boundary, batched circle fit.
 // See include/eventcalib_b200.h for the reference interface each entry point replaces.
+#include <sched.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -27,7 +28,7 @@ int ecb_check(ecb_ctx *ctx, cudaError_t e, const char *what) {
 int ecb_reserve(ecb_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap && b.p) return ECB_OK;
     if (b.p) {
-        cudaStreamSynchronize(ctx->stream);
+        ecb_stream_sync(ctx);
         cudaFree(b.p);
         b.p = nullptr;
         b.cap = 0;
@@ -45,6 +46,15 @@ __global__ void k_pull(uint32_t *__restrict__ dst, const uint32_t *__restrict__ 
         ((uint8_t *) dst)[words * 4 + threadIdx.x] = ((const uint8_t *) src)[words * 4 + threadIdx.x];
 }
 
+cudaError_t ecb_stream_sync(ecb_ctx *ctx) {
+    if (!ctx->sync_mode || !ctx->sync_ev) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->sync_ev, ctx->stream);
+    if (e != cudaSuccess) return e;
+    if (ctx->sync_mode == 1) return cudaEventSynchronize(ctx->sync_ev);  // sleeps until the driver wakes the thread
+    while ((e = cudaEventQuery(ctx->sync_ev)) == cudaErrorNotReady) sched_yield();  // polls, but gives the core away in between
+    return e;
+}
+
 static int reserve_pinned(ecb_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->pinned_cap) return ECB_OK;
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -59,10 +69,10 @@ static int reserve_pinned(ecb_ctx *ctx, size_t bytes) {
 // Device -> host copy + stream synchronisation through the context's pinned staging buffer: a cudaMemcpyAsync into
 // pageable memory takes the driver's slow staged path and serialises against other threads' transfers.
 int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes == 0) return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "stream synchronize");
+    if (bytes == 0) return ecb_check(ctx, ecb_stream_sync(ctx), "stream synchronize");
     if (bytes > ((size_t) 256 << 20)) {
         ECB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "device to host copy");
+        return ecb_check(ctx, ecb_stream_sync(ctx), "device to host copy");
     }
     int rc = reserve_pinned(ctx, bytes);
     if (rc) return rc;
@@ -79,7 +89,7 @@ int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     } else {
         ECB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ECB_CUDA(ctx, ecb_stream_sync(ctx));
     ctx->up_off = 0;  // every staged upload has been pulled
     memcpy(dst, ctx->pinned, bytes);
     return ECB_OK;
@@ -92,7 +102,7 @@ int ecb_h2d(ecb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     const size_t need = (bytes + 255) & ~(size_t) 255;
     if (ctx->up_off + need > ctx->up_cap) {
         // everything staged so far must have been pulled before the region is reused (or replaced)
-        ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ECB_CUDA(ctx, ecb_stream_sync(ctx));
         ctx->up_off = 0;
         if (need > ctx->up_cap) {
             if (ctx->up) cudaFreeHost(ctx->up);
@@ -152,6 +162,9 @@ int ecb_ctx_create(int device, void *stream, ecb_ctx **out) {
         }
         c->own_stream = true;
     }
+    if (const char *e = getenv("ECB_BLOCKING_SYNC"))
+        if (atoi(e) > 0 && cudaEventCreateWithFlags(&c->sync_ev, (atoi(e) == 1 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming) == cudaSuccess)
+            c->sync_mode = atoi(e) == 1 ? 1 : 2;
     *out = c;
     return ECB_OK;
 }
@@ -175,6 +188,7 @@ void ecb_ctx_destroy(ecb_ctx *c) {
     for (int i = 0; i < ECB_N_STAGES; ++i)
         for (int j = 0; j < 2; ++j)
             if (c->pev[i][j]) cudaEventDestroy(c->pev[i][j]);
+    if (c->sync_ev) cudaEventDestroy(c->sync_ev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->up) cudaFreeHost(c->up);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -187,7 +201,7 @@ uint64_t ecb_launch_count(const ecb_ctx *ctx) { return ctx ? ctx->launches : 0; 
 int ecb_synchronize(ecb_ctx *ctx) {
     if (!ctx) return ECB_ERR_ARG;
     cudaSetDevice(ctx->device);
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "stream synchronize");
+    return ecb_check(ctx, ecb_stream_sync(ctx), "stream synchronize");
 }
 
 int ecb_set_profiling(ecb_ctx *ctx, int on) {
@@ -204,7 +218,7 @@ int ecb_set_profiling(ecb_ctx *ctx, int on) {
 int ecb_stage_ms(ecb_ctx *ctx, float *out) {
     if (!ctx || !out) return ECB_ERR_ARG;
     cudaSetDevice(ctx->device);
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ECB_CUDA(ctx, ecb_stream_sync(ctx));
     for (int i = 0; i < ECB_N_STAGES; ++i) {
         out[i] = 0.f;
         if (ctx->pev_used[i]) ECB_CUDA(ctx, cudaEventElapsedTime(&out[i], ctx->pev[i][0], ctx->pev[i][1]));
@@ -486,13 +500,13 @@ int ecb_frontend_points(ecb_ctx *ctx, int polarity, double *xy, int32_t *labels)
     if (xy) {
         std::vector<uint32_t> pix(slots);
         ECB_CUDA(ctx, cudaMemcpyAsync(pix.data(), ctx->pts[polarity].p, slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ECB_CUDA(ctx, ecb_stream_sync(ctx));
         for (size_t i = 0; i < slots; ++i) {
             xy[2 * i] = (double) ECB_PIX_X(pix[i]);
             xy[2 * i + 1] = (double) ECB_PIX_Y(pix[i]);
         }
     }
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "points copy");
+    return ecb_check(ctx, ecb_stream_sync(ctx), "points copy");
 }
 
 int ecb_frontend_candidates(ecb_ctx *ctx, double *out, int max_cand) {
@@ -505,7 +519,7 @@ int ecb_frontend_candidates(ecb_ctx *ctx, double *out, int max_cand) {
     if (rc) return rc;
     ECB_CUDA(ctx, cudaMemcpy2DAsync(ctx->pinned, (size_t) k * 40, ctx->cand.p, (size_t) ctx->cand_stride * 40, (size_t) k * 40,
                                     (size_t) ctx->n_win, cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ECB_CUDA(ctx, ecb_stream_sync(ctx));
     for (int w = 0; w < ctx->n_win; ++w)
         memcpy(out + (size_t) w * max_cand * 5, (const char *) ctx->pinned + (size_t) w * k * 40, (size_t) k * 40);
     return ECB_OK;
@@ -522,7 +536,7 @@ int ecb_frontend_clusters(ecb_ctx *ctx, int window, int polarity, int32_t *raw_i
     ECB_CUDA(ctx, cudaMemcpyAsync(&h, (ProbHdr *) ctx->db_hdr.p + pb, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     ECB_CUDA(ctx, cudaMemcpyAsync(k.data(), (KeptCluster *) ctx->ktab.p + pb * max_k, sizeof(KeptCluster) * max_k,
                                   cudaMemcpyDeviceToHost, ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ECB_CUDA(ctx, ecb_stream_sync(ctx));
     int n = std::min(h.n_kept, cap);
     for (int i = 0; i < n; ++i) {
         if (raw_id) raw_id[i] = k[i].raw_id;
@@ -729,7 +743,7 @@ static int dbscan_batch(ecb_ctx *ctx, const double *xy, const int64_t *offsets, 
     if (labels) ECB_CUDA(ctx, cudaMemcpyAsync(labels, ctx->db_labels.p, (size_t) total * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ECB_CUDA(ctx, cudaMemcpyAsync(hdr.data(), ctx->db_hdr_b.p, (size_t) n_problems * sizeof(ProbHdr), cudaMemcpyDeviceToHost,
                                   ctx->stream));
-    ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ECB_CUDA(ctx, ecb_stream_sync(ctx));
     for (int k = 0; k < n_problems; ++k) {
         if (n_clusters) n_clusters[k] = hdr[(size_t) k].n_clusters;
         if (status) status[k] = hdr[(size_t) k].status;
@@ -794,7 +808,7 @@ int ecb_fit_circles(ecb_ctx *ctx, const double *xy, const int64_t *offsets, int 
                              (double *) ctx->fit_out.p)))
         return rc;
     ECB_CUDA(ctx, cudaMemcpyAsync(out, ctx->fit_out.p, (size_t) n_sets * 24, cudaMemcpyDeviceToHost, ctx->stream));
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "fit copy");
+    return ecb_check(ctx, ecb_stream_sync(ctx), "fit copy");
 }
 
 // ---- receive buffers of the multi-GPU exchange ----

@@ -35,6 +35,11 @@ struct ecb_ctx {
     int smem_optin = 0;
     int width = 0, height = 0;
     bool prof = false;
+    // How the host waits for the stream (ECB_BLOCKING_SYNC, read at creation): 0 cudaStreamSynchronize (spins), 1 sleep on a
+    // blocking event, 2 poll an event with sched_yield() in between — for many contexts / ranks on few host cores (8 ranks x 4
+    // slice threads on a 32-core box starve each other when every wait spins)
+    int sync_mode = 0;
+    cudaEvent_t sync_ev = nullptr;
     cudaEvent_t pev[ECB_N_STAGES][2] = {};
     bool pev_used[ECB_N_STAGES] = {};
 
@@ -71,6 +76,7 @@ struct ecb_ctx {
 int ecb_fail(ecb_ctx *ctx, int code, const char *fmt, ...);
 int ecb_reserve(ecb_ctx *ctx, DevBuf &b, size_t bytes);
 int ecb_check(ecb_ctx *ctx, cudaError_t e, const char *what);
+cudaError_t ecb_stream_sync(ecb_ctx *ctx);  // wait for the context's stream (spinning or sleeping, see blocking_sync)
 int ecb_d2h(ecb_ctx *ctx, void *dst, const void *src, size_t bytes);  // pinned-staged copy + stream sync
 // Small host -> device upload that does not touch the copy engines: the data is staged in mapped pinned memory and a
 // kernel on the context stream pulls it over PCIe, so it cannot queue behind another context's bulk record upload.

@@ -840,7 +840,7 @@ int ecb_cost_setup(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const doubl
     ECB_CUDA(ctx, cudaMemcpyAsync(st->d_ncp.p, st->n_cp.data(), (size_t) n_splines * 4, cudaMemcpyHostToDevice, ctx->stream));
     ECB_CUDA(ctx, cudaMemcpyAsync(st->d_cp_off.p, st->cp_off.data(), (size_t) n_splines * 4, cudaMemcpyHostToDevice, ctx->stream));
     ECB_CUDA(ctx, cudaMemcpyAsync(st->d_span_off.p, st->span_off.data(), (size_t) n_splines * 4, cudaMemcpyHostToDevice, ctx->stream));
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "cost setup");
+    return ecb_check(ctx, ecb_stream_sync(ctx), "cost setup");
 }
 
 int ecb_cost_set_rotation_model(ecb_ctx *ctx, int use_so3) {
@@ -1002,7 +1002,7 @@ int ecb_cost_get_association(ecb_ctx *ctx, int64_t *event_index, int32_t *circle
         ECB_CUDA(ctx, cudaMemcpyAsync(event_index, st->sel_event.p, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (n > 0 && circle_id)
         ECB_CUDA(ctx, cudaMemcpyAsync(circle_id, st->sel_circle.p, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "association copy");
+    return ecb_check(ctx, ecb_stream_sync(ctx), "association copy");
 }
 
 // ---- launches shared by the host-parameter entry points and the device-side LM loop (ecb_lmdev.cu) ----

@@ -763,7 +763,7 @@ int ecb_lm_device_create(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const
         return rc;
     }
     cudaMemcpyAsync(lm->tab.p, tabv.data(), tabv.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
+    ecb_stream_sync(ctx);
     const int *t = (const int *) lm->tab.p;
     lm->dims.C = C;
     lm->dims.n = n;
@@ -801,7 +801,7 @@ int ecb_lm_device_create(ecb_ctx *ctx, int n_splines, const int32_t *n_cp, const
                       (LmScalars *) (m + o_s)};
     lm->d_cand_cost = m + o_cc;
     *out = lm;
-    return ecb_check(ctx, cudaStreamSynchronize(ctx->stream), "device LM allocation");
+    return ecb_check(ctx, ecb_stream_sync(ctx), "device LM allocation");
 }
 
 void ecb_lm_device_destroy(ecb_lm_device *lm) {

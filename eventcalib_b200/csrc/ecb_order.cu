@@ -236,7 +236,7 @@ int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
             int rc = ecb_reserve(ctx, ctx->ord_htab, (size_t) nt * 8);
             if (rc) return rc;
             ECB_CUDA(ctx, cudaMemcpyAsync(ctx->ord_htab.p, tab.data(), (size_t) nt * 8, cudaMemcpyHostToDevice, ctx->stream));
-            ECB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ECB_CUDA(ctx, ecb_stream_sync(ctx));
             ctx->ord_htab_n = nt;
         }
         if (ctx->ord_htab_n == nt && nt > 0) a.htab = (const unsigned long long *) ctx->ord_htab.p;
