@@ -639,10 +639,17 @@ def main():
             dist.all_reduce(d_ne)
             xch_check = float((a_x - d_ne).abs().max().item() / max(float(d_ne.abs().max().item()), 1e-300))
 
+        d_kf_t = torch.from_numpy(np.ascontiguousarray(mine["kf_t"], np.float64)).cuda()
+        d_kf_c = torch.from_numpy(np.ascontiguousarray(mine["circles"], np.float64)).cuda()
+        d_lm = torch.from_numpy(np.ascontiguousarray(mine["landmarks"], np.float64)).cuda()
+
         def residual_eval():
             """one LM iteration's worth of evaluation: association + J^T J / J^T r + cost (both summed over the GPUs inside
             the fused exchange) + the cost-only evaluation of this rank's residuals"""
-            ctx.cost_associate(mine["kf_t"], mine["circles"], mine["landmarks"], mine["step"])
+            # device-resident step: the key-frame tables are inputs like the records and lie in HBM (ecb_cost_associate_device);
+            # the end-to-end step below uploads them from host arrays inside the timed region
+            ctx.cost_associate_device(d_kf_t.data_ptr(), d_kf_c.data_ptr(), len(mine["kf_t"]), mine["circles"].shape[1],
+                                      d_lm.data_ptr(), mine["step"])
             normal_eq_all_ranks(intr, rot, trans)
             ctx.cost_eval(intr, rot, trans)
 
@@ -773,6 +780,24 @@ def main():
             stage.setdefault(k, []).append(v)
     ctx.set_profiling(False)
     stage = {k: float(np.mean(v)) for k, v in stage.items() if np.mean(v) > 0}
+
+    if os.environ.get("ECB_BENCH_GAPS"):   # wall clock of every API call of the device-resident step against its kernels
+        calls = [("load_events_device", lambda: ctx.load_events_device(d_raw.data_ptr(), n)),
+                 ("frontend_run", lambda: ctx.frontend_run(win, prms[-1]))]
+        if do_res:
+            calls += [("cost_associate_device", lambda: ctx.cost_associate_device(d_kf_t.data_ptr(), d_kf_c.data_ptr(), len(mine["kf_t"]),
+                                                                                  mine["circles"].shape[1], d_lm.data_ptr(), mine["step"])),
+                      ("normal_eq", lambda: normal_eq_all_ranks(intr, rot, trans)),
+                      ("cost_eval", lambda: ctx.cost_eval(intr, rot, trans))]
+        acc = {k: [] for k, _ in calls}
+        for _ in range(5):
+            for k, f in calls:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                f()
+                torch.cuda.synchronize()
+                acc[k].append((time.perf_counter() - t0) * 1e3)
+        sys.stderr.write("GAPS " + " ".join("%s %.3f" % (k, float(np.median(v))) for k, v in acc.items()) + "\n")
 
     # end to end through the C ABI with host buffers
     s, c = step_e2e()

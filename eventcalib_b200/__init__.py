@@ -60,7 +60,7 @@ SYMBOLS = ["ecb_ctx_create", "ecb_ctx_destroy", "ecb_last_error", "ecb_launch_co
            "ecb_frontend_clusters", "ecb_frontend_rectify", "ecb_frontend_device_ptrs", "ecb_dbscan_run", "ecb_dbscan_run_batch",
            "ecb_dbscan_run_ordered", "ecb_dbscan_run_batch_ordered", "ecb_dbscan_run_nd",
            "ecb_fit_circles", "ecb_set_profiling", "ecb_stage_ms", "ecb_cost_setup", "ecb_cost_set_rotation_model", "ecb_cost_layout",
-           "ecb_cost_associate", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq",
+           "ecb_cost_associate", "ecb_cost_associate_device", "ecb_cost_get_association", "ecb_cost_set_residuals", "ecb_cost_eval", "ecb_cost_normal_eq",
            "ecb_exchange_buffer_bytes", "ecb_cost_normal_eq_exchange", "ecb_device_alloc", "ecb_device_free", "ecb_ipc_export",
            "ecb_ipc_open", "ecb_ipc_close", "ecb_enable_peer_access", "ecb_lm_default_options", "ecb_lm_create",
            "ecb_lm_destroy", "ecb_lm_dimension", "ecb_lm_begin", "ecb_lm_propose", "ecb_lm_feedback", "ecb_lm_update",
@@ -125,6 +125,7 @@ def load_library():
     lib.ecb_cost_setup.argtypes = [vp, i32, vp, vp, dbl, dbl]
     lib.ecb_cost_layout.argtypes = [vp, vp, vp, vp, vp]
     lib.ecb_cost_associate.argtypes = [vp, vp, vp, i32, i32, vp, dbl, vp]
+    lib.ecb_cost_associate_device.argtypes = [vp, vp, vp, i32, i32, vp, dbl, vp]
     lib.ecb_cost_get_association.argtypes = [vp, vp, vp, i64]
     lib.ecb_cost_set_residuals.argtypes = [vp, vp, vp, vp, vp, i64]
     lib.ecb_cost_eval.argtypes = [vp, vp, vp, vp, vp]
@@ -438,6 +439,13 @@ class Context:
         n = C.c_int64(0)
         self._chk(self.lib.ecb_cost_associate(self.h, _ptr(kf_t), _ptr(circles), len(kf_t), circles.shape[1], _ptr(lm),
                                               float(step), C.byref(n)))
+        return n.value
+
+    def cost_associate_device(self, d_kf_t, d_circles, n_keyframes, n_circles, d_landmarks, step):
+        """the same with device pointers (integers) of the three tables"""
+        n = C.c_int64(0)
+        self._chk(self.lib.ecb_cost_associate_device(self.h, C.c_void_p(d_kf_t), C.c_void_p(d_circles), int(n_keyframes),
+                                                     int(n_circles), C.c_void_p(d_landmarks), float(step), C.byref(n)))
         return n.value
 
     def cost_association(self):

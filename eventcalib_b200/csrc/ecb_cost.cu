@@ -883,8 +883,21 @@ int ecb_cost_set_residuals(ecb_ctx *ctx, const double *obs_xy, const double *lm_
     return prepare_records(ctx, st);
 }
 
+static int cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_circles, int n_keyframes, int n_circles,
+                          const double *landmarks_xyz, double motion_time_step, int64_t *n_residuals, bool on_device);
+
 int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_circles, int n_keyframes, int n_circles,
                        const double *landmarks_xyz, double motion_time_step, int64_t *n_residuals) {
+    return cost_associate(ctx, kf_time, kf_circles, n_keyframes, n_circles, landmarks_xyz, motion_time_step, n_residuals, false);
+}
+
+int ecb_cost_associate_device(ecb_ctx *ctx, const double *d_kf_time, const double *d_kf_circles, int n_keyframes, int n_circles,
+                              const double *d_landmarks_xyz, double motion_time_step, int64_t *n_residuals) {
+    return cost_associate(ctx, d_kf_time, d_kf_circles, n_keyframes, n_circles, d_landmarks_xyz, motion_time_step, n_residuals, true);
+}
+
+static int cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_circles, int n_keyframes, int n_circles,
+                          const double *landmarks_xyz, double motion_time_step, int64_t *n_residuals, bool on_device) {
     if (!ctx || !ctx->cost) return ecb_fail(ctx, ECB_ERR_STATE, "ecb_cost_setup first");
     if (!kf_time || !kf_circles || !landmarks_xyz || n_keyframes < 1 || n_circles < 1) return ECB_ERR_ARG;
     if (ctx->n_events <= 0) return ecb_fail(ctx, ECB_ERR_STATE, "no events loaded");
@@ -894,8 +907,10 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     int rc;
     const int64_t n = ctx->n_events;
     const int nb = (int) ((n + AS_THREADS - 1) / AS_THREADS);
-    if ((rc = ecb_reserve(ctx, st->kf_t, (size_t) n_keyframes * 8))) return rc;
-    if ((rc = ecb_reserve(ctx, st->kf_circ, (size_t) n_keyframes * n_circles * 24))) return rc;
+    if (!on_device) {
+        if ((rc = ecb_reserve(ctx, st->kf_t, (size_t) n_keyframes * 8))) return rc;
+        if ((rc = ecb_reserve(ctx, st->kf_circ, (size_t) n_keyframes * n_circles * 24))) return rc;
+    }
     if ((rc = ecb_reserve(ctx, st->lm_tab, (size_t) n_circles * 24))) return rc;
     const int n_circ32 = (n_circles + 1) & ~1;
     if ((rc = ecb_reserve(ctx, st->kf_c32, (size_t) n_keyframes * n_circ32 * 8))) return rc;
@@ -903,9 +918,18 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     if ((rc = ecb_reserve(ctx, st->ev_cnt, (size_t) nb * 4 + 16))) return rc;
     if ((rc = ecb_reserve(ctx, st->ev_tag, (size_t) n * 2 + 16))) return rc;
     if ((rc = ecb_reserve(ctx, st->ev_flag, (size_t) nb * 8 + 16))) return rc;
-    if ((rc = ecb_h2d(ctx, st->kf_t.p, kf_time, (size_t) n_keyframes * 8))) return rc;
-    if ((rc = ecb_h2d(ctx, st->kf_circ.p, kf_circles, (size_t) n_keyframes * n_circles * 24))) return rc;
-    if ((rc = ecb_h2d(ctx, st->lm_tab.p, landmarks_xyz, (size_t) n_circles * 24))) return rc;
+    // key-frame tables: uploaded from host arrays, or used where they lie when the caller keeps them on the device (the
+    // landmark table is copied either way: the evaluation kernels read it long after this call)
+    const double *d_kf_t = kf_time, *d_kf_circ = kf_circles;
+    if (!on_device) {
+        if ((rc = ecb_h2d(ctx, st->kf_t.p, kf_time, (size_t) n_keyframes * 8))) return rc;
+        if ((rc = ecb_h2d(ctx, st->kf_circ.p, kf_circles, (size_t) n_keyframes * n_circles * 24))) return rc;
+        if ((rc = ecb_h2d(ctx, st->lm_tab.p, landmarks_xyz, (size_t) n_circles * 24))) return rc;
+        d_kf_t = (const double *) st->kf_t.p;
+        d_kf_circ = (const double *) st->kf_circ.p;
+    } else {
+        ECB_CUDA(ctx, cudaMemcpyAsync(st->lm_tab.p, landmarks_xyz, (size_t) n_circles * 24, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     AssocArgs a;
     a.ev_t = (const double *) ctx->ev_t.p;
     a.ev_xyp = (const uint32_t *) ctx->ev_xyp.p;
@@ -914,8 +938,8 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     a.knot_off = (const int *) st->d_knot_off.p;
     a.ncp = (const int *) st->d_ncp.p;
     a.n_splines = st->n_splines;
-    a.kf_t = (const double *) st->kf_t.p;
-    a.kf_circ = (const double *) st->kf_circ.p;
+    a.kf_t = d_kf_t;
+    a.kf_circ = d_kf_circ;
     a.lm_tab = (const double *) st->lm_tab.p;
     a.kf_c32 = (const float2 *) st->kf_c32.p;
     a.K = n_keyframes;
@@ -923,7 +947,7 @@ int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_cir
     a.n_circ32 = n_circ32;
     a.gate2 = 5 * motion_time_step * 5 * motion_time_step;  // EventCalibSpline.cpp:168
     ECB_PROF_BEGIN(ctx, ECB_STAGE_ASSOC);
-    k_circ32<<<(n_keyframes * n_circ32 + 255) / 256, 256, 0, ctx->stream>>>((const double *) st->kf_circ.p, n_keyframes, n_circles,
+    k_circ32<<<(n_keyframes * n_circ32 + 255) / 256, 256, 0, ctx->stream>>>(d_kf_circ, n_keyframes, n_circles,
                                                                            n_circ32, (float2 *) st->kf_c32.p);
     ECB_LAUNCHED(ctx);
     k_assoc_count<<<nb, AS_THREADS, 0, ctx->stream>>>(a, (uint16_t *) st->ev_tag.p, (uint32_t *) st->ev_cnt.p);

@@ -34,6 +34,9 @@ __constant__ uint32_t c_prime[ORD_NSTAGE] = {13,    29,     59,     127,    257,
 static const uint32_t h_prime[ORD_NSTAGE] = {13,    29,     59,     127,    257,    541,     1109,   2357,   5087,
                                              10273, 20753,  42043,  85229,  172933, 351061,  712697, 1447153};
 
+#ifndef ECB_ORD_POS16
+#define ECB_ORD_POS16 1  // 16-bit per-position arrays when the problems are small enough (more CTAs per SM)
+#endif
 #ifndef ECB_ORD_HTAB
 #define ECB_ORD_HTAB 1  // coordinate hashes from a table (one entry per sensor column / row) instead of two murmur rounds per pixel
 #endif
@@ -98,7 +101,9 @@ __device__ __forceinline__ uint32_t bucket_of(uint64_t h, int stage) {
 }
 
 // SM: arrays in shared memory (pointers derived from the shared array only -> LDS/STS/ATOMS), else per-CTA L2 scratch
-template <bool SM>
+// PosT: type of the per-position arrays (positions, arrival indices, bucket numbers): 16 bits when the largest problem and its
+// bucket count stay below 2^15 — the shared-memory footprint decides how many CTAs an SM holds, and the kernel is latency-bound
+template <bool SM, typename PosT>
 __global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_order(const OrderArgs a) {
     extern __shared__ __align__(16) uint32_t smo[];
     __shared__ uint32_t ws[33];
@@ -108,12 +113,13 @@ __global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_ord
     if constexpr (SM) base = smo;
     else base = a.gscratch + (size_t) blockIdx.x * a.gscratch_stride;
     const int MC = a.m_cap, BC = a.b_cap;
-    uint32_t *cur = base, *nxtL = base + MC;       // ping-pong order lists (arrival indices)
-    uint32_t *chain = base + 2 * MC;               // next position in the bucket's chain
-    uint32_t *bk = base + 3 * MC;                  // bucket of position p (bit 31: p is the bucket's first position)
-    uint32_t *first = base + 4 * MC;               // [BC] first position, then the run start of the bucket
+    constexpr PosT P_NONE = (PosT) ~(PosT) 0, P_FLAG = (PosT) ((PosT) 1 << (8 * sizeof(PosT) - 1)), P_MASK = (PosT) (P_FLAG - 1);
+    uint32_t *first = base;                        // [BC] first position, then the run start of the bucket
     uint32_t *head = first + BC;                   // [BC] chain head
     uint32_t *cnt = head + BC;                     // [BC] bucket size
+    PosT *cur = reinterpret_cast<PosT *>(cnt + BC), *nxtL = cur + MC;  // ping-pong order lists (arrival indices)
+    PosT *chain = cur + 2 * MC;                    // next position in the bucket's chain
+    PosT *bk = cur + 3 * MC;                       // bucket of position p (top bit: p is the bucket's first position)
 
     for (;;) {
         __syncthreads();
@@ -139,13 +145,14 @@ __global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_ord
             __syncthreads();
             // A: bucket of every position of S = (old list order) ++ (new arrivals), first position, chains, sizes
             for (int p = tid; p < newN; p += nthr) {
-                const uint32_t e = p < prevN ? cur[p] : (uint32_t) p;
-                if (p >= prevN) cur[p] = e;
+                const uint32_t e = p < prevN ? (uint32_t) cur[p] : (uint32_t) p;
+                if (p >= prevN) cur[p] = (PosT) e;
                 const uint32_t px = arr[e] & 0x3FFFFFFFu;
                 const uint32_t b = bucket_of((ECB_ORD_HTAB && a.htab) ? hash_pixel_tab(px, a.htab) : hash_pixel(px), stage);
-                bk[p] = b;
+                bk[p] = (PosT) b;
                 atomicMin(&first[b], (uint32_t) p);
-                chain[p] = atomicExch(&head[b], (uint32_t) p);
+                const uint32_t prev = atomicExch(&head[b], (uint32_t) p);
+                chain[p] = prev == ECB_NONE ? P_NONE : (PosT) prev;
                 atomicAdd(&cnt[b], 1u);
             }
             __syncthreads();
@@ -158,10 +165,10 @@ __global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_ord
                 const int p = c + lane;
                 uint32_t hs = 0;
                 if (p < p1) {
-                    const uint32_t b = bk[p];
+                    const PosT b = bk[p];
                     if (first[b] == (uint32_t) p) {
                         hs = cnt[b];
-                        bk[p] = b | 0x80000000u;
+                        bk[p] = (PosT) (b | P_FLAG);
                     }
                 }
                 wsum += hs;
@@ -173,10 +180,11 @@ __global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_ord
             for (int w = wid + 1; w < nwarp; ++w) carry += ws[w];
             for (int c = ((p1 - p0 + 31) & ~31) - 32 + p0; c >= p0; c -= 32) {
                 const int p = c + lane;
-                uint32_t hs = 0, b = 0;
+                uint32_t hs = 0;
+                PosT b = 0;
                 if (p < p1) {
                     b = bk[p];
-                    if (b & 0x80000000u) hs = cnt[b & 0x7FFFFFFFu];
+                    if (b & P_FLAG) hs = cnt[b & P_MASK];
                 }
                 // exclusive suffix sum inside the warp (lanes above)
                 uint32_t inc = hs;
@@ -185,19 +193,23 @@ __global__ void __launch_bounds__(SM ? ORD_THREADS : ORD_THREADS_BIG) k_uset_ord
                     const uint32_t t = __shfl_down_sync(0xffffffffu, inc, o);
                     if (lane + o < 32) inc += t;
                 }
-                if (hs) first[b & 0x7FFFFFFFu] = carry + inc - hs;
+                if (hs) first[b & P_MASK] = carry + inc - hs;
                 carry += __shfl_sync(0xffffffffu, inc, 0);
             }
             __syncthreads();
             // C: place — inside the run, descending position
             for (int p = tid; p < newN; p += nthr) {
-                const uint32_t b = bk[p] & 0x7FFFFFFFu;
+                const uint32_t b = bk[p] & P_MASK;
                 uint32_t g = 0;
-                for (uint32_t q = head[b]; q != ECB_NONE; q = chain[q]) g += q > (uint32_t) p;
+                for (uint32_t q = head[b]; q != ECB_NONE;) {
+                    g += q > (uint32_t) p;
+                    const PosT nq = chain[q];
+                    q = nq == P_NONE ? ECB_NONE : (uint32_t) nq;
+                }
                 nxtL[first[b] + g] = cur[p];
             }
             __syncthreads();
-            uint32_t *t = cur;
+            PosT *t = cur;
             cur = nxtL;
             nxtL = t;
             if (m <= B) break;
@@ -243,11 +255,13 @@ int ecb_launch_order(ecb_ctx *ctx, OrderArgs &a, int max_m) {
     }
     a.m_cap = (max_m + 3) & ~3;
     a.b_cap = ((int) h_prime[st] + 3) & ~3;
-    const size_t words = (size_t) 4 * a.m_cap + (size_t) 3 * a.b_cap;
+    const bool pos16 = ECB_ORD_POS16 && a.m_cap < 0x7FFF && a.b_cap < 0x7FFF;  // positions, arrival indices and bucket numbers in 15 bits
+    const size_t words = (pos16 ? (size_t) 2 : (size_t) 4) * a.m_cap + (size_t) 3 * a.b_cap;
     const size_t limit = (size_t) ctx->smem_optin - 2 * 1024;
     a.arrays_in_smem = words * 4 <= limit;
     const size_t smem = a.arrays_in_smem ? words * 4 : 0;
-    void (*kern)(const OrderArgs) = a.arrays_in_smem ? k_uset_order<true> : k_uset_order<false>;
+    void (*kern)(const OrderArgs) = a.arrays_in_smem ? (pos16 ? k_uset_order<true, uint16_t> : k_uset_order<true, uint32_t>)
+                                                     : (pos16 ? k_uset_order<false, uint16_t> : k_uset_order<false, uint32_t>);
     ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit)  /* constant: race-free */);
     int per_sm = 1;
     const int threads = a.arrays_in_smem ? ORD_THREADS : ORD_THREADS_BIG;

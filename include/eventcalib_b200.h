@@ -203,6 +203,10 @@ int ecb_cost_layout(ecb_ctx *ctx, int32_t *total_cp, int32_t *total_spans, int64
  * each frame's features (r < 0 marks an absent feature), landmarks_xyz[n_circles][3] the board points. */
 int ecb_cost_associate(ecb_ctx *ctx, const double *kf_time, const double *kf_circles, int n_keyframes, int n_circles,
                        const double *landmarks_xyz, double motion_time_step, int64_t *n_residuals);
+/* The same with the three tables already in device memory (the counterpart of ecb_load_events_device: a caller that keeps the
+ * key frames on the GPU across optimisations does not pay their upload per call; the tables are read during this call only). */
+int ecb_cost_associate_device(ecb_ctx *ctx, const double *d_kf_time, const double *d_kf_circles, int n_keyframes, int n_circles,
+                              const double *d_landmarks_xyz, double motion_time_step, int64_t *n_residuals);
 int ecb_cost_get_association(ecb_ctx *ctx, int64_t *event_index, int32_t *circle_id, int64_t cap);
 /* ... or explicit residual blocks (host arrays, ordered by (spline, time)) */
 int ecb_cost_set_residuals(ecb_ctx *ctx, const double *obs_xy, const double *lm_xyz, const double *t,

@@ -45,6 +45,26 @@ def test_cost_and_normal_equations(ctx, problem):
     assert np.abs(H - H_ref).max() / np.abs(H_ref).max() < 1e-11
 
 
+def test_association_from_device_tables(ctx, problem):
+    """ecb_cost_associate_device: the key-frame tables already in device memory give the same residual blocks and the same
+    normal equations, bit for bit, as the upload from host arrays (test_association_exact pins those to the oracle)"""
+    import torch
+    ev, pb, P, n, oe, oc = problem
+    x = (pb["intrinsics"], pb["rot_cp"], pb["trans_cp"])
+    ref = ctx.cost_normal_eq(*x)
+    d_t = torch.from_numpy(np.ascontiguousarray(pb["kf_t"], np.float64)).cuda()
+    d_c = torch.from_numpy(np.ascontiguousarray(pb["circles"], np.float64)).cuda()
+    d_l = torch.from_numpy(np.ascontiguousarray(pb["landmarks"], np.float64)).cuda()
+    torch.cuda.synchronize()
+    n2 = ctx.cost_associate_device(d_t.data_ptr(), d_c.data_ptr(), len(pb["kf_t"]), pb["circles"].shape[1], d_l.data_ptr(), pb["step"])
+    assert n2 == n
+    ge, gc = ctx.cost_association()
+    assert np.array_equal(ge, oe) and np.array_equal(gc, oc)
+    del d_t, d_c   # the tables are read during the call only; the landmark table was copied
+    got = ctx.cost_normal_eq(*x)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
 def test_deterministic(ctx, problem):
     ev, pb, P, n, oe, oc = problem
     x = (pb["intrinsics"], pb["rot_cp"], pb["trans_cp"])
