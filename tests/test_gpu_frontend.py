@@ -30,7 +30,7 @@ def _first_arrival(ev, lo, hi, pol):
 
 
 def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4.0, min_pts=2, order_mode=0,
-                  median_mode=0, cluster_min=5, stats=None):
+                  median_mode=0, cluster_min=5, stats=None, rows_cols=36):
     import eventcalib_b200 as ecb
     from eventcalib_b200 import synth
     ctx.set_sensor(width, height)
@@ -38,7 +38,7 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
     assert n == len(ev["t"])
     rthr = ecb.radius_threshold(width, height, 9, 4, True, 5.5, 1.75)
     prm = ecb.default_params(eps=eps, min_pts=min_pts, fit_circle=fit_circle, radius_threshold=rthr,
-                             order_mode=order_mode, median_mode=median_mode, cluster_min=cluster_min)
+                             order_mode=order_mode, median_mode=median_mode, cluster_min=cluster_min, rows_cols=rows_cols)
     ctx.frontend_run(windows, prm)
     summ = ctx.summary()
     pts = [ctx.points(0), ctx.points(1)]
@@ -64,7 +64,7 @@ def _check_stream(ctx, oracle_mod, ev, windows, width, height, fit_circle, eps=4
             V.append(xy)
         # median_mode 1: the oracle runs the real std::nth_element over the BFS-ordered member lists, like the reference
         r = oracle_mod.extract(V[1], V[0], eps=eps, minS=min_pts, fitCircle=fit_circle, Rthr=rthr,
-                               canonical_median=(median_mode == 0), clusterMin=cluster_min)
+                               canonical_median=(median_mode == 0), clusterMin=cluster_min, rows_cols=rows_cols)
         for pol, key in ((0, "n"), (1, "p")):
             o, k = int(s["point_offset"][pol]), int(s["n_points"][pol])
             assert np.array_equal(pts[pol][1][o:o + k], r[key + "_labels"]), "labels differ window %d pol %d" % (w, pol)
@@ -110,6 +110,65 @@ def test_reference_exact_mode(ctx, oracle_mod, fit_circle):
         ctx.frontend_run(win, ecb.default_params(fit_circle=fit_circle, radius_threshold=rthr, order_mode=1, median_mode=mm))
         meds.append(np.concatenate([ctx.clusters(w, pol)[2] for w in range(len(win)) for pol in (0, 1)]))
     assert len(meds[0]) == len(meds[1]) and (meds[0] != meds[1]).any()
+
+
+def _shape_stream(seed, sorted_noise):
+    """Hand-built window: clusters that are symmetric about the image diagonal (x <-> y), so most squared norms occur twice and
+    the median norm of nearly every cluster is tied — each of them goes through the member-order pass.  Sizes / densities
+    straddle the limits of its small-cluster path (48 members, 32 visible neighbours, tree depth 48): 5x5 .. 8x8 blocks,
+    anti-diagonal lines of 47 / 48 / 49 / 60 pixels, rings, a filled disc; `sorted_noise` adds isolated pixels that arrive
+    first in ascending (x, y) — with order_mode 0 they make the emulated kd-tree a chain more than 48 levels deep."""
+    rng = np.random.default_rng(seed)
+    px = []
+    c = 12
+    for k in (5, 6, 7, 8):                      # k x k blocks centred on the diagonal
+        px += [(c + i, c + j) for i in range(k) for j in range(k)]
+        c += k + 14
+    for L in (47, 48, 49, 60):                  # anti-diagonal lines through a diagonal pixel
+        px += [(c + 30 + i - L // 2, c + 30 - (i - L // 2)) for i in range(L)]
+        c += 24
+    for r, cy in ((5.0, 120.0), (7.5, 170.0)):  # rings (left of the diagonal shapes)
+        for a in np.linspace(0, 2 * np.pi, int(8 * r), endpoint=False):
+            px.append((int(round(30.0 + r * np.cos(a))), int(round(cy + r * np.sin(a)))))
+    px += [(238 + i, 238 + j) for i in range(-6, 7) for j in range(-6, 7) if i * i + j * j <= 36]   # filled disc on the diagonal
+    px = list(dict.fromkeys(px))
+    assert all(0 <= x < 346 and 0 <= y < 260 for x, y in px)
+    px = [px[i] for i in rng.permutation(len(px))]
+    noise = [(4 + 5 * i, 254 + (i % 2) * 5) for i in range(60)] if sorted_noise else []
+    noise = [(x, y) for x, y in noise if 0 <= x < 346 and 0 <= y < 260]
+    pos = noise + px
+    # negative polarity: plain 3x3 blocks in the strip x >= 270 that the shapes never reach (nothing cancels)
+    neg = [(272 + 12 * (b % 6) + i, 10 + 40 * (b // 6) + j) for b in range(12) for i in range(3) for j in range(3)]
+    assert not set(pos) & set(neg)
+    ev = {"t": [], "x": [], "y": [], "p": []}
+    t = 5.0
+    for pol, pts in ((1, pos), (0, neg)):
+        for x, y in pts:
+            t += 1e-7
+            ev["t"].append(t)
+            ev["x"].append(x)
+            ev["y"].append(y)
+            ev["p"].append(pol)
+    return {"t": np.array(ev["t"]), "x": np.array(ev["x"], np.uint16), "y": np.array(ev["y"], np.uint16),
+            "p": np.array(ev["p"], np.uint8)}
+
+
+@pytest.mark.parametrize("order_mode", [0, 1])
+def test_member_order_small_cluster_limits(ctx, oracle_mod, order_mode):
+    """median_mode 1 on clusters around every limit of k_bfs_order's small-cluster path (ecb_bfs.cu: bfs_small) and on the
+    walk it falls back to: labels, kept clusters and std::nth_element medians equal the reference restatement."""
+    ev = _shape_stream(5, sorted_noise=True)
+    win = np.array([[4.0, 6.0]])
+    n_cand = _check_stream(ctx, oracle_mod, ev, win, 346, 260, 0, order_mode=order_mode, median_mode=1, rows_cols=4)
+    assert n_cand >= 0
+    # the medians are really order-dependent here: the canonical rule picks a different member somewhere
+    import eventcalib_b200 as ecb
+    rthr = ecb.radius_threshold(346, 260, 9, 4, True, 5.5, 1.75)
+    meds = []
+    for mm in (0, 1):
+        ctx.frontend_run(win, ecb.default_params(radius_threshold=rthr, order_mode=order_mode, median_mode=mm, rows_cols=4))
+        meds.append(np.concatenate([ctx.clusters(0, pol)[2] for pol in (0, 1)]))
+    assert len(meds[0]) == len(meds[1]) >= 16 and (meds[0] != meds[1]).any()
 
 
 def test_overlapping_and_empty_windows(ctx, oracle_mod):
