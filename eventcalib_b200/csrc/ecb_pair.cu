@@ -17,6 +17,9 @@ namespace {
 
 constexpr int PAIR_THREADS = 256;
 constexpr int KNN_MAX = 8;
+#ifndef ECB_PAIR_KM4
+#define ECB_PAIR_KM4 1  // knn_num <= 4 (the reference's default is 3): half-size candidate arrays, half the unrolled code
+#endif
 
 // Eigen PartialPivLU<Matrix3d>::solve, unblocked, first-max pivot [external: Eigen, not in /root/reference]
 // (kept out of line, like warp_abs_dev / warp_knn: k_pair inlined was 180 KB of SASS and stalled on instruction fetch)
@@ -82,6 +85,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <bool DIRECT>
 __device__ __noinline__ double warp_abs_dev(const uint32_t *pts, const uint32_t *mem, int sz, double cx, double cy, double r) {
     double s = 0;
+#pragma unroll 1  // clusters rarely exceed one warp's width; the unrolled FP64 sqrt bodies only cost instruction cache
     for (int i = threadIdx.x & 31; i < sz; i += 32) {
         const uint32_t p = DIRECT ? mem[i] : pts[mem[i]];
         const double dx = (double) ECB_PIX_X(p) - cx, dy = (double) ECB_PIX_Y(p) - cy;
@@ -123,6 +127,7 @@ __device__ __noinline__ void warp_knn(const int *mx, const int *my, int n, int q
     }
     for (int j = 0; j < k; ++j) {
         unsigned long long best = ~0ull;
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) {
             const long long dx = qx - mx[i], dy = qy - my[i];
             const unsigned long long key = ((unsigned long long) (dx * dx + dy * dy) << 32) | (unsigned) i;
@@ -143,7 +148,11 @@ __device__ __noinline__ void warp_knn(const int *mx, const int *my, int n, int q
 // Per-CTA tables over the kept clusters (max_k entries each): accepted circle (3 doubles), medians of both polarities,
 // accepted negative partner.  GT = false: in dynamic shared memory (pointers derived from the shared array only);
 // GT = true (very many kept clusters, e.g. noisy 1280x720 windows): in per-CTA global scratch.
-template <bool DIRECT, bool FIT, bool GT>
+// KM: capacity of the per-warp candidate arrays (>= knn_num).  The kernel is instruction-cache bound (ncu: 110 KB of SASS,
+// `no_instruction` the second largest stall at 4.8 per issue): the reference's default is 3 neighbours, and KM = 4 instead of 8
+// together with the un-unrolled member / staging loops takes the code to 63 KB and the kernel from 1.25 to 0.98 ms
+// (profiles/r2t_pair_code_size.md; folding the two candidate passes into one loop body — 50 KB — was slower again: 1.04 ms)
+template <bool DIRECT, bool FIT, bool GT, int KM = KNN_MAX>
 __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) uint32_t sm_dyn[];
     double (*acc_c)[3];
@@ -171,10 +180,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
         const KeptCluster *kn = a.ktab + (size_t) (2 * w) * a.max_k, *kp = a.ktab + (size_t) (2 * w + 1) * a.max_k;
         const int nkn = hn.n_kept, nkp = hp.n_kept;
         __syncthreads();
+#pragma unroll 1
         for (int i = tid; i < nkn; i += PAIR_THREADS) {
             mx[0][i] = kn[i].med_x;
             my[0][i] = kn[i].med_y;
         }
+#pragma unroll 1
         for (int i = tid; i < nkp; i += PAIR_THREADS) {
             mx[1][i] = kp[i].med_x;
             my[1][i] = kp[i].med_y;
@@ -190,7 +201,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
             // stage the kept clusters' member pixels once (coalesced list read, gathered pixel read), then every
             // fit-error loop runs out of shared memory
             const int totP = nkp ? kp[nkp - 1].mem_off + kp[nkp - 1].size : 0, totN = nkn ? kn[nkn - 1].mem_off + kn[nkn - 1].size : 0;
+#pragma unroll 1
             for (int i = tid; i < totN; i += PAIR_THREADS) sm_pix[i] = ptsN[memN[i]];
+#pragma unroll 1
             for (int i = tid; i < totP; i += PAIR_THREADS) sm_pix[a.smem_cap + i] = ptsP[memP[i]];
             memN = sm_pix;
             memP = sm_pix + a.smem_cap;
@@ -203,8 +216,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
                 if (lane == 0) pi = atomicAdd(&s_next, 1);
                 pi = __shfl_sync(0xffffffffu, pi, 0);
                 if (pi >= nkp) break;
-                int nidx[KNN_MAX], pidx[KNN_MAX];
-                unsigned long long d2[KNN_MAX];
+                int nidx[KM], pidx[KM];
+                unsigned long long d2[KM];
                 if (!FIT) {  // CirclesEventFrame.cpp:282-312
                     warp_knn(mx[0], my[0], nkn, mx[1][pi], my[1][pi], 1, nidx, d2);
                     if ((double) d2[0] > gate) continue;
@@ -226,8 +239,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
                         acc_c[pi][2] = r;
                     }
                 } else {  // CirclesEventFrame.cpp:180-281
-                    const int K = min(min(a.knn_num, KNN_MAX), min(nkn, nkp));
-                    double ferr[KNN_MAX], fr[KNN_MAX], fcx[KNN_MAX], fcy[KNN_MAX];
+                    const int K = min(min(a.knn_num, KM), min(nkn, nkp));
+                    double ferr[KM], fr[KM], fcx[KM], fcy[KM];
                     warp_knn(mx[0], my[0], nkn, mx[1][pi], my[1][pi], K, nidx, d2);
                     int real = K;
                     for (int oi = 0; oi < K; ++oi)
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
                     auto fit_pairs = [&](const int *plist, const int *nlist, bool p_varies, int cnt) {
                         int p = plist[0], n = nlist[0];
 #pragma unroll
-                        for (int q = 1; q < KNN_MAX; ++q)
+                        for (int q = 1; q < KM; ++q)
                             if (lane == q) {
                                 if (p_varies) p = plist[q]; else n = nlist[q];
                             }
@@ -508,7 +521,8 @@ int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     }
     ECB_PROF_BEGIN(ctx, ECB_STAGE_PAIR);
     void (*kern)(const PairArgs) = gt ? (a.fit_circle ? k_pair<false, true, true> : k_pair<false, false, true>)
-                                   : direct ? (a.fit_circle ? k_pair<true, true, false> : k_pair<true, false, false>)
+                                   : direct ? (a.fit_circle ? (ECB_PAIR_KM4 && a.knn_num <= 4 ? k_pair<true, true, false, 4> : k_pair<true, true, false>)
+                                                            : k_pair<true, false, false>)
                                             : (a.fit_circle ? k_pair<false, true, false> : k_pair<false, false, false>);
     ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cap)  /* constant: race-free */);
     kern<<<grid, PAIR_THREADS, smem, ctx->stream>>>(a);
