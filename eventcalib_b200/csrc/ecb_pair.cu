@@ -17,8 +17,14 @@ namespace {
 
 constexpr int PAIR_THREADS = 256;
 constexpr int KNN_MAX = 8;
+#ifndef ECB_PAIR_KM
+#define ECB_PAIR_KM 3      // capacity of the candidate arrays of the small variant (the reference's knn_num)
+#endif
+#ifndef ECB_PAIR_JROLL
+#define ECB_PAIR_JROLL 1   // the per-candidate loop of the pair evaluation stays rolled (63 -> 47 KB of SASS, 0.98 -> 0.91 ms)
+#endif
 #ifndef ECB_PAIR_KM4
-#define ECB_PAIR_KM4 1  // knn_num <= 4 (the reference's default is 3): half-size candidate arrays, half the unrolled code
+#define ECB_PAIR_KM4 1  // knn_num <= ECB_PAIR_KM: small candidate arrays, a fraction of the unrolled code
 #endif
 
 // Eigen PartialPivLU<Matrix3d>::solve, unblocked, first-max pivot [external: Eigen, not in /root/reference]
@@ -149,8 +155,8 @@ __device__ __noinline__ void warp_knn(const int *mx, const int *my, int n, int q
 // accepted negative partner.  GT = false: in dynamic shared memory (pointers derived from the shared array only);
 // GT = true (very many kept clusters, e.g. noisy 1280x720 windows): in per-CTA global scratch.
 // KM: capacity of the per-warp candidate arrays (>= knn_num).  The kernel is instruction-cache bound (ncu: 110 KB of SASS,
-// `no_instruction` the second largest stall at 4.8 per issue): the reference's default is 3 neighbours, and KM = 4 instead of 8
-// together with the un-unrolled member / staging loops takes the code to 63 KB and the kernel from 1.25 to 0.98 ms
+// `no_instruction` the second largest stall at 4.8 per issue): the reference's default is 3 neighbours, and KM = 3 instead of 8
+// together with the un-unrolled member / staging / candidate loops takes the code to 47 KB and the kernel from 1.25 to 0.91 ms
 // (profiles/r2t_pair_code_size.md; folding the two candidate passes into one loop body — 50 KB — was slower again: 1.04 ms)
 template <bool DIRECT, bool FIT, bool GT, int KM = KNN_MAX>
 __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
@@ -272,6 +278,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair(const PairArgs a) {
                             const double approx = sqrt(ddx * ddx + ddy * ddy) / 2;
                             lok = !(lr > a.rthr || lr > 2 * approx);
                         }
+#if ECB_PAIR_JROLL
+#pragma unroll 1
+#endif
                         for (int j = 0; j < cnt; ++j) {
                             const int pj = p_varies ? plist[j] : plist[0], nj = p_varies ? nlist[0] : nlist[j];
                             fcx[j] = __shfl_sync(0xffffffffu, lcx, j);
@@ -521,7 +530,7 @@ int ecb_launch_pair(ecb_ctx *ctx, PairArgs &a) {
     }
     ECB_PROF_BEGIN(ctx, ECB_STAGE_PAIR);
     void (*kern)(const PairArgs) = gt ? (a.fit_circle ? k_pair<false, true, true> : k_pair<false, false, true>)
-                                   : direct ? (a.fit_circle ? (ECB_PAIR_KM4 && a.knn_num <= 4 ? k_pair<true, true, false, 4> : k_pair<true, true, false>)
+                                   : direct ? (a.fit_circle ? (ECB_PAIR_KM4 && a.knn_num <= ECB_PAIR_KM ? k_pair<true, true, false, ECB_PAIR_KM> : k_pair<true, true, false>)
                                                             : k_pair<true, false, false>)
                                             : (a.fit_circle ? k_pair<false, true, false> : k_pair<false, false, false>);
     ECB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cap)  /* constant: race-free */);
