@@ -38,6 +38,9 @@ struct Smem {
 #ifndef ECB_CL_RANKORDER
 #define ECB_CL_RANKORDER 1  // steps 5 - 6 walk the points in row-major rank order instead of pid order
 #endif
+#ifndef ECB_CL_ROLL
+#define ECB_CL_ROLL 1     // one-or-two-trip bookkeeping loops stay rolled (code size)
+#endif
 #ifndef ECB_CL_UNSET
 #define ECB_CL_UNSET 1      // planes cleared once per CTA, every problem un-sets the words it touched
 #endif
@@ -151,8 +154,14 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             const int per = (NW + nthr - 1) / nthr;
             const int b = tid * per, e = min(NW, b + per);
             uint32_t c = 0;
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
             for (int i = b; i < e; ++i) c += __popc(s.U[i]);
             uint32_t ex = block_excl_scan(c, ws, &n_ranked);
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
             for (int i = b; i < e; ++i) {
                 s.wrank[i] = (RankT) ex;
                 ex += __popc(s.U[i]);
@@ -485,8 +494,14 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             const int per = (nw32 + nthr - 1) / nthr;
             const int b = tid * per, e = min(nw32, b + per);
             uint32_t c = 0;
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
             for (int i = b; i < e; ++i) c += __popc(seedmask[i]);
             uint32_t ex = block_excl_scan(c, ws, &n_clusters);
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
             for (int i = b; i < e; ++i) {
                 seedpref[i] = ex;
                 ex += __popc(seedmask[i]);
@@ -525,8 +540,14 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             const int per = (nc + nthr - 1) / nthr;
             const int b = tid * per, e = min(nc, b + per);
             uint32_t c = 0;
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
             for (int i = b; i < e; ++i) c += csize[i] >= a.cluster_min;
             uint32_t ex = block_excl_scan(c, ws, &n_kept);
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
             for (int i = b; i < e; ++i) {
                 const bool k = csize[i] >= a.cluster_min;
                 keptidx[i] = k ? ex : ECB_NONE;
@@ -547,6 +568,9 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
         __syncthreads();
         if (wid == 0) {  // member-list offsets: exclusive scan of k_size[0..n_kept)
             uint32_t run = 0;
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
             for (int base = 0; base < (int) n_kept; base += 32) {
                 uint32_t v = base + lane < (int) n_kept ? (uint32_t) k_size[base + lane] : 0;
                 uint32_t inc = warp_incl_scan(v);
@@ -584,8 +608,14 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                     __syncwarp();
                 }
                 __syncthreads();
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
                 for (int k = tid; k < (int) n_kept; k += nthr) {
                     uint32_t run = 0;
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
                     for (int w = 0; w < nwarp; ++w) {
                         const uint32_t t = cnt[w * n_kept + k];
                         cnt[w * n_kept + k] = run;
@@ -657,6 +687,9 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
             bool tie = false;
             if (key32) {
                 // (norm^2, pid) packed into one word: one shared load and one compare per pair
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
                 for (int i = lane; i < sz; i += 32) mnorm[base + i] = (mnorm[base + i] << pbits) | members[base + i];
                 __syncwarp();
                 uint32_t mkey = 0;
@@ -670,6 +703,9 @@ __global__ void __launch_bounds__(ECB_CL_THREADS, 2) k_cluster(const ClusterArgs
                 for (int o = 16; o > 0; o >>= 1) mkey = max(mkey, __shfl_xor_sync(0xffffffffu, mkey, o));
                 med = (int) (mkey & ((1u << pbits) - 1u));
                 int eq = 0;  // std::nth_element's pick among equal norms depends on the member order
+#if ECB_CL_ROLL
+#pragma unroll 1
+#endif
                 for (int i = lane; i < sz; i += 32) eq += (mnorm[base + i] >> pbits) == (mkey >> pbits);
                 tie = __reduce_add_sync(0xffffffffu, eq) > 1;
                 if (lane != 0) med = -1;
