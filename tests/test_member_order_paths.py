@@ -97,7 +97,7 @@ def _cloud(rng, kind, n, eps=4.0):
         pts = [(st * i + int(rng.integers(0, 2)), st * j) for i in range(12) for j in range(12) if rng.random() < 0.8]
         pts = list(dict.fromkeys(pts))
     else:                    # dense random blob
-        pts = list({(int(x), int(y)) for x, y in rng.integers(0, 40, size=(n, 2))})
+        pts = list({(int(x), int(y)) for x, y in rng.integers(0, int(8 * eps) + 8, size=(n, 2))})
     rng.shuffle(pts)
     return [tuple(p) for p in pts]
 
