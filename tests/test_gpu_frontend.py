@@ -117,7 +117,7 @@ def _shape_stream(seed, sorted_noise):
     the median norm of nearly every cluster is tied — each of them goes through the member-order pass.  Sizes / densities
     straddle the limits of its small-cluster path (48 members, 32 visible neighbours, tree depth 48): 5x5 .. 8x8 blocks,
     anti-diagonal lines of 47 / 48 / 49 / 60 pixels, rings, a filled disc; `sorted_noise` adds isolated pixels that arrive
-    first in ascending (x, y) — with order_mode 0 they make the emulated kd-tree a chain more than 48 levels deep."""
+    first in ascending x — with order_mode 0 they make the emulated kd-tree a chain more than 48 levels deep."""
     rng = np.random.default_rng(seed)
     px = []
     c = 12
@@ -131,10 +131,14 @@ def _shape_stream(seed, sorted_noise):
         for a in np.linspace(0, 2 * np.pi, int(8 * r), endpoint=False):
             px.append((int(round(30.0 + r * np.cos(a))), int(round(cy + r * np.sin(a)))))
     px += [(238 + i, 238 + j) for i in range(-6, 7) for j in range(-6, 7) if i * i + j * j <= 36]   # filled disc on the diagonal
+    for a in np.linspace(0, 2 * np.pi, 40, endpoint=False):                                      # a small ring far to the right
+        px.append((int(round(322.0 + 5.0 * np.cos(a))), int(round(120.0 + 5.0 * np.sin(a)))))
     px = list(dict.fromkeys(px))
     assert all(0 <= x < 346 and 0 <= y < 260 for x, y in px)
     px = [px[i] for i in rng.permutation(len(px))]
-    noise = [(4 + 5 * i, 254 + (i % 2) * 5) for i in range(60)] if sorted_noise else []
+    # isolated pixels along y = 0 with ascending x: inserted first and in this order (order_mode 0) they form ONE chain, so a
+    # cluster at large x hangs more than 48 levels deep in the emulated tree
+    noise = [(6 * i, 0) for i in range(57)] if sorted_noise else []
     noise = [(x, y) for x, y in noise if 0 <= x < 346 and 0 <= y < 260]
     pos = noise + px
     # negative polarity: plain 3x3 blocks in the strip x >= 270 that the shapes never reach (nothing cancels)
